@@ -1,0 +1,73 @@
+"""ctypes binding of libdsp_b200.so (include/dsp_b200.h).
+
+The product path has no CPU fallback: if the library is missing or cannot be loaded,
+``lib()`` raises and every operator that needs it fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdsp_b200.so")
+
+# every symbol include/dsp_b200.h declares (tests check the export list against this)
+SYMBOLS = (
+    "dsp_abi_version", "dsp_last_error", "dsp_create", "dsp_destroy", "dsp_set_param",
+    "dsp_pack_weights", "dsp_forward", "dsp_forward_host", "dsp_launch_count",
+    "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate",
+)
+
+MODULES = {"both_bilstm": 0, "seq_bilstm": 1, "signal_bilstm": 2}
+PRECISIONS = {"fp32": 0, "fp16": 1}
+
+
+class DspConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "seq_len", "signal_len", "num_layers1", "num_layers2", "num_classes", "hidden_size",
+        "vocab_size", "embedding_size", "is_base", "is_signallen", "module", "device",
+        "precision", "reserved")] + [("max_batch", C.c_int64)]
+
+
+class DspError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; raise if it is not there (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DspError(
+            "libdsp_b200.so is not built (%s). Run `python -m deepsignal_plant_b200.build` "
+            "(needs nvcc); there is no CPU or PyTorch fallback for this path." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, fp, i64, u64 = C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64
+    L.dsp_abi_version.restype = C.c_int
+    L.dsp_last_error.restype = C.c_char_p
+    L.dsp_create.argtypes = [C.POINTER(vp), C.POINTER(DspConfig)]
+    L.dsp_destroy.argtypes = [vp]
+    L.dsp_set_param.argtypes = [vp, C.c_char_p, fp, i64]
+    L.dsp_pack_weights.argtypes = [vp]
+    L.dsp_forward.argtypes = [vp, fp, fp, fp, fp, fp, C.POINTER(vp), u64, i64, fp, fp, vp, vp]
+    L.dsp_forward_host.argtypes = [vp, fp, fp, fp, fp, fp, u64, i64, fp, fp, vp]
+    L.dsp_launch_count.argtypes = [vp]
+    L.dsp_launch_count.restype = i64
+    L.dsp_set_timing.argtypes = [vp, C.c_int]
+    L.dsp_get_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(i64)]
+    L.dsp_freq_aggregate.argtypes = [C.c_int, vp, vp, vp, vp, i64, C.c_double, C.c_int,
+                                     vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
+    for name in SYMBOLS:
+        getattr(L, name)  # AttributeError here means header and library disagree
+    _lib = L
+    return L
+
+
+def check(status, what="libdsp_b200"):
+    if status != 0:
+        msg = lib().dsp_last_error()
+        raise DspError("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

@@ -1,0 +1,523 @@
+// C ABI of libdsp_b200 (include/dsp_b200.h): handle life cycle, weight packing,
+// forward orchestration, host-buffer streaming.  The arithmetic lives in kernels_f32.cu
+// (CUDA-core fp32) and kernels_tc.cu (tcgen05 FP16 operands).
+#include "common.cuh"
+#include "tc.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+namespace dsp {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int dev_alloc(Model* m, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return DSP_ERR_NOMEM;
+    }
+    m->device_allocs.push_back(*p);
+    return DSP_OK;
+}
+
+int upload(Model* m, float** dst, const std::vector<float>& host) {
+    int rc = dev_alloc(m, (void**)dst, host.size() * sizeof(float));
+    if (rc) return rc;
+    DSP_CUDA(cudaMemcpy(*dst, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return DSP_OK;
+}
+
+const std::vector<float>* find_param(Model* m, const std::string& name, int64_t numel) {
+    auto it = m->params.find(name);
+    if (it == m->params.end()) {
+        set_error("state_dict entry '%s' was not set before dsp_pack_weights", name.c_str());
+        return nullptr;
+    }
+    if ((int64_t)it->second.size() != numel) {
+        set_error("state_dict entry '%s' has %zu elements, expected %lld", name.c_str(), it->second.size(),
+                  (long long)numel);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+// nn.LSTM parameters of one stack -> kernel layouts.
+int pack_lstm_stack(Model* m, const char* prefix, int num_layers, int in0, int H,
+                    std::vector<LstmLayer>& out) {
+    out.clear();
+    for (int l = 0; l < num_layers; ++l) {
+        LstmLayer L;
+        L.K = (l == 0) ? in0 : 2 * H;
+        L.H = H;
+        const int Kp = ru(L.K, 4), Hp = ru(H, 4);
+        const std::vector<float>* raw[2][4];
+        for (int d = 0; d < 2; ++d) {
+            char name[128];
+            const char* sfx = d ? "_reverse" : "";
+            snprintf(name, sizeof(name), "%s.weight_ih_l%d%s", prefix, l, sfx);
+            const std::vector<float>* wih = find_param(m, name, (int64_t)4 * H * L.K);
+            snprintf(name, sizeof(name), "%s.weight_hh_l%d%s", prefix, l, sfx);
+            const std::vector<float>* whh = find_param(m, name, (int64_t)4 * H * H);
+            snprintf(name, sizeof(name), "%s.bias_ih_l%d%s", prefix, l, sfx);
+            const std::vector<float>* bih = find_param(m, name, (int64_t)4 * H);
+            snprintf(name, sizeof(name), "%s.bias_hh_l%d%s", prefix, l, sfx);
+            const std::vector<float>* bhh = find_param(m, name, (int64_t)4 * H);
+            if (!wih || !whh || !bih || !bhh) return DSP_ERR_STATE;
+            raw[d][0] = wih; raw[d][1] = whh; raw[d][2] = bih; raw[d][3] = bhh;
+            std::vector<float> wt((size_t)(Kp + Hp) * 4 * H, 0.f), bias((size_t)4 * H);
+            for (int g = 0; g < 4; ++g)
+                for (int j = 0; j < H; ++j) {
+                    const int row = g * H + j;
+                    for (int k = 0; k < L.K; ++k) wt[((size_t)k * 4 + g) * H + j] = (*wih)[(size_t)row * L.K + k];
+                    for (int k = 0; k < H; ++k) wt[((size_t)(Kp + k) * 4 + g) * H + j] = (*whh)[(size_t)row * H + k];
+                    bias[row] = (*bih)[row] + (*bhh)[row];
+                }
+            int rc = upload(m, &L.f32[d].wt, wt);
+            if (rc) return rc;
+            rc = upload(m, &L.f32[d].bias, bias);
+            if (rc) return rc;
+        }
+        if (m->cfg.precision == DSP_PRECISION_FP16) {
+            int rc = tc_pack_lstm_layer(m, L, raw[0][0]->data(), raw[0][1]->data(), raw[0][2]->data(), raw[0][3]->data(),
+                                        raw[1][0]->data(), raw[1][1]->data(), raw[1][2]->data(), raw[1][3]->data());
+            if (rc) return rc;
+        }
+        out.push_back(L);
+    }
+    return DSP_OK;
+}
+
+int pack_dense(Model* m, const char* prefix, int K, int J, DenseF32& D) {
+    std::string wn = std::string(prefix) + ".weight", bn = std::string(prefix) + ".bias";
+    const std::vector<float>* w = find_param(m, wn, (int64_t)J * K);
+    const std::vector<float>* b = find_param(m, bn, J);
+    if (!w || !b) return DSP_ERR_STATE;
+    D.K = K; D.J = J;
+    const int Kp = ru(K, 4);
+    std::vector<float> wt((size_t)Kp * J, 0.f);
+    for (int j = 0; j < J; ++j)
+        for (int k = 0; k < K; ++k) wt[(size_t)k * J + j] = (*w)[(size_t)j * K + k];
+    int rc = upload(m, &D.wt, wt);
+    if (rc) return rc;
+    rc = upload(m, &D.bias, *b);
+    if (rc) return rc;
+    if (m->cfg.precision == DSP_PRECISION_FP16) {
+        rc = tc_pack_dense(m, D, w->data(), b->data());
+        if (rc) return rc;
+    }
+    return DSP_OK;
+}
+
+bool has_seq(const Model* m) { return m->cfg.module != DSP_SIGNAL_BILSTM; }
+bool has_signal(const Model* m) { return m->cfg.module != DSP_SEQ_BILSTM; }
+
+struct StateGroup { int layers; int hidden; };
+
+void state_groups(const Model* m, StateGroup g[3]) {
+    g[0] = {has_seq(m) ? m->cfg.num_layers2 : 0, m->nhid_seq};
+    g[1] = {has_signal(m) ? m->cfg.num_layers2 : 0, m->nhid_signal};
+    g[2] = {m->cfg.num_layers1, m->cfg.hidden_size};
+}
+
+cudaEvent_t next_event(Model* m) {
+    if (m->event_next == m->event_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        m->event_pool.push_back(e);
+    }
+    return m->event_pool[m->event_next++];
+}
+
+struct Span {
+    Model* m; cudaStream_t st; cudaEvent_t a = nullptr;
+    int cls;
+    Span(Model* m_, int cls_, cudaStream_t st_) : m(m_), st(st_), cls(cls_) {
+        if (m->timing) { a = next_event(m); cudaEventRecord(a, st); }
+    }
+    ~Span() {
+        if (m->timing) { cudaEvent_t b = next_event(m); cudaEventRecord(b, st); m->spans.push_back({cls, a, b}); }
+    }
+};
+
+// One pass over n <= cap sites whose inputs already sit on the device.
+// states6: per group h0/c0 base pointers for THIS chunk and the dir stride (floats) of
+// each group; nullptr -> Philox.
+int forward_chunk(Model* m, const float* kmer, const float* means, const float* stds, const float* lens,
+                  const float* signals, const float* const* states6, const int64_t* state_stride,
+                  uint64_t seed, uint64_t chunk_id, int64_t n, float* logits, float* probs, int32_t* labels,
+                  cudaStream_t st) {
+    const dsp_config& c = m->cfg;
+    const int T = c.seq_len, H = c.hidden_size;
+    StateGroup grp[3];
+    state_groups(m, grp);
+    const float* h0[3]; const float* c0[3]; int64_t sstride[3];
+    if (states6) {
+        for (int g = 0; g < 3; ++g) { h0[g] = states6[2 * g]; c0[g] = states6[2 * g + 1]; sstride[g] = state_stride[g]; }
+    } else {
+        Span sp(m, 0, st);
+        float* p = m->states;
+        int64_t total = 0;
+        for (int g = 0; g < 3; ++g) {
+            int64_t cnt = (int64_t)grp[g].layers * 2 * n * grp[g].hidden;
+            h0[g] = p + total; total += cnt;
+            c0[g] = p + total; total += cnt;
+            sstride[g] = n * grp[g].hidden;
+        }
+        int rc = philox_normal(m, m->states, total, seed, chunk_id, st);
+        if (rc) return rc;
+    }
+    if (c.precision == DSP_PRECISION_FP16)
+        return tc_forward_chunk(m, kmer, means, stds, lens, signals, h0, c0, sstride, n, logits, probs, labels, st);
+
+    int rc;
+    int comb_off = 0;
+    if (has_seq(m)) {
+        { Span sp(m, 0, st); rc = f32_assemble_seq(m, kmer, means, stds, lens, n, m->xseq, st); if (rc) return rc; }
+        const float* x = m->xseq; int xs = T * m->kseq, xt = m->kseq;
+        int hs = m->nhid_seq;
+        for (int l = 0; l < c.num_layers2; ++l) {
+            Span sp(m, 1, st);
+            rc = f32_lstm_layer(m, m->lstm_seq[l], x, xs, xt, h0[0] + (int64_t)l * 2 * sstride[0],
+                                c0[0] + (int64_t)l * 2 * sstride[0], sstride[0], m->buf[l & 1], n, st);
+            if (rc) return rc;
+            x = m->buf[l & 1]; xs = T * 2 * hs; xt = 2 * hs;
+        }
+        { Span sp(m, 2, st); rc = f32_dense(m, m->fc_seq, x, n * T, 2 * hs, m->comb_in, H, 1, st); if (rc) return rc; }
+        comb_off = hs;
+    }
+    if (has_signal(m)) {
+        const float* x = signals; int xs = T * c.signal_len, xt = c.signal_len;
+        int hs = m->nhid_signal;
+        for (int l = 0; l < c.num_layers2; ++l) {
+            Span sp(m, 1, st);
+            rc = f32_lstm_layer(m, m->lstm_signal[l], x, xs, xt, h0[1] + (int64_t)l * 2 * sstride[1],
+                                c0[1] + (int64_t)l * 2 * sstride[1], sstride[1], m->buf[l & 1], n, st);
+            if (rc) return rc;
+            x = m->buf[l & 1]; xs = T * 2 * hs; xt = 2 * hs;
+        }
+        { Span sp(m, 2, st); rc = f32_dense(m, m->fc_signal, x, n * T, 2 * hs, m->comb_in + comb_off, H, 1, st); if (rc) return rc; }
+    }
+    const float* x = m->comb_in; int xs = T * H, xt = H;
+    for (int l = 0; l < c.num_layers1; ++l) {
+        Span sp(m, 1, st);
+        rc = f32_lstm_layer(m, m->lstm_comb[l], x, xs, xt, h0[2] + (int64_t)l * 2 * sstride[2],
+                            c0[2] + (int64_t)l * 2 * sstride[2], sstride[2], m->buf[l & 1], n, st);
+        if (rc) return rc;
+        x = m->buf[l & 1]; xs = T * 2 * H; xt = 2 * H;
+    }
+    { Span sp(m, 3, st); rc = f32_head(m, x, n, logits, probs, labels, st); if (rc) return rc; }
+    return DSP_OK;
+}
+
+bool is_device_accessible_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+}  // namespace dsp
+
+using namespace dsp;
+
+extern "C" {
+
+int dsp_abi_version(void) { return DSP_B200_ABI_VERSION; }
+const char* dsp_last_error(void) { return g_err; }
+
+int dsp_create(dsp_handle* out, const dsp_config* cfg) {
+    DSP_REQUIRE(out && cfg, DSP_ERR_INVALID, "dsp_create: null argument");
+    *out = nullptr;
+    DSP_REQUIRE(cfg->seq_len >= 1 && cfg->signal_len >= 1 && cfg->num_layers1 >= 1 && cfg->num_layers2 >= 1 &&
+                cfg->num_classes >= 1 && cfg->hidden_size >= 2 && cfg->vocab_size >= 1 && cfg->embedding_size >= 1,
+                DSP_ERR_INVALID, "dsp_create: non-positive dimension in config");
+    DSP_REQUIRE(cfg->module >= DSP_BOTH_BILSTM && cfg->module <= DSP_SIGNAL_BILSTM, DSP_ERR_INVALID,
+                "--model_type is not right!");
+    DSP_REQUIRE(cfg->precision == DSP_PRECISION_FP32 || cfg->precision == DSP_PRECISION_FP16, DSP_ERR_INVALID,
+                "dsp_create: unknown precision %d", cfg->precision);
+    DSP_REQUIRE(cfg->max_batch >= 1, DSP_ERR_INVALID, "dsp_create: max_batch must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("dsp_create: no CUDA device available (%s); this library has no CPU path",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return DSP_ERR_CUDA;
+    }
+    DSP_REQUIRE(cfg->device >= 0 && cfg->device < ndev, DSP_ERR_INVALID, "dsp_create: device %d out of range (%d)",
+                cfg->device, ndev);
+    DeviceGuard guard(cfg->device);
+    cudaDeviceProp prop;
+    DSP_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    DSP_REQUIRE(prop.major == 10, DSP_ERR_INVALID,
+                "dsp_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device,
+                prop.major, prop.minor);
+    dsp_model_s* m = new (std::nothrow) dsp_model_s();
+    DSP_REQUIRE(m, DSP_ERR_NOMEM, "dsp_create: out of host memory");
+    m->cfg = *cfg;
+    const int H = cfg->hidden_size;
+    if (cfg->module == DSP_BOTH_BILSTM) { m->nhid_seq = H / 2; m->nhid_signal = H - H / 2; }
+    else if (cfg->module == DSP_SEQ_BILSTM) { m->nhid_seq = H; }
+    else { m->nhid_signal = H; }
+    m->kseq = (cfg->is_base ? cfg->embedding_size : 0) + (cfg->is_signallen ? 3 : 2);
+    m->cap = cfg->max_batch;
+    const int T = cfg->seq_len;
+    int rc = DSP_OK;
+    StateGroup grp[3];
+    state_groups(m, grp);
+    for (int g = 0; g < 3; ++g) m->state_floats_per_site += (int64_t)grp[g].layers * 2 * grp[g].hidden * 2;
+    do {
+        if ((rc = dev_alloc(m, (void**)&m->states, sizeof(float) * m->cap * m->state_floats_per_site))) break;
+        if (cfg->precision == DSP_PRECISION_FP32) {
+            if ((rc = dev_alloc(m, (void**)&m->xseq, sizeof(float) * m->cap * T * m->kseq))) break;
+            if ((rc = dev_alloc(m, (void**)&m->buf[0], sizeof(float) * m->cap * T * 2 * H))) break;
+            if ((rc = dev_alloc(m, (void**)&m->buf[1], sizeof(float) * m->cap * T * 2 * H))) break;
+            if ((rc = dev_alloc(m, (void**)&m->comb_in, sizeof(float) * m->cap * T * H))) break;
+        } else {
+            if ((rc = tc_create(m))) break;
+        }
+    } while (0);
+    if (rc) { dsp_destroy(m); return rc; }
+    *out = m;
+    return DSP_OK;
+}
+
+int dsp_destroy(dsp_handle h) {
+    if (!h) return DSP_OK;
+    dsp_model_s* m = h;
+    DeviceGuard guard(m->cfg.device);
+    cudaDeviceSynchronize();
+    tc_destroy(m);
+    for (void* p : m->device_allocs) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (m->pinned_in[i]) cudaFreeHost(m->pinned_in[i]);
+        if (m->pinned_out[i]) cudaFreeHost(m->pinned_out[i]);
+        if (m->dev_in[i]) cudaFree(m->dev_in[i]);
+        if (m->dev_out[i]) cudaFree(m->dev_out[i]);
+        if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+        if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+    }
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->compute_stream) cudaStreamDestroy(m->compute_stream);
+    for (cudaEvent_t e : m->event_pool) cudaEventDestroy(e);
+    cudaGetLastError();
+    delete m;
+    return DSP_OK;
+}
+
+int dsp_set_param(dsp_handle h, const char* name, const float* host_data, int64_t numel) {
+    DSP_REQUIRE(h && name && host_data && numel >= 0, DSP_ERR_INVALID, "dsp_set_param: null argument");
+    h->params[name].assign(host_data, host_data + numel);
+    h->packed = false;
+    return DSP_OK;
+}
+
+int dsp_pack_weights(dsp_handle h) {
+    DSP_REQUIRE(h, DSP_ERR_INVALID, "dsp_pack_weights: null handle");
+    Model* m = h;
+    DeviceGuard guard(m->cfg.device);
+    const dsp_config& c = m->cfg;
+    // re-packing after a second load_state_dict: drop the previous arena
+    // (workspace pointers are kept; weights are re-uploaded into fresh allocations)
+    int rc;
+    const int H = c.hidden_size;
+    if (has_seq(m)) {
+        if (c.is_base) {
+            const std::vector<float>* e = find_param(m, "embed.weight", (int64_t)c.vocab_size * c.embedding_size);
+            if (!e) return DSP_ERR_STATE;
+            if ((rc = upload(m, &m->embed, *e))) return rc;
+        }
+        if ((rc = pack_lstm_stack(m, "lstm_seq", c.num_layers2, m->kseq, m->nhid_seq, m->lstm_seq))) return rc;
+        if ((rc = pack_dense(m, "fc_seq", 2 * m->nhid_seq, m->nhid_seq, m->fc_seq))) return rc;
+    }
+    if (has_signal(m)) {
+        if ((rc = pack_lstm_stack(m, "lstm_signal", c.num_layers2, c.signal_len, m->nhid_signal, m->lstm_signal))) return rc;
+        if ((rc = pack_dense(m, "fc_signal", 2 * m->nhid_signal, m->nhid_signal, m->fc_signal))) return rc;
+    }
+    if ((rc = pack_lstm_stack(m, "lstm_comb", c.num_layers1, H, H, m->lstm_comb))) return rc;
+    if ((rc = pack_dense(m, "fc1", 2 * H, H, m->fc1))) return rc;
+    if ((rc = pack_dense(m, "fc2", H, c.num_classes, m->fc2))) return rc;
+    if (c.precision == DSP_PRECISION_FP16) {
+        if ((rc = tc_finalize_pack(m))) return rc;
+    }
+    DSP_CUDA(cudaDeviceSynchronize());
+    m->packed = true;
+    return DSP_OK;
+}
+
+int dsp_forward(dsp_handle h, const float* kmer, const float* base_means, const float* base_stds,
+                const float* base_signal_lens, const float* signals, const float* const* states,
+                uint64_t seed, int64_t n, float* logits, float* probs, int32_t* labels, void* stream) {
+    DSP_REQUIRE(h, DSP_ERR_INVALID, "dsp_forward: null handle");
+    Model* m = h;
+    DSP_REQUIRE(m->packed, DSP_ERR_STATE, "dsp_forward: weights not packed (call dsp_pack_weights after dsp_set_param)");
+    DSP_REQUIRE(n >= 0, DSP_ERR_INVALID, "dsp_forward: negative batch");
+    if (n == 0) return DSP_OK;
+    DSP_REQUIRE(logits && probs, DSP_ERR_INVALID, "dsp_forward: null output pointer");
+    if (has_seq(m)) DSP_REQUIRE(kmer && base_means && base_stds && base_signal_lens, DSP_ERR_INVALID,
+                                "dsp_forward: sequence features are required for this module");
+    if (has_signal(m)) DSP_REQUIRE(signals, DSP_ERR_INVALID, "dsp_forward: signals are required for this module");
+    DeviceGuard guard(m->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dsp_config& c = m->cfg;
+    const int T = c.seq_len, C = c.num_classes;
+    if (m->timing) { m->spans.clear(); m->event_next = 0; }
+    StateGroup grp[3];
+    state_groups(m, grp);
+    uint64_t chunk_id = 0;
+    for (int64_t s = 0; s < n; s += m->cap, ++chunk_id) {
+        const int64_t cn = (n - s < m->cap) ? (n - s) : m->cap;
+        const float* st6[6]; int64_t stride[3];
+        if (states) {
+            for (int g = 0; g < 3; ++g) {
+                stride[g] = n * grp[g].hidden;
+                if (grp[g].layers > 0) {
+                    DSP_REQUIRE(states[2 * g] && states[2 * g + 1], DSP_ERR_INVALID, "dsp_forward: states[%d] is null", 2 * g);
+                    st6[2 * g] = states[2 * g] + s * grp[g].hidden;
+                    st6[2 * g + 1] = states[2 * g + 1] + s * grp[g].hidden;
+                } else { st6[2 * g] = st6[2 * g + 1] = nullptr; }
+            }
+        }
+        int rc = forward_chunk(m, kmer ? kmer + s * T : nullptr, base_means ? base_means + s * T : nullptr,
+                               base_stds ? base_stds + s * T : nullptr,
+                               base_signal_lens ? base_signal_lens + s * T : nullptr,
+                               signals ? signals + s * T * c.signal_len : nullptr,
+                               states ? st6 : nullptr, stride, seed, chunk_id, cn,
+                               logits + s * C, probs + s * C, labels ? labels + s : nullptr, st);
+        if (rc) return rc;
+    }
+    return DSP_OK;
+}
+
+int dsp_forward_host(dsp_handle h, const float* kmer, const float* base_means, const float* base_stds,
+                     const float* base_signal_lens, const float* signals, uint64_t seed, int64_t n,
+                     float* logits, float* probs, int32_t* labels) {
+    DSP_REQUIRE(h, DSP_ERR_INVALID, "dsp_forward_host: null handle");
+    Model* m = h;
+    DSP_REQUIRE(m->packed, DSP_ERR_STATE, "dsp_forward_host: weights not packed");
+    DSP_REQUIRE(n >= 0, DSP_ERR_INVALID, "dsp_forward_host: negative batch");
+    if (n == 0) return DSP_OK;
+    DSP_REQUIRE(logits && probs, DSP_ERR_INVALID, "dsp_forward_host: null output pointer");
+    if (has_seq(m)) DSP_REQUIRE(kmer && base_means && base_stds && base_signal_lens, DSP_ERR_INVALID,
+                                "dsp_forward_host: sequence features are required for this module");
+    if (has_signal(m)) DSP_REQUIRE(signals, DSP_ERR_INVALID, "dsp_forward_host: signals are required for this module");
+    DeviceGuard guard(m->cfg.device);
+    const dsp_config& c = m->cfg;
+    const int T = c.seq_len, S = c.signal_len, C = c.num_classes;
+    const int64_t cap = m->cap;
+    // per-site float counts of the staged sections
+    const int64_t f_seq = has_seq(m) ? 4 * T : 0, f_sig = has_signal(m) ? (int64_t)T * S : 0;
+    const size_t in_bytes = sizeof(float) * cap * (f_seq + f_sig);
+    const size_t out_bytes = cap * (sizeof(float) * 2 * C + sizeof(int32_t));
+    if (!m->copy_stream) {
+        DSP_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        DSP_CUDA(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            DSP_CUDA(cudaMallocHost(&m->pinned_in[i], in_bytes));
+            DSP_CUDA(cudaMallocHost(&m->pinned_out[i], out_bytes));
+            DSP_CUDA(cudaMalloc(&m->dev_in[i], in_bytes));
+            DSP_CUDA(cudaMalloc(&m->dev_out[i], out_bytes));
+            DSP_CUDA(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+            DSP_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    const bool direct = (!has_seq(m) || (is_device_accessible_host(kmer) && is_device_accessible_host(base_means) &&
+                                         is_device_accessible_host(base_stds) && is_device_accessible_host(base_signal_lens))) &&
+                        (!has_signal(m) || is_device_accessible_host(signals));
+    if (m->timing) { m->spans.clear(); m->event_next = 0; }
+    const int64_t nchunks = (n + cap - 1) / cap;
+    auto drain = [&](int64_t ci) -> int {   // copy results of chunk ci to the caller
+        const int b = (int)(ci & 1);
+        const int64_t s = ci * cap, cn = (n - s < cap) ? (n - s) : cap;
+        DSP_CUDA(cudaEventSynchronize(m->ev_done[b]));
+        const char* po = (const char*)m->pinned_out[b];
+        memcpy(logits + s * C, po, sizeof(float) * cn * C);
+        memcpy(probs + s * C, po + sizeof(float) * cap * C, sizeof(float) * cn * C);
+        if (labels) memcpy(labels + s, po + sizeof(float) * cap * 2 * C, sizeof(int32_t) * cn);
+        return DSP_OK;
+    };
+    for (int64_t ci = 0; ci < nchunks; ++ci) {
+        const int b = (int)(ci & 1);
+        const int64_t s = ci * cap, cn = (n - s < cap) ? (n - s) : cap;
+        if (ci >= 2) { int rc = drain(ci - 2); if (rc) return rc; }
+        float* din = (float*)m->dev_in[b];
+        float* d_kmer = din, *d_means = din + cap * T, *d_stds = din + 2 * cap * T, *d_lens = din + 3 * cap * T;
+        float* d_sig = din + cap * f_seq;
+        const float* src[5] = {kmer, base_means, base_stds, base_signal_lens, signals};
+        float* dst[5] = {d_kmer, d_means, d_stds, d_lens, d_sig};
+        const int64_t per[5] = {T, T, T, T, (int64_t)T * S};
+        for (int a = 0; a < 5; ++a) {
+            const bool used = (a < 4) ? has_seq(m) : has_signal(m);
+            if (!used) continue;
+            const float* from = src[a] + s * per[a];
+            if (!direct) {
+                float* stage = (float*)m->pinned_in[b] + (dst[a] - din);
+                memcpy(stage, from, sizeof(float) * cn * per[a]);
+                from = stage;
+            }
+            DSP_CUDA(cudaMemcpyAsync(dst[a], from, sizeof(float) * cn * per[a], cudaMemcpyHostToDevice, m->copy_stream));
+        }
+        DSP_CUDA(cudaEventRecord(m->ev_h2d[b], m->copy_stream));
+        DSP_CUDA(cudaStreamWaitEvent(m->compute_stream, m->ev_h2d[b], 0));
+        char* dout = (char*)m->dev_out[b];
+        float* d_logits = (float*)dout;
+        float* d_probs = (float*)(dout + sizeof(float) * cap * C);
+        int32_t* d_labels = (int32_t*)(dout + sizeof(float) * cap * 2 * C);
+        int rc = forward_chunk(m, d_kmer, d_means, d_stds, d_lens, d_sig, nullptr, nullptr, seed, (uint64_t)ci, cn,
+                               d_logits, d_probs, d_labels, m->compute_stream);
+        if (rc) return rc;
+        DSP_CUDA(cudaMemcpyAsync(m->pinned_out[b], dout, out_bytes, cudaMemcpyDeviceToHost, m->compute_stream));
+        DSP_CUDA(cudaEventRecord(m->ev_done[b], m->compute_stream));
+    }
+    for (int64_t ci = (nchunks >= 2 ? nchunks - 2 : 0); ci < nchunks; ++ci) { int rc = drain(ci); if (rc) return rc; }
+    return DSP_OK;
+}
+
+int64_t dsp_launch_count(dsp_handle h) { return h ? h->launches : 0; }
+
+int dsp_set_timing(dsp_handle h, int enable) {
+    DSP_REQUIRE(h, DSP_ERR_INVALID, "dsp_set_timing: null handle");
+    h->timing = enable != 0;
+    h->spans.clear();
+    h->event_next = 0;
+    return DSP_OK;
+}
+
+int dsp_get_timing(dsp_handle h, int which, float* ms, int64_t* launches) {
+    DSP_REQUIRE(h && ms, DSP_ERR_INVALID, "dsp_get_timing: null argument");
+    DeviceGuard guard(h->cfg.device);
+    float total = 0.f;
+    int64_t cnt = 0;
+    for (const TimingSpan& s : h->spans) {
+        if (s.cls != which) continue;
+        DSP_CUDA(cudaEventSynchronize(s.b));
+        float t = 0.f;
+        DSP_CUDA(cudaEventElapsedTime(&t, s.a, s.b));
+        total += t;
+        ++cnt;
+    }
+    *ms = total;
+    if (launches) *launches = cnt;
+    return DSP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+// Interface between api.cu and the tcgen05 (FP16-operand) path in kernels_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace dsp {
+
+int tc_create(Model* m);
+void tc_destroy(Model* m);
+// raw torch-layout parameters of both directions of one layer (weight_ih (4H,K),
+// weight_hh (4H,H), bias_ih (4H), bias_hh (4H)); d0 = forward, d1 = reverse
+int tc_pack_lstm_layer(Model* m, LstmLayer& L,
+                       const float* wih0, const float* whh0, const float* bih0, const float* bhh0,
+                       const float* wih1, const float* whh1, const float* bih1, const float* bhh1);
+int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b);
+int tc_finalize_pack(Model* m);
+int tc_forward_chunk(Model* m, const float* kmer, const float* means, const float* stds, const float* lens,
+                     const float* signals, const float* const* h0, const float* const* c0,
+                     const int64_t* state_stride, int64_t n, float* logits, float* probs, int32_t* labels,
+                     cudaStream_t st);
+
+}  // namespace dsp

@@ -1,0 +1,149 @@
+/*
+ * dsp_b200.h -- C ABI of libdsp_b200.so, the B200 (sm_100a) implementation of
+ * deepsignal-plant's per-site methylation classifier hot path.
+ *
+ * The reference (PengNi/deepsignal-plant v0.1.6) is pure Python and has no FFI of its
+ * own; the boundary it exposes for this path is the torch.nn.Module API of
+ * ModelBiLSTM (deepsignal_plant/models.py:99-240) as driven by _call_mods
+ * (deepsignal_plant/call_modifications.py:130-192) and, for the optional per-site
+ * aggregation, calculate_mods_frequency (deepsignal_plant/call_mods_freq.py:29-74).
+ * Each entry point below names the reference interface it stands behind.  The Python
+ * mirror of that interface lives in deepsignal_plant_b200/ and binds these symbols
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: plain C types only, no torch types.  Every function returns 0 on
+ * success and a non-zero dsp_status otherwise; dsp_last_error() returns a
+ * thread-local message for the last failure.  No exception crosses the ABI.
+ * Unless stated otherwise pointers are DEVICE pointers on the handle's device, the
+ * call only enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ * without synchronising.  A handle is not thread-safe: one handle per process x
+ * device, as in the reference's one-process-per-GPU worker model
+ * (call_modifications.py:405-414, 613-621).
+ */
+#ifndef DSP_B200_H
+#define DSP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSP_B200_ABI_VERSION 1
+
+typedef enum {
+    DSP_OK = 0,
+    DSP_ERR_INVALID = 1,     /* bad argument / unsupported shape */
+    DSP_ERR_CUDA = 2,        /* a CUDA runtime or driver call failed */
+    DSP_ERR_STATE = 3,       /* call order violated (e.g. forward before pack) */
+    DSP_ERR_NOMEM = 4
+} dsp_status;
+
+/* module = ModelBiLSTM's `module` argument (models.py:120-128) */
+typedef enum { DSP_BOTH_BILSTM = 0, DSP_SEQ_BILSTM = 1, DSP_SIGNAL_BILSTM = 2 } dsp_module;
+
+/* Arithmetic of the recurrent/dense contractions.
+ *   DSP_PRECISION_FP32: fp32 FMA on the CUDA cores (exact-order reference path).
+ *   DSP_PRECISION_FP16: FP16 operands, fp32 accumulation in TMEM via tcgen05.mma,
+ *                       fp32 cell state and gate math (the throughput path). */
+typedef enum { DSP_PRECISION_FP32 = 0, DSP_PRECISION_FP16 = 1 } dsp_precision;
+
+/* Mirrors the constructor arguments of ModelBiLSTM (models.py:103-106). */
+typedef struct {
+    int32_t seq_len;         /* 13 */
+    int32_t signal_len;      /* 16 */
+    int32_t num_layers1;     /* 3: layers of lstm_comb */
+    int32_t num_layers2;     /* 1: layers of lstm_seq / lstm_signal */
+    int32_t num_classes;     /* 2 */
+    int32_t hidden_size;     /* 256 */
+    int32_t vocab_size;      /* 16 */
+    int32_t embedding_size;  /* 4 */
+    int32_t is_base;         /* bool */
+    int32_t is_signallen;    /* bool */
+    int32_t module;          /* dsp_module */
+    int32_t device;          /* CUDA ordinal */
+    int32_t precision;       /* dsp_precision */
+    int32_t reserved;
+    int64_t max_batch;       /* sites per internal pass; workspace is sized for this */
+} dsp_config;
+
+typedef struct dsp_model_s* dsp_handle;
+
+int dsp_abi_version(void);
+const char* dsp_last_error(void);
+
+/* ModelBiLSTM.__init__ (models.py:103-164): allocates the packed-weight arena and the
+ * activation workspace for cfg->max_batch sites on cfg->device. */
+int dsp_create(dsp_handle* out, const dsp_config* cfg);
+int dsp_destroy(dsp_handle h);
+
+/* load_state_dict (call_modifications.py:219-223): hand over one state_dict entry.
+ * `name` is the reference's state_dict key (e.g. "lstm_comb.weight_hh_l1_reverse");
+ * `host_data` is a HOST pointer to `numel` contiguous float32 values in torch's
+ * row-major layout.  dsp_pack_weights() then converts everything that was set into the
+ * kernel layouts (gate-interleaved, bias_ih+bias_hh pre-summed, FP16 tiles) and
+ * uploads it; it fails with DSP_ERR_STATE if a key the configuration needs is missing. */
+int dsp_set_param(dsp_handle h, const char* name, const float* host_data, int64_t numel);
+int dsp_pack_weights(dsp_handle h);
+
+/* ModelBiLSTM.forward (models.py:178-240) for n sites.
+ *   kmer, base_means, base_stds, base_signal_lens: (n, seq_len) float32 (kmer holds
+ *     float-coded base codes, cast like `kmer.long()`, models.py:186); may be NULL for
+ *     signal_bilstm.   signals: (n, seq_len, signal_len) float32; may be NULL for seq_bilstm.
+ *   states: NULL, or 6 device pointers {seq_h0, seq_c0, signal_h0, signal_c0, comb_h0,
+ *     comb_c0}, each (num_layers*2, n, hidden) float32 indexed [layer*2+dir] -- the
+ *     tensors init_hidden returns (models.py:169-176).  With NULL the initial states
+ *     are drawn N(0,1) on the device from Philox4x32-10 keyed by (seed, site, slot),
+ *     which is what the reference does statistically (fresh torch.randn per call).
+ *   logits, probs: (n, num_classes) float32 outputs (forward returns both, :240).
+ *   labels: optional (n) int32 = argmax of probs, first index on ties
+ *     (torch.max(vlogits.data, 1), call_modifications.py:163); may be NULL. */
+int dsp_forward(dsp_handle h,
+                const float* kmer, const float* base_means, const float* base_stds,
+                const float* base_signal_lens, const float* signals,
+                const float* const* states, uint64_t seed, int64_t n,
+                float* logits, float* probs, int32_t* labels, void* stream);
+
+/* The same call with HOST buffers (the FloatTensor(...)/.cpu() boundary of _call_mods,
+ * call_modifications.py:159-169): inputs are staged through pinned ring buffers and
+ * copied host->device on a copy stream overlapped with compute, results are copied
+ * back; returns after the outputs are valid on the host.  Initial states are always
+ * Philox-drawn on the device. */
+int dsp_forward_host(dsp_handle h,
+                     const float* kmer, const float* base_means, const float* base_stds,
+                     const float* base_signal_lens, const float* signals,
+                     uint64_t seed, int64_t n,
+                     float* logits, float* probs, int32_t* labels);
+
+/* Number of kernels this library launched on behalf of `h` since creation. */
+int64_t dsp_launch_count(dsp_handle h);
+/* Milliseconds (CUDA events on the launching stream) spent in kernels of class `which`
+ * during the last dsp_forward when timing was enabled with dsp_set_timing(h, 1):
+ * 0 = feature assembly/state init, 1 = recurrent layers, 2 = per-timestep fc, 3 = head.
+ * Timing inserts event records only; it never synchronises inside dsp_forward. */
+int dsp_set_timing(dsp_handle h, int enable);
+int dsp_get_timing(dsp_handle h, int which, float* ms, int64_t* launches);
+
+/* calculate_mods_frequency (call_mods_freq.py:29-74) for records already parsed into
+ * columns (txt_formater.py:8-21).  All pointers are DEVICE pointers, n records in file
+ * order:
+ *   key   (uint64): site key = (chrom_id << 40) | pos, chrom_id assigned by the host;
+ *   p0,p1 (double): the parsed probabilities;  label (int32): called_label.
+ * Records with |p0-p1| < prob_cf are dropped (txt_formater.py:23-26).  Per key the
+ * probabilities are summed in float64 strictly in record order (call_mods_freq.py:60-61);
+ * counts are integers.  Outputs, one row per distinct key (capacity n), ordered by first
+ * callable appearance (dict insertion order) when sort_by_key == 0 or by key value
+ * when sort_by_key != 0:
+ *   out_key, out_first (index of the first callable record of the key, which supplies
+ *   strand / pos_in_strand / kmer, :55-59), out_p0, out_p1, out_met, out_unmet, out_cov.
+ * *n_sites_host receives the number of rows (the call synchronises `stream`). */
+int dsp_freq_aggregate(int device, const uint64_t* key, const double* p0, const double* p1,
+                       const int32_t* label, int64_t n, double prob_cf, int sort_by_key,
+                       uint64_t* out_key, int64_t* out_first, double* out_p0, double* out_p1,
+                       int32_t* out_met, int32_t* out_unmet, int32_t* out_cov,
+                       int64_t* n_sites_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSP_B200_H */
