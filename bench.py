@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""Benchmark of the ModelBiLSTM hot path (BASELINE.json metric: classified sites/s,
+both_bilstm bn13_sn16 hidden 256, batch 65536).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision fp16|fp32]
+
+One "step" = one batch of 65 536 synthetic sites through the forward pass.  Prints ONE JSON
+line (rank 0).  See DESIGN.md section "Measurement" for what every key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "classified sites/sec (ModelBiLSTM both_bilstm bn13_sn16 hidden 256)"
+UNIT = "sites/s"
+BATCH = 65536
+FLOP_PER_SITE = 118447104            # SURVEY.md section 8d (algorithmic, 2 x MAC)
+# recurrent layers only (lstm_seq + lstm_signal + 3 x lstm_comb), the dominant kernel class
+FLOP_PER_SITE_RECURRENT = 2 * (2 * 13 * 512 * (7 + 128) + 2 * 13 * 512 * (16 + 128)
+                               + 2 * 13 * 1024 * (256 + 256) + 2 * 2 * 13 * 1024 * (512 + 256))
+IN_BYTES_PER_SITE = 4 * (4 * 13 + 13 * 16)
+OUT_BYTES_PER_SITE = 4 * 2 * 2 + 4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d["bf16_tflops_sustained"]), tflops_burst=float(d["bf16_tflops"]),
+                    hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "samples": len(self.rows),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+
+
+def make_pool(n_buffers, batch, seed=0):
+    """`n_buffers` distinct batches: one generated pool, rolled copies (distinct bytes, so the
+    cycled inputs exceed L2: 4 x 68 MB > 126 MB)."""
+    from deepsignal_plant_b200 import synthetic
+    base = synthetic.make_features(batch, 13, 16, seed=seed)
+    keys = ("kmer", "base_means", "base_stds", "base_signal_lens", "signals")
+    return [tuple(np.ascontiguousarray(np.roll(base[k], 977 * b, axis=0)) for k in keys) for b in range(n_buffers)]
+
+
+def cpu_baseline_run(sites, threads):
+    """The numpy oracle port of the reference forward on host cores (oracle/ as checker /
+    baseline only).  Returns sites/s."""
+    import torch
+    from deepsignal_plant_b200 import synthetic
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    from oracle import model_oracle
+    cfg = model_oracle.make_cfg()
+    torch.manual_seed(1234)
+    params = {k: v.detach().numpy() for k, v in ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict().items()}
+    feats = synthetic.make_features(sites, 13, 16, seed=0)
+    states = synthetic.make_states(cfg, sites, seed=4321)
+    keys = ("kmer", "base_means", "base_stds", "base_signal_lens", "signals")
+    t0 = time.perf_counter()
+    for s in range(0, sites, 512):            # the reference's default --batch_size 512
+        sub = {g: tuple(x[:, s:s + 512] for x in hc) for g, hc in states.items()}
+        model_oracle.forward(params, cfg, *(feats[k][s:s + 512] for k in keys), sub)
+    dt = time.perf_counter() - t0
+    return sites / dt, dt
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 4096
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline_run(512, cores)
+    vals = []
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_baseline_run(sample, cores)
+        vals.append(v)
+        t_all += dt
+    value = sample * args.steps / t_all
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "both_bilstm bn13_sn16 h256 inference, batch 65536 (config 2)",
+                       "note": "reference CPU path restated in numpy (oracle port; the reference is pure Python/torch "
+                               "and /root/reference does not travel); each step = %d-site sample in batches of 512" % sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d sites per step, batch 512, numpy fp32 (threaded BLAS)" % sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DSP_B200_PRECISION", "fp32"))
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--buffers", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.steps is None:
+        args.steps = 20 if args.precision == "fp16" else 4
+    if args.impl == "reference":
+        if args.steps > 8:
+            args.steps = 8
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    from deepsignal_plant_b200 import _native
+    import ctypes as C
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+
+    torch.manual_seed(1234)
+    model = ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True, module="both_bilstm", device=local,
+                        precision=args.precision, max_batch=args.batch, seed=rank).cuda(local).eval()
+    pool = make_pool(args.buffers, args.batch, seed=rank)
+    dev_pool = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in pool]
+    pin_pool = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in pool]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------
+    for i in range(W):
+        model(*dev_pool[i % len(dev_pool)])
+    torch.cuda.synchronize()
+    L = _native.lib()
+
+    # ---- timed region: inputs resident in HBM ------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    _native.check(L.dsp_set_timing(model._handle, 1))
+    launches0 = model.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms, kern_launches = 0.0, 0
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        model(*dev_pool[i % len(dev_pool)])
+    ev1.record()
+    barrier()
+    launches = model.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    # recurrent-layer kernel time of the LAST step (events recorded on the launching stream)
+    t = C.c_float()
+    cnt = C.c_int64()
+    _native.check(L.dsp_get_timing(model._handle, 1, C.byref(t), C.byref(cnt)))
+    kern_ms, kern_launches = float(t.value), int(cnt.value)
+    _native.check(L.dsp_set_timing(model._handle, 0))
+    clocks = sampler.summary()
+
+    # ---- e2e: host buffers through the public host API, H2D + D2H inside ----------------
+    e2e_steps = args.steps
+    for i in range(2):
+        model.forward_host(*(a.numpy() for a in pin_pool[i % len(pin_pool)]))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        model.forward_host(*(a.numpy() for a in pin_pool[i % len(pin_pool)]))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    tt = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tt[0]), float(tt[1])
+    value = world * args.batch * args.steps / (ms * 1e-3)
+    e2e_value = world * args.batch * e2e_steps / (e2e_ms * 1e-3)
+
+    pk = peaks()
+    achieved = (FLOP_PER_SITE_RECURRENT * args.batch / (kern_ms * 1e-3) / 1e12) if kern_ms > 0 else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands / f32 accumulate" if args.precision == "fp16" else "f32", "data": "synthetic",
+        "config": {"workload": "both_bilstm bn13_sn16 h256 inference, batch 65536 (BASELINE.json configs[1]), "
+                               "random-init weights seed 1234, in-kernel Philox initial states",
+                   "batch": args.batch, "precision": args.precision,
+                   "l2": "%d distinct input batches cycled (%.0f MB > L2)" % (args.buffers, args.buffers * args.batch * IN_BYTES_PER_SITE / 1e6),
+                   "parallelism": "site-batch shards, one process per GPU, no collective"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": (achieved / pk["tflops"]) if achieved else None, "traffic": None,
+                     "kernel": "recurrent BiLSTM layer kernels (%d launches/step, %.3f ms/step)" % (kern_launches, kern_ms),
+                     "peak_source": pk["source"],
+                     "whole_step_frac": value / world * FLOP_PER_SITE / 1e12 / pk["tflops"]},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": args.batch * IN_BYTES_PER_SITE,
+                "d2h_bytes_per_step": args.batch * OUT_BYTES_PER_SITE, "api": "ModelBiLSTM.forward_host (dsp_forward_host), pinned host buffers"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            sample = 8192
+            v, dt = cpu_baseline_run(sample, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d sites, batch 512, numpy fp32 oracle (threaded BLAS), %.1f s" % (sample, dt)}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

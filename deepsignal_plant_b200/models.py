@@ -84,7 +84,7 @@ class ModelBiLSTM(nn.Module):
         self.fc1 = nn.Linear(hidden_size * 2, hidden_size)
         self.fc2 = nn.Linear(hidden_size, num_classes)
 
-        self.precision = precision or os.environ.get("DSP_B200_PRECISION", "fp16")
+        self.precision = precision or os.environ.get("DSP_B200_PRECISION", "fp32")
         if self.precision not in _native.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_native.PRECISIONS))
         self.max_batch = int(max_batch)

@@ -1,0 +1,103 @@
+"""CPU: host-side mirror of the reference interface (constructor, state_dict contract,
+text formatting, synthetic data) -- no kernel calls."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from deepsignal_plant_b200 import call_modifications as cm
+from deepsignal_plant_b200 import synthetic
+from deepsignal_plant_b200.models import ModelBiLSTM
+
+
+def test_constructor_contract():
+    m = ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True, module="both_bilstm", device=0)
+    assert m.get_model_type() == "BiLSTM"
+    sd = m.state_dict()
+    assert sum(v.numel() for v in sd.values()) == 4694082
+    assert tuple(sd["embed.weight"].shape) == (16, 4)
+    assert tuple(sd["lstm_seq.weight_ih_l0"].shape) == (512, 7)
+    assert tuple(sd["lstm_signal.weight_ih_l0_reverse"].shape) == (512, 16)
+    assert tuple(sd["lstm_comb.weight_ih_l2"].shape) == (1024, 512)
+    assert tuple(sd["fc1.weight"].shape) == (256, 512) and tuple(sd["fc2.weight"].shape) == (2, 256)
+    with pytest.raises(ValueError, match="--model_type is not right!"):
+        ModelBiLSTM(module="bogus")
+    seq = ModelBiLSTM(module="seq_bilstm")
+    assert "lstm_signal.weight_ih_l0" not in seq.state_dict() and tuple(seq.state_dict()["lstm_seq.weight_hh_l0"].shape) == (1024, 256)
+    sig = ModelBiLSTM(module="signal_bilstm")
+    assert "embed.weight" not in sig.state_dict()
+
+
+def test_checkpoint_roundtrip_like_call_mods_q(tmp_path):
+    # call_modifications.py:219-223: torch.load -> dict.update -> load_state_dict
+    torch.manual_seed(3)
+    a = ModelBiLSTM(hidden_size=32)
+    path = tmp_path / "both_bilstm.b13_s16_epoch1.ckpt"
+    torch.save(a.state_dict(), path)
+    b = ModelBiLSTM(hidden_size=32)
+    para = torch.load(path, map_location=torch.device("cpu"))
+    d = b.state_dict()
+    d.update(para)
+    b.load_state_dict(d)
+    for k, v in a.state_dict().items():
+        assert torch.equal(v, b.state_dict()[k])
+
+
+def test_train_mode_is_refused():
+    m = ModelBiLSTM(hidden_size=32)
+    m.train()
+    x = torch.zeros(2, 13)
+    with pytest.raises(RuntimeError, match="inference only"):
+        m(x, x, x, x, torch.zeros(2, 13, 16))
+
+
+def test_init_hidden_consumes_rng_like_reference():
+    m = ModelBiLSTM(hidden_size=32)
+    torch.manual_seed(5)
+    h0, c0 = m.init_hidden(7, 3, 32)
+    torch.manual_seed(5)
+    assert torch.equal(h0, torch.randn(6, 7, 32)) and torch.equal(c0, torch.randn(6, 7, 32))
+
+
+def test_format_calls_matches_reference_lines():
+    e = cases.MANIFEST["callmods"]
+    probs = np.load(cases.GOLD + "/callmods_%d_probs.npz" % e["rng_seed"])["probs"]
+    lines = cases.read_gz("callmods_%d.tsv.gz" % e["rng_seed"]).splitlines()
+    feats = synthetic.make_features(e["n"], 13, 16, seed=e["feature_seed"])
+    info = synthetic.make_sampleinfo(e["n"], seed=e["feature_seed"])
+    got = cm.format_calls(info, feats["kmer"], probs, probs.argmax(1))
+    assert got == lines
+
+
+def test_format_calls_extreme_probabilities():
+    # scientific notation, exact 0/1, ties: must print like str(np.float32) does
+    probs = np.array([[1e-6, 1 - 1e-6], [0.0, 1.0], [1.0, 0.0], [0.5, 0.5], [5.6e-5, 1 - 5.6e-5],
+                      [0.3333333, 0.6666667]], np.float32)
+    from oracle import callmods_oracle
+    info = ["c\t1\t+\t1\tr\tt"] * len(probs)
+    kmers = np.tile(np.arange(13) % 16, (len(probs), 1))
+    want, labels = callmods_oracle.call_lines(info, kmers, probs)
+    assert cm.format_calls(info, kmers, probs, labels) == want
+    assert want[0].split("\t")[6] == "1e-06" and want[1].split("\t")[6:8] == ["0.0", "1.0"]
+
+
+def test_kmer_centre_short_kmers():
+    assert cm.kmer_centre(np.array([[0, 1, 2]])).tolist() == ["ACG"]
+    assert cm.kmer_centre(np.array([[0, 1, 2, 3, 4, 5, 6]], np.float32)).tolist() == ["CGTNW"]
+
+
+def test_synthetic_rectangle_rule():
+    f = synthetic.make_features(64, 13, 16, seed=3)
+    lens = f["base_signal_lens"].astype(int)
+    sig = f["signals"]
+    for n in range(64):
+        for t in range(13):
+            L = lens[n, t]
+            row = sig[n, t]
+            if L < 16:
+                left = (16 - L) // 2
+                assert (row[:left] == 0).all() and (row[left + L:] == 0).all()
+            assert np.count_nonzero(row) <= min(L, 16)
+    assert (f["kmer"][:, 6] == 1).all()
+    g = synthetic.make_features(64, 13, 16, seed=3)
+    assert all(np.array_equal(f[k], g[k]) for k in f)

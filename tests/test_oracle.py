@@ -1,0 +1,59 @@
+"""CPU: the oracle restatements against the fixtures the reference produced."""
+import numpy as np
+import pytest
+
+import cases
+from deepsignal_plant_b200 import synthetic
+from oracle import model_oracle, callmods_oracle, freq_oracle
+
+
+@pytest.mark.parametrize("name", cases.FORWARD_CASES)
+def test_model_oracle_matches_reference_golden(name):
+    case = cases.load_case(name)                     # also checks the sha256 pins
+    case = cases.slice_case(case, min(case["entry"]["n"], 1024))
+    f = case["feats"]
+    logits, probs = model_oracle.forward(case["params"], case["cfg"], f["kmer"], f["base_means"], f["base_stds"],
+                                         f["base_signal_lens"], f["signals"], case["states"])
+    assert np.abs(probs - case["probs"]).max() < 5e-6
+    assert np.abs(logits - case["logits"]).max() < 2e-5
+    assert (probs.argmax(1) == case["probs"].argmax(1)).all()
+
+
+def test_flops_per_site_match_survey():
+    # SURVEY.md section 8d
+    assert model_oracle.flops_per_site(model_oracle.make_cfg()) == 118447104
+    assert model_oracle.flops_per_site(model_oracle.make_cfg(module="seq_bilstm")) == 126727168
+    assert model_oracle.flops_per_site(model_oracle.make_cfg(module="signal_bilstm")) == 127206400
+    assert model_oracle.flops_per_site(model_oracle.make_cfg(seq_len=17, signal_len=20)) == 154950656
+
+
+def test_callmods_oracle_matches_reference_lines():
+    e = cases.MANIFEST["callmods"]
+    probs = np.load(cases.GOLD + "/callmods_%d_probs.npz" % e["rng_seed"])["probs"]
+    lines = cases.read_gz("callmods_%d.tsv.gz" % e["rng_seed"]).splitlines()
+    feats = synthetic.make_features(e["n"], 13, 16, seed=e["feature_seed"])
+    info = synthetic.make_sampleinfo(e["n"], seed=e["feature_seed"])
+    got, labels = callmods_oracle.call_lines(info, feats["kmer"], probs)
+    assert got == lines
+    assert (labels == np.array([int(l.split("\t")[8]) for l in lines])).all()
+
+
+def _freq_inputs():
+    edge = open(cases.GOLD + "/freq_edge_input.tsv").read().splitlines()
+    synth = synthetic.make_callmods_records(100000, n_chrom=12, n_pos=900, seed=5)
+    return {"edge": edge, "synth": synth}
+
+
+FREQ_CASES = sorted(k for k in cases.MANIFEST["freq"] if k.startswith("freq_"))
+
+
+@pytest.fixture(scope="module")
+def freq_inputs():
+    return _freq_inputs()
+
+
+@pytest.mark.parametrize("name", FREQ_CASES)
+def test_freq_oracle_matches_reference_bytes(name, freq_inputs):
+    e = cases.MANIFEST["freq"][name]
+    table = freq_oracle.aggregate(freq_inputs[e["input"]], e["prob_cf"])
+    assert freq_oracle.render(table, e["sort"], e["bed"]) == cases.read_gz(name + ".txt.gz")
