@@ -1,0 +1,422 @@
+"""Per-site modification frequency (``call_freq``) with the aggregation on the GPU.
+
+Mirrors ``deepsignal_plant/call_mods_freq.py`` of the reference:
+
+* ``calculate_mods_frequency(mods_files, prob_cf, contig_name=None)`` (``:29-74``)
+* ``write_sitekey2stats(sitekey2stats, result_file, is_sort, is_bed, is_gzip)`` (``:77-122``)
+* ``call_mods_frequency_to_file(args)`` (``:218-296``; the ``--contigs/--nproc`` per-contig
+  multiprocess split is not reproduced -- one GPU pass handles all contigs)
+
+and ``utils/txt_formater.py`` (``ModRecord`` parsing rules, ``SiteStats`` attributes,
+``split_key``).  The text is parsed into columns on the host, the segmented reduction --
+callable filter, grouping by (chrom, pos), ordered float64 replay, integer counts, output
+ordering -- runs in ``dsp_freq_aggregate`` (csrc/freq.cu), and the bytes written are
+identical to the reference's.  With ``torch.distributed`` initialised,
+``aggregate_records_distributed`` shards records by site key across ranks with one
+variable-size all-to-all (NCCL over NVLink) and no partial-sum merging, because float64
+addition is order sensitive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import io
+import os
+import time
+
+import numpy as np
+
+from . import _native
+
+key_sep = "||"
+POS_BITS = 40
+
+
+def split_key(key):
+    """``utils/txt_formater.py:29-31``."""
+    words = key.split(key_sep)
+    return words[0], int(words[1])
+
+
+class SiteStats:
+    """``utils/txt_formater.py:34-46`` (attribute names kept)."""
+    __slots__ = ("_strand", "_pos_in_strand", "_kmer", "_prob_0", "_prob_1", "_met", "_unmet", "_coverage")
+
+    def __init__(self, strand, pos_in_strand, kmer):
+        self._strand = strand
+        self._pos_in_strand = pos_in_strand
+        self._kmer = kmer
+        self._prob_0 = 0.0
+        self._prob_1 = 0.0
+        self._met = 0
+        self._unmet = 0
+        self._coverage = 0
+
+
+class Records:
+    """Column form of call_mods lines (``utils/txt_formater.py:8-21``), file order."""
+
+    def __init__(self, chrom, pos, strand, pos_in_strand, p0, p1, label, kmer):
+        self.chrom = np.asarray(chrom, dtype=object)
+        self.pos = np.asarray(pos, dtype=np.int64)
+        self.strand = np.asarray(strand, dtype=object)
+        self.pos_in_strand = np.asarray(pos_in_strand, dtype=np.int64)
+        self.p0 = np.asarray(p0, dtype=np.float64)
+        self.p1 = np.asarray(p1, dtype=np.float64)
+        self.label = np.asarray(label, dtype=np.int32)
+        self.kmer = np.asarray(kmer, dtype=object)
+
+    def __len__(self):
+        return int(self.pos.shape[0])
+
+    @staticmethod
+    def concat(parts):
+        parts = [p for p in parts if len(p)]
+        if not parts:
+            return Records([], [], [], [], [], [], [], [])
+        return Records(*(np.concatenate([getattr(p, f) for p in parts]) for f in
+                         ("chrom", "pos", "strand", "pos_in_strand", "p0", "p1", "label", "kmer")))
+
+
+def parse_lines(lines):
+    """Parse call_mods text lines (an iterable of str) into ``Records``.  Field rules of
+    ``ModRecord.__init__``: ``line.strip().split('\\t')``; pos / pos_in_strand / label via
+    ``int``; probabilities via ``float`` (correctly rounded decimal -> float64)."""
+    chrom, pos, strand, pis, p0, p1, label, kmer = [], [], [], [], [], [], [], []
+    for line in lines:
+        w = line.strip().split("\t")
+        chrom.append(w[0]); pos.append(int(w[1])); strand.append(w[2]); pis.append(int(w[3]))
+        p0.append(float(w[6])); p1.append(float(w[7])); label.append(int(w[8])); kmer.append(w[9])
+    return Records(chrom, pos, strand, pis, p0, p1, label, kmer)
+
+
+def read_mods_file(path):
+    """One call_mods file (plain or .gz, ``call_mods_freq.py:45-48``) -> ``Records``."""
+    import pandas as pd
+    if os.path.getsize(path) == 0:
+        return Records([], [], [], [], [], [], [], [])
+    try:
+        df = pd.read_csv(path, sep="\t", header=None, usecols=[0, 1, 2, 3, 6, 7, 8, 9],
+                         names=list(range(10)), dtype={0: str, 2: str, 9: str, 1: np.int64, 3: np.int64,
+                                                       6: np.float64, 7: np.float64, 8: np.int64},
+                         float_precision="round_trip", na_filter=False, quoting=3,
+                         compression="gzip" if path.endswith(".gz") else None, engine="c")
+        return Records(df[0].str.strip().to_numpy(object), df[1].to_numpy(), df[2].to_numpy(object), df[3].to_numpy(),
+                       df[6].to_numpy(), df[7].to_numpy(), df[8].to_numpy().astype(np.int32),
+                       df[9].str.strip().to_numpy(object))
+    except Exception:
+        opener = gzip.open if path.endswith(".gz") else open
+        with opener(path, "rt") as f:
+            return parse_lines(f)
+
+
+class FreqTable:
+    """Result of the aggregation in column form, one row per site, in output order.
+    Behaves like the reference's ``sitekey2stats`` dict (``"chrom||pos" -> SiteStats``) for
+    callers that index it, without materialising one Python object per site."""
+
+    def __init__(self, chrom, pos, strand, pos_in_strand, kmer, prob_0, prob_1, met, unmet, coverage,
+                 first_index, n_records=0, n_used=0):
+        self.chrom, self.pos, self.strand, self.pos_in_strand, self.kmer = chrom, pos, strand, pos_in_strand, kmer
+        self.prob_0, self.prob_1, self.met, self.unmet, self.coverage = prob_0, prob_1, met, unmet, coverage
+        self.first_index = first_index
+        self.n_records, self.n_used = n_records, n_used
+        self._index = None
+
+    def __len__(self):
+        return int(self.pos.shape[0])
+
+    def keys(self):
+        return [key_sep.join([c, str(p)]) for c, p in zip(self.chrom.tolist(), self.pos.tolist())]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def _row(self, i):
+        s = SiteStats(self.strand[i], int(self.pos_in_strand[i]), self.kmer[i])
+        s._prob_0, s._prob_1 = float(self.prob_0[i]), float(self.prob_1[i])
+        s._met, s._unmet, s._coverage = int(self.met[i]), int(self.unmet[i]), int(self.coverage[i])
+        return s
+
+    def __getitem__(self, key):
+        if self._index is None:
+            self._index = {k: i for i, k in enumerate(self.keys())}
+        return self._row(self._index[key])
+
+    def items(self):
+        return ((k, self._row(i)) for i, k in enumerate(self.keys()))
+
+    def reorder(self, order):
+        f = lambda a: a[order]
+        return FreqTable(f(self.chrom), f(self.pos), f(self.strand), f(self.pos_in_strand), f(self.kmer),
+                         f(self.prob_0), f(self.prob_1), f(self.met), f(self.unmet), f(self.coverage),
+                         f(self.first_index), self.n_records, self.n_used)
+
+    def sorted(self):
+        """``sorted(keys, key=split_key)`` (``call_mods_freq.py:88``): (chrom str, pos int)."""
+        uniq, inv = np.unique(self.chrom.astype(str), return_inverse=True)   # code-point order, like Python str
+        return self.reorder(np.lexsort((self.pos, inv)))
+
+
+def _chrom_ids(chrom):
+    """Chromosome ids by rank in Python string order, so that integer key order equals the
+    reference's ``(chrom, pos)`` tuple order."""
+    names = sorted(set(chrom.tolist()))
+    rank = {c: i for i, c in enumerate(names)}
+    ids = np.fromiter((rank[c] for c in chrom.tolist()), dtype=np.int64, count=len(chrom))
+    return ids, names
+
+
+def make_keys(chrom_ids, pos):
+    if len(pos) and (pos.min() < 0 or pos.max() >= (1 << POS_BITS)):
+        raise ValueError("positions must be in [0, 2^%d)" % POS_BITS)
+    return (chrom_ids.astype(np.uint64) << np.uint64(POS_BITS)) | pos.astype(np.uint64)
+
+
+def _aggregate_device(keys, p0, p1, label, prob_cf, sort_by_key, device):
+    """numpy columns -> (key, first, s0, s1, met, unmet, cov) numpy arrays via the GPU."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("call_freq aggregation needs a CUDA device; there is no CPU path")
+    L = _native.lib()
+    n = int(keys.shape[0])
+    dev = torch.device("cuda", device)
+    with torch.cuda.device(dev):
+        t_key = torch.from_numpy(keys.view(np.int64)).to(dev)
+        t_p0 = torch.from_numpy(np.ascontiguousarray(p0)).to(dev)
+        t_p1 = torch.from_numpy(np.ascontiguousarray(p1)).to(dev)
+        t_lab = torch.from_numpy(np.ascontiguousarray(label, dtype=np.int32)).to(dev)
+        out = _aggregate_tensors(t_key, t_p0, t_p1, t_lab, prob_cf, sort_by_key, dev)
+        return tuple(t.cpu().numpy() for t in out)
+
+
+def _aggregate_tensors(t_key, t_p0, t_p1, t_lab, prob_cf, sort_by_key, dev):
+    """Device tensors in, device tensors out (rows = sites)."""
+    import torch
+    L = _native.lib()
+    n = int(t_key.shape[0])
+    o_key = torch.empty(n, dtype=torch.int64, device=dev)
+    o_first = torch.empty(n, dtype=torch.int64, device=dev)
+    o_p0 = torch.empty(n, dtype=torch.float64, device=dev)
+    o_p1 = torch.empty(n, dtype=torch.float64, device=dev)
+    o_met = torch.empty(n, dtype=torch.int32, device=dev)
+    o_unmet = torch.empty(n, dtype=torch.int32, device=dev)
+    o_cov = torch.empty(n, dtype=torch.int32, device=dev)
+    nsites = C.c_int64(0)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _native.check(L.dsp_freq_aggregate(dev.index, t_key.data_ptr(), t_p0.data_ptr(), t_p1.data_ptr(), t_lab.data_ptr(),
+                                       n, float(prob_cf), int(bool(sort_by_key)),
+                                       o_key.data_ptr(), o_first.data_ptr(), o_p0.data_ptr(), o_p1.data_ptr(),
+                                       o_met.data_ptr(), o_unmet.data_ptr(), o_cov.data_ptr(),
+                                       C.byref(nsites), stream), "dsp_freq_aggregate")
+    m = int(nsites.value)
+    return tuple(t[:m] for t in (o_key, o_first, o_p0, o_p1, o_met, o_unmet, o_cov))
+
+
+def aggregate_records(rec, prob_cf, contig_name=None, sort_by_key=False, device=0):
+    """``calculate_mods_frequency`` on parsed records -> ``FreqTable`` (rows ordered by first
+    callable appearance, or by (chrom, pos) when ``sort_by_key``)."""
+    n_total = len(rec)
+    if contig_name is not None:                       # call_mods_freq.py:52
+        keep = np.fromiter((c == contig_name for c in rec.chrom.tolist()), dtype=bool, count=n_total)
+        rec = Records(*(getattr(rec, f)[keep] for f in ("chrom", "pos", "strand", "pos_in_strand", "p0", "p1", "label", "kmer")))
+    if len(rec) == 0:
+        e = np.empty(0)
+        return FreqTable(np.empty(0, object), e.astype(np.int64), np.empty(0, object), e.astype(np.int64), np.empty(0, object),
+                         e, e, e.astype(np.int32), e.astype(np.int32), e.astype(np.int32), e.astype(np.int64), n_total, 0)
+    ids, names = _chrom_ids(rec.chrom)
+    keys = make_keys(ids, rec.pos)
+    k, first, s0, s1, met, unmet, cov = _aggregate_device(keys, rec.p0, rec.p1, rec.label, prob_cf, sort_by_key, device)
+    k = k.view(np.uint64)
+    names = np.asarray(names, dtype=object)
+    chrom = names[(k >> np.uint64(POS_BITS)).astype(np.int64)]
+    pos = (k & np.uint64((1 << POS_BITS) - 1)).astype(np.int64)
+    return FreqTable(chrom, pos, rec.strand[first], rec.pos_in_strand[first], rec.kmer[first], s0, s1, met, unmet, cov,
+                     first, n_total, int(cov.sum()))
+
+
+def calculate_mods_frequency(mods_files, prob_cf, contig_name=None, device=0):
+    """call mod_freq from call_mods files (``call_mods_freq.py:29-74``).  Files are read in
+    argument order; returns a ``FreqTable`` (dict-like ``sitekey2stats``)."""
+    if type(mods_files) is str:
+        mods_files = [mods_files, ]
+    rec = Records.concat([read_mods_file(f) for f in mods_files])
+    count = len(rec)
+    table = aggregate_records(rec, prob_cf, contig_name, False, device)
+    used = table.n_used
+    if count > 0:
+        if contig_name is None:
+            print("{:.2f}% ({} of {}) calls used..".format(used / float(count) * 100, used, count))
+        else:
+            print("{:.2f}% ({} of {}) calls used for {}..".format(used / float(count) * 100, used, count, contig_name))
+    return table
+
+
+def render_table(table, is_sort=False, is_bed=False):
+    """Text of ``write_sitekey2stats`` (``call_mods_freq.py:87-120``) for a ``FreqTable``."""
+    if not isinstance(table, FreqTable):
+        table = _table_from_mapping(table)
+    if is_sort:
+        table = table.sorted()
+    out = io.StringIO()
+    chrom, pos, strand = table.chrom.tolist(), table.pos.tolist(), table.strand.tolist()
+    cov, met, unmet = table.coverage.tolist(), table.met.tolist(), table.unmet.tolist()
+    if is_bed:
+        for c, p, s, cv, mt in zip(chrom, pos, strand, cov, met):
+            if cv > 0:
+                rmet = float(mt) / cv
+                out.write("\t".join([c, str(p), str(p + 1), ".", str(cv), s, str(p), str(p + 1), "0,0,0", str(cv),
+                                     str(int(round(rmet * 100 + 0.001, 0)))]) + "\n")
+    else:
+        pis, kmer = table.pos_in_strand.tolist(), table.kmer.tolist()
+        s0, s1 = table.prob_0.tolist(), table.prob_1.tolist()
+        for c, p, s, q, a, b, mt, um, cv, k in zip(chrom, pos, strand, pis, s0, s1, met, unmet, cov, kmer):
+            if cv > 0:
+                out.write("%s\t%d\t%s\t%d\t%.3f\t%.3f\t%d\t%d\t%d\t%.4f\t%s\n" % (c, p, s, q, a, b, mt, um, cv,
+                                                                                 float(mt) / cv, k))
+    return out.getvalue()
+
+
+def _table_from_mapping(d):
+    keys = list(d.keys())
+    rows = [d[k] for k in keys]
+    cp = [split_key(k) for k in keys]
+    obj = lambda xs: np.asarray(xs, dtype=object)
+    return FreqTable(obj([c for c, _ in cp]), np.asarray([p for _, p in cp], np.int64), obj([r._strand for r in rows]),
+                     np.asarray([r._pos_in_strand for r in rows], np.int64), obj([r._kmer for r in rows]),
+                     np.asarray([r._prob_0 for r in rows], np.float64), np.asarray([r._prob_1 for r in rows], np.float64),
+                     np.asarray([r._met for r in rows], np.int32), np.asarray([r._unmet for r in rows], np.int32),
+                     np.asarray([r._coverage for r in rows], np.int32), np.arange(len(rows), dtype=np.int64))
+
+
+def write_sitekey2stats(sitekey2stats, result_file, is_sort, is_bed, is_gzip):
+    """write methylfreq of sites into files (``call_mods_freq.py:77-122``)."""
+    text = render_table(sitekey2stats, is_sort, is_bed)
+    if is_gzip:
+        if not result_file.endswith(".gz"):
+            result_file += ".gz"
+        wf = gzip.open(result_file, "wt")
+    else:
+        wf = open(result_file, "w")
+    wf.write(text)
+    wf.flush()
+    wf.close()
+
+
+# ---- multi-GPU: shard by site key, one all-to-all, no partial sums -------------------------
+
+def owner_of_key(keys, world):
+    """Rank that owns a site key: multiplicative hash of the 64-bit key, mod world."""
+    h = (keys.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(33)
+    return (h % np.uint64(world)).astype(np.int64)
+
+
+def exchange_rows(rows, dest, world, rank, dev, group=None):
+    """Variable-size all-to-all of int64 rows: row i goes to rank dest[i]; rows bound for the
+    same rank keep their order; the result concatenates what source ranks 0..world-1 sent,
+    in rank order.  One ``batch_isend_irecv`` = NCCL grouped send/recv over NVLink on GPUs
+    (gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    order = np.argsort(dest, kind="stable")
+    counts = np.bincount(dest, minlength=world).astype(np.int64)
+    send = torch.from_numpy(np.ascontiguousarray(rows[order])).to(dev)
+    t_counts = torch.from_numpy(counts).to(dev)
+    all_counts = [torch.empty_like(t_counts) for _ in range(world)]
+    dist.all_gather(all_counts, t_counts, group=group)
+    recv_counts = [int(c[rank]) for c in all_counts]
+    width = rows.shape[1]
+    recv = [torch.empty((c, width), dtype=torch.int64, device=dev) for c in recv_counts]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    ops = []
+    for r in range(world):
+        if r == rank:
+            recv[r].copy_(send[offs[r]:offs[r + 1]])
+            continue
+        if counts[r]:
+            ops.append(dist.P2POp(dist.isend, send[offs[r]:offs[r + 1]].contiguous(), r, group=group))
+        if recv_counts[r]:
+            ops.append(dist.P2POp(dist.irecv, recv[r], r, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return torch.cat(recv, 0)
+
+
+def _gpu_local_aggregate(got, prob_cf, dev):
+    """(m,5) int64 device rows [key, p0 bits, p1 bits, label, gidx] -> (s,7) int64 device rows
+    [key, first_gidx, s0 bits, s1 bits, met, unmet, cov] via dsp_freq_aggregate."""
+    import torch
+    if got.shape[0] == 0:
+        return torch.empty((0, 7), dtype=torch.int64, device=dev)
+    key = got[:, 0].contiguous()
+    p0 = got[:, 1].contiguous().view(torch.float64)
+    p1 = got[:, 2].contiguous().view(torch.float64)
+    lab = got[:, 3].to(torch.int32).contiguous()
+    k, first, s0, s1, met, unmet, cov = _aggregate_tensors(key, p0, p1, lab, prob_cf, True, dev)
+    return torch.stack([k, got[:, 4][first], s0.view(torch.int64), s1.view(torch.int64),
+                        met.to(torch.int64), unmet.to(torch.int64), cov.to(torch.int64)], dim=1)
+
+
+def aggregate_records_distributed(keys, p0, p1, label, gidx, prob_cf, sort_by_key=False, device=None,
+                                  group=None, local_aggregate=None):
+    """Multi-GPU ``calculate_mods_frequency``.  Every rank passes ITS contiguous shard of the
+    records in file order (numpy columns; ``gidx`` = global record index, ascending across
+    ranks).  Callable records are routed to ``owner_of_key`` with one variable-size
+    all-to-all, so all records of a site reach one rank in ascending global order and the
+    float64 sums are the reference's bit for bit (no partial-sum merge: float64 addition is
+    order sensitive).  Each rank aggregates its keys with ``dsp_freq_aggregate``; the
+    per-site rows are collected on rank 0 and ordered by first callable appearance (dict
+    insertion order) or by key.  Returns on rank 0 a tuple of numpy arrays (key uint64,
+    first_gidx, s0, s1, met, unmet, cov); ``None`` elsewhere.
+
+    ``local_aggregate(rows, prob_cf) -> rows7`` replaces the GPU step in the CPU (gloo) tests."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", device) if device is not None else torch.device("cpu")
+    keep = ~(np.abs(p0 - p1) < prob_cf)                   # txt_formater.py:23-26, before the exchange
+    keys, p0, p1, label, gidx = keys[keep], p0[keep], p1[keep], label[keep], gidx[keep]
+    rows = np.stack([keys.view(np.int64), np.ascontiguousarray(p0).view(np.int64),
+                     np.ascontiguousarray(p1).view(np.int64), label.astype(np.int64), gidx.astype(np.int64)], axis=1)
+    got = exchange_rows(rows, owner_of_key(keys, world), world, rank, dev, group)
+    if local_aggregate is None:
+        if device is None:
+            raise RuntimeError("call_freq aggregation needs a CUDA device; there is no CPU path")
+        with torch.cuda.device(dev):
+            mine = _gpu_local_aggregate(got, prob_cf, dev)
+    else:
+        mine = torch.from_numpy(np.ascontiguousarray(local_aggregate(got.cpu().numpy(), prob_cf))).to(dev)
+    mine_np = mine.cpu().numpy()
+    merged = exchange_rows(mine_np, np.zeros(mine_np.shape[0], np.int64), world, rank, dev, group)
+    if rank != 0:
+        return None
+    m = merged.cpu().numpy()
+    order = np.argsort(m[:, 0].view(np.uint64), kind="stable") if sort_by_key else np.argsort(m[:, 1], kind="stable")
+    m = m[order]
+    return (m[:, 0].copy().view(np.uint64), m[:, 1].copy(), m[:, 2].copy().view(np.float64), m[:, 3].copy().view(np.float64),
+            m[:, 4].astype(np.int32), m[:, 5].astype(np.int32), m[:, 6].astype(np.int32))
+
+
+def call_mods_frequency_to_file(args):
+    """``call_mods_freq.py:218-296``: collect files, aggregate, write."""
+    print("[main]call_freq starts..")
+    start = time.time()
+    mods_files = []
+    for ipath in args.input_path:
+        input_path = os.path.abspath(ipath)
+        if os.path.isdir(input_path):
+            for ifile in os.listdir(input_path):
+                if args.file_uid is None or ifile.find(args.file_uid) != -1:
+                    mods_files.append("/".join([input_path, ifile]))
+        elif os.path.isfile(input_path):
+            mods_files.append(input_path)
+        else:
+            raise ValueError("--input_path is not a file or a directory!")
+    print("get {} input file(s)..".format(len(mods_files)))
+    print("read the input files..")
+    sites_stats = calculate_mods_frequency(mods_files, args.prob_cf)
+    print("write the result..")
+    write_sitekey2stats(sites_stats, args.result_file, args.sort, args.bed, args.gzip)
+    print("[main]call_freq costs %.1f seconds.." % (time.time() - start))

@@ -1,0 +1,195 @@
+"""call_freq: host logic + 2-rank gloo exchange on CPU; bit-exact GPU aggregation (-m gpu)."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from deepsignal_plant_b200 import call_mods_freq as cf
+from deepsignal_plant_b200 import synthetic
+from oracle import freq_oracle
+
+FREQ_CASES = sorted(k for k in cases.MANIFEST["freq"] if k.startswith("freq_"))
+
+
+def inputs(key):
+    if key == "edge":
+        return open(cases.GOLD + "/freq_edge_input.tsv").read().splitlines()
+    return synthetic.make_callmods_records(100000, n_chrom=12, n_pos=900, seed=5)
+
+
+class _Row:
+    def __init__(self, r):
+        self._strand, self._pos_in_strand, self._kmer, self._prob_0, self._prob_1, self._met, self._unmet, self._coverage = r
+
+
+def test_parse_matches_reference_field_rules(tmp_path):
+    lines = inputs("edge")
+    rec = cf.parse_lines(lines)
+    assert len(rec) == len(lines) and rec.chrom[1] == "chr10" and rec.pos[1] == 5 and rec.label[1] == 1
+    assert rec.p0[6] == float("5.6e-05") and rec.p1[7] == float("0.999999")
+    p = tmp_path / "a.tsv.gz"
+    with gzip.open(p, "wt") as f:
+        f.write("\n".join(lines) + "\n")
+    rec2 = cf.read_mods_file(str(p))
+    for fld in ("chrom", "pos", "strand", "pos_in_strand", "p0", "p1", "label", "kmer"):
+        assert (getattr(rec, fld) == getattr(rec2, fld)).all(), fld
+
+
+@pytest.mark.parametrize("name", FREQ_CASES)
+def test_render_from_oracle_table_matches_reference_bytes(name):
+    # the writer half (write_sitekey2stats) on a table built by the oracle
+    e = cases.MANIFEST["freq"][name]
+    table = freq_oracle.aggregate(inputs(e["input"]), e["prob_cf"])
+    mapping = {cf.key_sep.join([c, str(p)]): _Row(r) for (c, p), r in table.items()}
+    assert cf.render_table(mapping, e["sort"], e["bed"]) == cases.read_gz(name + ".txt.gz")
+
+
+def test_key_order_equals_python_tuple_order():
+    chrom = np.array(["chr10", "chr2", "chrX", "chr1", "chr10"], dtype=object)
+    pos = np.array([5, 100, 1, 7, 4], dtype=np.int64)
+    ids, names = cf._chrom_ids(chrom)
+    keys = cf.make_keys(ids, pos)
+    want = sorted(range(5), key=lambda i: (chrom[i], int(pos[i])))
+    assert np.argsort(keys, kind="stable").tolist() == want
+    with pytest.raises(ValueError):
+        cf.make_keys(ids, np.array([-1, 0, 0, 0, 0]))
+
+
+def _numpy_local_aggregate(rows, prob_cf):
+    """Test-side stand-in for the GPU step: ordered float64 replay per key (oracle semantics)."""
+    out = {}
+    for k, b0, b1, lab, g in rows.tolist():
+        p0 = np.int64(b0).view(np.float64).item()
+        p1 = np.int64(b1).view(np.float64).item()
+        r = out.get(k)
+        if r is None:
+            r = out[k] = [k, g, 0.0, 0.0, 0, 0, 0]
+        r[2] += p0
+        r[3] += p1
+        r[4 if lab == 1 else 5] += 1
+        r[6] += 1
+    res = np.zeros((len(out), 7), np.int64)
+    for i, r in enumerate(sorted(out.values())):
+        res[i] = [r[0], r[1], np.float64(r[2]).view(np.int64), np.float64(r[3]).view(np.int64), r[4], r[5], r[6]]
+    return res
+
+
+def _worker(rank, world, port, prob_cf, sort_by_key, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lines = synthetic.make_callmods_records(20000, n_chrom=6, n_pos=300, seed=9)
+    rec = cf.parse_lines(lines)
+    ids, names = cf._chrom_ids(rec.chrom)
+    keys = cf.make_keys(ids, rec.pos)
+    n = len(rec)
+    lo, hi = rank * n // world, (rank + 1) * n // world          # contiguous shards, file order
+    res = cf.aggregate_records_distributed(keys[lo:hi], rec.p0[lo:hi], rec.p1[lo:hi], rec.label[lo:hi],
+                                           np.arange(lo, hi, dtype=np.int64), prob_cf, sort_by_key,
+                                           device=None, local_aggregate=_numpy_local_aggregate)
+    if rank == 0:
+        q.put(tuple(a.tolist() for a in res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,prob_cf,sort_by_key", [(2, 0.0, False), (2, 0.5, True), (3, 0.1, False)])
+def test_distributed_exchange_gloo(world, prob_cf, sort_by_key):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, prob_cf, sort_by_key, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    key, first, s0, s1, met, unmet, cov = got
+    lines = synthetic.make_callmods_records(20000, n_chrom=6, n_pos=300, seed=9)
+    table = freq_oracle.aggregate(lines, prob_cf)
+    rec = cf.parse_lines(lines)
+    ids, names = cf._chrom_ids(rec.chrom)
+    items = list(table.items())
+    if sort_by_key:
+        items.sort(key=lambda kv: kv[0])
+    assert len(items) == len(key)
+    for i, ((chrom, pos), row) in enumerate(items):
+        assert key[i] == (names.index(chrom) << cf.POS_BITS) | pos
+        assert s0[i] == row[3] and s1[i] == row[4]                # float64, bit-exact
+        assert (met[i], unmet[i], cov[i]) == (row[5], row[6], row[7])
+        assert rec.chrom[first[i]] == chrom and rec.pos[first[i]] == pos
+
+
+def test_owner_of_key_is_balanced_and_deterministic():
+    keys = cf.make_keys(np.repeat(np.arange(5), 1000), np.tile(np.arange(1000), 5))
+    own = cf.owner_of_key(keys, 8)
+    assert (own == cf.owner_of_key(keys, 8)).all()
+    cnt = np.bincount(own, minlength=8)
+    assert cnt.min() > 0.7 * len(keys) / 8 and cnt.max() < 1.3 * len(keys) / 8
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FREQ_CASES)
+def test_gpu_freq_bit_exact_against_reference_bytes(name, tmp_path):
+    e = cases.MANIFEST["freq"][name]
+    lines = inputs(e["input"])
+    half = len(lines) // 2
+    a, b = tmp_path / "a.tsv", tmp_path / "b.tsv.gz"
+    a.write_text("\n".join(lines[:half]) + "\n")
+    with gzip.open(b, "wt") as f:
+        f.write("\n".join(lines[half:]) + "\n")
+    table = cf.calculate_mods_frequency([str(a), str(b)], e["prob_cf"])
+    out = tmp_path / "out.txt"
+    cf.write_sitekey2stats(table, str(out), e["sort"], e["bed"], False)
+    assert out.read_text() == cases.read_gz(name + ".txt.gz")
+
+
+@pytest.mark.gpu
+def test_gpu_freq_dict_view_and_contig_filter():
+    lines = inputs("edge")
+    rec = cf.parse_lines(lines)
+    t = cf.aggregate_records(rec, 0.0)
+    want = freq_oracle.aggregate(lines, 0.0)
+    assert t.keys() == [cf.key_sep.join([c, str(p)]) for c, p in want]
+    row = t["chr2||100"]
+    assert (row._strand, row._coverage, row._met, row._unmet) == ("+", 2, 1, 1)
+    t2 = cf.aggregate_records(rec, 0.0, contig_name="chr1")
+    assert cf.render_table(t2) == freq_oracle.render(freq_oracle.aggregate(lines, 0.0, "chr1"))
+    assert len(cf.aggregate_records(cf.parse_lines([]), 0.0)) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_freq_large_random_property():
+    # size-independent properties at a size the Python oracle would need minutes for:
+    # coverage sums to the callable count; met+unmet == coverage; permuting records of
+    # DIFFERENT sites does not change any site's sums (order only matters within a site).
+    rng = np.random.default_rng(1)
+    n = 3_000_000
+    pos = rng.integers(0, 200_000, n)
+    chrom = rng.integers(0, 4, n)
+    keys = cf.make_keys(chrom, pos)
+    p1 = rng.random(n)
+    p0 = 1.0 - p1
+    label = (p1 > 0.5).astype(np.int32)
+    k, first, s0, s1, met, unmet, cov = cf._aggregate_device(keys, p0, p1, label, 0.2, True, 0)
+    callable_ = ~(np.abs(p0 - p1) < 0.2)
+    assert cov.sum() == callable_.sum() and ((met + unmet) == cov).all()
+    assert (np.diff(k.view(np.uint64).astype(np.int64)) > 0).all()
+    # reference sums for a few sites, ordered replay on the host
+    for j in rng.integers(0, len(k), 50):
+        idx = np.nonzero((keys == k.view(np.uint64)[j]) & callable_)[0]
+        a = 0.0
+        for i in idx:
+            a += p0[i]
+        assert a == s0[j] and first[j] == idx[0] and cov[j] == len(idx)
+    # stable partition by chromosome keeps within-site order -> identical results
+    order = np.argsort(chrom, kind="stable")
+    k2, _, s0b, s1b, *_ = cf._aggregate_device(keys[order], p0[order], p1[order], label[order], 0.2, True, 0)
+    assert (k2 == k).all() and (s0b == s0).all() and (s1b == s1).all()
