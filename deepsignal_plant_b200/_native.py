@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libdsp_b200.so")
 SYMBOLS = (
     "dsp_abi_version", "dsp_last_error", "dsp_create", "dsp_destroy", "dsp_set_param",
     "dsp_pack_weights", "dsp_forward", "dsp_forward_host", "dsp_launch_count",
-    "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate",
+    "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate", "dsp_selftest",
 )
 
 MODULES = {"both_bilstm": 0, "seq_bilstm": 1, "signal_bilstm": 2}
@@ -61,6 +61,7 @@ def lib():
     L.dsp_get_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(i64)]
     L.dsp_freq_aggregate.argtypes = [C.c_int, vp, vp, vp, vp, i64, C.c_double, C.c_int,
                                      vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
+    L.dsp_selftest.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here means header and library disagree
     _lib = L

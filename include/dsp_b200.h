@@ -143,6 +143,12 @@ int dsp_freq_aggregate(int device, const uint64_t* key, const double* p0, const 
                        int32_t* out_met, int32_t* out_unmet, int32_t* out_cov,
                        int64_t* n_sites_host, void* stream);
 
+/* Known-answer test of the tcgen05/TMEM/bulk-copy building blocks on `device`: a one-CTA
+ * FP16 GEMM with FP32 accumulation checked against a double-precision host product.
+ * which: 0,1 = both operands from shared memory; 2,3 = A operand staged in TMEM.
+ * *max_abs_err receives the largest absolute deviation. */
+int dsp_selftest(int device, int which, double* max_abs_err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,3 +142,12 @@ def test_oracle_agrees_on_fresh_seed():
     cases.inject_states(model, states, torch.device("cuda:0"))
     logits, probs = model(*(torch.from_numpy(feats[k]).cuda(0) for k in cases.FEATURE_KEYS))
     assert np.abs(probs.cpu().numpy() - want_probs).max() < FP32_TOL
+
+
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
+def test_tcgen05_building_blocks(which):
+    import ctypes as C
+    from deepsignal_plant_b200 import _native
+    err = C.c_double()
+    _native.check(_native.lib().dsp_selftest(0, which, C.byref(err)), "dsp_selftest")
+    assert 0 <= err.value < 1e-3, err.value
