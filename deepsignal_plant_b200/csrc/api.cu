@@ -138,26 +138,6 @@ void state_groups(const Model* m, StateGroup g[3]) {
     g[2] = {m->cfg.num_layers1, m->cfg.hidden_size};
 }
 
-cudaEvent_t next_event(Model* m) {
-    if (m->event_next == m->event_pool.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        m->event_pool.push_back(e);
-    }
-    return m->event_pool[m->event_next++];
-}
-
-struct Span {
-    Model* m; cudaStream_t st; cudaEvent_t a = nullptr;
-    int cls;
-    Span(Model* m_, int cls_, cudaStream_t st_) : m(m_), st(st_), cls(cls_) {
-        if (m->timing) { a = next_event(m); cudaEventRecord(a, st); }
-    }
-    ~Span() {
-        if (m->timing) { cudaEvent_t b = next_event(m); cudaEventRecord(b, st); m->spans.push_back({cls, a, b}); }
-    }
-};
-
 // One pass over n <= cap sites whose inputs already sit on the device.
 // states6: per group h0/c0 base pointers for THIS chunk and the dir stride (floats) of
 // each group; nullptr -> Philox.

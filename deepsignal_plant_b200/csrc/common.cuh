@@ -100,6 +100,27 @@ struct Model {
     void* tc_state = nullptr;               // owned by kernels_tc.cu
 };
 
+inline cudaEvent_t next_event(Model* m) {
+    if (m->event_next == m->event_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        m->event_pool.push_back(e);
+    }
+    return m->event_pool[m->event_next++];
+}
+
+// CUDA-event bracket around the launches of one kernel class (dsp_set_timing / dsp_get_timing).
+struct Span {
+    Model* m; cudaStream_t st; cudaEvent_t a = nullptr;
+    int cls;
+    Span(Model* m_, int cls_, cudaStream_t st_) : m(m_), st(st_), cls(cls_) {
+        if (m->timing) { a = next_event(m); cudaEventRecord(a, st); }
+    }
+    ~Span() {
+        if (m->timing) { cudaEvent_t b = next_event(m); cudaEventRecord(b, st); m->spans.push_back({cls, a, b}); }
+    }
+};
+
 // ---- fp32 CUDA-core path (kernels_f32.cu) --------------------------------------------
 int f32_assemble_seq(Model* m, const float* kmer, const float* means, const float* stds,
                      const float* lens, int64_t n, float* xseq, cudaStream_t st);
@@ -110,6 +131,9 @@ int f32_dense(Model* m, const DenseF32& D, const float* x, int64_t rows, int x_r
               float* y, int y_row_stride, int relu, cudaStream_t st);
 int f32_head(Model* m, const float* y_last, int64_t n, float* logits, float* probs,
              int32_t* labels, cudaStream_t st);
+// same head on a flat (n, 2H) fp32 matrix [h_fwd(T-1) | h_bwd(0)]
+int f32_head_flat(Model* m, const float* hfinal, int64_t n, float* logits, float* probs,
+                  int32_t* labels, cudaStream_t st);
 int philox_normal(Model* m, float* out, int64_t count, uint64_t seed, uint64_t stream_id,
                   cudaStream_t st);
 

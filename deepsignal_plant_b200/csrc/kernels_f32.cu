@@ -303,11 +303,7 @@ int f32_lstm_layer(Model* m, const LstmLayer& L, const float* x, int x_row_strid
     const int Kp = ru(L.K, 4), Hp = ru(L.H, 4);
     size_t smem = sizeof(float) * TS * (size_t)(Kp + 3 * Hp);
     DSP_REQUIRE(smem <= 227 * 1024, DSP_ERR_INVALID, "fp32 LSTM layer K=%d H=%d exceeds shared memory", L.K, L.H);
-    static size_t configured = 0;
-    if (smem > configured) {
-        DSP_CUDA(cudaFuncSetAttribute(lstm_layer_f32_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = 227 * 1024;
-    }
+    DSP_CUDA(cudaFuncSetAttribute(lstm_layer_f32_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     int threads = L.H >= 256 ? 256 : ru(L.H, 32);
     dim3 grid((unsigned)((n + TS - 1) / TS), 2);
     lstm_layer_f32_kernel<TS><<<grid, threads, smem, st>>>(
@@ -331,20 +327,29 @@ int f32_dense(Model* m, const DenseF32& D, const float* x, int64_t rows, int x_r
     return DSP_OK;
 }
 
+static int head_launch(Model* m, const float* y_last, int T, int64_t n, float* logits, float* probs,
+                       int32_t* labels, cudaStream_t st);
+
 int f32_head(Model* m, const float* y_last, int64_t n, float* logits, float* probs,
              int32_t* labels, cudaStream_t st) {
+    return head_launch(m, y_last, m->cfg.seq_len, n, logits, probs, labels, st);
+}
+
+int f32_head_flat(Model* m, const float* hfinal, int64_t n, float* logits, float* probs,
+                  int32_t* labels, cudaStream_t st) {
+    return head_launch(m, hfinal, 1, n, logits, probs, labels, st);     // T = 1: row r is (r, 2H)
+}
+
+static int head_launch(Model* m, const float* y_last, int T, int64_t n, float* logits, float* probs,
+                       int32_t* labels, cudaStream_t st) {
     if (n == 0) return DSP_OK;
     const dsp_config& c = m->cfg;
     const int H = c.hidden_size, J1 = m->fc1.J, C = c.num_classes;
     size_t smem = sizeof(float) * TS * (size_t)(ru(2 * H, 4) + ru(J1, 4) + C);
     DSP_REQUIRE(smem <= 227 * 1024, DSP_ERR_INVALID, "head too wide for shared memory");
-    static bool configured = false;
-    if (!configured) {
-        DSP_CUDA(cudaFuncSetAttribute(head_f32_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        configured = true;
-    }
+    DSP_CUDA(cudaFuncSetAttribute(head_f32_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     head_f32_kernel<TS><<<(unsigned)((n + TS - 1) / TS), 256, smem, st>>>(
-        y_last, H, c.seq_len, n, m->fc1.wt, m->fc1.bias, J1, m->fc2.wt, m->fc2.bias, C, logits, probs, labels);
+        y_last, H, T, n, m->fc1.wt, m->fc1.bias, J1, m->fc2.wt, m->fc2.bias, C, logits, probs, labels);
     m->launches++;
     DSP_CUDA(cudaGetLastError());
     return DSP_OK;

@@ -1,13 +1,613 @@
-// tcgen05 path -- placeholder until the tensor-core kernels land.
+// tcgen05 / TMEM path of the ModelBiLSTM forward (DSP_PRECISION_FP16).
+//
+// Arithmetic: FP16 MMA operands (weights, layer inputs, h_{t-1}), FP32 accumulation in TMEM,
+// FP32 bias, FP32 cell state and gate math.  Reference semantics: deepsignal_plant/models.py
+// :178-240 and torch nn.LSTM (gate order i,f,g,o; reverse direction walks t = T-1..0).
+//
+// Data layout.  A site tile is 128 sites (= the 128 TMEM lanes = M of the MMA).  Every MMA
+// operand lives in HBM as 16 KB "slabs" (128 rows x 64 fp16, 128-byte swizzled, see
+// tc_prims.cuh) so that one linear cp.async.bulk brings it to shared memory ready for
+// tcgen05.mma:
+//   activations  [tile][t][slab][128 rows x 128 B]     (x_t of a layer = slabs of one (tile,t))
+//   weights      [dir][chunk][kslab][128 rows x 128 B] (chunk = 128 gate columns = 32 hidden
+//                units x {i,f,g,o}, column = half*64 + j*4 + gate for unit chunk*32+half*16+j)
+//
+// One CTA of lstm_layer_kernel owns (site tile, direction) for all T steps:
+//   warp 0  : streams weight slabs through a shared-memory ring (bulk async copies, mbarriers)
+//   warp 2  : loads the x_t slabs of each step
+//   warp 1  : one thread issues tcgen05.mma; per step and chunk
+//                 acc[128 x 128] = x_t * W_ih_chunk^T   (A from shared memory)
+//                                + h_{t-1} * W_hh_chunk^T (A from TMEM)
+//             into one of two TMEM accumulators
+//   warps 4-11: epilogue; thread = site; reads its accumulator row, adds the bias, applies the
+//             gate non-linearities, updates the cell state it keeps in registers for all T
+//             steps, writes h_t as packed FP16 straight into the TMEM A operand of the next
+//             step and as a slab image to HBM for the next layer.
+// h and c never leave the SM between steps; gate pre-activations never touch HBM.
 #include "tc.cuh"
+#include "tc_prims.cuh"
+#include <vector>
+#include <cstring>
+
 namespace dsp {
-int tc_create(Model*) { set_error("DSP_PRECISION_FP16 path is not built in this revision"); return DSP_ERR_INVALID; }
-void tc_destroy(Model*) {}
-int tc_pack_lstm_layer(Model*, LstmLayer&, const float*, const float*, const float*, const float*,
-                       const float*, const float*, const float*, const float*) { return DSP_ERR_INVALID; }
-int tc_pack_dense(Model*, DenseF32&, const float*, const float*) { return DSP_ERR_INVALID; }
-int tc_finalize_pack(Model*) { return DSP_ERR_INVALID; }
-int tc_forward_chunk(Model*, const float*, const float*, const float*, const float*, const float*,
-                     const float* const*, const float* const*, const int64_t*, int64_t, float*, float*, int32_t*,
-                     cudaStream_t) { return DSP_ERR_INVALID; }
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int SLAB_BYTES = TILE * SLAB_ROW_BYTES;   // 16 KB
+constexpr int NTHREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct LayerParams {
+    const uint8_t* x_img;      // [tiles][T][KSX] slabs
+    const uint8_t* w_img;      // [dir][NCH][KS] slabs
+    const float* bias;         // [dir][NCH*128] in chunk column order
+    const float* h0;           // [dir][n][H] fp32 (LSTM only)
+    const float* c0;
+    int64_t state_dir_stride;
+    uint8_t* y_img;            // output image: [tiles][T][y_slabs] slabs
+    float* hfinal;             // [tiles*128][2H] fp32, last step of each direction (or null)
+    int64_t n;
+    int T;
+    int xk16;                  // K16 steps of the x part (= KSX*4 unless the input is narrow)
+    int y_slabs;
+    int y_col_off;             // FC: first output column
+    int write_y;
+};
+
+template <int KSX> struct RingStages { static constexpr int value = (KSX >= 8) ? 6 : 8; };
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------
+// KSX: x slabs per step; H: hidden size of the layer (LSTM) ; IS_FC: dense+ReLU instead of LSTM
+// (then NCOLS = number of output columns, no recurrence).
+template <int KSX, int H, bool IS_FC, int NOUT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+layer_kernel(const LayerParams p) {
+    constexpr int NST = RingStages<KSX>::value;
+    constexpr int NCH = IS_FC ? NOUT / 128 : H / 32;       // 128-column chunks per step
+    constexpr int KSH = IS_FC ? 0 : H / 64;                // h slabs (K of the recurrent part)
+    constexpr int KS = KSX + KSH;
+    constexpr int HCOLS = IS_FC ? 0 : H / 2;               // TMEM columns of one h buffer
+    constexpr uint32_t IDESC = make_idesc_f16(128, 128);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_x = smem;                                   // KSX slabs
+    uint8_t* s_w = smem + (size_t)KSX * SLAB_BYTES;        // NST slabs
+    __shared__ __align__(8) uint64_t bars[2 * NST + 2 * KSX + 5];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t b_wfull = smem_u32(&bars[0]), b_wempty = smem_u32(&bars[NST]);
+    const uint32_t b_xfull = smem_u32(&bars[2 * NST]), b_xempty = smem_u32(&bars[2 * NST + KSX]);
+    const uint32_t b_accfull = smem_u32(&bars[2 * NST + 2 * KSX]), b_accempty = b_accfull + 16;
+    const uint32_t b_hready = b_accfull + 32;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, dir = IS_FC ? 0 : blockIdx.y;
+    const int T = p.T;
+
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
+        for (int i = 0; i < KSX; ++i) { mbar_init(b_xfull + 8 * i, 1); mbar_init(b_xempty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, EPI_WARPS); }
+        mbar_init(b_hready, EPI_WARPS);
+        mbar_fence_init();
+    }
+    if (warp == 3) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t t_acc = tmem;                 // two accumulators: columns [0,128) and [128,256)
+    const uint32_t t_h = tmem + 256;             // two h buffers of HCOLS columns at +0 and +128
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0) {
+            // ---- weight slab producer ---------------------------------------------------------
+            if (elect_one()) {
+                const uint8_t* wsrc = p.w_img + (size_t)dir * NCH * KS * SLAB_BYTES;
+                uint32_t stage = 0, phase = 0;
+                for (int step = 0; step < T; ++step)
+                    for (int i = 0; i < NCH * KS; ++i) {
+                        mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+                        mbar_arrive_expect_tx(b_wfull + 8 * stage, SLAB_BYTES);
+                        bulk_g2s(smem_u32(s_w + (size_t)stage * SLAB_BYTES), wsrc + (size_t)i * SLAB_BYTES, SLAB_BYTES,
+                                 b_wfull + 8 * stage);
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+            }
+        } else if (warp == 2) {
+            // ---- x_t slab producer ------------------------------------------------------------
+            if (elect_one()) {
+                for (int step = 0; step < T; ++step) {
+                    const int t = dir ? (T - 1 - step) : step;
+                    const uint8_t* xsrc = p.x_img + ((size_t)tile * T + t) * KSX * SLAB_BYTES;
+                    for (int j = 0; j < KSX; ++j) {
+                        mbar_wait(b_xempty + 8 * j, (step & 1) ^ 1);
+                        mbar_arrive_expect_tx(b_xfull + 8 * j, SLAB_BYTES);
+                        bulk_g2s(smem_u32(s_x + (size_t)j * SLAB_BYTES), xsrc + (size_t)j * SLAB_BYTES, SLAB_BYTES, b_xfull + 8 * j);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ---- MMA issuer ---------------------------------------------------------------------
+            if (elect_one()) {
+                uint32_t stage = 0, phase = 0;
+                for (int step = 0; step < T; ++step) {
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        const uint32_t g = (uint32_t)(step * NCH + ch);
+                        const uint32_t buf = g & 1u, use = g >> 1;
+                        mbar_wait(b_accempty + 8 * buf, (use & 1u) ^ 1u);
+                        tc_fence_after();
+                        const uint32_t acc = t_acc + buf * 128u;
+                        uint32_t accum = 0;
+                        for (int ks = 0; ks < KSX; ++ks) {
+                            if (ch == 0) { mbar_wait(b_xfull + 8 * ks, step & 1); }
+                            mbar_wait(b_wfull + 8 * stage, phase);
+                            tc_fence_after();
+                            const uint32_t a_base = smem_u32(s_x + (size_t)ks * SLAB_BYTES);
+                            const uint32_t b_base = smem_u32(s_w + (size_t)stage * SLAB_BYTES);
+                            const int nk = min(4, p.xk16 - ks * 4);
+                            for (int k = 0; k < nk; ++k) {
+                                mma_ss(acc, make_smem_desc(a_base + k * 32), make_smem_desc(b_base + k * 32), IDESC, accum);
+                                accum = 1;
+                            }
+                            mma_commit(b_wempty + 8 * stage);
+                            if (ch == NCH - 1) mma_commit(b_xempty + 8 * ks);
+                            if (++stage == NST) { stage = 0; phase ^= 1; }
+                        }
+                        if constexpr (!IS_FC) {
+                            if (ch == 0) { mbar_wait(b_hready, step & 1); tc_fence_after(); }
+                            const uint32_t a_t = t_h + (uint32_t)(step & 1) * 128u;
+                            for (int ks = 0; ks < KSH; ++ks) {
+                                mbar_wait(b_wfull + 8 * stage, phase);
+                                tc_fence_after();
+                                const uint32_t b_base = smem_u32(s_w + (size_t)stage * SLAB_BYTES);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    mma_ts(acc, a_t + (uint32_t)(ks * 32 + k * 8), make_smem_desc(b_base + k * 32), IDESC, accum);
+                                    accum = 1;
+                                }
+                                mma_commit(b_wempty + 8 * stage);
+                                if (++stage == NST) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                        mma_commit(b_accfull + 8 * buf);
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- epilogue warps: thread = site row ------------------------------------------------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int ew = warp - 4;
+        const int q = ew & 3;                        // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                    // which 64 of the chunk's 128 columns
+        const int row = q * 32 + lane;
+        const int64_t site = (int64_t)tile * TILE + row;
+        const bool valid = site < p.n;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const float* bias = p.bias + (size_t)dir * NCH * 128 + half * 64;
+
+        if constexpr (IS_FC) {
+            for (int step = 0; step < T; ++step) {
+                uint8_t* ybase = p.y_img + ((size_t)tile * T + step) * p.y_slabs * SLAB_BYTES;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const uint32_t g = (uint32_t)(step * NCH + ch);
+                    const uint32_t buf = g & 1u, use = g >> 1;
+                    mbar_wait(b_accfull + 8 * buf, use & 1u);
+                    tc_fence_after();
+                    const int col0 = p.y_col_off + ch * 128 + half * 64;      // multiple of 64
+                    uint8_t* yslab = ybase + (size_t)(col0 >> 6) * SLAB_BYTES + row * SLAB_ROW_BYTES;
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        uint32_t v[32];
+                        tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(half * 64 + part * 32), v);
+                        tmem_ld_wait();
+                        if (part == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(b_accempty + 8 * buf);
+                        }
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = c8 * 8 + e * 2;
+                                const float a = fmaxf(__uint_as_float(v[j]) + __ldg(bias + ch * 128 + part * 32 + j), 0.f);
+                                const float b = fmaxf(__uint_as_float(v[j + 1]) + __ldg(bias + ch * 128 + part * 32 + j + 1), 0.f);
+                                o[e] = pack_half2(a, b);
+                            }
+                            const int chunk = part * 4 + c8;
+                            *reinterpret_cast<uint4*>(yslab + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+            }
+        } else {
+            constexpr int UPT = 16;                   // hidden units per thread per chunk
+            float c[NCH][UPT];
+            // initial states: c0 -> registers, h0 -> TMEM h buffer 0 (packed FP16 pairs)
+            {
+                const float* h0 = p.h0 + (size_t)dir * p.state_dir_stride + (size_t)site * H;
+                const float* c0 = p.c0 + (size_t)dir * p.state_dir_stride + (size_t)site * H;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const int u0 = ch * 32 + half * UPT;
+                    float hv[UPT];
+#pragma unroll
+                    for (int j4 = 0; j4 < UPT; j4 += 4) {
+                        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), hq = cv;
+                        if (valid) {
+                            cv = *reinterpret_cast<const float4*>(c0 + u0 + j4);
+                            hq = *reinterpret_cast<const float4*>(h0 + u0 + j4);
+                        }
+                        c[ch][j4] = cv.x; c[ch][j4 + 1] = cv.y; c[ch][j4 + 2] = cv.z; c[ch][j4 + 3] = cv.w;
+                        hv[j4] = hq.x; hv[j4 + 1] = hq.y; hv[j4 + 2] = hq.z; hv[j4 + 3] = hq.w;
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = pack_half2(hv[2 * j], hv[2 * j + 1]);
+                    tmem_st8(t_h + lane_addr + (uint32_t)(u0 >> 1), pk);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_hready);
+            }
+            for (int step = 0; step < T; ++step) {
+                const int t = dir ? (T - 1 - step) : step;
+                const bool last = (step == T - 1);
+                uint8_t* ybase = p.y_img + ((size_t)tile * T + t) * p.y_slabs * SLAB_BYTES + row * SLAB_ROW_BYTES;
+                const uint32_t t_hnext = t_h + (uint32_t)((step + 1) & 1) * 128u + lane_addr;
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const uint32_t buf = (uint32_t)ch & 1u;                   // NCH is even
+                    const uint32_t use = (uint32_t)(step * NCH + ch) >> 1;
+                    mbar_wait(b_accfull + 8 * buf, use & 1u);
+                    tc_fence_after();
+                    const int u0 = ch * 32 + half * UPT;
+                    float hv[UPT];
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        uint32_t v[32];
+                        tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(half * 64 + part * 32), v);
+                        tmem_ld_wait();
+                        if (part == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(b_accempty + 8 * buf);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int j = part * 8 + jj;
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 128 + j * 4));
+                            const float gi = clampf(__uint_as_float(v[jj * 4 + 0]) + b4.x, -40.f, 40.f);
+                            const float gf = clampf(__uint_as_float(v[jj * 4 + 1]) + b4.y, -40.f, 40.f);
+                            const float gg = clampf(__uint_as_float(v[jj * 4 + 2]) + b4.z, -40.f, 40.f);
+                            const float go = clampf(__uint_as_float(v[jj * 4 + 3]) + b4.w, -40.f, 40.f);
+                            const float ei = ex2_approx(-LOG2E * gi);
+                            const float ef = ex2_approx(-LOG2E * gf);
+                            const float eg = ex2_approx(-2.f * LOG2E * gg);
+                            const float eo = ex2_approx(-LOG2E * go);
+                            const float sf = rcp_approx(1.f + ef);
+                            const float ig = (1.f - eg) * rcp_approx((1.f + ei) * (1.f + eg));   // sigmoid(i)*tanh(g)
+                            const float cn = fmaf(sf, c[ch][j], ig);
+                            c[ch][j] = cn;
+                            const float ec = ex2_approx(-2.f * LOG2E * clampf(cn, -40.f, 40.f));
+                            hv[j] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));            // sigmoid(o)*tanh(c)
+                        }
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = pack_half2(hv[2 * j], hv[2 * j + 1]);
+                    tmem_st8(t_hnext + (uint32_t)(u0 >> 1), pk);
+                    if (p.write_y) {
+                        const int col = dir * H + u0;                          // multiple of 16
+                        uint8_t* yslab = ybase + (size_t)(col >> 6) * SLAB_BYTES;
+                        const int chunk = (col & 63) >> 3;
+                        *reinterpret_cast<uint4*>(yslab + (((chunk) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(yslab + (((chunk + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                    if (last && p.hfinal != nullptr && valid) {
+                        float* hf = p.hfinal + (size_t)site * (2 * H) + dir * H + u0;
+#pragma unroll
+                        for (int j4 = 0; j4 < UPT; j4 += 4)
+                            *reinterpret_cast<float4*>(hf + j4) = make_float4(hv[j4], hv[j4 + 1], hv[j4 + 2], hv[j4 + 3]);
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_hready);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) tmem_dealloc(tmem, 512);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Feature assembly into slab images (models.py:182-195): per (site, t) one row of
+// [embed(kmer) | mean | std | len | 0...] (seq) and of the signal rectangle (signal), FP16.
+__global__ void prep_images_kernel(const float* __restrict__ kmer, const float* __restrict__ means,
+                                   const float* __restrict__ stds, const float* __restrict__ lens,
+                                   const float* __restrict__ signals, const float* __restrict__ embed,
+                                   int E, int vocab, int use_len, int S, int T, int64_t n, int64_t n_pad,
+                                   uint8_t* __restrict__ xseq_img, uint8_t* __restrict__ xsig_img) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (site, t)
+    if (idx >= n_pad * T) return;
+    const int64_t site = idx / T;
+    const int t = (int)(idx - site * T);
+    const int64_t tile = site >> 7;
+    const int row = (int)(site & 127);
+    const bool valid = site < n;
+    const size_t slab = ((size_t)tile * T + t) * SLAB_BYTES;
+    if (xseq_img) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = 0.f;
+        if (valid) {
+            int c = 0;
+            if (E > 0) {
+                long long code = (long long)kmer[site * T + t];
+                code = code < 0 ? 0 : (code >= vocab ? vocab - 1 : code);
+                for (int e = 0; e < E && c < 16; ++e) f[c++] = embed[code * E + e];
+            }
+            if (c < 16) f[c++] = means[site * T + t];
+            if (c < 16) f[c++] = stds[site * T + t];
+            if (use_len && c < 16) f[c++] = lens[site * T + t];
+        }
+        uint8_t* dst = xseq_img + slab + row * SLAB_ROW_BYTES;
+#pragma unroll
+        for (int chunk = 0; chunk < 2; ++chunk) {
+            uint4 o;
+            o.x = pack_half2(f[chunk * 8 + 0], f[chunk * 8 + 1]); o.y = pack_half2(f[chunk * 8 + 2], f[chunk * 8 + 3]);
+            o.z = pack_half2(f[chunk * 8 + 4], f[chunk * 8 + 5]); o.w = pack_half2(f[chunk * 8 + 6], f[chunk * 8 + 7]);
+            *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = o;
+        }
+    }
+    if (xsig_img) {
+        const float* src = signals + (site * T + t) * S;
+        uint8_t* dst = xsig_img + slab + row * SLAB_ROW_BYTES;
+        const int nchunk = ((S + 15) / 16) * 2;
+        for (int chunk = 0; chunk < nchunk; ++chunk) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int k = chunk * 8 + i; f[i] = (valid && k < S) ? src[k] : 0.f; }
+            uint4 o;
+            o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]); o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = o;
+        }
+    }
+}
+
+// ---- host-side packing ------------------------------------------------------------------------
+struct TcLstmPack {
+    uint8_t* w_img = nullptr;   // [2][NCH][KS] slabs
+    float* bias = nullptr;      // [2][NCH*128]
+    int KSX = 0, xk16 = 0;
+};
+struct TcDensePack {
+    uint8_t* w_img = nullptr;   // [NCH][KS] slabs
+    float* bias = nullptr;      // [NCH*128]
+    int KS = 0;
+};
+struct TcState {
+    uint8_t* xseq_img = nullptr;
+    uint8_t* xsig_img = nullptr;
+    uint8_t* ybuf[2] = {nullptr, nullptr};
+    uint8_t* comb_img = nullptr;
+    float* hfinal = nullptr;
+    int64_t tiles = 0;
+    std::vector<TcLstmPack*> lstm_packs;
+    std::vector<TcDensePack*> dense_packs;
+};
+
+void put_half(std::vector<uint8_t>& img, size_t slab_index, int row, int col, float v) {
+    __half h = __float2half_rn(v);
+    memcpy(&img[slab_index * SLAB_BYTES + slab_offset_bytes(row, col)], &h, 2);
+}
+
+int tc_alloc(Model* m, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); return DSP_ERR_NOMEM; }
+    m->device_allocs.push_back(*p);
+    return DSP_OK;
+}
+
+template <int KSX, int H, bool IS_FC, int NOUT>
+int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
+    constexpr int NST = RingStages<KSX>::value;
+    const size_t smem = (size_t)(KSX + NST) * SLAB_BYTES + 1024;
+    auto kern = layer_kernel<KSX, H, IS_FC, NOUT>;
+    DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)tiles, IS_FC ? 1 : 2);
+    kern<<<grid, NTHREADS, smem, st>>>(p);
+    m->launches++;
+    DSP_CUDA(cudaGetLastError());
+    return DSP_OK;
+}
+
+int launch_lstm(Model* m, int KSX, int H, const LayerParams& p, int64_t tiles, cudaStream_t st) {
+    if (H == 128) {
+        if (KSX == 1) return launch_layer<1, 128, false, 0>(m, p, tiles, st);
+        if (KSX == 4) return launch_layer<4, 128, false, 0>(m, p, tiles, st);
+    } else if (H == 256) {
+        if (KSX == 1) return launch_layer<1, 256, false, 0>(m, p, tiles, st);
+        if (KSX == 4) return launch_layer<4, 256, false, 0>(m, p, tiles, st);
+        if (KSX == 8) return launch_layer<8, 256, false, 0>(m, p, tiles, st);
+    }
+    set_error("tcgen05 path: unsupported LSTM layer shape (x slabs %d, hidden %d)", KSX, H);
+    return DSP_ERR_INVALID;
+}
+
+int launch_fc(Model* m, int KS, int NOUT, const LayerParams& p, int64_t tiles, cudaStream_t st) {
+    if (KS == 4 && NOUT == 128) return launch_layer<4, 0, true, 128>(m, p, tiles, st);
+    if (KS == 8 && NOUT == 256) return launch_layer<8, 0, true, 256>(m, p, tiles, st);
+    set_error("tcgen05 path: unsupported dense shape (K slabs %d, N %d)", KS, NOUT);
+    return DSP_ERR_INVALID;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+int tc_create(Model* m) {
+    const dsp_config& c = m->cfg;
+    DSP_REQUIRE(c.hidden_size == 256, DSP_ERR_INVALID,
+                "DSP_PRECISION_FP16 (tcgen05) supports hidden_size 256 (got %d); use DSP_PRECISION_FP32", c.hidden_size);
+    DSP_REQUIRE(c.signal_len <= 64 && m->kseq <= 16, DSP_ERR_INVALID,
+                "DSP_PRECISION_FP16 supports signal_len <= 64 and <= 16 sequence features per base");
+    TcState* s = new TcState();
+    m->tc_state = s;
+    s->tiles = (m->cap + TILE - 1) / TILE;
+    const size_t per_tile_t = (size_t)s->tiles * c.seq_len * SLAB_BYTES;
+    int rc;
+    if (c.module != DSP_SIGNAL_BILSTM) if ((rc = tc_alloc(m, (void**)&s->xseq_img, per_tile_t))) return rc;
+    if (c.module != DSP_SEQ_BILSTM) if ((rc = tc_alloc(m, (void**)&s->xsig_img, per_tile_t))) return rc;
+    if ((rc = tc_alloc(m, (void**)&s->ybuf[0], per_tile_t * 8))) return rc;
+    if ((rc = tc_alloc(m, (void**)&s->ybuf[1], per_tile_t * 8))) return rc;
+    if ((rc = tc_alloc(m, (void**)&s->comb_img, per_tile_t * 4))) return rc;
+    if ((rc = tc_alloc(m, (void**)&s->hfinal, sizeof(float) * (size_t)s->tiles * TILE * 2 * c.hidden_size))) return rc;
+    return DSP_OK;
+}
+
+void tc_destroy(Model* m) {
+    TcState* s = (TcState*)m->tc_state;
+    if (!s) return;
+    for (auto* p : s->lstm_packs) delete p;
+    for (auto* p : s->dense_packs) delete p;
+    delete s;
+    m->tc_state = nullptr;
+}
+
+int tc_pack_lstm_layer(Model* m, LstmLayer& L,
+                       const float* wih0, const float* whh0, const float* bih0, const float* bhh0,
+                       const float* wih1, const float* whh1, const float* bih1, const float* bhh1) {
+    TcState* s = (TcState*)m->tc_state;
+    const int H = L.H, K = L.K;
+    DSP_REQUIRE(H == 128 || H == 256, DSP_ERR_INVALID, "tcgen05 path: LSTM hidden size %d unsupported", H);
+    const int KSX = (K + 63) / 64, KSH = H / 64, KS = KSX + KSH, NCH = H / 32;
+    DSP_REQUIRE(KSX == 1 || KSX == 4 || KSX == 8, DSP_ERR_INVALID, "tcgen05 path: LSTM input width %d unsupported", K);
+    TcLstmPack* pk = new TcLstmPack();
+    s->lstm_packs.push_back(pk);
+    pk->KSX = KSX;
+    pk->xk16 = (K + 15) / 16;
+    std::vector<uint8_t> img((size_t)2 * NCH * KS * SLAB_BYTES, 0);
+    std::vector<float> bias((size_t)2 * NCH * 128);
+    const float* wih[2] = {wih0, wih1}; const float* whh[2] = {whh0, whh1};
+    const float* bih[2] = {bih0, bih1}; const float* bhh[2] = {bhh0, bhh1};
+    for (int d = 0; d < 2; ++d)
+        for (int ch = 0; ch < NCH; ++ch)
+            for (int col = 0; col < 128; ++col) {
+                const int half = col >> 6, j = (col & 63) >> 2, g = col & 3;
+                const int unit = ch * 32 + half * 16 + j;
+                const int wrow = g * H + unit;                      // torch gate blocks i,f,g,o
+                bias[((size_t)d * NCH + ch) * 128 + col] = bih[d][wrow] + bhh[d][wrow];
+                for (int k = 0; k < K; ++k)
+                    put_half(img, ((size_t)d * NCH + ch) * KS + (k >> 6), col, k & 63, wih[d][(size_t)wrow * K + k]);
+                for (int k = 0; k < H; ++k)
+                    put_half(img, ((size_t)d * NCH + ch) * KS + KSX + (k >> 6), col, k & 63, whh[d][(size_t)wrow * H + k]);
+            }
+    int rc;
+    if ((rc = tc_alloc(m, (void**)&pk->w_img, img.size()))) return rc;
+    if ((rc = tc_alloc(m, (void**)&pk->bias, bias.size() * sizeof(float)))) return rc;
+    DSP_CUDA(cudaMemcpy(pk->w_img, img.data(), img.size(), cudaMemcpyHostToDevice));
+    DSP_CUDA(cudaMemcpy(pk->bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    L.tc = pk;
+    return DSP_OK;
+}
+
+int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b) {
+    TcState* s = (TcState*)m->tc_state;
+    // only the per-timestep fc layers run on the tensor cores; fc1/fc2 (head) stay fp32
+    if (!(D.J == 128 || D.J == 256) || D.K != 2 * D.J) { D.tc = nullptr; return DSP_OK; }
+    const int KS = D.K / 64, NCH = D.J / 128;
+    TcDensePack* pk = new TcDensePack();
+    s->dense_packs.push_back(pk);
+    pk->KS = KS;
+    std::vector<uint8_t> img((size_t)NCH * KS * SLAB_BYTES, 0);
+    for (int n = 0; n < D.J; ++n)
+        for (int k = 0; k < D.K; ++k)
+            put_half(img, (size_t)(n >> 7) * KS + (k >> 6), n & 127, k & 63, w[(size_t)n * D.K + k]);
+    int rc;
+    if ((rc = tc_alloc(m, (void**)&pk->w_img, img.size()))) return rc;
+    if ((rc = tc_alloc(m, (void**)&pk->bias, sizeof(float) * D.J))) return rc;
+    DSP_CUDA(cudaMemcpy(pk->w_img, img.data(), img.size(), cudaMemcpyHostToDevice));
+    DSP_CUDA(cudaMemcpy(pk->bias, b, sizeof(float) * D.J, cudaMemcpyHostToDevice));
+    D.tc = pk;
+    return DSP_OK;
+}
+
+int tc_finalize_pack(Model*) { return DSP_OK; }
+
+int tc_forward_chunk(Model* m, const float* kmer, const float* means, const float* stds, const float* lens,
+                     const float* signals, const float* const* h0, const float* const* c0,
+                     const int64_t* sstride, int64_t n, float* logits, float* probs, int32_t* labels,
+                     cudaStream_t st) {
+    TcState* s = (TcState*)m->tc_state;
+    const dsp_config& c = m->cfg;
+    const int T = c.seq_len, H = c.hidden_size;
+    const int64_t tiles = (n + TILE - 1) / TILE;
+    const bool seq = c.module != DSP_SIGNAL_BILSTM, sig = c.module != DSP_SEQ_BILSTM;
+    {
+        Span sp(m, 0, st);
+        const int64_t total = tiles * TILE * T;
+        prep_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            kmer, means, stds, lens, signals, m->embed, c.is_base ? c.embedding_size : 0, c.vocab_size, c.is_signallen,
+            c.signal_len, T, n, tiles * TILE, seq ? s->xseq_img : nullptr, sig ? s->xsig_img : nullptr);
+        m->launches++;
+        DSP_CUDA(cudaGetLastError());
+    }
+    auto run_stack = [&](std::vector<LstmLayer>& layers, const uint8_t* x0, int grp, int hid, bool is_comb) -> int {
+        const uint8_t* x = x0;
+        for (size_t l = 0; l < layers.size(); ++l) {
+            TcLstmPack* pk = (TcLstmPack*)layers[l].tc;
+            const bool final_layer = is_comb && l + 1 == layers.size();
+            LayerParams p{};
+            p.x_img = x; p.w_img = pk->w_img; p.bias = pk->bias;
+            p.h0 = h0[grp] + (int64_t)l * 2 * sstride[grp]; p.c0 = c0[grp] + (int64_t)l * 2 * sstride[grp];
+            p.state_dir_stride = sstride[grp];
+            p.y_img = s->ybuf[l & 1]; p.hfinal = final_layer ? s->hfinal : nullptr;
+            p.n = n; p.T = T; p.xk16 = pk->xk16; p.y_slabs = 2 * hid / 64; p.y_col_off = 0; p.write_y = final_layer ? 0 : 1;
+            Span sp(m, 1, st);
+            int rc = launch_lstm(m, pk->KSX, hid, p, tiles, st);
+            if (rc) return rc;
+            x = s->ybuf[l & 1];
+        }
+        return DSP_OK;
+    };
+    auto run_fc = [&](DenseF32& D, const uint8_t* x, int col_off) -> int {
+        TcDensePack* pk = (TcDensePack*)D.tc;
+        DSP_REQUIRE(pk != nullptr, DSP_ERR_INVALID, "tcgen05 path: dense layer %dx%d unsupported", D.J, D.K);
+        LayerParams p{};
+        p.x_img = x; p.w_img = pk->w_img; p.bias = pk->bias; p.y_img = s->comb_img; p.n = n; p.T = T;
+        p.xk16 = pk->KS * 4; p.y_slabs = H / 64; p.y_col_off = col_off; p.write_y = 1;
+        Span sp(m, 2, st);
+        return launch_fc(m, pk->KS, D.J, p, tiles, st);
+    };
+    int rc;
+    int comb_off = 0;
+    if (seq) {
+        if ((rc = run_stack(m->lstm_seq, s->xseq_img, 0, m->nhid_seq, false))) return rc;
+        if ((rc = run_fc(m->fc_seq, s->ybuf[(m->lstm_seq.size() - 1) & 1], 0))) return rc;
+        comb_off = m->nhid_seq;
+    }
+    if (sig) {
+        if ((rc = run_stack(m->lstm_signal, s->xsig_img, 1, m->nhid_signal, false))) return rc;
+        if ((rc = run_fc(m->fc_signal, s->ybuf[(m->lstm_signal.size() - 1) & 1], comb_off))) return rc;
+    }
+    if ((rc = run_stack(m->lstm_comb, s->comb_img, 2, H, true))) return rc;
+    Span sp(m, 3, st);
+    return f32_head_flat(m, s->hfinal, n, logits, probs, labels, st);
+}
+
+}  // namespace dsp

@@ -84,7 +84,13 @@ class ModelBiLSTM(nn.Module):
         self.fc1 = nn.Linear(hidden_size * 2, hidden_size)
         self.fc2 = nn.Linear(hidden_size, num_classes)
 
-        self.precision = precision or os.environ.get("DSP_B200_PRECISION", "fp32")
+        precision = precision or os.environ.get("DSP_B200_PRECISION", "auto")
+        if precision == "auto":
+            # the tcgen05 kernels cover the shapes the reference ships models for (hidden 256);
+            # anything else runs on the fp32 CUDA-core kernels
+            kseq = (embedding_size if is_base else 0) + (3 if is_signallen else 2)
+            precision = "fp16" if (hidden_size == 256 and signal_len <= 64 and kseq <= 16) else "fp32"
+        self.precision = precision
         if self.precision not in _native.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(_native.PRECISIONS))
         self.max_batch = int(max_batch)

@@ -50,6 +50,25 @@ def test_fp32_path_matches_reference(name):
     print("%s fp32: max|dprob|=%.2e agreement=%.5f" % (name, err, agree))
 
 
+FP16_CASES = [n for n in cases.FORWARD_CASES if cases.MANIFEST["forward"][n]["ctor"]["hidden_size"] == 256]
+
+
+@pytest.mark.parametrize("name", FP16_CASES)
+def test_fp16_tensor_core_path_matches_reference(name):
+    case = cases.load_case(name)
+    logits, probs, labels, _ = run_case(case, "fp16")
+    err, agree = check(case, logits, probs, labels, PROB_TOL, LABEL_AGREEMENT)
+    print("%s fp16: max|dprob|=%.2e agreement=%.5f" % (name, err, agree))
+
+
+def test_fp16_ragged_batches_and_chunking():
+    case = cases.load_case("both_13_16_s2")
+    for n, mb in ((1, 4096), (127, 4096), (129, 4096), (1000, 256)):
+        sub = cases.slice_case(case, n)
+        logits, probs, labels, _ = run_case(sub, "fp16", max_batch=mb)
+        check(sub, logits, probs, labels, PROB_TOL, 0.999 if n >= 1000 else 1.0 - 1.5 / n)
+
+
 def test_ragged_and_tiny_batches_fp32():
     case = cases.load_case("both_small_odd")
     for n in (1, 2, 17, 255):
