@@ -106,7 +106,8 @@ int pack_lstm_stack(Model* m, const char* prefix, int num_layers, int in0, int H
     return DSP_OK;
 }
 
-int pack_dense(Model* m, const char* prefix, int K, int J, DenseF32& D) {
+// kind: 0 = fp32 layout only, 1 = also a tensor-core per-timestep fc, 2 = also the tensor-core head (fc1)
+int pack_dense(Model* m, const char* prefix, int K, int J, DenseF32& D, int kind) {
     std::string wn = std::string(prefix) + ".weight", bn = std::string(prefix) + ".bias";
     const std::vector<float>* w = find_param(m, wn, (int64_t)J * K);
     const std::vector<float>* b = find_param(m, bn, J);
@@ -120,8 +121,8 @@ int pack_dense(Model* m, const char* prefix, int K, int J, DenseF32& D) {
     if (rc) return rc;
     rc = upload(m, &D.bias, *b);
     if (rc) return rc;
-    if (m->cfg.precision == DSP_PRECISION_FP16) {
-        rc = tc_pack_dense(m, D, w->data(), b->data());
+    if (m->cfg.precision == DSP_PRECISION_FP16 && kind != 0) {
+        rc = (kind == 2) ? tc_pack_head(m, D, w->data(), b->data()) : tc_pack_dense(m, D, w->data(), b->data());
         if (rc) return rc;
     }
     return DSP_OK;
@@ -150,6 +151,9 @@ int forward_chunk(Model* m, const float* kmer, const float* means, const float* 
     StateGroup grp[3];
     state_groups(m, grp);
     const float* h0[3]; const float* c0[3]; int64_t sstride[3];
+    if (!states6 && c.precision == DSP_PRECISION_FP16)      // states are drawn inside the layer kernels
+        return tc_forward_chunk(m, kmer, means, stds, lens, signals, nullptr, nullptr, nullptr, seed, chunk_id, n,
+                                logits, probs, labels, st);
     if (states6) {
         for (int g = 0; g < 3; ++g) { h0[g] = states6[2 * g]; c0[g] = states6[2 * g + 1]; sstride[g] = state_stride[g]; }
     } else {
@@ -166,7 +170,7 @@ int forward_chunk(Model* m, const float* kmer, const float* means, const float* 
         if (rc) return rc;
     }
     if (c.precision == DSP_PRECISION_FP16)
-        return tc_forward_chunk(m, kmer, means, stds, lens, signals, h0, c0, sstride, n, logits, probs, labels, st);
+        return tc_forward_chunk(m, kmer, means, stds, lens, signals, h0, c0, sstride, seed, chunk_id, n, logits, probs, labels, st);
 
     int rc;
     int comb_off = 0;
@@ -327,15 +331,15 @@ int dsp_pack_weights(dsp_handle h) {
             if ((rc = upload(m, &m->embed, *e))) return rc;
         }
         if ((rc = pack_lstm_stack(m, "lstm_seq", c.num_layers2, m->kseq, m->nhid_seq, m->lstm_seq))) return rc;
-        if ((rc = pack_dense(m, "fc_seq", 2 * m->nhid_seq, m->nhid_seq, m->fc_seq))) return rc;
+        if ((rc = pack_dense(m, "fc_seq", 2 * m->nhid_seq, m->nhid_seq, m->fc_seq, 1))) return rc;
     }
     if (has_signal(m)) {
         if ((rc = pack_lstm_stack(m, "lstm_signal", c.num_layers2, c.signal_len, m->nhid_signal, m->lstm_signal))) return rc;
-        if ((rc = pack_dense(m, "fc_signal", 2 * m->nhid_signal, m->nhid_signal, m->fc_signal))) return rc;
+        if ((rc = pack_dense(m, "fc_signal", 2 * m->nhid_signal, m->nhid_signal, m->fc_signal, 1))) return rc;
     }
     if ((rc = pack_lstm_stack(m, "lstm_comb", c.num_layers1, H, H, m->lstm_comb))) return rc;
-    if ((rc = pack_dense(m, "fc1", 2 * H, H, m->fc1))) return rc;
-    if ((rc = pack_dense(m, "fc2", H, c.num_classes, m->fc2))) return rc;
+    if ((rc = pack_dense(m, "fc1", 2 * H, H, m->fc1, 2))) return rc;
+    if ((rc = pack_dense(m, "fc2", H, c.num_classes, m->fc2, 0))) return rc;
     if (c.precision == DSP_PRECISION_FP16) {
         if ((rc = tc_finalize_pack(m))) return rc;
     }

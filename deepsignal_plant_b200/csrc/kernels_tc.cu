@@ -28,6 +28,7 @@
 #include "tc_prims.cuh"
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace dsp {
 
@@ -45,8 +46,12 @@ struct LayerParams {
     const uint8_t* x_img;      // [tiles][T][KSX] slabs
     const uint8_t* w_img;      // [dir][NCH][KS] slabs
     const float* bias;         // [dir][NCH*128] in chunk column order
-    const float* h0;           // [dir][n][H] fp32 (LSTM only)
+    const float* h0;           // [dir][n][H] fp32 (LSTM only); null: draw N(0,1) in-kernel (Philox)
     const float* c0;
+    uint64_t seed;             // Philox key
+    uint32_t rng_call;         // Philox counter word 3 (chunk / call id)
+    uint32_t rng_slot;         // state slot id of this layer ((group*8 + layer) * 2), dir is added in-kernel
+    int64_t site_base;         // global index of this chunk's first site
     int64_t state_dir_stride;
     uint8_t* y_img;            // output image: [tiles][T][y_slabs] slabs
     float* hfinal;             // [tiles*128][2H] fp32, last step of each direction (or null)
@@ -55,20 +60,58 @@ struct LayerParams {
     int xk16;                  // K16 steps of the x part (= KSX*4 unless the input is narrow)
     int y_slabs;
     int y_col_off;             // FC: first output column
-    int write_y;
+    int write_y;               // 1: every step at (tile, t); 2: only the last step of the direction, at (tile, 0)
+    // MODE_HEAD only
+    const float* w2t;          // fc2 weight, [hidden][C]
+    const float* b2;
+    float* logits;
+    float* probs;
+    int32_t* labels;
+    int num_classes;
 };
 
-template <int KSX> struct RingStages { static constexpr int value = (KSX >= 8) ? 6 : 8; };
+constexpr int STG_SLABS = 2;                        // weight slabs per ring stage (one mbarrier per stage)
+constexpr int STG_BYTES = STG_SLABS * TILE * SLAB_ROW_BYTES;
+enum { MODE_LSTM = 0, MODE_FC = 1, MODE_HEAD = 2 };
+constexpr int HEAD_MAX_CLASSES = 8;
+template <int KSX, int MODE> struct RingStages { static constexpr int value = (MODE == MODE_HEAD) ? 2 : (KSX >= 8) ? 3 : 4; };
+
+// Philox4x32-10 (Salmon et al., SC'11) + Box-Muller: four N(0,1) values per counter.  Used to
+// draw the initial LSTM states in-kernel (the reference draws torch.randn per call,
+// models.py:169-176), keyed by (seed; site, state slot, call) so no state ever crosses HBM.
+__device__ __forceinline__ float4 philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    // uniforms in (0,1]: (x + 1) * 2^-32 never returns 0, so the log is finite
+    const float u0 = ((float)c0 + 1.0f) * 2.3283064365386963e-10f, u1 = (float)c1 * 2.3283064365386963e-10f;
+    const float u2 = ((float)c2 + 1.0f) * 2.3283064365386963e-10f, u3 = (float)c3 * 2.3283064365386963e-10f;
+    const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+    float s0, cs0, s1, cs1;
+    __sincosf(6.283185307179586f * u1, &s0, &cs0);
+    __sincosf(6.283185307179586f * u3, &s1, &cs1);
+    return make_float4(r0 * cs0, r0 * s0, r1 * cs1, r1 * s1);
+}
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // ---------------------------------------------------------------------------------------------
-// KSX: x slabs per step; H: hidden size of the layer (LSTM) ; IS_FC: dense+ReLU instead of LSTM
-// (then NCOLS = number of output columns, no recurrence).
-template <int KSX, int H, bool IS_FC, int NOUT>
+// KSX: x slabs per step; H: hidden size of the layer (LSTM); MODE: what the epilogue does --
+//   MODE_LSTM  recurrent layer (A = [x_t | h_{t-1}], gate math, cell update)
+//   MODE_FC    dense + ReLU per timestep, NOUT output columns, written as a slab image
+//   MODE_HEAD  fc1 + ReLU + fc2 + softmax (+argmax) on [h_fwd(T-1) | h_bwd(0)] (models.py:229-240)
+// CL: thread-block cluster size; the CL CTAs of a cluster work on CL different site tiles of the
+// same direction and share every weight slab: each CTA issues 1/CL of the bulk copies as
+// cluster multicasts, so a slab is read from L2 once per cluster instead of once per CTA.
+template <int KSX, int H, int MODE, int NOUT, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 layer_kernel(const LayerParams p) {
-    constexpr int NST = RingStages<KSX>::value;
+    constexpr bool IS_FC = MODE != MODE_LSTM;              // no recurrence: x part only
+    constexpr int NST = RingStages<KSX, MODE>::value;
     constexpr int NCH = IS_FC ? NOUT / 128 : H / 32;       // 128-column chunks per step
     constexpr int KSH = IS_FC ? 0 : H / 64;                // h slabs (K of the recurrent part)
     constexpr int KS = KSX + KSH;
@@ -78,7 +121,7 @@ layer_kernel(const LayerParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* s_x = smem;                                   // KSX slabs
-    uint8_t* s_w = smem + (size_t)KSX * SLAB_BYTES;        // NST slabs
+    uint8_t* s_w = smem + (size_t)KSX * SLAB_BYTES;        // NST ring stages of STG_SLABS slabs
     __shared__ __align__(8) uint64_t bars[2 * NST + 2 * KSX + 5];
     __shared__ uint32_t tmem_base_s;
     const uint32_t b_wfull = smem_u32(&bars[0]), b_wempty = smem_u32(&bars[NST]);
@@ -91,7 +134,7 @@ layer_kernel(const LayerParams p) {
     const int T = p.T;
 
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, 1); }
+        for (int i = 0; i < NST; ++i) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, CL); }
         for (int i = 0; i < KSX; ++i) { mbar_init(b_xfull + 8 * i, 1); mbar_init(b_xempty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, EPI_WARPS); }
         mbar_init(b_hready, EPI_WARPS);
@@ -100,7 +143,10 @@ layer_kernel(const LayerParams p) {
     if (warp == 3) tmem_alloc(smem_u32(&tmem_base_s), 512);
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();    // peers' barriers are initialised before anything lands on them
     tc_fence_after();
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     const uint32_t tmem = tmem_base_s;
     const uint32_t t_acc = tmem;                 // two accumulators: columns [0,128) and [128,256)
     const uint32_t t_h = tmem + 256;             // two h buffers of HCOLS columns at +0 and +128
@@ -108,17 +154,33 @@ layer_kernel(const LayerParams p) {
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0) {
-            // ---- weight slab producer ---------------------------------------------------------
+            // ---- weight producer: ring stages of STG_SLABS consecutive slabs ------------------------
             if (elect_one()) {
                 const uint8_t* wsrc = p.w_img + (size_t)dir * NCH * KS * SLAB_BYTES;
-                uint32_t stage = 0, phase = 0;
+                uint32_t stage = 0, phase = 0, issued = 0;
                 for (int step = 0; step < T; ++step)
-                    for (int i = 0; i < NCH * KS; ++i) {
-                        mbar_wait(b_wempty + 8 * stage, phase ^ 1);
-                        mbar_arrive_expect_tx(b_wfull + 8 * stage, SLAB_BYTES);
-                        bulk_g2s(smem_u32(s_w + (size_t)stage * SLAB_BYTES), wsrc + (size_t)i * SLAB_BYTES, SLAB_BYTES,
-                                 b_wfull + 8 * stage);
-                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        // MODE_HEAD walks T passes over different weight images (split-precision terms)
+                        const uint8_t* src = wsrc + ((size_t)(MODE == MODE_HEAD ? step : 0) * NCH + ch) * KS * SLAB_BYTES;
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {               // x part, then h part
+                            const int nslab_total = part == 0 ? KSX : KSH;
+                            for (int s0 = 0; s0 < nslab_total; s0 += STG_SLABS) {
+                                const uint32_t bytes = (uint32_t)min(STG_SLABS, nslab_total - s0) * SLAB_BYTES;
+                                // the stage is free once every CTA of the cluster has consumed it
+                                mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+                                mbar_arrive_expect_tx(b_wfull + 8 * stage, bytes);
+                                const uint32_t dst = smem_u32(s_w + (size_t)stage * STG_BYTES);
+                                if constexpr (CL == 1) {
+                                    bulk_g2s(dst, src, bytes, b_wfull + 8 * stage);
+                                } else if (issued % CL == crank) {
+                                    bulk_g2s_multicast(dst, src, bytes, b_wfull + 8 * stage, CMASK);
+                                }
+                                ++issued;
+                                src += bytes;
+                                if (++stage == NST) { stage = 0; phase ^= 1; }
+                            }
+                        }
                     }
             }
         } else if (warp == 2) {
@@ -126,7 +188,10 @@ layer_kernel(const LayerParams p) {
             if (elect_one()) {
                 for (int step = 0; step < T; ++step) {
                     const int t = dir ? (T - 1 - step) : step;
-                    const uint8_t* xsrc = p.x_img + ((size_t)tile * T + t) * KSX * SLAB_BYTES;
+                    // MODE_HEAD: pass 0 and 2 read the hi image, pass 1 the lo image of [h_fwd | h_bwd]
+                    const uint8_t* xsrc = (MODE == MODE_HEAD)
+                        ? p.x_img + ((size_t)tile * 2 + (step == 1 ? 1 : 0)) * KSX * SLAB_BYTES
+                        : p.x_img + ((size_t)tile * T + t) * KSX * SLAB_BYTES;
                     for (int j = 0; j < KSX; ++j) {
                         mbar_wait(b_xempty + 8 * j, (step & 1) ^ 1);
                         mbar_arrive_expect_tx(b_xfull + 8 * j, SLAB_BYTES);
@@ -135,50 +200,90 @@ layer_kernel(const LayerParams p) {
                 }
             }
         } else if (warp == 1) {
-            // ---- MMA issuer ---------------------------------------------------------------------
-            if (elect_one()) {
-                uint32_t stage = 0, phase = 0;
-                for (int step = 0; step < T; ++step) {
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        const uint32_t g = (uint32_t)(step * NCH + ch);
-                        const uint32_t buf = g & 1u, use = g >> 1;
-                        mbar_wait(b_accempty + 8 * buf, (use & 1u) ^ 1u);
+            // ---- MMA issuer: the whole warp walks the schedule (warp-uniform control flow keeps the
+            // descriptors in uniform registers); one elected lane issues tcgen05.mma / commit ----------
+            const bool leader = elect_one();
+            const uint32_t a_lo0 = smem_desc_lo(smem_u32(s_x)), b_lo0 = smem_desc_lo(smem_u32(s_w));
+            const int xk16 = p.xk16;
+            uint32_t stage = 0, phase = 0;
+            for (int step = 0; step < T; ++step) {
+                const uint32_t a_t = t_h + (uint32_t)(step & 1) * 128u;
+                for (int ch = 0; ch < NCH; ++ch) {
+                    // MODE_HEAD: chunk ch accumulates into buffer ch over all T passes
+                    const uint32_t g = (MODE == MODE_HEAD) ? (uint32_t)ch : (uint32_t)(step * NCH + ch);
+                    const uint32_t buf = g & 1u, use = g >> 1;
+                    if (MODE != MODE_HEAD || step == 0) mbar_wait(b_accempty + 8 * buf, (use & 1u) ^ 1u);
+                    if (MODE == MODE_LSTM && step == 0 && ch == 0) mbar_wait(b_hready, 0);   // c0 was staged in the accumulators
+                    tc_fence_after();
+                    const uint32_t acc = t_acc + buf * 128u;
+                    const bool fresh = (MODE != MODE_HEAD) || step == 0;      // first MMA overwrites the accumulator
+                    // ---- x part: A from shared memory ----
+#pragma unroll
+                    for (int s0 = 0; s0 < KSX; s0 += STG_SLABS) {
+                        if (ch == 0) {
+#pragma unroll
+                            for (int j = 0; j < STG_SLABS; ++j) if (s0 + j < KSX) mbar_wait(b_xfull + 8 * (s0 + j), step & 1);
+                        }
+                        mbar_wait(b_wfull + 8 * stage, phase);
                         tc_fence_after();
-                        const uint32_t acc = t_acc + buf * 128u;
-                        uint32_t accum = 0;
-                        for (int ks = 0; ks < KSX; ++ks) {
-                            if (ch == 0) { mbar_wait(b_xfull + 8 * ks, step & 1); }
+                        const uint32_t b_lo = b_lo0 + stage * (STG_BYTES >> 4);
+                        if (leader) {
+#pragma unroll
+                            for (int j = 0; j < STG_SLABS; ++j) {
+                                if (s0 + j < KSX) {
+                                    const uint32_t al = a_lo0 + (uint32_t)(s0 + j) * (SLAB_BYTES >> 4);
+                                    const uint32_t bl = b_lo + (uint32_t)j * (SLAB_BYTES >> 4);
+                                    if (KSX * 4 == xk16) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            if (s0 + j == 0 && k == 0) { if (fresh) mma_ss_lo<0>(acc, al, bl, IDESC); else mma_ss_lo<1>(acc, al, bl, IDESC); }
+                                            else mma_ss_lo<1>(acc, al + k * 2, bl + k * 2, IDESC);
+                                        }
+                                    } else {                                  // narrow first-layer input
+                                        for (int k = 0; k < xk16 - (s0 + j) * 4 && k < 4; ++k) {
+                                            if (s0 + j == 0 && k == 0) mma_ss_lo<0>(acc, al, bl, IDESC);
+                                            else mma_ss_lo<1>(acc, al + k * 2, bl + k * 2, IDESC);
+                                        }
+                                    }
+                                }
+                            }
+                            if constexpr (CL == 1) mma_commit(b_wempty + 8 * stage);
+                            else mma_commit_multicast(b_wempty + 8 * stage, CMASK);
+                            if (ch == NCH - 1) {
+#pragma unroll
+                                for (int j = 0; j < STG_SLABS; ++j) if (s0 + j < KSX) mma_commit(b_xempty + 8 * (s0 + j));
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+                    // ---- recurrent part: A = h_{t-1} from TMEM ----
+                    if constexpr (!IS_FC) {
+                        if (ch == 0) { mbar_wait(b_hready, step & 1); tc_fence_after(); }
+#pragma unroll
+                        for (int s0 = 0; s0 < KSH; s0 += STG_SLABS) {
                             mbar_wait(b_wfull + 8 * stage, phase);
                             tc_fence_after();
-                            const uint32_t a_base = smem_u32(s_x + (size_t)ks * SLAB_BYTES);
-                            const uint32_t b_base = smem_u32(s_w + (size_t)stage * SLAB_BYTES);
-                            const int nk = min(4, p.xk16 - ks * 4);
-                            for (int k = 0; k < nk; ++k) {
-                                mma_ss(acc, make_smem_desc(a_base + k * 32), make_smem_desc(b_base + k * 32), IDESC, accum);
-                                accum = 1;
+                            const uint32_t b_lo = b_lo0 + stage * (STG_BYTES >> 4);
+                            if (leader) {
+#pragma unroll
+                                for (int j = 0; j < STG_SLABS; ++j) {
+                                    if (s0 + j < KSH) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            mma_ts_lo<1>(acc, a_t + (uint32_t)((s0 + j) * 32 + k * 8),
+                                                         b_lo + (uint32_t)j * (SLAB_BYTES >> 4) + k * 2, IDESC);
+                                    }
+                                }
+                                if constexpr (CL == 1) mma_commit(b_wempty + 8 * stage);
+                                else mma_commit_multicast(b_wempty + 8 * stage, CMASK);
                             }
-                            mma_commit(b_wempty + 8 * stage);
-                            if (ch == NCH - 1) mma_commit(b_xempty + 8 * ks);
+                            __syncwarp();
                             if (++stage == NST) { stage = 0; phase ^= 1; }
                         }
-                        if constexpr (!IS_FC) {
-                            if (ch == 0) { mbar_wait(b_hready, step & 1); tc_fence_after(); }
-                            const uint32_t a_t = t_h + (uint32_t)(step & 1) * 128u;
-                            for (int ks = 0; ks < KSH; ++ks) {
-                                mbar_wait(b_wfull + 8 * stage, phase);
-                                tc_fence_after();
-                                const uint32_t b_base = smem_u32(s_w + (size_t)stage * SLAB_BYTES);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    mma_ts(acc, a_t + (uint32_t)(ks * 32 + k * 8), make_smem_desc(b_base + k * 32), IDESC, accum);
-                                    accum = 1;
-                                }
-                                mma_commit(b_wempty + 8 * stage);
-                                if (++stage == NST) { stage = 0; phase ^= 1; }
-                            }
-                        }
-                        mma_commit(b_accfull + 8 * buf);
                     }
+                    if (leader && (MODE != MODE_HEAD || step == T - 1)) mma_commit(b_accfull + 8 * buf);
+                    __syncwarp();
                 }
             }
         }
@@ -194,7 +299,67 @@ layer_kernel(const LayerParams p) {
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const float* bias = p.bias + (size_t)dir * NCH * 128 + half * 64;
 
-        if constexpr (IS_FC) {
+        if constexpr (MODE == MODE_HEAD) {
+            // z = relu(fc1(x)); logits = fc2(z); probs = softmax(logits).  Each thread owns 64 of the
+            // NOUT fc1 columns of its site per chunk and accumulates its share of the fc2 dot products;
+            // the two column halves of a site meet through shared memory.
+            __shared__ float head_part[2][TILE][HEAD_MAX_CLASSES];
+            const int C = p.num_classes;
+            float part_sum[HEAD_MAX_CLASSES];
+#pragma unroll
+            for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc) part_sum[cc] = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const uint32_t buf = (uint32_t)ch & 1u, use = (uint32_t)ch >> 1;
+                mbar_wait(b_accfull + 8 * buf, use & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    uint32_t v[32];
+                    tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(half * 64 + part * 32), v);
+                    tmem_ld_wait();
+                    if (part == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(b_accempty + 8 * buf);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = ch * 128 + half * 64 + part * 32 + j;
+                        const float z = fmaxf(__uint_as_float(v[j]) + __ldg(p.bias + col), 0.f);
+#pragma unroll
+                        for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc)
+                            if (cc < C) part_sum[cc] = fmaf(z, __ldg(p.w2t + (size_t)col * C + cc), part_sum[cc]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc) head_part[half][row][cc] = part_sum[cc];
+            asm volatile("bar.sync 1, 256;" ::: "memory");           // the 8 epilogue warps only
+            if (half == 0 && valid) {
+                float lg[HEAD_MAX_CLASSES];
+                float mx = -3.0e38f;
+                int arg = 0;
+#pragma unroll
+                for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc) {
+                    lg[cc] = 0.f;
+                    if (cc < C) {
+                        lg[cc] = head_part[0][row][cc] + head_part[1][row][cc] + __ldg(p.b2 + cc);
+                        if (lg[cc] > mx) { mx = lg[cc]; arg = cc; }
+                    }
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc) if (cc < C) sum += expf(lg[cc] - mx);
+#pragma unroll
+                for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc)
+                    if (cc < C) {
+                        p.logits[site * C + cc] = lg[cc];
+                        p.probs[site * C + cc] = expf(lg[cc] - mx) / sum;
+                    }
+                if (p.labels) p.labels[site] = arg;
+            }
+        } else if constexpr (MODE == MODE_FC) {
             for (int step = 0; step < T; ++step) {
                 uint8_t* ybase = p.y_img + ((size_t)tile * T + step) * p.y_slabs * SLAB_BYTES;
 #pragma unroll
@@ -235,7 +400,33 @@ layer_kernel(const LayerParams p) {
             constexpr int UPT = 16;                   // hidden units per thread per chunk
             float c[NCH][UPT];
             // initial states: c0 -> registers, h0 -> TMEM h buffer 0 (packed FP16 pairs)
-            {
+            if (p.h0 == nullptr) {
+                // drawn here (Philox): a compact loop stores h0 straight into the TMEM operand buffer and
+                // parks c0 in the (still unused) accumulator columns, from where it is read into registers
+                const uint64_t gs = (uint64_t)(p.site_base + site);
+                const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+                const uint32_t slot0 = (p.rng_slot + (uint32_t)dir) << 16;
+                const uint32_t t_stage = t_acc + lane_addr + (uint32_t)(half * NCH * UPT);
+#pragma unroll 1
+                for (int i = 0; i < NCH * (UPT / 4); ++i) {
+                    const int unit = (i >> 2) * 32 + half * UPT + (i & 3) * 4;
+                    const uint32_t slot = slot0 | (uint32_t)(unit >> 2);
+                    const float4 hq = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot, p.rng_call, k0, k1);
+                    const float4 cv = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot | 0x8000u, p.rng_call, k0, k1);
+                    tmem_st2(t_h + lane_addr + (uint32_t)(unit >> 1), pack_half2(hq.x, hq.y), pack_half2(hq.z, hq.w));
+                    tmem_st4(t_stage + (uint32_t)(i * 4), __float_as_uint(cv.x), __float_as_uint(cv.y), __float_as_uint(cv.z),
+                             __float_as_uint(cv.w));
+                }
+                tmem_st_wait();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    uint32_t v[16];
+                    tmem_ld16(t_stage + (uint32_t)(ch * UPT), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < UPT; ++j) c[ch][j] = __uint_as_float(v[j]);
+                }
+            } else {
                 const float* h0 = p.h0 + (size_t)dir * p.state_dir_stride + (size_t)site * H;
                 const float* c0 = p.c0 + (size_t)dir * p.state_dir_stride + (size_t)site * H;
 #pragma unroll
@@ -258,14 +449,16 @@ layer_kernel(const LayerParams p) {
                     tmem_st8(t_h + lane_addr + (uint32_t)(u0 >> 1), pk);
                 }
                 tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(b_hready);
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_hready);
             for (int step = 0; step < T; ++step) {
                 const int t = dir ? (T - 1 - step) : step;
                 const bool last = (step == T - 1);
-                uint8_t* ybase = p.y_img + ((size_t)tile * T + t) * p.y_slabs * SLAB_BYTES + row * SLAB_ROW_BYTES;
+                uint8_t* ybase = p.y_img + ((size_t)tile * (p.write_y == 2 ? 2 : T) + (p.write_y == 2 ? 0 : t)) * p.y_slabs * SLAB_BYTES
+                                 + row * SLAB_ROW_BYTES;
+                const bool do_write = p.write_y == 1 || (p.write_y == 2 && last);
                 const uint32_t t_hnext = t_h + (uint32_t)((step + 1) & 1) * 128u + lane_addr;
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
@@ -309,12 +502,24 @@ layer_kernel(const LayerParams p) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) pk[j] = pack_half2(hv[2 * j], hv[2 * j + 1]);
                     tmem_st8(t_hnext + (uint32_t)(u0 >> 1), pk);
-                    if (p.write_y) {
+                    if (do_write) {
                         const int col = dir * H + u0;                          // multiple of 16
                         uint8_t* yslab = ybase + (size_t)(col >> 6) * SLAB_BYTES;
                         const int chunk = (col & 63) >> 3;
                         *reinterpret_cast<uint4*>(yslab + (((chunk) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         *reinterpret_cast<uint4*>(yslab + (((chunk + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        if (p.write_y == 2) {
+                            // second image: FP16 residuals h - fp16(h), so the head sees h to ~22 bits
+                            uint32_t lo[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const __half2 hh = *reinterpret_cast<const __half2*>(&pk[j]);
+                                lo[j] = pack_half2(hv[2 * j] - __low2float(hh), hv[2 * j + 1] - __high2float(hh));
+                            }
+                            uint8_t* lslab = yslab + (size_t)p.y_slabs * SLAB_BYTES;
+                            *reinterpret_cast<uint4*>(lslab + (((chunk) ^ (row & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            *reinterpret_cast<uint4*>(lslab + (((chunk + 1) ^ (row & 7)) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                        }
                     }
                     if (last && p.hfinal != nullptr && valid) {
                         float* hf = p.hfinal + (size_t)site * (2 * H) + dir * H + u0;
@@ -332,6 +537,7 @@ layer_kernel(const LayerParams p) {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();    // no CTA leaves while peers may still signal it
     if (warp == 3) tmem_dealloc(tmem, 512);
 }
 
@@ -407,6 +613,9 @@ struct TcState {
     uint8_t* ybuf[2] = {nullptr, nullptr};
     uint8_t* comb_img = nullptr;
     float* hfinal = nullptr;
+    uint8_t* hfin_img = nullptr;   // [tiles][hi,lo][2H/64] slabs: [h_fwd(T-1) | h_bwd(0)] as FP16 hi + FP16 residual
+    TcDensePack* head_pack = nullptr;
+    bool tc_head = false;
     int64_t tiles = 0;
     std::vector<TcLstmPack*> lstm_packs;
     std::vector<TcDensePack*> dense_packs;
@@ -424,35 +633,52 @@ int tc_alloc(Model* m, void** p, size_t bytes) {
     return DSP_OK;
 }
 
-template <int KSX, int H, bool IS_FC, int NOUT>
-int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
-    constexpr int NST = RingStages<KSX>::value;
-    const size_t smem = (size_t)(KSX + NST) * SLAB_BYTES + 1024;
-    auto kern = layer_kernel<KSX, H, IS_FC, NOUT>;
+int g_cluster = 2;     // cluster size used for the layer kernels (1, 2 or 4); DSP_B200_CLUSTER overrides
+
+template <int KSX, int H, int MODE, int NOUT, int CL>
+int launch_layer_cl(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
+    constexpr int NST = RingStages<KSX, MODE>::value;
+    const size_t smem = (size_t)KSX * SLAB_BYTES + (size_t)NST * STG_BYTES + 1024;
+    auto kern = layer_kernel<KSX, H, MODE, NOUT, CL>;
     DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)tiles, IS_FC ? 1 : 2);
-    kern<<<grid, NTHREADS, smem, st>>>(p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((tiles + CL - 1) / CL * CL), MODE != MODE_LSTM ? 1 : 2);   // padded tiles: workspace is padded too
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DSP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     m->launches++;
-    DSP_CUDA(cudaGetLastError());
     return DSP_OK;
+}
+
+template <int KSX, int H, int MODE, int NOUT>
+int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
+    if (g_cluster == 4) return launch_layer_cl<KSX, H, MODE, NOUT, 4>(m, p, tiles, st);
+    if (g_cluster == 2) return launch_layer_cl<KSX, H, MODE, NOUT, 2>(m, p, tiles, st);
+    return launch_layer_cl<KSX, H, MODE, NOUT, 1>(m, p, tiles, st);
 }
 
 int launch_lstm(Model* m, int KSX, int H, const LayerParams& p, int64_t tiles, cudaStream_t st) {
     if (H == 128) {
-        if (KSX == 1) return launch_layer<1, 128, false, 0>(m, p, tiles, st);
-        if (KSX == 4) return launch_layer<4, 128, false, 0>(m, p, tiles, st);
+        if (KSX == 1) return launch_layer<1, 128, MODE_LSTM, 0>(m, p, tiles, st);
+        if (KSX == 4) return launch_layer<4, 128, MODE_LSTM, 0>(m, p, tiles, st);
     } else if (H == 256) {
-        if (KSX == 1) return launch_layer<1, 256, false, 0>(m, p, tiles, st);
-        if (KSX == 4) return launch_layer<4, 256, false, 0>(m, p, tiles, st);
-        if (KSX == 8) return launch_layer<8, 256, false, 0>(m, p, tiles, st);
+        if (KSX == 1) return launch_layer<1, 256, MODE_LSTM, 0>(m, p, tiles, st);
+        if (KSX == 4) return launch_layer<4, 256, MODE_LSTM, 0>(m, p, tiles, st);
+        if (KSX == 8) return launch_layer<8, 256, MODE_LSTM, 0>(m, p, tiles, st);
     }
     set_error("tcgen05 path: unsupported LSTM layer shape (x slabs %d, hidden %d)", KSX, H);
     return DSP_ERR_INVALID;
 }
 
 int launch_fc(Model* m, int KS, int NOUT, const LayerParams& p, int64_t tiles, cudaStream_t st) {
-    if (KS == 4 && NOUT == 128) return launch_layer<4, 0, true, 128>(m, p, tiles, st);
-    if (KS == 8 && NOUT == 256) return launch_layer<8, 0, true, 256>(m, p, tiles, st);
+    if (KS == 4 && NOUT == 128) return launch_layer<4, 0, MODE_FC, 128>(m, p, tiles, st);
+    if (KS == 8 && NOUT == 256) return launch_layer<8, 0, MODE_FC, 256>(m, p, tiles, st);
     set_error("tcgen05 path: unsupported dense shape (K slabs %d, N %d)", KS, NOUT);
     return DSP_ERR_INVALID;
 }
@@ -468,7 +694,12 @@ int tc_create(Model* m) {
                 "DSP_PRECISION_FP16 supports signal_len <= 64 and <= 16 sequence features per base");
     TcState* s = new TcState();
     m->tc_state = s;
-    s->tiles = (m->cap + TILE - 1) / TILE;
+    if (const char* e = getenv("DSP_B200_CLUSTER")) {
+        const int v = atoi(e);
+        DSP_REQUIRE(v == 1 || v == 2 || v == 4, DSP_ERR_INVALID, "DSP_B200_CLUSTER must be 1, 2 or 4");
+        g_cluster = v;
+    }
+    s->tiles = ((m->cap + TILE - 1) / TILE + 3) / 4 * 4;     // padded to the largest cluster size
     const size_t per_tile_t = (size_t)s->tiles * c.seq_len * SLAB_BYTES;
     int rc;
     if (c.module != DSP_SIGNAL_BILSTM) if ((rc = tc_alloc(m, (void**)&s->xseq_img, per_tile_t))) return rc;
@@ -477,6 +708,8 @@ int tc_create(Model* m) {
     if ((rc = tc_alloc(m, (void**)&s->ybuf[1], per_tile_t * 8))) return rc;
     if ((rc = tc_alloc(m, (void**)&s->comb_img, per_tile_t * 4))) return rc;
     if ((rc = tc_alloc(m, (void**)&s->hfinal, sizeof(float) * (size_t)s->tiles * TILE * 2 * c.hidden_size))) return rc;
+    if ((rc = tc_alloc(m, (void**)&s->hfin_img, (size_t)s->tiles * 2 * (2 * c.hidden_size / 64) * SLAB_BYTES))) return rc;
+    s->tc_head = c.num_classes <= HEAD_MAX_CLASSES;
     return DSP_OK;
 }
 
@@ -528,7 +761,8 @@ int tc_pack_lstm_layer(Model* m, LstmLayer& L,
 
 int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b) {
     TcState* s = (TcState*)m->tc_state;
-    // only the per-timestep fc layers run on the tensor cores; fc1/fc2 (head) stay fp32
+    // per-timestep fc layers and fc1 (K = 2J, J in {128, 256}) run on the tensor cores; fc2 is
+    // applied in fp32 inside the head epilogue
     if (!(D.J == 128 || D.J == 256) || D.K != 2 * D.J) { D.tc = nullptr; return DSP_OK; }
     const int KS = D.K / 64, NCH = D.J / 128;
     TcDensePack* pk = new TcDensePack();
@@ -547,12 +781,41 @@ int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b) {
     return DSP_OK;
 }
 
+// fc1 for the head: three weight images [W_hi, W_hi, W_lo] matching the activation passes
+// [h_hi, h_lo, h_hi]: (h_hi + h_lo)(W_hi + W_lo) without the lo*lo term, i.e. fc1 to ~fp32 accuracy
+// on the FP16 tensor pipe.
+int tc_pack_head(Model* m, DenseF32& D, const float* w, const float* b) {
+    TcState* s = (TcState*)m->tc_state;
+    if (!(D.J == 256 && D.K == 512)) { s->tc_head = false; return DSP_OK; }
+    const int KS = D.K / 64, NCH = D.J / 128;
+    TcDensePack* pk = new TcDensePack();
+    s->dense_packs.push_back(pk);
+    s->head_pack = pk;
+    pk->KS = KS;
+    std::vector<uint8_t> img((size_t)3 * NCH * KS * SLAB_BYTES, 0);
+    for (int n = 0; n < D.J; ++n)
+        for (int k = 0; k < D.K; ++k) {
+            const float wv = w[(size_t)n * D.K + k];
+            const float hi = __half2float(__float2half_rn(wv));
+            const size_t slab = (size_t)(n >> 7) * KS + (k >> 6);
+            put_half(img, (size_t)0 * NCH * KS + slab, n & 127, k & 63, hi);
+            put_half(img, (size_t)1 * NCH * KS + slab, n & 127, k & 63, hi);
+            put_half(img, (size_t)2 * NCH * KS + slab, n & 127, k & 63, wv - hi);
+        }
+    int rc;
+    if ((rc = tc_alloc(m, (void**)&pk->w_img, img.size()))) return rc;
+    if ((rc = tc_alloc(m, (void**)&pk->bias, sizeof(float) * D.J))) return rc;
+    DSP_CUDA(cudaMemcpy(pk->w_img, img.data(), img.size(), cudaMemcpyHostToDevice));
+    DSP_CUDA(cudaMemcpy(pk->bias, b, sizeof(float) * D.J, cudaMemcpyHostToDevice));
+    return DSP_OK;
+}
+
 int tc_finalize_pack(Model*) { return DSP_OK; }
 
 int tc_forward_chunk(Model* m, const float* kmer, const float* means, const float* stds, const float* lens,
                      const float* signals, const float* const* h0, const float* const* c0,
-                     const int64_t* sstride, int64_t n, float* logits, float* probs, int32_t* labels,
-                     cudaStream_t st) {
+                     const int64_t* sstride, uint64_t seed, uint64_t chunk_id, int64_t n,
+                     float* logits, float* probs, int32_t* labels, cudaStream_t st) {
     TcState* s = (TcState*)m->tc_state;
     const dsp_config& c = m->cfg;
     const int T = c.seq_len, H = c.hidden_size;
@@ -574,10 +837,16 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
             const bool final_layer = is_comb && l + 1 == layers.size();
             LayerParams p{};
             p.x_img = x; p.w_img = pk->w_img; p.bias = pk->bias;
-            p.h0 = h0[grp] + (int64_t)l * 2 * sstride[grp]; p.c0 = c0[grp] + (int64_t)l * 2 * sstride[grp];
-            p.state_dir_stride = sstride[grp];
-            p.y_img = s->ybuf[l & 1]; p.hfinal = final_layer ? s->hfinal : nullptr;
-            p.n = n; p.T = T; p.xk16 = pk->xk16; p.y_slabs = 2 * hid / 64; p.y_col_off = 0; p.write_y = final_layer ? 0 : 1;
+            if (h0) {
+                p.h0 = h0[grp] + (int64_t)l * 2 * sstride[grp]; p.c0 = c0[grp] + (int64_t)l * 2 * sstride[grp];
+                p.state_dir_stride = sstride[grp];
+            }
+            p.seed = seed; p.rng_call = (uint32_t)chunk_id; p.rng_slot = (uint32_t)((grp * 8 + (int)l) * 2);
+            p.site_base = (int64_t)chunk_id * m->cap;
+            const bool head_tc = final_layer && s->tc_head;
+            p.y_img = head_tc ? s->hfin_img : s->ybuf[l & 1]; p.hfinal = (final_layer && !head_tc) ? s->hfinal : nullptr;
+            p.n = n; p.T = T; p.xk16 = pk->xk16; p.y_slabs = 2 * hid / 64; p.y_col_off = 0;
+            p.write_y = final_layer ? (head_tc ? 2 : 0) : 1;
             Span sp(m, 1, st);
             int rc = launch_lstm(m, pk->KSX, hid, p, tiles, st);
             if (rc) return rc;
@@ -607,7 +876,13 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
     }
     if ((rc = run_stack(m->lstm_comb, s->comb_img, 2, H, true))) return rc;
     Span sp(m, 3, st);
-    return f32_head_flat(m, s->hfinal, n, logits, probs, labels, st);
+    if (!s->tc_head) return f32_head_flat(m, s->hfinal, n, logits, probs, labels, st);
+    TcDensePack* pk = s->head_pack;
+    DSP_REQUIRE(pk != nullptr && pk->KS == 8 && m->fc1.J == 256, DSP_ERR_INVALID, "tcgen05 path: head shape unsupported");
+    LayerParams p{};
+    p.x_img = s->hfin_img; p.w_img = pk->w_img; p.bias = pk->bias; p.n = n; p.T = 3; p.xk16 = 32;
+    p.w2t = m->fc2.wt; p.b2 = m->fc2.bias; p.logits = logits; p.probs = probs; p.labels = labels; p.num_classes = c.num_classes;
+    return launch_layer<8, 0, MODE_HEAD, 256>(m, p, tiles, st);
 }
 
 }  // namespace dsp

@@ -12,10 +12,12 @@ int tc_pack_lstm_layer(Model* m, LstmLayer& L,
                        const float* wih0, const float* whh0, const float* bih0, const float* bhh0,
                        const float* wih1, const float* whh1, const float* bih1, const float* bhh1);
 int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b);
+int tc_pack_head(Model* m, DenseF32& fc1, const float* w, const float* b);
 int tc_finalize_pack(Model* m);
 int tc_forward_chunk(Model* m, const float* kmer, const float* means, const float* stds, const float* lens,
                      const float* signals, const float* const* h0, const float* const* c0,
-                     const int64_t* state_stride, int64_t n, float* logits, float* probs, int32_t* labels,
-                     cudaStream_t st);
+                     const int64_t* state_stride, uint64_t seed, uint64_t chunk_id, int64_t n,
+                     float* logits, float* probs, int32_t* labels, cudaStream_t st);
+// h0 == nullptr: the layer kernels draw N(0,1) initial states themselves (Philox keyed by seed)
 
 }  // namespace dsp

@@ -94,6 +94,103 @@ selftest_kernel(const __half* __restrict__ a_slabs, const __half* __restrict__ a
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- MMA issue-rate probe ---------------------------------------------------------------------
+// One CTA per SM; one thread issues `iters` groups of 8 MMAs (operands resident, zero-filled),
+// optionally while another warp streams 32 KB bulk copies into a different part of shared
+// memory and/or four warps keep reading TMEM.  Reports SM cycles per MMA.
+//   mode bit0: A from TMEM (TS) instead of shared memory (SS); bit1: N = 256 instead of 128;
+//   bit2: concurrent bulk copies; bit3: concurrent tcgen05.ld traffic
+__global__ void __launch_bounds__(256, 1)
+mma_rate_kernel(const uint8_t* __restrict__ src, int iters, int mode, unsigned long long* __restrict__ cycles_out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                       // 16 KB
+    uint8_t* sB = smem + 16384;               // 32 KB (N up to 256)
+    uint8_t* sL = smem + 49152;               // 2 x 32 KB landing zone for the concurrent copies
+    __shared__ __align__(8) uint64_t bars[4];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ volatile int stop_flag;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        mbar_fence_init();
+        stop_flag = 0;
+    }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    // mode bits 4-5: number of independent accumulator chains the MMAs rotate over (1,2,4);
+    // bit 6: N = 64
+    const int N = (mode & 64) ? 64 : (mode & 2) ? 256 : 128;
+    const int chains = 1 << ((mode >> 4) & 3);
+    const uint32_t idesc = make_idesc_f16(128, N);
+    if (warp == 0) {
+        // warp-uniform loop, one elected lane issues (same structure as the layer kernels)
+        const bool leader = elect_one();
+        const uint32_t a_lo = smem_desc_lo(smem_u32(sA)), b_lo = smem_desc_lo(smem_u32(sB));
+        const uint32_t d0 = tmem, d1 = tmem + (uint32_t)((chains > 1) ? N : 0);
+        const long long t0 = clock64();
+        if (mode & 1) {
+            for (int it = 0; it < iters; ++it) {
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        mma_ts_lo<1>((k & 1) ? d1 : d0, tmem + 384 + (k & 3) * 8, b_lo + (k & 3) * 2, idesc);
+                }
+                __syncwarp();
+            }
+        } else {
+            for (int it = 0; it < iters; ++it) {
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        mma_ss_lo<1>((k & 1) ? d1 : d0, a_lo + (k & 3) * 2, b_lo + (k & 3) * 2, idesc);
+                }
+                __syncwarp();
+            }
+        }
+        if (leader) mma_commit(smem_u32(&bars[0]));
+        __syncwarp();
+        mbar_wait(smem_u32(&bars[0]), 0);
+        const long long t1 = clock64();
+        if (leader) { cycles_out[blockIdx.x] = (unsigned long long)(t1 - t0); stop_flag = 1; }
+    } else if (warp == 1 && (mode & 4)) {
+        if (tid == 32) {
+            uint32_t ph[2] = {0, 0};
+            int buf = 0;
+            size_t off = (size_t)blockIdx.x * 65536;
+            while (!stop_flag) {
+                const uint32_t bar = smem_u32(&bars[1 + buf]);
+                mbar_arrive_expect_tx(bar, 32768);
+                bulk_g2s(smem_u32(sL + buf * 32768), src + (off & ((64u << 20) - 1)), 32768, bar);
+                off += 32768;
+                if (buf == 1) {   // keep two copies in flight: wait for the older one
+                    mbar_wait(smem_u32(&bars[1]), ph[0]); ph[0] ^= 1;
+                    mbar_wait(smem_u32(&bars[2]), ph[1]); ph[1] ^= 1;
+                }
+                buf ^= 1;
+            }
+            if (buf == 1) { mbar_wait(smem_u32(&bars[1]), ph[0]); }
+        }
+    } else if (warp >= 4 && (mode & 8)) {
+        uint32_t acc = 0;
+        while (!stop_flag) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256, v);
+            tmem_ld_wait();
+            acc += v[0] + v[31];
+        }
+        if (acc == 0x12345678u) cycles_out[0] = 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 void to_slabs(const std::vector<__half>& m, int rows, int K, std::vector<__half>& out) {
     const int KS = K / SLAB_K;
     out.assign((size_t)rows * K, __float2half(0.f));
@@ -120,8 +217,32 @@ extern "C" int dsp_selftest(int device, int which, double* max_abs_err) {
         return DSP_ERR_CUDA;
     }
     DSP_REQUIRE(device >= 0 && device < ndev, DSP_ERR_INVALID, "dsp_selftest: bad device");
-    DSP_REQUIRE(which >= 0 && which <= 3, DSP_ERR_INVALID, "dsp_selftest: unknown test %d", which);
+    DSP_REQUIRE((which >= 0 && which <= 3) || (which >= 100 && which < 228), DSP_ERR_INVALID, "dsp_selftest: unknown test %d", which);
     DSP_CUDA(cudaSetDevice(device));
+    if (which >= 100) {
+        // MMA rate probe: returns average SM cycles per tcgen05.mma over all SMs
+        const int mode = which - 100, iters = 2000;
+        int nsm = 0;
+        DSP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+        uint8_t* src; unsigned long long* cyc;
+        DSP_CUDA(cudaMalloc(&src, (size_t)64 << 20));
+        DSP_CUDA(cudaMemset(src, 0, (size_t)64 << 20));
+        DSP_CUDA(cudaMalloc(&cyc, sizeof(unsigned long long) * nsm));
+        const size_t smem = 49152 + 65536 + 1024;
+        DSP_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int rep = 0; rep < 2; ++rep) {
+            mma_rate_kernel<<<nsm, 256, smem>>>(src, iters, mode, cyc);
+            DSP_CUDA(cudaGetLastError());
+            DSP_CUDA(cudaDeviceSynchronize());
+        }
+        std::vector<unsigned long long> h(nsm);
+        DSP_CUDA(cudaMemcpy(h.data(), cyc, sizeof(unsigned long long) * nsm, cudaMemcpyDeviceToHost));
+        cudaFree(src); cudaFree(cyc);
+        double sum = 0;
+        for (auto v : h) sum += (double)v;
+        *max_abs_err = sum / nsm / ((double)iters * 8);
+        return DSP_OK;
+    }
     const int N = (which == 1 || which == 3) ? 256 : 128;
     const int KS = which == 0 ? 1 : which == 1 ? 3 : which == 2 ? 2 : 4;
     const int K = KS * tc::SLAB_K;

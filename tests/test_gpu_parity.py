@@ -108,6 +108,25 @@ def test_philox_states_are_standard_normal_and_fresh():
     assert abs(p1[:, 1].std() - case["probs"][:, 1].std()) < 1e-3
 
 
+def test_fp16_in_kernel_philox_states():
+    # tcgen05 path draws the states inside the layer kernels: fresh per call, N(0,1)-like effect
+    case = cases.slice_case(cases.load_case("both_13_16_s1234"), 4096)
+    dev = torch.device("cuda:0")
+    model = cases.build_model(case["entry"], precision="fp16").cuda(0)
+    args = [torch.from_numpy(case["feats"][k]).to(dev) for k in cases.FEATURE_KEYS]
+    p1 = model(*args)[1].cpu().numpy()
+    p2 = model(*args)[1].cpu().numpy()
+    assert np.isfinite(p1).all()
+    d = np.abs(p1 - p2).max()
+    assert 1e-4 < d < 0.1
+    assert abs(p1[:, 1].mean() - case["probs"][:, 1].mean()) < 2e-3
+    assert abs(p1[:, 1].std() - case["probs"][:, 1].std()) < 1e-3
+    # same site at two different positions of the batch gets different states
+    args2 = [a.roll(1, 0) for a in args]
+    p3 = model(*args2)[1].cpu().numpy()
+    assert np.abs(np.roll(p3, -1, 0) - p1).max() > 1e-4
+
+
 def test_init_hidden_mode_reproduces_reference_rng_stream():
     # state_mode="init_hidden" draws torch.randn on the CPU generator in the reference's order,
     # so seeding alone reproduces the reference's _call_mods run (same batching).
