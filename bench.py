@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DSP_B200_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("DSP_B200_PRECISION", "fp16"), choices=["fp16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--buffers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

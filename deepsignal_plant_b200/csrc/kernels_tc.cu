@@ -4,26 +4,25 @@
 // FP32 bias, FP32 cell state and gate math.  Reference semantics: deepsignal_plant/models.py
 // :178-240 and torch nn.LSTM (gate order i,f,g,o; reverse direction walks t = T-1..0).
 //
-// Data layout.  A site tile is 128 sites (= the 128 TMEM lanes = M of the MMA).  Every MMA
-// operand lives in HBM as 16 KB "slabs" (128 rows x 64 fp16, 128-byte swizzled, see
-// tc_prims.cuh) so that one linear cp.async.bulk brings it to shared memory ready for
-// tcgen05.mma:
-//   activations  [tile][t][slab][128 rows x 128 B]     (x_t of a layer = slabs of one (tile,t))
-//   weights      [dir][chunk][kslab][128 rows x 128 B] (chunk = 128 gate columns = 32 hidden
-//                units x {i,f,g,o}, column = half*64 + j*4 + gate for unit chunk*32+half*16+j)
+// Data layout.  A site tile is 128 sites (= the 128 TMEM lanes of one SM).  Every MMA operand
+// lives in HBM as "slabs" (rows x 64 fp16, 128-byte swizzled, see tc_prims.cuh) so that one
+// linear cp.async.bulk brings it to shared memory ready for tcgen05.mma:
+//   activations  [tile][t][slab][128 rows x 128 B]      (x_t of a layer = slabs of one (tile,t))
+//   weights      [dir][cta rank][stream order][64 rows x 128 B]; a chunk = 128 gate columns =
+//                32 hidden units x {i,f,g,o}; column n of a chunk = unit pair (n >> 3), gate
+//                (n >> 1) & 3, unit parity n & 1 (adjacent columns = the same gate of two
+//                adjacent units, so the epilogue works on packed fp32 pairs); CTA rank r of a
+//                pair holds columns [64 r, 64 r + 64).
 //
-// One CTA of lstm_layer_kernel owns (site tile, direction) for all T steps:
-//   warp 0  : streams weight slabs through a shared-memory ring (bulk async copies, mbarriers)
-//   warp 2  : loads the x_t slabs of each step
-//   warp 1  : one thread issues tcgen05.mma; per step and chunk
-//                 acc[128 x 128] = x_t * W_ih_chunk^T   (A from shared memory)
-//                                + h_{t-1} * W_hh_chunk^T (A from TMEM)
-//             into one of two TMEM accumulators
-//   warps 4-11: epilogue; thread = site; reads its accumulator row, adds the bias, applies the
-//             gate non-linearities, updates the cell state it keeps in registers for all T
-//             steps, writes h_t as packed FP16 straight into the TMEM A operand of the next
-//             step and as a slab image to HBM for the next layer.
-// h and c never leave the SM between steps; gate pre-activations never touch HBM.
+// A CTA PAIR (cluster of 2, tcgen05 cta_group::2, M = 256) owns two site tiles of one
+// direction for all T steps; see layer_kernel.  Per step and chunk
+//     acc[256 x 128] = x_t * W_ih_chunk^T      (A from shared memory)
+//                    + h_{t-1} * W_hh_chunk^T  (A from TMEM)
+// into one of two TMEM accumulators; the epilogue warps (thread = site) read their accumulator
+// row, apply the gate non-linearities, update the cell state they keep in registers for all
+// T steps, and write h_t as packed FP16 straight into the TMEM A operand of the next step and
+// as a slab image to HBM for the next layer.  h and c never leave the SM between steps; gate
+// pre-activations never touch HBM.
 #include "tc.cuh"
 #include "tc_prims.cuh"
 #include <vector>
@@ -37,15 +36,25 @@ using namespace tc;
 namespace {
 
 constexpr int TILE = 128;
-constexpr int SLAB_BYTES = TILE * SLAB_ROW_BYTES;   // 16 KB
+constexpr int SLAB_BYTES = TILE * SLAB_ROW_BYTES;   // 16 KB: one A-operand slab (128 site rows x 64 fp16)
+constexpr int HSLAB_BYTES = SLAB_BYTES / 2;         // 8 KB: one CTA's half (64 weight rows) of a B slab
 constexpr int NTHREADS = 384;
 constexpr int EPI_WARPS = 8;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr uint16_t PAIR_MASK = 3;                   // both CTAs of the pair
+
+// Which of the five exponentials of an LSTM cell update are evaluated on the FMA pipe (degree-5
+// polynomial, ~2e-7 relative error, same class as ex2.approx) instead of the 16-lane MUFU pipe,
+// which would otherwise bound the epilogue: bit0 tanh(g), bit1 tanh(c), bit2 sigmoid(i),
+// bit3 sigmoid(f), bit4 sigmoid(o).
+#ifndef DSP_POLY_MASK
+#define DSP_POLY_MASK 3
+#endif
 
 struct LayerParams {
     const uint8_t* x_img;      // [tiles][T][KSX] slabs
-    const uint8_t* w_img;      // [dir][NCH][KS] slabs
-    const float* bias;         // [dir][NCH*128] in chunk column order
+    const uint8_t* w_img;      // [dir][cta rank][stream order] half slabs
+    const float* bias;         // [dir][NCH*128] in chunk column order (LSTM: pre-scaled like the weights)
     const float* h0;           // [dir][n][H] fp32 (LSTM only); null: draw N(0,1) in-kernel (Philox)
     const float* c0;
     uint64_t seed;             // Philox key
@@ -70,11 +79,13 @@ struct LayerParams {
     int num_classes;
 };
 
-constexpr int STG_SLABS = 2;                        // weight slabs per ring stage (one mbarrier per stage)
-constexpr int STG_BYTES = STG_SLABS * TILE * SLAB_ROW_BYTES;
 enum { MODE_LSTM = 0, MODE_FC = 1, MODE_HEAD = 2 };
 constexpr int HEAD_MAX_CLASSES = 8;
-template <int KSX, int MODE> struct RingStages { static constexpr int value = (MODE == MODE_HEAD) ? 2 : (KSX >= 8) ? 3 : 4; };
+// weight ring: NST stages of STG half slabs (one mbarrier pair per stage)
+template <int KSX> struct RingCfg {
+    static constexpr int STG = KSX >= 8 ? 2 : 4;
+    static constexpr int NST = KSX >= 8 ? 5 : 4;
+};
 
 // Philox4x32-10 (Salmon et al., SC'11) + Box-Muller: four N(0,1) values per counter.  Used to
 // draw the initial LSTM states in-kernel (the reference draws torch.randn per call,
@@ -97,31 +108,99 @@ __device__ __forceinline__ float4 philox_normal4(uint32_t c0, uint32_t c1, uint3
     return make_float4(r0 * cs0, r0 * s0, r1 * cs1, r1 * s1);
 }
 
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// ---- gate math on pairs of hidden units ---------------------------------------------------------
+// 2^x for two values.  POLY: round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-5
+// polynomial for 2^f on the FMA pipe (packed FFMA2), n added into the exponent field;
+// otherwise MUFU ex2.approx.  HI_CLAMP bounds the result (callers divide by 1 + result).
+template <bool POLY, bool HI_CLAMP>
+__device__ __forceinline__ float2 exp2_pair(float2 x) {
+    if constexpr (POLY) {
+        x.x = fmaxf(fminf(x.x, 60.f), -126.f);
+        x.y = fmaxf(fminf(x.y, 60.f), -126.f);
+        const float MG = 12582912.f;                      // 1.5 * 2^23: x + MG holds round(x) in its low mantissa bits
+        const float2 t = add2(x, make_float2(MG, MG));
+        const float2 r = add2(t, make_float2(-MG, -MG));
+        const float2 f = fma2(r, make_float2(-1.f, -1.f), x);
+        float2 q = fma2(make_float2(0.0013390863f, 0.0013390863f), f, make_float2(0.009676032f, 0.009676032f));
+        q = fma2(q, f, make_float2(0.05550357f, 0.05550357f));
+        q = fma2(q, f, make_float2(0.24022107f, 0.24022107f));
+        q = fma2(q, f, make_float2(0.6931472f, 0.6931472f));
+        q = fma2(q, f, make_float2(1.0000001f, 1.0000001f));
+        q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+        q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+        return q;
+    } else {
+        if constexpr (HI_CLAMP) { x.x = fminf(x.x, 60.f); x.y = fminf(x.y, 60.f); }
+        return make_float2(ex2_approx(x.x), ex2_approx(x.y));
+    }
+}
+
+// One LSTM cell update for two hidden units (torch nn.LSTM: c' = s(f) c + s(i) tanh(g),
+// h = s(o) tanh(c')).  The inputs are the gate pre-activations already multiplied by
+// -log2(e) (i, f, o) and -2 log2(e) (g) -- the factors are folded into the packed weights and
+// biases -- so sigmoid(z) = 1 / (1 + 2^a) and tanh(z) = (1 - 2^a) / (1 + 2^a).
+template <int PM>
+__device__ __forceinline__ void lstm_cell2(float2 ai, float2 af, float2 ag, float2 ao, float2& c, float2& h) {
+    const float2 ONE = make_float2(1.f, 1.f), NEG1 = make_float2(-1.f, -1.f);
+    const float2 ei = exp2_pair<((PM >> 2) & 1) != 0, false>(ai);
+    const float2 ef = exp2_pair<((PM >> 3) & 1) != 0, false>(af);
+    const float2 eg = exp2_pair<(PM & 1) != 0, true>(ag);
+    const float2 eo = exp2_pair<((PM >> 4) & 1) != 0, false>(ao);
+    const float2 F = add2(ef, ONE);
+    const float2 sf = make_float2(rcp_approx(F.x), rcp_approx(F.y));
+    const float2 AG = mul2(add2(ei, ONE), add2(eg, ONE));
+    const float2 rg = make_float2(rcp_approx(AG.x), rcp_approx(AG.y));
+    const float2 ig = mul2(fma2(eg, NEG1, ONE), rg);                       // sigmoid(i) * tanh(g)
+    const float2 cn = fma2(sf, c, ig);
+    c = cn;
+    const float2 ec = exp2_pair<((PM >> 1) & 1) != 0, true>(mul2(cn, make_float2(-2.f * LOG2E, -2.f * LOG2E)));
+    const float2 D = mul2(add2(eo, ONE), add2(ec, ONE));
+    const float2 rd = make_float2(rcp_approx(D.x), rcp_approx(D.y));
+    h = mul2(fma2(ec, NEG1, ONE), rd);                                     // sigmoid(o) * tanh(c')
+}
 
 // ---------------------------------------------------------------------------------------------
 // KSX: x slabs per step; H: hidden size of the layer (LSTM); MODE: what the epilogue does --
 //   MODE_LSTM  recurrent layer (A = [x_t | h_{t-1}], gate math, cell update)
 //   MODE_FC    dense + ReLU per timestep, NOUT output columns, written as a slab image
 //   MODE_HEAD  fc1 + ReLU + fc2 + softmax (+argmax) on [h_fwd(T-1) | h_bwd(0)] (models.py:229-240)
-// CL: thread-block cluster size; the CL CTAs of a cluster work on CL different site tiles of the
-// same direction and share every weight slab: each CTA issues 1/CL of the bulk copies as
-// cluster multicasts, so a slab is read from L2 once per cluster instead of once per CTA.
-template <int KSX, int H, int MODE, int NOUT, int CL>
+//
+// The kernel runs as CTA pairs (thread-block clusters of 2 on one TPC, tcgen05 cta_group::2):
+// the two CTAs own two different site tiles of the same direction and execute every MMA
+// together as M = 256.  Each CTA stages only HALF of every weight slab (64 of the 128 gate
+// columns of a chunk), so the shared-memory fill rate per SM that bounds a single-CTA M = 128
+// formulation (one full weight pass per tile and timestep) is halved.  The leader CTA (rank 0)
+// issues all MMAs; completion is multicast to both CTAs' barriers; the peer CTA forwards its
+// "data landed" and "accumulator drained" events to the leader's barriers.
+//
+// Warp roles (both CTAs unless noted):
+//   warp 0     weight producer: streams this CTA's half slabs through a ring (cp.async.bulk)
+//   warp 1     leader: MMA issuer / peer: relay of its full-barriers to the leader
+//   warp 2     x_t slab producer (own tile)
+//   warp 3     TMEM allocation
+//   warps 4-11 epilogue, thread = (site row, 64-column half of the chunk)
+// Per step and chunk pair (c, c+1) the issue order is X(c) X(c+1) H(c) H(c+1), X = x_t part
+// from shared memory into accumulator c&1, H = h_{t-1} part from TMEM, so that at a step
+// boundary two x parts cover the tail of the previous step's gate math.
+template <int KSX, int H, int MODE, int NOUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 layer_kernel(const LayerParams p) {
     constexpr bool IS_FC = MODE != MODE_LSTM;              // no recurrence: x part only
-    constexpr int NST = RingStages<KSX, MODE>::value;
+    constexpr int STG = RingCfg<KSX>::STG, NST = RingCfg<KSX>::NST;
     constexpr int NCH = IS_FC ? NOUT / 128 : H / 32;       // 128-column chunks per step
     constexpr int KSH = IS_FC ? 0 : H / 64;                // h slabs (K of the recurrent part)
     constexpr int KS = KSX + KSH;
-    constexpr int HCOLS = IS_FC ? 0 : H / 2;               // TMEM columns of one h buffer
-    constexpr uint32_t IDESC = make_idesc_f16(128, 128);
+    constexpr int W_STEP = NCH * KS;                       // half slabs streamed per step
+    constexpr int NBIAS = NCH * 128;
+    constexpr uint32_t IDESC = make_idesc_f16(256, 128);
+    static_assert(W_STEP % STG == 0, "a step must be a whole number of ring stages");
+    static_assert(IS_FC || NCH % 2 == 0, "chunks are issued in pairs");
 
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* s_x = smem;                                   // KSX slabs
-    uint8_t* s_w = smem + (size_t)KSX * SLAB_BYTES;        // NST ring stages of STG_SLABS slabs
+    uint8_t* s_w = smem + (size_t)KSX * SLAB_BYTES;        // NST ring stages of STG half slabs
+    float* s_bias = reinterpret_cast<float*>(s_w + (size_t)NST * STG * HSLAB_BYTES);
     __shared__ __align__(8) uint64_t bars[2 * NST + 2 * KSX + 5];
     __shared__ uint32_t tmem_base_s;
     const uint32_t b_wfull = smem_u32(&bars[0]), b_wempty = smem_u32(&bars[NST]);
@@ -132,56 +211,45 @@ layer_kernel(const LayerParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, dir = IS_FC ? 0 : blockIdx.y;
     const int T = p.T;
+    const uint32_t crank = cluster_ctarank();              // 0 = leader
 
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(b_wfull + 8 * i, 1); mbar_init(b_wempty + 8 * i, CL); }
-        for (int i = 0; i < KSX; ++i) { mbar_init(b_xfull + 8 * i, 1); mbar_init(b_xempty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, EPI_WARPS); }
-        mbar_init(b_hready, EPI_WARPS);
+        // barriers the leader's MMA thread waits on collect one arrival per CTA
+        const uint32_t both = crank == 0 ? 2u : 1u;
+        for (int i = 0; i < NST; ++i) { mbar_init(b_wfull + 8 * i, both); mbar_init(b_wempty + 8 * i, 1); }
+        for (int i = 0; i < KSX; ++i) { mbar_init(b_xfull + 8 * i, both); mbar_init(b_xempty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, 2 * EPI_WARPS); }
+        mbar_init(b_hready, 2 * EPI_WARPS);
         mbar_fence_init();
     }
-    if (warp == 3) tmem_alloc(smem_u32(&tmem_base_s), 512);
+    if (warp == 3) tmem_alloc_pair(smem_u32(&tmem_base_s), 512);
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();    // peers' barriers are initialised before anything lands on them
+    cluster_sync_all();                          // the peer's barriers exist before anything lands on them
     tc_fence_after();
-    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
-    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     const uint32_t tmem = tmem_base_s;
     const uint32_t t_acc = tmem;                 // two accumulators: columns [0,128) and [128,256)
-    const uint32_t t_h = tmem + 256;             // two h buffers of HCOLS columns at +0 and +128
+    const uint32_t t_h = tmem + 256;             // two h buffers of H/2 columns at +0 and +128
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0) {
-            // ---- weight producer: ring stages of STG_SLABS consecutive slabs ------------------------
+            // ---- weight producer: this CTA's half slabs, linear in stream order -----------------------
             if (elect_one()) {
-                const uint8_t* wsrc = p.w_img + (size_t)dir * NCH * KS * SLAB_BYTES;
-                uint32_t stage = 0, phase = 0, issued = 0;
-                for (int step = 0; step < T; ++step)
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        // MODE_HEAD walks T passes over different weight images (split-precision terms)
-                        const uint8_t* src = wsrc + ((size_t)(MODE == MODE_HEAD ? step : 0) * NCH + ch) * KS * SLAB_BYTES;
-#pragma unroll
-                        for (int part = 0; part < 2; ++part) {               // x part, then h part
-                            const int nslab_total = part == 0 ? KSX : KSH;
-                            for (int s0 = 0; s0 < nslab_total; s0 += STG_SLABS) {
-                                const uint32_t bytes = (uint32_t)min(STG_SLABS, nslab_total - s0) * SLAB_BYTES;
-                                // the stage is free once every CTA of the cluster has consumed it
-                                mbar_wait(b_wempty + 8 * stage, phase ^ 1);
-                                mbar_arrive_expect_tx(b_wfull + 8 * stage, bytes);
-                                const uint32_t dst = smem_u32(s_w + (size_t)stage * STG_BYTES);
-                                if constexpr (CL == 1) {
-                                    bulk_g2s(dst, src, bytes, b_wfull + 8 * stage);
-                                } else if (issued % CL == crank) {
-                                    bulk_g2s_multicast(dst, src, bytes, b_wfull + 8 * stage, CMASK);
-                                }
-                                ++issued;
-                                src += bytes;
-                                if (++stage == NST) { stage = 0; phase ^= 1; }
-                            }
-                        }
+                const size_t total = (size_t)(MODE == MODE_HEAD ? T : 1) * W_STEP;
+                const uint8_t* wsrc = p.w_img + ((size_t)dir * 2 + crank) * total * HSLAB_BYTES;
+                uint32_t stage = 0, phase = 0;
+                for (int step = 0; step < T; ++step) {
+                    // MODE_HEAD walks T passes over different weight images (split-precision terms)
+                    const uint8_t* src = wsrc + (size_t)(MODE == MODE_HEAD ? step : 0) * W_STEP * HSLAB_BYTES;
+                    for (int s = 0; s < W_STEP; s += STG) {
+                        mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+                        mbar_arrive_expect_tx(b_wfull + 8 * stage, STG * HSLAB_BYTES);
+                        bulk_g2s(smem_u32(s_w + (size_t)stage * STG * HSLAB_BYTES), src, STG * HSLAB_BYTES, b_wfull + 8 * stage);
+                        src += (size_t)STG * HSLAB_BYTES;
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
+                }
             }
         } else if (warp == 2) {
             // ---- x_t slab producer ------------------------------------------------------------
@@ -199,91 +267,102 @@ layer_kernel(const LayerParams p) {
                     }
                 }
             }
+        } else if (warp == 1 && crank != 0) {
+            // ---- peer relay: forward "my half landed" to the leader's barriers, in consumption order --
+            const uint32_t r_wfull = mapa_u32(b_wfull, 0), r_xfull = mapa_u32(b_xfull, 0);
+            uint32_t stage = 0, phase = 0;
+            for (int step = 0; step < T; ++step) {
+                for (int j = 0; j < KSX; ++j) {
+                    mbar_wait(b_xfull + 8 * j, step & 1);
+                    if (lane == 0) mbar_arrive_cluster(r_xfull + 8 * j);
+                }
+                for (int s = 0; s < W_STEP; s += STG) {
+                    mbar_wait(b_wfull + 8 * stage, phase);
+                    if (lane == 0) mbar_arrive_cluster(r_wfull + 8 * stage);
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                }
+            }
         } else if (warp == 1) {
-            // ---- MMA issuer: the whole warp walks the schedule (warp-uniform control flow keeps the
-            // descriptors in uniform registers); one elected lane issues tcgen05.mma / commit ----------
+            // ---- MMA issuer (leader CTA): the whole warp walks the schedule (warp-uniform control flow
+            // keeps the descriptors in uniform registers); one elected lane issues tcgen05.mma / commit --
             const bool leader = elect_one();
             const uint32_t a_lo0 = smem_desc_lo(smem_u32(s_x)), b_lo0 = smem_desc_lo(smem_u32(s_w));
             const int xk16 = p.xk16;
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, in_stage = 0;
+            // half slab to consume next: wait for its stage when entering one; returns its descriptor
+            auto w_acquire = [&]() -> uint32_t {
+                if (in_stage == 0) { mbar_wait_cluster(b_wfull + 8 * stage, phase); tc_fence_after(); }
+                return b_lo0 + (stage * STG + in_stage) * (uint32_t)(HSLAB_BYTES >> 4);
+            };
+            auto w_release = [&]() {
+                if (++in_stage == STG) {
+                    if (leader) mma2_commit(b_wempty + 8 * stage, PAIR_MASK);
+                    in_stage = 0;
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                }
+                __syncwarp();
+            };
+            // x part of one chunk: A = x_t slabs in shared memory (both CTAs, own tile each)
+            auto issue_x = [&](uint32_t acc, bool fresh, bool first_use, bool last_use, int step) {
+#pragma unroll
+                for (int j = 0; j < KSX; ++j) {
+                    if (first_use) { mbar_wait_cluster(b_xfull + 8 * j, step & 1); tc_fence_after(); }
+                    const uint32_t bl = w_acquire();
+                    if (leader) {
+                        const uint32_t al = a_lo0 + (uint32_t)j * (SLAB_BYTES >> 4);
+                        const int nk = (KSX * 4 == xk16) ? 4 : min(4, xk16 - 4 * j);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < nk) {
+                                if (j == 0 && k == 0 && fresh) mma2_ss_lo<0>(acc, al, bl, IDESC);
+                                else mma2_ss_lo<1>(acc, al + k * 2, bl + k * 2, IDESC);
+                            }
+                        }
+                        if (last_use) mma2_commit(b_xempty + 8 * j, PAIR_MASK);
+                    }
+                    w_release();
+                }
+            };
             for (int step = 0; step < T; ++step) {
-                const uint32_t a_t = t_h + (uint32_t)(step & 1) * 128u;
-                for (int ch = 0; ch < NCH; ++ch) {
-                    // MODE_HEAD: chunk ch accumulates into buffer ch over all T passes
-                    const uint32_t g = (MODE == MODE_HEAD) ? (uint32_t)ch : (uint32_t)(step * NCH + ch);
-                    const uint32_t buf = g & 1u, use = g >> 1;
-                    if (MODE != MODE_HEAD || step == 0) mbar_wait(b_accempty + 8 * buf, (use & 1u) ^ 1u);
-                    if (MODE == MODE_LSTM && step == 0 && ch == 0) mbar_wait(b_hready, 0);   // c0 was staged in the accumulators
-                    tc_fence_after();
-                    const uint32_t acc = t_acc + buf * 128u;
-                    const bool fresh = (MODE != MODE_HEAD) || step == 0;      // first MMA overwrites the accumulator
-                    // ---- x part: A from shared memory ----
+                if constexpr (MODE == MODE_LSTM) {
+                    const uint32_t a_t = t_h + (uint32_t)(step & 1) * 128u;
+                    if (step == 0) mbar_wait_cluster(b_hready, 0);        // c0 was staged in the accumulator columns
+                    for (int pr = 0; pr < NCH / 2; ++pr) {
+                        const uint32_t use = (uint32_t)(step * (NCH / 2) + pr);
 #pragma unroll
-                    for (int s0 = 0; s0 < KSX; s0 += STG_SLABS) {
-                        if (ch == 0) {
-#pragma unroll
-                            for (int j = 0; j < STG_SLABS; ++j) if (s0 + j < KSX) mbar_wait(b_xfull + 8 * (s0 + j), step & 1);
-                        }
-                        mbar_wait(b_wfull + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint32_t b_lo = b_lo0 + stage * (STG_BYTES >> 4);
-                        if (leader) {
-#pragma unroll
-                            for (int j = 0; j < STG_SLABS; ++j) {
-                                if (s0 + j < KSX) {
-                                    const uint32_t al = a_lo0 + (uint32_t)(s0 + j) * (SLAB_BYTES >> 4);
-                                    const uint32_t bl = b_lo + (uint32_t)j * (SLAB_BYTES >> 4);
-                                    if (KSX * 4 == xk16) {
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k) {
-                                            if (s0 + j == 0 && k == 0) { if (fresh) mma_ss_lo<0>(acc, al, bl, IDESC); else mma_ss_lo<1>(acc, al, bl, IDESC); }
-                                            else mma_ss_lo<1>(acc, al + k * 2, bl + k * 2, IDESC);
-                                        }
-                                    } else {                                  // narrow first-layer input
-                                        for (int k = 0; k < xk16 - (s0 + j) * 4 && k < 4; ++k) {
-                                            if (s0 + j == 0 && k == 0) mma_ss_lo<0>(acc, al, bl, IDESC);
-                                            else mma_ss_lo<1>(acc, al + k * 2, bl + k * 2, IDESC);
-                                        }
-                                    }
-                                }
-                            }
-                            if constexpr (CL == 1) mma_commit(b_wempty + 8 * stage);
-                            else mma_commit_multicast(b_wempty + 8 * stage, CMASK);
-                            if (ch == NCH - 1) {
-#pragma unroll
-                                for (int j = 0; j < STG_SLABS; ++j) if (s0 + j < KSX) mma_commit(b_xempty + 8 * (s0 + j));
-                            }
-                        }
-                        __syncwarp();
-                        if (++stage == NST) { stage = 0; phase ^= 1; }
-                    }
-                    // ---- recurrent part: A = h_{t-1} from TMEM ----
-                    if constexpr (!IS_FC) {
-                        if (ch == 0) { mbar_wait(b_hready, step & 1); tc_fence_after(); }
-#pragma unroll
-                        for (int s0 = 0; s0 < KSH; s0 += STG_SLABS) {
-                            mbar_wait(b_wfull + 8 * stage, phase);
+                        for (int e = 0; e < 2; ++e) {
+                            mbar_wait_cluster(b_accempty + 8 * e, (use & 1u) ^ 1u);
                             tc_fence_after();
-                            const uint32_t b_lo = b_lo0 + stage * (STG_BYTES >> 4);
-                            if (leader) {
+                            issue_x(t_acc + e * 128u, true, pr == 0 && e == 0, pr == NCH / 2 - 1 && e == 1, step);
+                        }
+                        if (pr == 0) { mbar_wait_cluster(b_hready, step & 1); tc_fence_after(); }
 #pragma unroll
-                                for (int j = 0; j < STG_SLABS; ++j) {
-                                    if (s0 + j < KSH) {
+                        for (int e = 0; e < 2; ++e) {
 #pragma unroll
-                                        for (int k = 0; k < 4; ++k)
-                                            mma_ts_lo<1>(acc, a_t + (uint32_t)((s0 + j) * 32 + k * 8),
-                                                         b_lo + (uint32_t)j * (SLAB_BYTES >> 4) + k * 2, IDESC);
-                                    }
+                            for (int j = 0; j < KSH; ++j) {
+                                const uint32_t bl = w_acquire();
+                                if (leader) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        mma2_ts_lo<1>(t_acc + e * 128u, a_t + (uint32_t)(j * 32 + k * 8), bl + k * 2, IDESC);
                                 }
-                                if constexpr (CL == 1) mma_commit(b_wempty + 8 * stage);
-                                else mma_commit_multicast(b_wempty + 8 * stage, CMASK);
+                                w_release();
                             }
+                            if (leader) mma2_commit(b_accfull + 8 * e, PAIR_MASK);
                             __syncwarp();
-                            if (++stage == NST) { stage = 0; phase ^= 1; }
                         }
                     }
-                    if (leader && (MODE != MODE_HEAD || step == T - 1)) mma_commit(b_accfull + 8 * buf);
-                    __syncwarp();
+                } else {
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        // MODE_HEAD: chunk ch accumulates into buffer ch over all T passes
+                        const uint32_t g = (MODE == MODE_HEAD) ? (uint32_t)ch : (uint32_t)(step * NCH + ch);
+                        const uint32_t buf = g & 1u, use = g >> 1;
+                        const bool fresh = (MODE != MODE_HEAD) || step == 0;
+                        if (MODE != MODE_HEAD) { mbar_wait_cluster(b_accempty + 8 * buf, (use & 1u) ^ 1u); tc_fence_after(); }
+                        issue_x(t_acc + buf * 128u, fresh, ch == 0, ch == NCH - 1, step);
+                        if (leader && (MODE != MODE_HEAD || step == T - 1)) mma2_commit(b_accfull + 8 * buf, PAIR_MASK);
+                        __syncwarp();
+                    }
                 }
             }
         }
@@ -297,7 +376,11 @@ layer_kernel(const LayerParams p) {
         const int64_t site = (int64_t)tile * TILE + row;
         const bool valid = site < p.n;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const float* bias = p.bias + (size_t)dir * NCH * 128 + half * 64;
+        // "accumulator drained" / "h written" go to the leader's barriers
+        const uint32_t r_accempty = mapa_u32(b_accempty, 0), r_hready = mapa_u32(b_hready, 0);
+
+        for (int i = tid - 128; i < NBIAS; i += EPI_WARPS * 32) s_bias[i] = p.bias[(size_t)dir * NBIAS + i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // the 8 epilogue warps only
 
         if constexpr (MODE == MODE_HEAD) {
             // z = relu(fc1(x)); logits = fc2(z); probs = softmax(logits).  Each thread owns 64 of the
@@ -318,15 +401,10 @@ layer_kernel(const LayerParams p) {
                     uint32_t v[32];
                     tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(half * 64 + part * 32), v);
                     tmem_ld_wait();
-                    if (part == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(b_accempty + 8 * buf);
-                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int col = ch * 128 + half * 64 + part * 32 + j;
-                        const float z = fmaxf(__uint_as_float(v[j]) + __ldg(p.bias + col), 0.f);
+                        const float z = fmaxf(__uint_as_float(v[j]) + s_bias[col], 0.f);
 #pragma unroll
                         for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc)
                             if (cc < C) part_sum[cc] = fmaf(z, __ldg(p.w2t + (size_t)col * C + cc), part_sum[cc]);
@@ -335,7 +413,7 @@ layer_kernel(const LayerParams p) {
             }
 #pragma unroll
             for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc) head_part[half][row][cc] = part_sum[cc];
-            asm volatile("bar.sync 1, 256;" ::: "memory");           // the 8 epilogue warps only
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (half == 0 && valid) {
                 float lg[HEAD_MAX_CLASSES];
                 float mx = -3.0e38f;
@@ -378,16 +456,17 @@ layer_kernel(const LayerParams p) {
                         if (part == 1) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(b_accempty + 8 * buf);
+                            if (lane == 0) mbar_arrive_cluster(r_accempty + 8 * buf);
                         }
+                        const float* bs = s_bias + ch * 128 + half * 64 + part * 32;
 #pragma unroll
                         for (int c8 = 0; c8 < 4; ++c8) {
                             uint32_t o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int j = c8 * 8 + e * 2;
-                                const float a = fmaxf(__uint_as_float(v[j]) + __ldg(bias + ch * 128 + part * 32 + j), 0.f);
-                                const float b = fmaxf(__uint_as_float(v[j + 1]) + __ldg(bias + ch * 128 + part * 32 + j + 1), 0.f);
+                                const float a = fmaxf(__uint_as_float(v[j]) + bs[j], 0.f);
+                                const float b = fmaxf(__uint_as_float(v[j + 1]) + bs[j + 1], 0.f);
                                 o[e] = pack_half2(a, b);
                             }
                             const int chunk = part * 4 + c8;
@@ -398,7 +477,7 @@ layer_kernel(const LayerParams p) {
             }
         } else {
             constexpr int UPT = 16;                   // hidden units per thread per chunk
-            float c[NCH][UPT];
+            float2 c2[NCH][UPT / 2];                  // cell state, fp32, in registers for all T steps
             // initial states: c0 -> registers, h0 -> TMEM h buffer 0 (packed FP16 pairs)
             if (p.h0 == nullptr) {
                 // drawn here (Philox): a compact loop stores h0 straight into the TMEM operand buffer and
@@ -424,7 +503,7 @@ layer_kernel(const LayerParams p) {
                     tmem_ld16(t_stage + (uint32_t)(ch * UPT), v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < UPT; ++j) c[ch][j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < UPT / 2; ++j) c2[ch][j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                 }
             } else {
                 const float* h0 = p.h0 + (size_t)dir * p.state_dir_stride + (size_t)site * H;
@@ -440,7 +519,7 @@ layer_kernel(const LayerParams p) {
                             cv = *reinterpret_cast<const float4*>(c0 + u0 + j4);
                             hq = *reinterpret_cast<const float4*>(h0 + u0 + j4);
                         }
-                        c[ch][j4] = cv.x; c[ch][j4 + 1] = cv.y; c[ch][j4 + 2] = cv.z; c[ch][j4 + 3] = cv.w;
+                        c2[ch][j4 / 2] = make_float2(cv.x, cv.y); c2[ch][j4 / 2 + 1] = make_float2(cv.z, cv.w);
                         hv[j4] = hq.x; hv[j4 + 1] = hq.y; hv[j4 + 2] = hq.z; hv[j4 + 3] = hq.w;
                     }
                     uint32_t pk[8];
@@ -452,7 +531,8 @@ layer_kernel(const LayerParams p) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(b_hready);
+            if (lane == 0) mbar_arrive_cluster(r_hready);
+            const uint32_t s_bias_u32 = smem_u32(s_bias);
             for (int step = 0; step < T; ++step) {
                 const int t = dir ? (T - 1 - step) : step;
                 const bool last = (step == T - 1);
@@ -462,45 +542,40 @@ layer_kernel(const LayerParams p) {
                 const uint32_t t_hnext = t_h + (uint32_t)((step + 1) & 1) * 128u + lane_addr;
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
-                    const uint32_t buf = (uint32_t)ch & 1u;                   // NCH is even
-                    const uint32_t use = (uint32_t)(step * NCH + ch) >> 1;
+                    const uint32_t buf = (uint32_t)ch & 1u;                   // chunk pair (c, c+1) -> buffers 0, 1
+                    const uint32_t use = (uint32_t)(step * (NCH / 2) + (ch >> 1));
                     mbar_wait(b_accfull + 8 * buf, use & 1u);
                     tc_fence_after();
                     const int u0 = ch * 32 + half * UPT;
-                    float hv[UPT];
+                    float2 h2[UPT / 2];
 #pragma unroll
                     for (int part = 0; part < 2; ++part) {
                         uint32_t v[32];
                         tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(half * 64 + part * 32), v);
+                        // biases of this part's 8 units (warp-wide broadcast reads) while the TMEM load is in flight
+                        float4 bq[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) bq[i] = lds128(s_bias_u32 + (uint32_t)((ch * 128 + half * 64 + part * 32 + i * 4) * 4));
                         tmem_ld_wait();
                         if (part == 1) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(b_accempty + 8 * buf);
+                            if (lane == 0) mbar_arrive_cluster(r_accempty + 8 * buf);
                         }
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const int j = part * 8 + jj;
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 128 + j * 4));
-                            const float gi = clampf(__uint_as_float(v[jj * 4 + 0]) + b4.x, -40.f, 40.f);
-                            const float gf = clampf(__uint_as_float(v[jj * 4 + 1]) + b4.y, -40.f, 40.f);
-                            const float gg = clampf(__uint_as_float(v[jj * 4 + 2]) + b4.z, -40.f, 40.f);
-                            const float go = clampf(__uint_as_float(v[jj * 4 + 3]) + b4.w, -40.f, 40.f);
-                            const float ei = ex2_approx(-LOG2E * gi);
-                            const float ef = ex2_approx(-LOG2E * gf);
-                            const float eg = ex2_approx(-2.f * LOG2E * gg);
-                            const float eo = ex2_approx(-LOG2E * go);
-                            const float sf = rcp_approx(1.f + ef);
-                            const float ig = (1.f - eg) * rcp_approx((1.f + ei) * (1.f + eg));   // sigmoid(i)*tanh(g)
-                            const float cn = fmaf(sf, c[ch][j], ig);
-                            c[ch][j] = cn;
-                            const float ec = ex2_approx(-2.f * LOG2E * clampf(cn, -40.f, 40.f));
-                            hv[j] = (1.f - ec) * rcp_approx((1.f + eo) * (1.f + ec));            // sigmoid(o)*tanh(c)
+                        for (int qq = 0; qq < 4; ++qq) {
+                            // columns of one unit pair: i i' f f' g g' o o'
+                            const float4 b0 = bq[2 * qq], b1 = bq[2 * qq + 1];
+                            const float2 ai = add2(make_float2(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1])), make_float2(b0.x, b0.y));
+                            const float2 af = add2(make_float2(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3])), make_float2(b0.z, b0.w));
+                            const float2 ag = add2(make_float2(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5])), make_float2(b1.x, b1.y));
+                            const float2 ao = add2(make_float2(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7])), make_float2(b1.z, b1.w));
+                            lstm_cell2<DSP_POLY_MASK>(ai, af, ag, ao, c2[ch][part * 4 + qq], h2[part * 4 + qq]);
                         }
                     }
                     uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = pack_half2(hv[2 * j], hv[2 * j + 1]);
+                    for (int j = 0; j < 8; ++j) pk[j] = pack_half2(h2[j].x, h2[j].y);
                     tmem_st8(t_hnext + (uint32_t)(u0 >> 1), pk);
                     if (do_write) {
                         const int col = dir * H + u0;                          // multiple of 16
@@ -514,7 +589,7 @@ layer_kernel(const LayerParams p) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const __half2 hh = *reinterpret_cast<const __half2*>(&pk[j]);
-                                lo[j] = pack_half2(hv[2 * j] - __low2float(hh), hv[2 * j + 1] - __high2float(hh));
+                                lo[j] = pack_half2(h2[j].x - __low2float(hh), h2[j].y - __high2float(hh));
                             }
                             uint8_t* lslab = yslab + (size_t)p.y_slabs * SLAB_BYTES;
                             *reinterpret_cast<uint4*>(lslab + (((chunk) ^ (row & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -524,21 +599,21 @@ layer_kernel(const LayerParams p) {
                     if (last && p.hfinal != nullptr && valid) {
                         float* hf = p.hfinal + (size_t)site * (2 * H) + dir * H + u0;
 #pragma unroll
-                        for (int j4 = 0; j4 < UPT; j4 += 4)
-                            *reinterpret_cast<float4*>(hf + j4) = make_float4(hv[j4], hv[j4 + 1], hv[j4 + 2], hv[j4 + 3]);
+                        for (int j = 0; j < UPT / 2; j += 2)
+                            *reinterpret_cast<float4*>(hf + 2 * j) = make_float4(h2[j].x, h2[j].y, h2[j + 1].x, h2[j + 1].y);
                     }
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(b_hready);
+                if (lane == 0) mbar_arrive_cluster(r_hready);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();    // no CTA leaves while peers may still signal it
-    if (warp == 3) tmem_dealloc(tmem, 512);
+    cluster_sync_all();                          // no CTA leaves while the pair may still touch it
+    if (warp == 3) tmem_dealloc_pair(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -597,13 +672,15 @@ __global__ void prep_images_kernel(const float* __restrict__ kmer, const float* 
 }
 
 // ---- host-side packing ------------------------------------------------------------------------
+// Weight images are written per CTA rank of the pair: [dir][rank][half slab in stream order], a half
+// slab = the 64 B rows (gate / output columns) rank r contributes to a 128-column chunk.
 struct TcLstmPack {
-    uint8_t* w_img = nullptr;   // [2][NCH][KS] slabs
-    float* bias = nullptr;      // [2][NCH*128]
+    uint8_t* w_img = nullptr;   // [2][2][NCH*KS] half slabs
+    float* bias = nullptr;      // [2][NCH*128], scaled like the weights
     int KSX = 0, xk16 = 0;
 };
 struct TcDensePack {
-    uint8_t* w_img = nullptr;   // [NCH][KS] slabs
+    uint8_t* w_img = nullptr;   // [2][NCH*KS] (x passes for the head) half slabs
     float* bias = nullptr;      // [NCH*128]
     int KS = 0;
 };
@@ -621,9 +698,10 @@ struct TcState {
     std::vector<TcDensePack*> dense_packs;
 };
 
-void put_half(std::vector<uint8_t>& img, size_t slab_index, int row, int col, float v) {
+// element (row n of a 128-row chunk, k within a 64-wide K slab) of stream half slab s
+void put_half(std::vector<uint8_t>& img, size_t rank_base, size_t s, int n, int k, float v) {
     __half h = __float2half_rn(v);
-    memcpy(&img[slab_index * SLAB_BYTES + slab_offset_bytes(row, col)], &h, 2);
+    memcpy(&img[(rank_base + s) * HSLAB_BYTES + slab_offset_bytes((uint32_t)(n & 63), (uint32_t)k)], &h, 2);
 }
 
 int tc_alloc(Model* m, void** p, size_t bytes) {
@@ -633,34 +711,26 @@ int tc_alloc(Model* m, void** p, size_t bytes) {
     return DSP_OK;
 }
 
-int g_cluster = 2;     // cluster size used for the layer kernels (1, 2 or 4); DSP_B200_CLUSTER overrides
-
-template <int KSX, int H, int MODE, int NOUT, int CL>
-int launch_layer_cl(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
-    constexpr int NST = RingStages<KSX, MODE>::value;
-    const size_t smem = (size_t)KSX * SLAB_BYTES + (size_t)NST * STG_BYTES + 1024;
-    auto kern = layer_kernel<KSX, H, MODE, NOUT, CL>;
+template <int KSX, int H, int MODE, int NOUT>
+int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
+    constexpr int NCH = MODE != MODE_LSTM ? NOUT / 128 : H / 32;
+    const size_t smem = (size_t)KSX * SLAB_BYTES + (size_t)RingCfg<KSX>::NST * RingCfg<KSX>::STG * HSLAB_BYTES
+                        + (size_t)NCH * 128 * sizeof(float) + 1024;
+    auto kern = layer_kernel<KSX, H, MODE, NOUT>;
     DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((tiles + CL - 1) / CL * CL), MODE != MODE_LSTM ? 1 : 2);   // padded tiles: workspace is padded too
+    cfg.gridDim = dim3((unsigned)((tiles + 1) / 2 * 2), MODE != MODE_LSTM ? 1 : 2);   // CTA pairs: the workspace is padded too
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     DSP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     m->launches++;
     return DSP_OK;
-}
-
-template <int KSX, int H, int MODE, int NOUT>
-int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
-    if (g_cluster == 4) return launch_layer_cl<KSX, H, MODE, NOUT, 4>(m, p, tiles, st);
-    if (g_cluster == 2) return launch_layer_cl<KSX, H, MODE, NOUT, 2>(m, p, tiles, st);
-    return launch_layer_cl<KSX, H, MODE, NOUT, 1>(m, p, tiles, st);
 }
 
 int launch_lstm(Model* m, int KSX, int H, const LayerParams& p, int64_t tiles, cudaStream_t st) {
@@ -694,12 +764,7 @@ int tc_create(Model* m) {
                 "DSP_PRECISION_FP16 supports signal_len <= 64 and <= 16 sequence features per base");
     TcState* s = new TcState();
     m->tc_state = s;
-    if (const char* e = getenv("DSP_B200_CLUSTER")) {
-        const int v = atoi(e);
-        DSP_REQUIRE(v == 1 || v == 2 || v == 4, DSP_ERR_INVALID, "DSP_B200_CLUSTER must be 1, 2 or 4");
-        g_cluster = v;
-    }
-    s->tiles = ((m->cap + TILE - 1) / TILE + 3) / 4 * 4;     // padded to the largest cluster size
+    s->tiles = ((m->cap + TILE - 1) / TILE + 1) / 2 * 2;     // whole CTA pairs
     const size_t per_tile_t = (size_t)s->tiles * c.seq_len * SLAB_BYTES;
     int rc;
     if (c.module != DSP_SIGNAL_BILSTM) if ((rc = tc_alloc(m, (void**)&s->xseq_img, per_tile_t))) return rc;
@@ -709,6 +774,12 @@ int tc_create(Model* m) {
     if ((rc = tc_alloc(m, (void**)&s->comb_img, per_tile_t * 4))) return rc;
     if ((rc = tc_alloc(m, (void**)&s->hfinal, sizeof(float) * (size_t)s->tiles * TILE * 2 * c.hidden_size))) return rc;
     if ((rc = tc_alloc(m, (void**)&s->hfin_img, (size_t)s->tiles * 2 * (2 * c.hidden_size / 64) * SLAB_BYTES))) return rc;
+    // activations of padding rows / the padding tile of an odd batch are read by the MMAs (results
+    // discarded): keep them finite
+    DSP_CUDA(cudaMemset(s->ybuf[0], 0, per_tile_t * 8));
+    DSP_CUDA(cudaMemset(s->ybuf[1], 0, per_tile_t * 8));
+    DSP_CUDA(cudaMemset(s->comb_img, 0, per_tile_t * 4));
+    DSP_CUDA(cudaMemset(s->hfin_img, 0, (size_t)s->tiles * 2 * (2 * c.hidden_size / 64) * SLAB_BYTES));
     s->tc_head = c.num_classes <= HEAD_MAX_CLASSES;
     return DSP_OK;
 }
@@ -734,22 +805,31 @@ int tc_pack_lstm_layer(Model* m, LstmLayer& L,
     s->lstm_packs.push_back(pk);
     pk->KSX = KSX;
     pk->xk16 = (K + 15) / 16;
-    std::vector<uint8_t> img((size_t)2 * NCH * KS * SLAB_BYTES, 0);
+    const size_t per_rank = (size_t)NCH * KS;                       // half slabs per (dir, rank)
+    std::vector<uint8_t> img((size_t)2 * 2 * per_rank * HSLAB_BYTES, 0);
     std::vector<float> bias((size_t)2 * NCH * 128);
     const float* wih[2] = {wih0, wih1}; const float* whh[2] = {whh0, whh1};
     const float* bih[2] = {bih0, bih1}; const float* bhh[2] = {bhh0, bhh1};
     for (int d = 0; d < 2; ++d)
-        for (int ch = 0; ch < NCH; ++ch)
-            for (int col = 0; col < 128; ++col) {
-                const int half = col >> 6, j = (col & 63) >> 2, g = col & 3;
-                const int unit = ch * 32 + half * 16 + j;
+        for (int ch = 0; ch < NCH; ++ch) {
+            // stream order of a chunk pair (c, c+1): X(c) X(c+1) H(c) H(c+1)
+            const size_t pair_base = (size_t)(ch >> 1) * 2 * KS;
+            const size_t sx = pair_base + (size_t)(ch & 1) * KSX, sh = pair_base + 2 * KSX + (size_t)(ch & 1) * KSH;
+            for (int n = 0; n < 128; ++n) {
+                // column n of the chunk: unit pair (n >> 3), gate (n >> 1) & 3, unit parity n & 1
+                const int g = (n >> 1) & 3;
+                const int unit = ch * 32 + (n >> 3) * 2 + (n & 1);
                 const int wrow = g * H + unit;                      // torch gate blocks i,f,g,o
-                bias[((size_t)d * NCH + ch) * 128 + col] = bih[d][wrow] + bhh[d][wrow];
+                // sigmoid(z) = 1/(1 + 2^(-log2e z)), tanh(z) = (1 - 2^(-2 log2e z))/(1 + 2^(-2 log2e z))
+                const float scale = (g == 2) ? -2.f * LOG2E : -LOG2E;
+                const size_t rank_base = ((size_t)d * 2 + (n >> 6)) * per_rank;
+                bias[((size_t)d * NCH + ch) * 128 + n] = scale * (bih[d][wrow] + bhh[d][wrow]);
                 for (int k = 0; k < K; ++k)
-                    put_half(img, ((size_t)d * NCH + ch) * KS + (k >> 6), col, k & 63, wih[d][(size_t)wrow * K + k]);
+                    put_half(img, rank_base, sx + (k >> 6), n, k & 63, scale * wih[d][(size_t)wrow * K + k]);
                 for (int k = 0; k < H; ++k)
-                    put_half(img, ((size_t)d * NCH + ch) * KS + KSX + (k >> 6), col, k & 63, whh[d][(size_t)wrow * H + k]);
+                    put_half(img, rank_base, sh + (k >> 6), n, k & 63, scale * whh[d][(size_t)wrow * H + k]);
             }
+        }
     int rc;
     if ((rc = tc_alloc(m, (void**)&pk->w_img, img.size()))) return rc;
     if ((rc = tc_alloc(m, (void**)&pk->bias, bias.size() * sizeof(float)))) return rc;
@@ -768,10 +848,11 @@ int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b) {
     TcDensePack* pk = new TcDensePack();
     s->dense_packs.push_back(pk);
     pk->KS = KS;
-    std::vector<uint8_t> img((size_t)NCH * KS * SLAB_BYTES, 0);
+    const size_t per_rank = (size_t)NCH * KS;
+    std::vector<uint8_t> img((size_t)2 * per_rank * HSLAB_BYTES, 0);
     for (int n = 0; n < D.J; ++n)
         for (int k = 0; k < D.K; ++k)
-            put_half(img, (size_t)(n >> 7) * KS + (k >> 6), n & 127, k & 63, w[(size_t)n * D.K + k]);
+            put_half(img, (size_t)((n >> 6) & 1) * per_rank, (size_t)(n >> 7) * KS + (k >> 6), n & 127, k & 63, w[(size_t)n * D.K + k]);
     int rc;
     if ((rc = tc_alloc(m, (void**)&pk->w_img, img.size()))) return rc;
     if ((rc = tc_alloc(m, (void**)&pk->bias, sizeof(float) * D.J))) return rc;
@@ -781,7 +862,7 @@ int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b) {
     return DSP_OK;
 }
 
-// fc1 for the head: three weight images [W_hi, W_hi, W_lo] matching the activation passes
+// fc1 for the head: three weight passes [W_hi, W_hi, W_lo] matching the activation passes
 // [h_hi, h_lo, h_hi]: (h_hi + h_lo)(W_hi + W_lo) without the lo*lo term, i.e. fc1 to ~fp32 accuracy
 // on the FP16 tensor pipe.
 int tc_pack_head(Model* m, DenseF32& D, const float* w, const float* b) {
@@ -792,15 +873,17 @@ int tc_pack_head(Model* m, DenseF32& D, const float* w, const float* b) {
     s->dense_packs.push_back(pk);
     s->head_pack = pk;
     pk->KS = KS;
-    std::vector<uint8_t> img((size_t)3 * NCH * KS * SLAB_BYTES, 0);
+    const size_t per_pass = (size_t)NCH * KS, per_rank = 3 * per_pass;
+    std::vector<uint8_t> img((size_t)2 * per_rank * HSLAB_BYTES, 0);
     for (int n = 0; n < D.J; ++n)
         for (int k = 0; k < D.K; ++k) {
             const float wv = w[(size_t)n * D.K + k];
             const float hi = __half2float(__float2half_rn(wv));
+            const size_t rank_base = (size_t)((n >> 6) & 1) * per_rank;
             const size_t slab = (size_t)(n >> 7) * KS + (k >> 6);
-            put_half(img, (size_t)0 * NCH * KS + slab, n & 127, k & 63, hi);
-            put_half(img, (size_t)1 * NCH * KS + slab, n & 127, k & 63, hi);
-            put_half(img, (size_t)2 * NCH * KS + slab, n & 127, k & 63, wv - hi);
+            put_half(img, rank_base, 0 * per_pass + slab, n & 127, k & 63, hi);
+            put_half(img, rank_base, 1 * per_pass + slab, n & 127, k & 63, hi);
+            put_half(img, rank_base, 2 * per_pass + slab, n & 127, k & 63, wv - hi);
         }
     int rc;
     if ((rc = tc_alloc(m, (void**)&pk->w_img, img.size()))) return rc;
@@ -819,7 +902,7 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
     TcState* s = (TcState*)m->tc_state;
     const dsp_config& c = m->cfg;
     const int T = c.seq_len, H = c.hidden_size;
-    const int64_t tiles = (n + TILE - 1) / TILE;
+    const int64_t tiles = ((n + TILE - 1) / TILE + 1) / 2 * 2;     // whole CTA pairs; padding rows are zero-filled
     const bool seq = c.module != DSP_SIGNAL_BILSTM, sig = c.module != DSP_SEQ_BILSTM;
     {
         Span sp(m, 0, st);

@@ -171,6 +171,87 @@ __device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t cta_
                  ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC execute one MMA of M = 256 ---------
+// Each CTA contributes its own 128 A rows (shared memory or TMEM, same offsets in both CTAs) and
+// HALF of the B rows (N/2 each, same shared-memory offset in both CTAs); each CTA receives its
+// 128 accumulator rows x N columns in its own TMEM.  Only the leader CTA (cluster rank 0) issues.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int ACCUM>
+__device__ __forceinline__ void mma2_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+        "mov.b64 da, {%1, %4};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(SMEM_DESC_HI), "n"(ACCUM) : "memory");
+}
+template <int ACCUM>
+__device__ __forceinline__ void mma2_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(SMEM_DESC_HI), "n"(ACCUM) : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on the barrier at this
+// shared-memory offset in every CTA of cta_mask
+__device__ __forceinline__ void mma2_commit(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// address of the same shared-memory location in another CTA of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+// arrive on a barrier that may live in another CTA (address from mapa_u32)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier whose arrivals may come from another CTA of the cluster.  What these
+// barriers order is tensor-memory and async-proxy traffic (fenced with tcgen05.fence / completed
+// through the barrier itself), not generic-proxy stores, so CTA-scope semantics suffice and no
+// cluster-scope MEMBAR lands in the hot loops.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+
+__device__ __forceinline__ float4 lds128(uint32_t smem_addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+    return v;
+}
+
+// ---- packed fp32 pairs (FADD2 / FMUL2 / FFMA2): one issue slot for two lanes of work ----------------
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
 // ---- TMEM <-> registers (32 lanes x 32-bit, N consecutive columns per thread) -----------------------
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
