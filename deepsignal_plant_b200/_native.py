@@ -9,12 +9,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsp_b200.so")
+LIB_PATH = os.environ.get("DSP_B200_LIB") or os.path.join(_HERE, "libdsp_b200.so")
 
 # every symbol include/dsp_b200.h declares (tests check the export list against this)
 SYMBOLS = (
     "dsp_abi_version", "dsp_last_error", "dsp_create", "dsp_destroy", "dsp_set_param",
-    "dsp_pack_weights", "dsp_forward", "dsp_forward_host", "dsp_launch_count",
+    "dsp_pack_weights", "dsp_forward", "dsp_forward_host", "dsp_forward_host_submit",
+    "dsp_forward_host_wait", "dsp_launch_count",
     "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate", "dsp_selftest",
 )
 
@@ -55,6 +56,8 @@ def lib():
     L.dsp_pack_weights.argtypes = [vp]
     L.dsp_forward.argtypes = [vp, fp, fp, fp, fp, fp, C.POINTER(vp), u64, i64, fp, fp, vp, vp]
     L.dsp_forward_host.argtypes = [vp, fp, fp, fp, fp, fp, u64, i64, fp, fp, vp]
+    L.dsp_forward_host_submit.argtypes = [vp, fp, fp, fp, fp, fp, u64, i64, fp, fp, vp, C.POINTER(i64)]
+    L.dsp_forward_host_wait.argtypes = [vp, i64]
     L.dsp_launch_count.argtypes = [vp]
     L.dsp_launch_count.restype = i64
     L.dsp_set_timing.argtypes = [vp, C.c_int]

@@ -16,7 +16,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libdsp_b200.so")
+# experiment builds: DSP_B200_VARIANT=name DSP_B200_DEFINES="-DX=1 ..." -> libdsp_b200_name.so
+# (selected at run time with DSP_B200_LIB=/path/to/libdsp_b200_name.so)
+VARIANT = os.environ.get("DSP_B200_VARIANT", "")
+EXTRA = os.environ.get("DSP_B200_DEFINES", "").split()
+OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libdsp_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
@@ -32,7 +37,7 @@ def _digest(paths):
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(p.encode() + b"\0" + f.read())
-    h.update(" ".join(ARCH + FLAGS).encode())
+    h.update(" ".join(ARCH + FLAGS + EXTRA).encode())
     return h.hexdigest()
 
 
@@ -48,7 +53,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + ARCH + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [NVCC] + ARCH + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

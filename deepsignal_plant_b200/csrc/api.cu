@@ -264,6 +264,7 @@ int dsp_create(dsp_handle* out, const dsp_config* cfg) {
     else { m->nhid_signal = H; }
     m->kseq = (cfg->is_base ? cfg->embedding_size : 0) + (cfg->is_signallen ? 3 : 2);
     m->cap = cfg->max_batch;
+    m->n_sm = prop.multiProcessorCount;
     const int T = cfg->seq_len;
     int rc = DSP_OK;
     StateGroup grp[3];
@@ -292,7 +293,7 @@ int dsp_destroy(dsp_handle h) {
     cudaDeviceSynchronize();
     tc_destroy(m);
     for (void* p : m->device_allocs) cudaFree(p);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Model::NBUF; ++i) {
         if (m->pinned_in[i]) cudaFreeHost(m->pinned_in[i]);
         if (m->pinned_out[i]) cudaFreeHost(m->pinned_out[i]);
         if (m->dev_in[i]) cudaFree(m->dev_in[i]);
@@ -300,6 +301,7 @@ int dsp_destroy(dsp_handle h) {
         if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
         if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
     }
+    for (int i = 0; i < Model::NTICKET; ++i) if (m->ev_ticket[i]) cudaEventDestroy(m->ev_ticket[i]);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->compute_stream) cudaStreamDestroy(m->compute_stream);
     for (cudaEvent_t e : m->event_pool) cudaEventDestroy(e);
@@ -392,68 +394,88 @@ int dsp_forward(dsp_handle h, const float* kmer, const float* base_means, const 
     return DSP_OK;
 }
 
-int dsp_forward_host(dsp_handle h, const float* kmer, const float* base_means, const float* base_stds,
-                     const float* base_signal_lens, const float* signals, uint64_t seed, int64_t n,
-                     float* logits, float* probs, int32_t* labels) {
-    DSP_REQUIRE(h, DSP_ERR_INVALID, "dsp_forward_host: null handle");
-    Model* m = h;
-    DSP_REQUIRE(m->packed, DSP_ERR_STATE, "dsp_forward_host: weights not packed");
-    DSP_REQUIRE(n >= 0, DSP_ERR_INVALID, "dsp_forward_host: negative batch");
-    if (n == 0) return DSP_OK;
-    DSP_REQUIRE(logits && probs, DSP_ERR_INVALID, "dsp_forward_host: null output pointer");
-    if (has_seq(m)) DSP_REQUIRE(kmer && base_means && base_stds && base_signal_lens, DSP_ERR_INVALID,
-                                "dsp_forward_host: sequence features are required for this module");
-    if (has_signal(m)) DSP_REQUIRE(signals, DSP_ERR_INVALID, "dsp_forward_host: signals are required for this module");
-    DeviceGuard guard(m->cfg.device);
+// Host-buffer path.  The batch is cut into chunks of host_chunk sites (two full waves of CTA
+// pairs); chunk i+1 crosses PCIe on the copy stream while chunk i computes, through a ring of
+// NBUF device buffers that is carried across calls, so that back-to-back submissions overlap too.
+// Pinned (device-accessible) caller memory is copied from / to directly; pageable memory is staged
+// through pinned buffers of the library (synchronous entry point only).
+static int host_setup(Model* m) {
+    if (m->copy_stream) return DSP_OK;
     const dsp_config& c = m->cfg;
     const int T = c.seq_len, S = c.signal_len, C = c.num_classes;
-    const int64_t cap = m->cap;
-    // per-site float counts of the staged sections
+    const int64_t two_waves = (int64_t)m->n_sm * 128;
+    m->host_chunk = m->cap < two_waves ? m->cap : two_waves;
     const int64_t f_seq = has_seq(m) ? 4 * T : 0, f_sig = has_signal(m) ? (int64_t)T * S : 0;
-    const size_t in_bytes = sizeof(float) * cap * (f_seq + f_sig);
-    const size_t out_bytes = cap * (sizeof(float) * 2 * C + sizeof(int32_t));
-    if (!m->copy_stream) {
-        DSP_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-        DSP_CUDA(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            DSP_CUDA(cudaMallocHost(&m->pinned_in[i], in_bytes));
-            DSP_CUDA(cudaMallocHost(&m->pinned_out[i], out_bytes));
-            DSP_CUDA(cudaMalloc(&m->dev_in[i], in_bytes));
-            DSP_CUDA(cudaMalloc(&m->dev_out[i], out_bytes));
-            DSP_CUDA(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
-            DSP_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
-        }
+    const size_t in_bytes = sizeof(float) * m->host_chunk * (f_seq + f_sig);
+    const size_t out_bytes = m->host_chunk * (sizeof(float) * 2 * C + sizeof(int32_t));
+    DSP_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    DSP_CUDA(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < Model::NBUF; ++i) {
+        DSP_CUDA(cudaMalloc(&m->dev_in[i], in_bytes));
+        DSP_CUDA(cudaMalloc(&m->dev_out[i], out_bytes));
+        DSP_CUDA(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+        DSP_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
     }
-    const bool direct = (!has_seq(m) || (is_device_accessible_host(kmer) && is_device_accessible_host(base_means) &&
-                                         is_device_accessible_host(base_stds) && is_device_accessible_host(base_signal_lens))) &&
-                        (!has_signal(m) || is_device_accessible_host(signals));
+    for (int i = 0; i < Model::NTICKET; ++i) DSP_CUDA(cudaEventCreateWithFlags(&m->ev_ticket[i], cudaEventDisableTiming));
+    return DSP_OK;
+}
+
+static int host_check_args(Model* m, const char* who, const float* kmer, const float* base_means, const float* base_stds,
+                           const float* base_signal_lens, const float* signals, int64_t n, float* logits, float* probs) {
+    DSP_REQUIRE(m->packed, DSP_ERR_STATE, "%s: weights not packed", who);
+    DSP_REQUIRE(n >= 0, DSP_ERR_INVALID, "%s: negative batch", who);
+    if (n == 0) return DSP_OK;
+    DSP_REQUIRE(logits && probs, DSP_ERR_INVALID, "%s: null output pointer", who);
+    if (has_seq(m)) DSP_REQUIRE(kmer && base_means && base_stds && base_signal_lens, DSP_ERR_INVALID,
+                                "%s: sequence features are required for this module", who);
+    if (has_signal(m)) DSP_REQUIRE(signals, DSP_ERR_INVALID, "%s: signals are required for this module", who);
+    return DSP_OK;
+}
+
+// enqueue all chunks of one batch; blocking == false requires direct (pinned) inputs and outputs
+static int host_enqueue(Model* m, const float* kmer, const float* base_means, const float* base_stds,
+                        const float* base_signal_lens, const float* signals, uint64_t seed, int64_t n,
+                        float* logits, float* probs, int32_t* labels, bool direct_in, bool direct_out) {
+    const dsp_config& c = m->cfg;
+    const int T = c.seq_len, S = c.signal_len, C = c.num_classes;
+    const int64_t hc = m->host_chunk;
+    const int64_t f_seq = has_seq(m) ? 4 * T : 0, f_sig = has_signal(m) ? (int64_t)T * S : 0;
+    const size_t in_bytes = sizeof(float) * hc * (f_seq + f_sig);
+    const size_t out_bytes = hc * (sizeof(float) * 2 * C + sizeof(int32_t));
     if (m->timing) { m->spans.clear(); m->event_next = 0; }
-    const int64_t nchunks = (n + cap - 1) / cap;
-    auto drain = [&](int64_t ci) -> int {   // copy results of chunk ci to the caller
-        const int b = (int)(ci & 1);
-        const int64_t s = ci * cap, cn = (n - s < cap) ? (n - s) : cap;
-        DSP_CUDA(cudaEventSynchronize(m->ev_done[b]));
-        const char* po = (const char*)m->pinned_out[b];
-        memcpy(logits + s * C, po, sizeof(float) * cn * C);
-        memcpy(probs + s * C, po + sizeof(float) * cap * C, sizeof(float) * cn * C);
-        if (labels) memcpy(labels + s, po + sizeof(float) * cap * 2 * C, sizeof(int32_t) * cn);
+    const int64_t nchunks = (n + hc - 1) / hc;
+    struct Pending { int64_t s, cn; int b; bool live; } pend[Model::NBUF] = {};
+    auto drain = [&](Pending& pd) -> int {       // staged results of one chunk -> caller memory
+        if (!pd.live) return DSP_OK;
+        DSP_CUDA(cudaEventSynchronize(m->ev_done[pd.b]));
+        const char* po = (const char*)m->pinned_out[pd.b];
+        memcpy(logits + pd.s * C, po, sizeof(float) * pd.cn * C);
+        memcpy(probs + pd.s * C, po + sizeof(float) * hc * C, sizeof(float) * pd.cn * C);
+        if (labels) memcpy(labels + pd.s, po + sizeof(float) * hc * 2 * C, sizeof(int32_t) * pd.cn);
+        pd.live = false;
         return DSP_OK;
     };
     for (int64_t ci = 0; ci < nchunks; ++ci) {
-        const int b = (int)(ci & 1);
-        const int64_t s = ci * cap, cn = (n - s < cap) ? (n - s) : cap;
-        if (ci >= 2) { int rc = drain(ci - 2); if (rc) return rc; }
+        const int b = (int)(m->host_chunks_enqueued++ % Model::NBUF);
+        const int64_t s = ci * hc, cn = (n - s < hc) ? (n - s) : hc;
+        if (!direct_out) { int rc = drain(pend[b]); if (rc) return rc; }
+        // the device buffers of slot b are free once the chunk that used them last has finished
+        DSP_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_done[b], 0));
         float* din = (float*)m->dev_in[b];
-        float* d_kmer = din, *d_means = din + cap * T, *d_stds = din + 2 * cap * T, *d_lens = din + 3 * cap * T;
-        float* d_sig = din + cap * f_seq;
+        float* d_kmer = din, *d_means = din + hc * T, *d_stds = din + 2 * hc * T, *d_lens = din + 3 * hc * T;
+        float* d_sig = din + hc * f_seq;
         const float* src[5] = {kmer, base_means, base_stds, base_signal_lens, signals};
         float* dst[5] = {d_kmer, d_means, d_stds, d_lens, d_sig};
         const int64_t per[5] = {T, T, T, T, (int64_t)T * S};
+        if (!direct_in) {
+            if (!m->pinned_in[b]) DSP_CUDA(cudaMallocHost(&m->pinned_in[b], in_bytes));
+            DSP_CUDA(cudaEventSynchronize(m->ev_h2d[b]));          // previous copy out of this staging buffer is done
+        }
         for (int a = 0; a < 5; ++a) {
             const bool used = (a < 4) ? has_seq(m) : has_signal(m);
             if (!used) continue;
             const float* from = src[a] + s * per[a];
-            if (!direct) {
+            if (!direct_in) {
                 float* stage = (float*)m->pinned_in[b] + (dst[a] - din);
                 memcpy(stage, from, sizeof(float) * cn * per[a]);
                 from = stage;
@@ -464,15 +486,82 @@ int dsp_forward_host(dsp_handle h, const float* kmer, const float* base_means, c
         DSP_CUDA(cudaStreamWaitEvent(m->compute_stream, m->ev_h2d[b], 0));
         char* dout = (char*)m->dev_out[b];
         float* d_logits = (float*)dout;
-        float* d_probs = (float*)(dout + sizeof(float) * cap * C);
-        int32_t* d_labels = (int32_t*)(dout + sizeof(float) * cap * 2 * C);
+        float* d_probs = (float*)(dout + sizeof(float) * hc * C);
+        int32_t* d_labels = (int32_t*)(dout + sizeof(float) * hc * 2 * C);
         int rc = forward_chunk(m, d_kmer, d_means, d_stds, d_lens, d_sig, nullptr, nullptr, seed, (uint64_t)ci, cn,
                                d_logits, d_probs, d_labels, m->compute_stream);
         if (rc) return rc;
-        DSP_CUDA(cudaMemcpyAsync(m->pinned_out[b], dout, out_bytes, cudaMemcpyDeviceToHost, m->compute_stream));
+        if (direct_out) {
+            DSP_CUDA(cudaMemcpyAsync(logits + s * C, d_logits, sizeof(float) * cn * C, cudaMemcpyDeviceToHost, m->compute_stream));
+            DSP_CUDA(cudaMemcpyAsync(probs + s * C, d_probs, sizeof(float) * cn * C, cudaMemcpyDeviceToHost, m->compute_stream));
+            if (labels) DSP_CUDA(cudaMemcpyAsync(labels + s, d_labels, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, m->compute_stream));
+        } else {
+            if (!m->pinned_out[b]) DSP_CUDA(cudaMallocHost(&m->pinned_out[b], out_bytes));
+            DSP_CUDA(cudaMemcpyAsync(m->pinned_out[b], dout, out_bytes, cudaMemcpyDeviceToHost, m->compute_stream));
+            pend[b] = {s, cn, b, true};
+        }
         DSP_CUDA(cudaEventRecord(m->ev_done[b], m->compute_stream));
     }
-    for (int64_t ci = (nchunks >= 2 ? nchunks - 2 : 0); ci < nchunks; ++ci) { int rc = drain(ci); if (rc) return rc; }
+    if (!direct_out) for (int b = 0; b < Model::NBUF; ++b) { int rc = drain(pend[b]); if (rc) return rc; }
+    return DSP_OK;
+}
+
+int dsp_forward_host(dsp_handle h, const float* kmer, const float* base_means, const float* base_stds,
+                     const float* base_signal_lens, const float* signals, uint64_t seed, int64_t n,
+                     float* logits, float* probs, int32_t* labels) {
+    DSP_REQUIRE(h, DSP_ERR_INVALID, "dsp_forward_host: null handle");
+    Model* m = h;
+    int rc = host_check_args(m, "dsp_forward_host", kmer, base_means, base_stds, base_signal_lens, signals, n, logits, probs);
+    if (rc || n == 0) return rc;
+    DeviceGuard guard(m->cfg.device);
+    if ((rc = host_setup(m))) return rc;
+    const bool direct_in = (!has_seq(m) || (is_device_accessible_host(kmer) && is_device_accessible_host(base_means) &&
+                                            is_device_accessible_host(base_stds) && is_device_accessible_host(base_signal_lens))) &&
+                           (!has_signal(m) || is_device_accessible_host(signals));
+    const bool direct_out = is_device_accessible_host(logits) && is_device_accessible_host(probs) &&
+                            (!labels || is_device_accessible_host(labels));
+    if ((rc = host_enqueue(m, kmer, base_means, base_stds, base_signal_lens, signals, seed, n, logits, probs, labels,
+                           direct_in, direct_out))) return rc;
+    DSP_CUDA(cudaStreamSynchronize(m->compute_stream));
+    return DSP_OK;
+}
+
+int dsp_forward_host_submit(dsp_handle h, const float* kmer, const float* base_means, const float* base_stds,
+                            const float* base_signal_lens, const float* signals, uint64_t seed, int64_t n,
+                            float* logits, float* probs, int32_t* labels, int64_t* ticket) {
+    DSP_REQUIRE(h && ticket, DSP_ERR_INVALID, "dsp_forward_host_submit: null argument");
+    Model* m = h;
+    int rc = host_check_args(m, "dsp_forward_host_submit", kmer, base_means, base_stds, base_signal_lens, signals, n, logits, probs);
+    if (rc) return rc;
+    DeviceGuard guard(m->cfg.device);
+    if ((rc = host_setup(m))) return rc;
+    const bool direct = (!has_seq(m) || (is_device_accessible_host(kmer) && is_device_accessible_host(base_means) &&
+                                         is_device_accessible_host(base_stds) && is_device_accessible_host(base_signal_lens))) &&
+                        (!has_signal(m) || is_device_accessible_host(signals)) &&
+                        (n == 0 || (is_device_accessible_host(logits) && is_device_accessible_host(probs) &&
+                                    (!labels || is_device_accessible_host(labels))));
+    DSP_REQUIRE(direct, DSP_ERR_INVALID,
+                "dsp_forward_host_submit: every host buffer must be page-locked (cudaHostAlloc / cudaHostRegister / "
+                "torch pin_memory); use dsp_forward_host for pageable memory");
+    if (n > 0 && (rc = host_enqueue(m, kmer, base_means, base_stds, base_signal_lens, signals, seed, n, logits, probs, labels,
+                                    true, true))) return rc;
+    const uint64_t t = m->tickets_issued++;
+    DSP_CUDA(cudaEventRecord(m->ev_ticket[t % Model::NTICKET], m->compute_stream));
+    *ticket = (int64_t)t;
+    return DSP_OK;
+}
+
+int dsp_forward_host_wait(dsp_handle h, int64_t ticket) {
+    DSP_REQUIRE(h, DSP_ERR_INVALID, "dsp_forward_host_wait: null handle");
+    Model* m = h;
+    DSP_REQUIRE(ticket >= 0 && (uint64_t)ticket < m->tickets_issued, DSP_ERR_INVALID, "dsp_forward_host_wait: unknown ticket");
+    DeviceGuard guard(m->cfg.device);
+    if ((uint64_t)ticket + Model::NTICKET <= m->tickets_issued) {
+        // its event slot was re-used by a later submission on the same stream: that one finishing implies this one did
+        DSP_CUDA(cudaEventSynchronize(m->ev_ticket[(m->tickets_issued - 1) % Model::NTICKET]));
+        return DSP_OK;
+    }
+    DSP_CUDA(cudaEventSynchronize(m->ev_ticket[(uint64_t)ticket % Model::NTICKET]));
     return DSP_OK;
 }
 

@@ -84,12 +84,18 @@ struct Model {
 
     // host staging for dsp_forward_host
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
-    void* pinned_in[2] = {nullptr, nullptr};
-    void* pinned_out[2] = {nullptr, nullptr};
-    void* dev_in[2] = {nullptr, nullptr};
-    void* dev_out[2] = {nullptr, nullptr};
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    int64_t host_chunk = 0;
+    static constexpr int NBUF = 3;          // chunks in flight: copy in / compute / copy out
+    static constexpr int NTICKET = 8;
+    void* pinned_in[NBUF] = {};             // staging for pageable caller memory (lazily allocated)
+    void* pinned_out[NBUF] = {};
+    void* dev_in[NBUF] = {};
+    void* dev_out[NBUF] = {};
+    cudaEvent_t ev_h2d[NBUF] = {}, ev_done[NBUF] = {};
+    cudaEvent_t ev_ticket[NTICKET] = {};
+    int64_t host_chunk = 0;                 // sites per staged chunk (two full waves of CTA pairs)
+    uint64_t host_chunks_enqueued = 0;      // buffer ring position, carried across calls
+    uint64_t tickets_issued = 0;
+    int n_sm = 0;
 
     int64_t launches = 0;
     bool timing = false;

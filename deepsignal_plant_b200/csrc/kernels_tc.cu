@@ -38,17 +38,21 @@ namespace {
 constexpr int TILE = 128;
 constexpr int SLAB_BYTES = TILE * SLAB_ROW_BYTES;   // 16 KB: one A-operand slab (128 site rows x 64 fp16)
 constexpr int HSLAB_BYTES = SLAB_BYTES / 2;         // 8 KB: one CTA's half (64 weight rows) of a B slab
-constexpr int NTHREADS = 384;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                        // 4 per scheduler: enough independent work to keep the MUFU pipe busy
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;      // warps 0-3: producers / MMA issuer / TMEM; 4-19: epilogue
+constexpr int CPT = 128 / (EPI_WARPS / 4);          // accumulator columns per epilogue thread per chunk (32)
+constexpr int UPT = CPT / 4;                        // hidden units per epilogue thread per chunk (8)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr uint16_t PAIR_MASK = 3;                   // both CTAs of the pair
 
 // Which of the five exponentials of an LSTM cell update are evaluated on the FMA pipe (degree-5
-// polynomial, ~2e-7 relative error, same class as ex2.approx) instead of the 16-lane MUFU pipe,
-// which would otherwise bound the epilogue: bit0 tanh(g), bit1 tanh(c), bit2 sigmoid(i),
-// bit3 sigmoid(f), bit4 sigmoid(o).
+// polynomial, ~2e-7 relative error, same class as ex2.approx) instead of the 16-lane MUFU pipe:
+// bit0 tanh(g), bit1 tanh(c), bit2 sigmoid(i), bit3 sigmoid(f), bit4 sigmoid(o).  With 16
+// epilogue warps the MUFU pipe keeps up with the tensor pipe, and the whole step is bound by the
+// 1 kW power cap, where one MUFU op costs less than the ~7 FMA-pipe instructions that replace
+// it (measured, profiles/r01_run8_epilogue_variants.log): default 0.
 #ifndef DSP_POLY_MASK
-#define DSP_POLY_MASK 3
+#define DSP_POLY_MASK 0
 #endif
 
 struct LayerParams {
@@ -82,9 +86,9 @@ struct LayerParams {
 enum { MODE_LSTM = 0, MODE_FC = 1, MODE_HEAD = 2 };
 constexpr int HEAD_MAX_CLASSES = 8;
 // weight ring: NST stages of STG half slabs (one mbarrier pair per stage)
-template <int KSX> struct RingCfg {
+template <int KSX, int MODE> struct RingCfg {
     static constexpr int STG = KSX >= 8 ? 2 : 4;
-    static constexpr int NST = KSX >= 8 ? 5 : 4;
+    static constexpr int NST = KSX >= 8 ? (MODE == 2 ? 4 : 5) : 4;
 };
 
 // Philox4x32-10 (Salmon et al., SC'11) + Box-Muller: four N(0,1) values per counter.  Used to
@@ -115,8 +119,8 @@ __device__ __forceinline__ float4 philox_normal4(uint32_t c0, uint32_t c1, uint3
 template <bool POLY, bool HI_CLAMP>
 __device__ __forceinline__ float2 exp2_pair(float2 x) {
     if constexpr (POLY) {
-        x.x = fmaxf(fminf(x.x, 60.f), -126.f);
-        x.y = fmaxf(fminf(x.y, 60.f), -126.f);
+        x.x = fmaxf(fminf(x.x, 40.f), -126.f);
+        x.y = fmaxf(fminf(x.y, 40.f), -126.f);
         const float MG = 12582912.f;                      // 1.5 * 2^23: x + MG holds round(x) in its low mantissa bits
         const float2 t = add2(x, make_float2(MG, MG));
         const float2 r = add2(t, make_float2(-MG, -MG));
@@ -130,7 +134,7 @@ __device__ __forceinline__ float2 exp2_pair(float2 x) {
         q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
         return q;
     } else {
-        if constexpr (HI_CLAMP) { x.x = fminf(x.x, 60.f); x.y = fminf(x.y, 60.f); }
+        if constexpr (HI_CLAMP) { x.x = fminf(x.x, 40.f); x.y = fminf(x.y, 40.f); }   // (1 + 2^40)^3 stays finite
         return make_float2(ex2_approx(x.x), ex2_approx(x.y));
     }
 }
@@ -142,16 +146,36 @@ __device__ __forceinline__ float2 exp2_pair(float2 x) {
 template <int PM>
 __device__ __forceinline__ void lstm_cell2(float2 ai, float2 af, float2 ag, float2 ao, float2& c, float2& h) {
     const float2 ONE = make_float2(1.f, 1.f), NEG1 = make_float2(-1.f, -1.f);
-    const float2 ei = exp2_pair<((PM >> 2) & 1) != 0, false>(ai);
-    const float2 ef = exp2_pair<((PM >> 3) & 1) != 0, false>(af);
+#ifdef DSP_EPI_STUB   // measurement build only: no transcendental work, just enough arithmetic to keep every input live
+    c = fma2(af, make_float2(1e-3f, 1e-3f), c);
+    h = fma2(add2(ai, add2(ag, ao)), make_float2(1e-2f, 1e-2f), mul2(c, make_float2(1e-3f, 1e-3f)));
+    return;
+#endif
+#ifdef DSP_MERGE_RCP
+    constexpr bool CLAMP_IF = true;
+#else
+    constexpr bool CLAMP_IF = false;
+#endif
+    const float2 ei = exp2_pair<((PM >> 2) & 1) != 0, CLAMP_IF>(ai);
+    const float2 ef = exp2_pair<((PM >> 3) & 1) != 0, CLAMP_IF>(af);
     const float2 eg = exp2_pair<(PM & 1) != 0, true>(ag);
     const float2 eo = exp2_pair<((PM >> 4) & 1) != 0, false>(ao);
+#ifdef DSP_MERGE_RCP
+    // c' = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ef)(1+ei)(1+eg)]: one reciprocal instead of two
+    // (needs bounded ei, ef: callers of this variant clamp them through HI_CLAMP below)
+    const float2 F = add2(ef, ONE);
+    const float2 AG = mul2(add2(ei, ONE), add2(eg, ONE));
+    const float2 num = fma2(c, AG, mul2(fma2(eg, NEG1, ONE), F));
+    const float2 den = mul2(F, AG);
+    const float2 cn = mul2(num, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+#else
     const float2 F = add2(ef, ONE);
     const float2 sf = make_float2(rcp_approx(F.x), rcp_approx(F.y));
     const float2 AG = mul2(add2(ei, ONE), add2(eg, ONE));
     const float2 rg = make_float2(rcp_approx(AG.x), rcp_approx(AG.y));
     const float2 ig = mul2(fma2(eg, NEG1, ONE), rg);                       // sigmoid(i) * tanh(g)
     const float2 cn = fma2(sf, c, ig);
+#endif
     c = cn;
     const float2 ec = exp2_pair<((PM >> 1) & 1) != 0, true>(mul2(cn, make_float2(-2.f * LOG2E, -2.f * LOG2E)));
     const float2 D = mul2(add2(eo, ONE), add2(ec, ONE));
@@ -178,7 +202,7 @@ __device__ __forceinline__ void lstm_cell2(float2 ai, float2 af, float2 ag, floa
 //   warp 1     leader: MMA issuer / peer: relay of its full-barriers to the leader
 //   warp 2     x_t slab producer (own tile)
 //   warp 3     TMEM allocation
-//   warps 4-11 epilogue, thread = (site row, 64-column half of the chunk)
+//   warps 4-19 epilogue, thread = (site row, 32-column slice of the chunk)
 // Per step and chunk pair (c, c+1) the issue order is X(c) X(c+1) H(c) H(c+1), X = x_t part
 // from shared memory into accumulator c&1, H = h_{t-1} part from TMEM, so that at a step
 // boundary two x parts cover the tail of the previous step's gate math.
@@ -186,7 +210,7 @@ template <int KSX, int H, int MODE, int NOUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 layer_kernel(const LayerParams p) {
     constexpr bool IS_FC = MODE != MODE_LSTM;              // no recurrence: x part only
-    constexpr int STG = RingCfg<KSX>::STG, NST = RingCfg<KSX>::NST;
+    constexpr int STG = RingCfg<KSX, MODE>::STG, NST = RingCfg<KSX, MODE>::NST;
     constexpr int NCH = IS_FC ? NOUT / 128 : H / 32;       // 128-column chunks per step
     constexpr int KSH = IS_FC ? 0 : H / 64;                // h slabs (K of the recurrent part)
     constexpr int KS = KSX + KSH;
@@ -195,6 +219,7 @@ layer_kernel(const LayerParams p) {
     constexpr uint32_t IDESC = make_idesc_f16(256, 128);
     static_assert(W_STEP % STG == 0, "a step must be a whole number of ring stages");
     static_assert(IS_FC || NCH % 2 == 0, "chunks are issued in pairs");
+    static_assert(EPI_WARPS == 16 && CPT == 32 && UPT == 8, "the epilogue code below is written for 32-column slices");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -232,7 +257,7 @@ layer_kernel(const LayerParams p) {
     const uint32_t t_h = tmem + 256;             // two h buffers of H/2 columns at +0 and +128
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp == 0) {
             // ---- weight producer: this CTA's half slabs, linear in stream order -----------------------
             if (elect_one()) {
@@ -368,10 +393,10 @@ layer_kernel(const LayerParams p) {
         }
     } else {
         // ---- epilogue warps: thread = site row ------------------------------------------------------
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int ew = warp - 4;
-        const int q = ew & 3;                        // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                    // which 64 of the chunk's 128 columns
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int sl = ew >> 2;                      // which CPT-column slice of the chunk's 128 columns
         const int row = q * 32 + lane;
         const int64_t site = (int64_t)tile * TILE + row;
         const bool valid = site < p.n;
@@ -380,13 +405,13 @@ layer_kernel(const LayerParams p) {
         const uint32_t r_accempty = mapa_u32(b_accempty, 0), r_hready = mapa_u32(b_hready, 0);
 
         for (int i = tid - 128; i < NBIAS; i += EPI_WARPS * 32) s_bias[i] = p.bias[(size_t)dir * NBIAS + i];
-        asm volatile("bar.sync 1, 256;" ::: "memory");           // the 8 epilogue warps only
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");           // the epilogue warps only
 
         if constexpr (MODE == MODE_HEAD) {
             // z = relu(fc1(x)); logits = fc2(z); probs = softmax(logits).  Each thread owns 64 of the
             // NOUT fc1 columns of its site per chunk and accumulates its share of the fc2 dot products;
             // the two column halves of a site meet through shared memory.
-            __shared__ float head_part[2][TILE][HEAD_MAX_CLASSES];
+            __shared__ float head_part[EPI_WARPS / 4][TILE][HEAD_MAX_CLASSES];
             const int C = p.num_classes;
             float part_sum[HEAD_MAX_CLASSES];
 #pragma unroll
@@ -396,25 +421,22 @@ layer_kernel(const LayerParams p) {
                 const uint32_t buf = (uint32_t)ch & 1u, use = (uint32_t)ch >> 1;
                 mbar_wait(b_accfull + 8 * buf, use & 1u);
                 tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(sl * CPT), v);
+                tmem_ld_wait();
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {
-                    uint32_t v[32];
-                    tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(half * 64 + part * 32), v);
-                    tmem_ld_wait();
+                for (int j = 0; j < 32; ++j) {
+                    const int col = ch * 128 + sl * CPT + j;
+                    const float z = fmaxf(__uint_as_float(v[j]) + s_bias[col], 0.f);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = ch * 128 + half * 64 + part * 32 + j;
-                        const float z = fmaxf(__uint_as_float(v[j]) + s_bias[col], 0.f);
-#pragma unroll
-                        for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc)
-                            if (cc < C) part_sum[cc] = fmaf(z, __ldg(p.w2t + (size_t)col * C + cc), part_sum[cc]);
-                    }
+                    for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc)
+                        if (cc < C) part_sum[cc] = fmaf(z, __ldg(p.w2t + (size_t)col * C + cc), part_sum[cc]);
                 }
             }
 #pragma unroll
-            for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc) head_part[half][row][cc] = part_sum[cc];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0 && valid) {
+            for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc) head_part[sl][row][cc] = part_sum[cc];
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            if (sl == 0 && valid) {
                 float lg[HEAD_MAX_CLASSES];
                 float mx = -3.0e38f;
                 int arg = 0;
@@ -422,7 +444,10 @@ layer_kernel(const LayerParams p) {
                 for (int cc = 0; cc < HEAD_MAX_CLASSES; ++cc) {
                     lg[cc] = 0.f;
                     if (cc < C) {
-                        lg[cc] = head_part[0][row][cc] + head_part[1][row][cc] + __ldg(p.b2 + cc);
+                        float a = __ldg(p.b2 + cc);
+#pragma unroll
+                        for (int s4 = 0; s4 < EPI_WARPS / 4; ++s4) a += head_part[s4][row][cc];
+                        lg[cc] = a;
                         if (lg[cc] > mx) { mx = lg[cc]; arg = cc; }
                     }
                 }
@@ -446,37 +471,31 @@ layer_kernel(const LayerParams p) {
                     const uint32_t buf = g & 1u, use = g >> 1;
                     mbar_wait(b_accfull + 8 * buf, use & 1u);
                     tc_fence_after();
-                    const int col0 = p.y_col_off + ch * 128 + half * 64;      // multiple of 64
+                    const int col0 = p.y_col_off + ch * 128 + sl * CPT;       // multiple of 32
                     uint8_t* yslab = ybase + (size_t)(col0 >> 6) * SLAB_BYTES + row * SLAB_ROW_BYTES;
+                    uint32_t v[32];
+                    tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(sl * CPT), v);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(r_accempty + 8 * buf);
+                    const float* bs = s_bias + ch * 128 + sl * CPT;
 #pragma unroll
-                    for (int part = 0; part < 2; ++part) {
-                        uint32_t v[32];
-                        tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(half * 64 + part * 32), v);
-                        tmem_ld_wait();
-                        if (part == 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(r_accempty + 8 * buf);
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = c8 * 8 + e * 2;
+                            const float a = fmaxf(__uint_as_float(v[j]) + bs[j], 0.f);
+                            const float b = fmaxf(__uint_as_float(v[j + 1]) + bs[j + 1], 0.f);
+                            o[e] = pack_half2(a, b);
                         }
-                        const float* bs = s_bias + ch * 128 + half * 64 + part * 32;
-#pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) {
-                            uint32_t o[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int j = c8 * 8 + e * 2;
-                                const float a = fmaxf(__uint_as_float(v[j]) + bs[j], 0.f);
-                                const float b = fmaxf(__uint_as_float(v[j + 1]) + bs[j + 1], 0.f);
-                                o[e] = pack_half2(a, b);
-                            }
-                            const int chunk = part * 4 + c8;
-                            *reinterpret_cast<uint4*>(yslab + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                        }
+                        const int chunk = ((col0 & 63) >> 3) + c8;
+                        *reinterpret_cast<uint4*>(yslab + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                     }
                 }
             }
         } else {
-            constexpr int UPT = 16;                   // hidden units per thread per chunk
             float2 c2[NCH][UPT / 2];                  // cell state, fp32, in registers for all T steps
             // initial states: c0 -> registers, h0 -> TMEM h buffer 0 (packed FP16 pairs)
             if (p.h0 == nullptr) {
@@ -485,10 +504,10 @@ layer_kernel(const LayerParams p) {
                 const uint64_t gs = (uint64_t)(p.site_base + site);
                 const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
                 const uint32_t slot0 = (p.rng_slot + (uint32_t)dir) << 16;
-                const uint32_t t_stage = t_acc + lane_addr + (uint32_t)(half * NCH * UPT);
+                const uint32_t t_stage = t_acc + lane_addr + (uint32_t)(sl * NCH * UPT);
 #pragma unroll 1
                 for (int i = 0; i < NCH * (UPT / 4); ++i) {
-                    const int unit = (i >> 2) * 32 + half * UPT + (i & 3) * 4;
+                    const int unit = (i / (UPT / 4)) * 32 + sl * UPT + (i % (UPT / 4)) * 4;
                     const uint32_t slot = slot0 | (uint32_t)(unit >> 2);
                     const float4 hq = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot, p.rng_call, k0, k1);
                     const float4 cv = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot | 0x8000u, p.rng_call, k0, k1);
@@ -499,8 +518,8 @@ layer_kernel(const LayerParams p) {
                 tmem_st_wait();
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
-                    uint32_t v[16];
-                    tmem_ld16(t_stage + (uint32_t)(ch * UPT), v);
+                    uint32_t v[8];
+                    tmem_ld8(t_stage + (uint32_t)(ch * UPT), v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < UPT / 2; ++j) c2[ch][j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
@@ -510,29 +529,23 @@ layer_kernel(const LayerParams p) {
                 const float* c0 = p.c0 + (size_t)dir * p.state_dir_stride + (size_t)site * H;
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
-                    const int u0 = ch * 32 + half * UPT;
-                    float hv[UPT];
-#pragma unroll
-                    for (int j4 = 0; j4 < UPT; j4 += 4) {
-                        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), hq = cv;
-                        if (valid) {
-                            cv = *reinterpret_cast<const float4*>(c0 + u0 + j4);
-                            hq = *reinterpret_cast<const float4*>(h0 + u0 + j4);
-                        }
-                        c2[ch][j4 / 2] = make_float2(cv.x, cv.y); c2[ch][j4 / 2 + 1] = make_float2(cv.z, cv.w);
-                        hv[j4] = hq.x; hv[j4 + 1] = hq.y; hv[j4 + 2] = hq.z; hv[j4 + 3] = hq.w;
+                    const int u0 = ch * 32 + sl * UPT;
+                    float4 cv0 = make_float4(0.f, 0.f, 0.f, 0.f), cv1 = cv0, hq0 = cv0, hq1 = cv0;
+                    if (valid) {
+                        cv0 = *reinterpret_cast<const float4*>(c0 + u0); cv1 = *reinterpret_cast<const float4*>(c0 + u0 + 4);
+                        hq0 = *reinterpret_cast<const float4*>(h0 + u0); hq1 = *reinterpret_cast<const float4*>(h0 + u0 + 4);
                     }
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = pack_half2(hv[2 * j], hv[2 * j + 1]);
-                    tmem_st8(t_h + lane_addr + (uint32_t)(u0 >> 1), pk);
+                    c2[ch][0] = make_float2(cv0.x, cv0.y); c2[ch][1] = make_float2(cv0.z, cv0.w);
+                    c2[ch][2] = make_float2(cv1.x, cv1.y); c2[ch][3] = make_float2(cv1.z, cv1.w);
+                    tmem_st4(t_h + lane_addr + (uint32_t)(u0 >> 1), pack_half2(hq0.x, hq0.y), pack_half2(hq0.z, hq0.w),
+                             pack_half2(hq1.x, hq1.y), pack_half2(hq1.z, hq1.w));
                 }
                 tmem_st_wait();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(r_hready);
-            const uint32_t s_bias_u32 = smem_u32(s_bias);
+            const uint32_t s_bias_u32 = smem_u32(s_bias) + (uint32_t)(sl * CPT * 4);
             for (int step = 0; step < T; ++step) {
                 const int t = dir ? (T - 1 - step) : step;
                 const bool last = (step == T - 1);
@@ -546,54 +559,52 @@ layer_kernel(const LayerParams p) {
                     const uint32_t use = (uint32_t)(step * (NCH / 2) + (ch >> 1));
                     mbar_wait(b_accfull + 8 * buf, use & 1u);
                     tc_fence_after();
-                    const int u0 = ch * 32 + half * UPT;
+                    const int u0 = ch * 32 + sl * UPT;
                     float2 h2[UPT / 2];
 #pragma unroll
-                    for (int part = 0; part < 2; ++part) {
-                        uint32_t v[32];
-                        tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(half * 64 + part * 32), v);
-                        // biases of this part's 8 units (warp-wide broadcast reads) while the TMEM load is in flight
-                        float4 bq[8];
+                    for (int part = 0; part < CPT / 16; ++part) {
+                        uint32_t v[16];
+                        tmem_ld16(t_acc + buf * 128u + lane_addr + (uint32_t)(sl * CPT + part * 16), v);
+                        // biases of this part's 4 units (warp-wide broadcast reads) while the TMEM load is in flight
+                        float4 bq[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) bq[i] = lds128(s_bias_u32 + (uint32_t)((ch * 128 + half * 64 + part * 32 + i * 4) * 4));
+                        for (int i = 0; i < 4; ++i) bq[i] = lds128(s_bias_u32 + (uint32_t)((ch * 128 + part * 16 + i * 4) * 4));
                         tmem_ld_wait();
-                        if (part == 1) {
+                        if (part == CPT / 16 - 1) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(r_accempty + 8 * buf);
                         }
 #pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
+                        for (int qq = 0; qq < 2; ++qq) {
                             // columns of one unit pair: i i' f f' g g' o o'
                             const float4 b0 = bq[2 * qq], b1 = bq[2 * qq + 1];
                             const float2 ai = add2(make_float2(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1])), make_float2(b0.x, b0.y));
                             const float2 af = add2(make_float2(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3])), make_float2(b0.z, b0.w));
                             const float2 ag = add2(make_float2(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5])), make_float2(b1.x, b1.y));
                             const float2 ao = add2(make_float2(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7])), make_float2(b1.z, b1.w));
-                            lstm_cell2<DSP_POLY_MASK>(ai, af, ag, ao, c2[ch][part * 4 + qq], h2[part * 4 + qq]);
+                            lstm_cell2<DSP_POLY_MASK>(ai, af, ag, ao, c2[ch][part * 2 + qq], h2[part * 2 + qq]);
                         }
                     }
-                    uint32_t pk[8];
+                    uint32_t pk[UPT / 2];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = pack_half2(h2[j].x, h2[j].y);
-                    tmem_st8(t_hnext + (uint32_t)(u0 >> 1), pk);
+                    for (int j = 0; j < UPT / 2; ++j) pk[j] = pack_half2(h2[j].x, h2[j].y);
+                    tmem_st4(t_hnext + (uint32_t)(u0 >> 1), pk[0], pk[1], pk[2], pk[3]);
                     if (do_write) {
-                        const int col = dir * H + u0;                          // multiple of 16
+                        const int col = dir * H + u0;                          // multiple of 8
                         uint8_t* yslab = ybase + (size_t)(col >> 6) * SLAB_BYTES;
                         const int chunk = (col & 63) >> 3;
                         *reinterpret_cast<uint4*>(yslab + (((chunk) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4*>(yslab + (((chunk + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         if (p.write_y == 2) {
                             // second image: FP16 residuals h - fp16(h), so the head sees h to ~22 bits
-                            uint32_t lo[8];
+                            uint32_t lo[UPT / 2];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
+                            for (int j = 0; j < UPT / 2; ++j) {
                                 const __half2 hh = *reinterpret_cast<const __half2*>(&pk[j]);
                                 lo[j] = pack_half2(h2[j].x - __low2float(hh), h2[j].y - __high2float(hh));
                             }
                             uint8_t* lslab = yslab + (size_t)p.y_slabs * SLAB_BYTES;
                             *reinterpret_cast<uint4*>(lslab + (((chunk) ^ (row & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                            *reinterpret_cast<uint4*>(lslab + (((chunk + 1) ^ (row & 7)) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                         }
                     }
                     if (last && p.hfinal != nullptr && valid) {
@@ -714,7 +725,7 @@ int tc_alloc(Model* m, void** p, size_t bytes) {
 template <int KSX, int H, int MODE, int NOUT>
 int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
     constexpr int NCH = MODE != MODE_LSTM ? NOUT / 128 : H / 32;
-    const size_t smem = (size_t)KSX * SLAB_BYTES + (size_t)RingCfg<KSX>::NST * RingCfg<KSX>::STG * HSLAB_BYTES
+    const size_t smem = (size_t)KSX * SLAB_BYTES + (size_t)RingCfg<KSX, MODE>::NST * RingCfg<KSX, MODE>::STG * HSLAB_BYTES
                         + (size_t)NCH * 128 * sizeof(float) + 1024;
     auto kern = layer_kernel<KSX, H, MODE, NOUT>;
     DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -270,5 +270,43 @@ class ModelBiLSTM(nn.Module):
                 logits.ctypes.data, probs.ctypes.data, labels.ctypes.data), "dsp_forward_host")
         return logits, probs, labels
 
+    # ---- streaming form of forward_host: page-locked buffers, submissions overlap ------------
+    def submit_host(self, kmer, base_means, base_stds, base_signal_lens, signals, logits, probs, labels=None):
+        """Enqueue one batch held in PAGE-LOCKED host memory (``torch`` tensors created with
+        ``pin_memory()``/``pin_memory=True``, float32 contiguous; ``labels`` int32) and return a
+        ticket immediately; ``logits``/``probs``/``labels`` (pinned outputs the caller owns) are
+        valid after ``wait_host(ticket)``.  Submissions run in order, and batch i+1's host->device
+        copies overlap batch i's kernels (``dsp_forward_host_submit``)."""
+        dev = self._param_device()
+        if dev.type != "cuda":
+            raise RuntimeError("ModelBiLSTM parameters are on %s; this implementation has no CPU fallback" % dev)
+        if self.training:
+            raise RuntimeError("inference only; call .eval()")
+        has_seq = self.module != "signal_bilstm"
+        has_sig = self.module != "seq_bilstm"
+
+        def chk(t, dtype):
+            if t is None:
+                return None
+            if not (torch.is_tensor(t) and t.device.type == "cpu" and t.is_pinned() and t.is_contiguous() and t.dtype == dtype):
+                raise ValueError("submit_host needs contiguous page-locked CPU tensors of dtype %s" % dtype)
+            return t.data_ptr()
+        n = (kmer if has_seq else signals).shape[0]
+        args = [chk(x, torch.float32) if used else None for x, used in
+                ((kmer, has_seq), (base_means, has_seq), (base_stds, has_seq), (base_signal_lens, has_seq), (signals, has_sig))]
+        if tuple(logits.shape) != (n, self.num_classes) or tuple(probs.shape) != (n, self.num_classes):
+            raise ValueError("output tensors must be (n, num_classes)")
+        outs = [chk(logits, torch.float32), chk(probs, torch.float32), chk(labels, torch.int32)]
+        ticket = C.c_int64(-1)
+        with torch.cuda.device(dev):
+            handle = self._ensure_handle(dev)
+            self._calls += 1
+            _native.check(_native.lib().dsp_forward_host_submit(
+                handle, *args, (self.seed << 20) + self._calls, n, *outs, C.byref(ticket)), "dsp_forward_host_submit")
+        return int(ticket.value)
+
+    def wait_host(self, ticket):
+        _native.check(_native.lib().dsp_forward_host_wait(self._handle, int(ticket)), "dsp_forward_host_wait")
+
     def launch_count(self):
         return int(_native.lib().dsp_launch_count(self._handle)) if self._handle else 0

@@ -115,6 +115,18 @@ int dsp_forward_host(dsp_handle h,
                      uint64_t seed, int64_t n,
                      float* logits, float* probs, int32_t* labels);
 
+/* Asynchronous form for page-locked caller memory (every input and output buffer pinned):
+ * submit enqueues the copies and kernels of one batch and returns a ticket at once; the
+ * outputs are valid after dsp_forward_host_wait(h, ticket).  Submissions run in order and
+ * overlap: batch i+1 crosses PCIe while batch i computes.  This is the streaming loop a
+ * call_mods worker runs over successive feature batches (call_modifications.py:232-249). */
+int dsp_forward_host_submit(dsp_handle h,
+                            const float* kmer, const float* base_means, const float* base_stds,
+                            const float* base_signal_lens, const float* signals,
+                            uint64_t seed, int64_t n,
+                            float* logits, float* probs, int32_t* labels, int64_t* ticket);
+int dsp_forward_host_wait(dsp_handle h, int64_t ticket);
+
 /* Number of kernels this library launched on behalf of `h` since creation. */
 int64_t dsp_launch_count(dsp_handle h);
 /* Milliseconds (CUDA events on the launching stream) spent in kernels of class `which`

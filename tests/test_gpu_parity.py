@@ -166,6 +166,36 @@ def test_forward_host_matches_device_path():
     np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-5)
 
 
+def test_streaming_host_api_pipelines_batches():
+    # submit_host / wait_host: pinned buffers in and out, several batches in flight, chunked staging
+    case = cases.slice_case(cases.load_case("both_13_16_s2"), 5000)
+    model = cases.build_model(case["entry"], precision="fp16", max_batch=2048).cuda(0)
+    f = case["feats"]
+    ins = [torch.from_numpy(f[k]).pin_memory() for k in cases.FEATURE_KEYS]
+    outs = [(torch.empty((5000, 2)).pin_memory(), torch.empty((5000, 2)).pin_memory(),
+             torch.empty((5000,), dtype=torch.int32).pin_memory()) for _ in range(3)]
+    tickets = [model.submit_host(*ins, *o) for o in outs]
+    for t in reversed(tickets):
+        model.wait_host(t)
+    for logits, probs, labels in outs:
+        p = probs.numpy()
+        assert np.isfinite(p).all() and np.abs(p - case["probs"]).max() < 0.05      # Philox states, not the golden ones
+        assert (labels.numpy() == p.argmax(1)).all()
+        np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
+    assert np.abs(outs[0][1].numpy() - outs[1][1].numpy()).max() > 1e-5            # fresh states per submission
+    with pytest.raises(ValueError, match="page-locked"):
+        model.submit_host(*(torch.from_numpy(f[k]) for k in cases.FEATURE_KEYS), *outs[0])
+
+
+def test_forward_host_pageable_and_ragged_chunks_fp16():
+    case = cases.slice_case(cases.load_case("both_13_16_s1"), 4500)
+    model = cases.build_model(case["entry"], precision="fp16", max_batch=1024).cuda(0)     # 5 staged chunks, last ragged
+    f = case["feats"]
+    logits, probs, labels = model.forward_host(*(f[k] for k in cases.FEATURE_KEYS))
+    assert np.isfinite(probs).all() and np.abs(probs - case["probs"]).max() < 0.05
+    assert (labels == probs.argmax(1)).all()
+
+
 def test_oracle_agrees_on_fresh_seed():
     # a case that is NOT in the fixtures: oracle and CUDA path on the same seeded inputs
     cfg = model_oracle.make_cfg(seq_len=11, signal_len=10, hidden_size=48, num_layers1=2)
