@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Multi-GPU call_freq check (launch under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tools/freq_multigpu_check.py --records 8000000
+
+Every rank takes a contiguous shard of the same seeded synthetic call records (file order =
+generation order), the shards are aggregated with one key-hash all-to-all over NCCL
+(call_mods_freq.aggregate_records_distributed) and rank 0 compares the merged table, bit for
+bit, with the single-GPU aggregation of all records.  Prints one JSON line on rank 0."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deepsignal_plant_b200 import call_mods_freq as cf  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--records", type=int, default=4_000_000)
+    ap.add_argument("--prob_cf", type=float, default=0.2)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rng = np.random.default_rng(7)
+    n = args.records
+    chrom = rng.integers(0, 5, n)
+    pos = rng.integers(0, max(n // 20, 1), n)            # coverage ~20 per site over 5 chromosomes
+    keys = cf.make_keys(chrom, pos)
+    p1 = np.round(rng.random(n), 6)
+    p0 = np.round(1.0 - p1, 6)
+    label = (p1 > p0).astype(np.int32)
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    gidx = np.arange(lo, hi, dtype=np.int64)
+    for it in range(2):                                   # first pass warms NCCL / CUB up
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = cf.aggregate_records_distributed(keys[lo:hi], p0[lo:hi], p1[lo:hi], label[lo:hi], gidx, args.prob_cf,
+                                               sort_by_key=True, device=local)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        want = cf._aggregate_device(keys, p0, p1, label, args.prob_cf, True, local)
+        k, first, s0, s1, met, unmet, cov = res
+        ok = (k.view(np.uint64) == want[0].view(np.uint64)).all() and (first == want[1]).all() \
+            and (s0.view(np.int64) == want[2].view(np.int64)).all() and (s1.view(np.int64) == want[3].view(np.int64)).all() \
+            and (met == want[4]).all() and (unmet == want[5]).all() and (cov == want[6]).all()
+        print(json.dumps({"check": "freq multi-GPU == single-GPU, bit for bit", "ok": bool(ok), "world": world,
+                          "records": n, "sites": int(len(k)), "seconds": float(tt[0]),
+                          "records_per_s": n / float(tt[0])}), flush=True)
+        if not ok:
+            sys.exit(1)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
