@@ -17,6 +17,7 @@ SYMBOLS = (
     "dsp_pack_weights", "dsp_forward", "dsp_forward_host", "dsp_forward_host_submit",
     "dsp_forward_host_wait", "dsp_launch_count",
     "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate", "dsp_selftest",
+    "dsp_parse_features", "dsp_format_calls",
 )
 
 MODULES = {"both_bilstm": 0, "seq_bilstm": 1, "signal_bilstm": 2}
@@ -65,6 +66,10 @@ def lib():
     L.dsp_freq_aggregate.argtypes = [C.c_int, vp, vp, vp, vp, i64, C.c_double, C.c_int,
                                      vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
     L.dsp_selftest.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    i32 = C.c_int32
+    L.dsp_parse_features.argtypes = [vp, i64, i32, i32, i32, i64, fp, fp, fp, fp, fp, vp, vp, vp, vp,
+                                     C.POINTER(i64), C.POINTER(i64), i32]
+    L.dsp_format_calls.argtypes = [vp, vp, vp, vp, i32, fp, vp, i64, vp, i64, C.POINTER(i64), i32]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here means header and library disagree
     _lib = L

@@ -11,6 +11,12 @@ operations, and the model call goes to the CUDA kernels of ``libdsp_b200``.
 """
 from __future__ import annotations
 
+import gzip
+import os
+import queue
+import threading
+import time
+
 import numpy as np
 import torch
 
@@ -109,3 +115,173 @@ def _call_mods(features_batch, model, batch_size, device=0):
         pred_str.extend(format_calls(sampleinfo[s:e], kmers_a[s:e], probs, predicted))
     accuracy = np.mean(accuracys) if len(accuracys) > 0 else 0
     return pred_str, accuracy, batch_num
+
+
+# ---- the call_mods pipeline over a feature file (call_modifications.py:195-282, 532-640) -----------
+
+def load_model(args, device=0):
+    """Model construction and checkpoint loading exactly as ``_call_mods_q`` does it
+    (``call_modifications.py:214-228``)."""
+    model = ModelBiLSTM(args.seq_len, args.signal_len, args.layernum1, args.layernum2, args.class_num,
+                        args.dropout_rate, args.hid_rnn,
+                        args.n_vocab, args.n_embed, str2bool(args.is_base), str2bool(args.is_signallen),
+                        module=args.model_type, device=device,
+                        max_batch=getattr(args, "max_batch", 65536))
+    para_dict = torch.load(args.model_path, map_location=torch.device("cpu"))
+    model_dict = model.state_dict()
+    model_dict.update(para_dict)
+    model.load_state_dict(model_dict)
+    del model_dict
+    if not torch.cuda.is_available():
+        raise RuntimeError("deepsignal_plant_b200 call_mods needs a CUDA device; there is no CPU path")
+    model = model.cuda(device)
+    model.eval()
+    return model
+
+
+def call_mods_stream(model, batches, write, depth=2):
+    """Drive the model over an iterable of ``feature_io.FeatureBatch`` (page-locked tensors):
+    batch i+1 is submitted before batch i is collected, so its host->device copies overlap
+    batch i's kernels; ``write(bytes)`` receives each batch's output lines in order.
+    Returns (sites, mean per-batch accuracy against the label column, batches) -- the
+    bookkeeping ``_call_mods_q`` keeps (``:230,255-257``)."""
+    from . import feature_io
+    C_ = model.num_classes
+    if C_ != 2:
+        raise ValueError("call_mods output format is defined for class_num == 2 (prob_0, prob_1)")
+    outs = []
+    inflight = []
+    sites, acc, nb = 0, [], 0
+
+    def collect():
+        nonlocal sites, nb
+        b, tk, (lg, pr, lb) = inflight.pop(0)
+        model.wait_host(tk)
+        probs, labels = pr[:b.n].numpy(), lb[:b.n].numpy()
+        write(feature_io.format_calls(b, probs, labels))
+        acc.append(float(np.mean(b.labels.numpy() == labels)))
+        sites += b.n
+        nb += 1
+        outs.append((lg, pr, lb))
+
+    for b in batches:
+        cap = b.kmer.shape[0]
+        slot = None
+        for i, o in enumerate(outs):
+            if o[0].shape[0] >= cap:
+                slot = outs.pop(i)
+                break
+        if slot is None:
+            slot = (torch.empty((cap, C_), dtype=torch.float32).pin_memory(),
+                    torch.empty((cap, C_), dtype=torch.float32).pin_memory(),
+                    torch.empty((cap,), dtype=torch.int32).pin_memory())
+        lg, pr, lb = slot
+        tk = model.submit_host(*b.arrays(), lg[:b.n], pr[:b.n], lb[:b.n])
+        inflight.append((b, tk, slot))
+        if len(inflight) >= depth:
+            collect()
+    while inflight:
+        collect()
+    return sites, (float(np.mean(acc)) if acc else 0.0), nb
+
+
+def _shard_of_file(path, rank, world):
+    """Contiguous byte shard of rank ``rank`` (lines that start inside it); ``None`` = whole file."""
+    if world <= 1:
+        return None
+    size = os.path.getsize(path)
+    return (size * rank // world, size * (rank + 1) // world)
+
+
+def call_mods(args):
+    """``call_modifications.py:532-640`` for a feature-file input: read -> call -> write, output
+    lines in file order.  Under ``torchrun`` (one process per GPU, RANK/WORLD_SIZE set) every rank
+    takes a contiguous byte shard of the (uncompressed) feature file, writes its own part and rank
+    0 concatenates the parts in rank order -- no collective touches the data path."""
+    from . import feature_io
+    print("[main] call_mods starts..")
+    start = time.time()
+    print("cuda availability: {}".format(torch.cuda.is_available()))
+    model_path = os.path.abspath(args.model_path)
+    if not os.path.exists(model_path):
+        raise ValueError("--model_path is not set right!")
+    input_path = os.path.abspath(args.input_path)
+    if not os.path.exists(input_path):
+        raise ValueError("--input_path does not exist!")
+    if os.path.isdir(input_path):
+        raise ValueError("--input_path is a directory of fast5 files: feature extraction is outside this "
+                         "implementation; run `deepsignal_plant extract` first and pass its feature file")
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    args.model_path = model_path
+    model = load_model(args, device)
+
+    result_file = args.result_file
+    if args.gzip and not result_file.endswith(".gz"):
+        result_file += ".gz"                                   # call_modifications.py:264-266
+    my_file = result_file if world == 1 else "%s.part%05d" % (result_file, rank)
+    opener = (lambda p: gzip.open(p, "wb")) if args.gzip else (lambda p: open(p, "wb"))
+    wq = queue.Queue(maxsize=8)
+
+    def writer():                                              # _write_predstr_to_file (:262-282)
+        with opener(my_file) as wf:
+            while True:
+                item = wq.get()
+                if item is None:
+                    return
+                wf.write(item)
+
+    wt = threading.Thread(target=writer, daemon=True)
+    wt.start()
+    rq = queue.Queue(maxsize=2)
+    reader = feature_io.FeatureFileReader(input_path, args.seq_len, args.signal_len,
+                                          batch_sites=getattr(args, "max_batch", 65536), slots=6,
+                                          nthreads=max(1, args.nproc), byte_range=_shard_of_file(input_path, rank, world))
+    err = []
+
+    def read():                                                # _read_features_file (:55-127)
+        try:
+            for b in reader:
+                rq.put(b)
+        except BaseException as e:                             # surfaced in the main thread
+            err.append(e)
+        rq.put(None)
+
+    rt = threading.Thread(target=read, daemon=True)
+    rt.start()
+
+    def batches():
+        while True:
+            b = rq.get()
+            if b is None:
+                return
+            yield b
+
+    sites, accuracy, nb = call_mods_stream(model, batches(), wq.put)
+    wq.put(None)
+    wt.join()
+    rt.join()
+    if err:
+        raise err[0]
+    print("call_mods rank {}: {} sites in {} feature-batches".format(rank, sites, nb))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        if rank == 0:
+            with open(result_file, "wb") as out:
+                for r in range(world):
+                    part = "%s.part%05d" % (result_file, r)
+                    with open(part, "rb") as f:
+                        while True:
+                            blk = f.read(1 << 24)
+                            if not blk:
+                                break
+                            out.write(blk)
+                    os.remove(part)
+        dist.barrier()
+    print("[main] call_mods costs %.2f seconds.." % (time.time() - start))
+    return sites

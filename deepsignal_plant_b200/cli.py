@@ -1,0 +1,86 @@
+"""Command line of the B200 hot path: the ``call_mods`` and ``call_freq`` sub-commands of
+``deepsignal_plant`` (``deepsignal_plant/deepsignal_plant.py:106-107,204-316,438-475``) with the
+reference's flag names and defaults.
+
+    python -m deepsignal_plant_b200 call_mods -i features.tsv -m model.ckpt -o calls.tsv
+    python -m deepsignal_plant_b200 call_freq -i calls.tsv -o freq.tsv [--bed] [--sort]
+
+Multi-GPU: launch ``call_mods`` under torchrun, one process per GPU; the feature file is cut into
+contiguous shards and the output is concatenated in file order.  ``extract``, ``train`` and
+``denoise`` stay with the reference (they are not on the accelerated path)."""
+from __future__ import annotations
+
+import argparse
+import sys
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(prog="deepsignal_plant_b200",
+                                     description="deepsignal-plant call_mods / call_freq on B200 (sm_100a) kernels")
+    sub = parser.add_subparsers(title="modules", dest="module")
+    cm = sub.add_parser("call_mods", description="call modifications")
+    cf = sub.add_parser("call_freq", description="call frequency of modifications at genome level")
+
+    g = cm.add_argument_group("INPUT")
+    g.add_argument("--input_path", "-i", action="store", type=str, required=True,
+                   help="a signal_feature file from `deepsignal_plant extract` (plain or .gz)")
+    g.add_argument("--f5_batch_size", action="store", type=int, default=30, required=False,
+                   help="accepted for compatibility; batches are cut by site count here")
+    g = cm.add_argument_group("CALL")
+    g.add_argument("--model_path", "-m", action="store", type=str, required=True, help="file path of the trained model (.ckpt)")
+    g.add_argument("--model_type", type=str, default="both_bilstm", choices=["both_bilstm", "seq_bilstm", "signal_bilstm"])
+    g.add_argument("--seq_len", type=int, default=13)
+    g.add_argument("--signal_len", type=int, default=16)
+    g.add_argument("--layernum1", type=int, default=3)
+    g.add_argument("--layernum2", type=int, default=1)
+    g.add_argument("--class_num", type=int, default=2)
+    g.add_argument("--dropout_rate", type=float, default=0)
+    g.add_argument("--n_vocab", type=int, default=16)
+    g.add_argument("--n_embed", type=int, default=4)
+    g.add_argument("--is_base", type=str, default="yes")
+    g.add_argument("--is_signallen", type=str, default="yes")
+    g.add_argument("--batch_size", "-b", default=512, type=int,
+                   help="accepted for compatibility; the kernels take whole staged batches (--max_batch)")
+    g.add_argument("--hid_rnn", type=int, default=256)
+    g.add_argument("--max_batch", type=int, default=65536, help="sites per staged batch (workspace size)")
+    g = cm.add_argument_group("OUTPUT")
+    g.add_argument("--result_file", "-o", action="store", type=str, required=True)
+    g.add_argument("--gzip", action="store_true", default=False)
+    cm.add_argument("--nproc", "-p", action="store", type=int, default=10, help="host threads for parsing / formatting")
+    cm.add_argument("--nproc_gpu", action="store", type=int, default=2,
+                    help="accepted for compatibility; use torchrun for one process per GPU")
+
+    g = cf.add_argument_group("INPUT")
+    g.add_argument("--input_path", "-i", action="append", type=str, required=True)
+    g.add_argument("--file_uid", type=str, action="store", required=False, default=None)
+    g = cf.add_argument_group("OUTPUT")
+    g.add_argument("--result_file", "-o", action="store", type=str, required=True)
+    g.add_argument("--bed", action="store_true", default=False)
+    g.add_argument("--sort", action="store_true", default=False)
+    g.add_argument("--gzip", action="store_true", default=False)
+    g = cf.add_argument_group("CAlCULATE")
+    g.add_argument("--prob_cf", type=float, action="store", required=False, default=0.5)
+    g = cf.add_argument_group("PARALLEL")
+    g.add_argument("--contigs", action="store", type=str, required=False, default=None,
+                   help="accepted for compatibility; all contigs are aggregated in one GPU pass")
+    g.add_argument("--nproc", action="store", type=int, required=False, default=1)
+    return parser
+
+
+def main(argv=None):
+    parser = build_parser()
+    args = parser.parse_args(argv)
+    if args.module == "call_mods":
+        from .call_modifications import call_mods
+        call_mods(args)
+    elif args.module == "call_freq":
+        from .call_mods_freq import call_mods_frequency_to_file
+        call_mods_frequency_to_file(args)
+    else:
+        parser.print_help()
+        return 2
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,267 @@
+// Host-side text <-> batch conversion around the hot path (plain C++17, multi-threaded; no
+// device code -- it lives in this library so that the feature stream can be parsed straight
+// into the page-locked buffers dsp_forward_host_submit copies from).
+//
+//   dsp_parse_features  feature file of `deepsignal_plant extract` (12 tab-separated columns,
+//                       extract_features.py:381-395) -> the five float32 arrays ModelBiLSTM.forward
+//                       takes, as _read_features_file builds them line by line
+//                       (call_modifications.py:55-127) and FloatTensor converts them
+//                       (utils/constants_torch.py:10-13: Python float = double, then float32).
+//   dsp_format_calls    probabilities -> call_mods text lines (call_modifications.py:175-188):
+//                       float32 renormalise / round(6), str() of a numpy float32 (shortest
+//                       round-trip digits, scientific below 1e-4), argmax label, centre 5-mer.
+#include "common.cuh"
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace dsp {
+namespace {
+
+// utils/process_utils.py:22-29 (base2code_dna); anything else is a KeyError in the reference
+int base_code(char ch) {
+    switch (ch) {
+        case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+        case 'N': return 4; case 'W': return 5; case 'S': return 6; case 'M': return 7;
+        case 'K': return 8; case 'R': return 9; case 'Y': return 10; case 'B': return 11;
+        case 'V': return 12; case 'D': return 13; case 'H': return 14; case 'Z': return 15;
+        default: return -1;
+    }
+}
+
+inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+// Python float(str): decimal -> nearest double; the float32 tensor then rounds the double
+bool parse_double(const char* b, const char* e, double* out) {
+    while (b < e && is_space(*b)) ++b;
+    while (e > b && is_space(e[-1])) --e;
+    if (b < e && *b == '+') ++b;
+    if (b >= e) return false;
+    auto r = std::from_chars(b, e, *out);
+    if (r.ec == std::errc::result_out_of_range) { *out = (*b == '-') ? -HUGE_VAL : HUGE_VAL; return r.ptr == e; }   // float('1e999') == inf
+    return r.ec == std::errc() && r.ptr == e;
+}
+
+bool parse_int(const char* b, const char* e, long long* out) {
+    while (b < e && is_space(*b)) ++b;
+    while (e > b && is_space(e[-1])) --e;
+    if (b < e && *b == '+') ++b;
+    if (b >= e) return false;
+    auto r = std::from_chars(b, e, *out);
+    return r.ec == std::errc() && r.ptr == e;
+}
+
+// `count` values separated by `sep` in [b, e)
+template <typename F>
+bool split_exact(const char* b, const char* e, char sep, int count, F&& each) {
+    for (int i = 0; i < count; ++i) {
+        const char* s = (i + 1 < count) ? (const char*)memchr(b, sep, (size_t)(e - b)) : e;
+        if (s == nullptr) return false;
+        if (i + 1 == count && memchr(b, sep, (size_t)(e - b)) != nullptr) return false;   // too many fields
+        if (!each(i, b, s)) return false;
+        b = s + 1;
+    }
+    return true;
+}
+
+struct ParseJob {
+    const char* text; const int64_t* begin; const int64_t* end; int T, S;
+    float *kmer, *means, *stds, *lens, *signals; int32_t* labels; int32_t *info_len, *kmer_off;
+};
+
+// returns 0 or the 1-based index of the offending column
+int parse_line(const ParseJob& j, int64_t i) {
+    const char* b = j.text + j.begin[i];
+    const char* e = j.text + j.end[i];
+    const char* f[13];
+    f[0] = b;
+    int nf = 1;
+    for (const char* p = b; p < e && nf <= 12; ++p) if (*p == '\t') f[nf++] = p + 1;
+    if (nf != 12) return 13;
+    f[12] = e + 1;
+    const int T = j.T, S = j.S;
+    j.info_len[i] = (int32_t)(f[6] - 1 - b);
+    j.kmer_off[i] = (int32_t)(f[6] - b);
+    if (f[7] - 1 - f[6] != T) return 7;
+    for (int t = 0; t < T; ++t) {
+        const int code = base_code(f[6][t]);
+        if (code < 0) return 7;
+        j.kmer[i * T + t] = (float)code;
+    }
+    double d;
+    if (!split_exact(f[7], f[8] - 1, ',', T, [&](int t, const char* x, const char* y) {
+            if (!parse_double(x, y, &d)) return false; j.means[i * T + t] = (float)d; return true; })) return 8;
+    if (!split_exact(f[8], f[9] - 1, ',', T, [&](int t, const char* x, const char* y) {
+            if (!parse_double(x, y, &d)) return false; j.stds[i * T + t] = (float)d; return true; })) return 9;
+    long long v;
+    if (!split_exact(f[9], f[10] - 1, ',', T, [&](int t, const char* x, const char* y) {
+            if (!parse_int(x, y, &v)) return false; j.lens[i * T + t] = (float)v; return true; })) return 10;
+    if (!split_exact(f[10], f[11] - 1, ';', T, [&](int t, const char* x, const char* y) {
+            return split_exact(x, y, ',', S, [&](int s, const char* p, const char* q) {
+                if (!parse_double(p, q, &d)) return false; j.signals[(i * T + t) * S + s] = (float)d; return true; }); })) return 11;
+    if (!parse_int(f[11], e, &v)) return 12;
+    j.labels[i] = (int32_t)v;
+    return 0;
+}
+
+template <typename F>
+void parallel_for(int64_t n, int nthreads, F&& body) {
+    if (nthreads <= 1 || n < 256) { body(0, n); return; }
+    std::vector<std::thread> th;
+    const int64_t per = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t lo = t * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        th.emplace_back([=, &body] { body(lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
+// str(numpy.float32(x)): shortest digits that round-trip in float32 (Dragon4, unique), positional
+// for 1e-4 <= |x| < 1e16 (compared as a value), scientific otherwise, at least one digit after a positional point,
+// exponent with at least two digits
+int format_f32(float x, char* out) {
+    if (std::isnan(x)) { memcpy(out, "nan", 3); return 3; }
+    if (std::isinf(x)) { if (x < 0) { memcpy(out, "-inf", 4); return 4; } memcpy(out, "inf", 3); return 3; }
+    char* o = out;
+    if (std::signbit(x)) { *o++ = '-'; x = -x; }
+    if (x == 0.f) { memcpy(o, "0.0", 3); return (int)(o + 3 - out); }
+    char buf[48];
+    auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest
+    char digits[16]; int nd = 0; const char* p = buf;
+    for (; p < r.ptr && *p != 'e'; ++p) if (*p != '.') digits[nd++] = *p;
+    int ex = 0; { ++p; bool neg = (*p == '-'); ++p; for (; p < r.ptr; ++p) ex = ex * 10 + (*p - '0'); if (neg) ex = -ex; }
+    // numpy decides on the VALUE (float32(1e-4) = 9.9999997e-05 prints as '1e-04'), not on the digits
+    if ((double)x >= 1e-4 && (double)x < 1e16) {
+        if (ex < 0) {
+            *o++ = '0'; *o++ = '.';
+            for (int k = 0; k < -ex - 1; ++k) *o++ = '0';
+            memcpy(o, digits, nd); o += nd;
+        } else {
+            for (int k = 0; k <= ex; ++k) *o++ = k < nd ? digits[k] : '0';
+            *o++ = '.';
+            if (nd > ex + 1) { memcpy(o, digits + ex + 1, nd - ex - 1); o += nd - ex - 1; } else *o++ = '0';
+        }
+    } else {
+        *o++ = digits[0];
+        if (nd > 1) { *o++ = '.'; memcpy(o, digits + 1, nd - 1); o += nd - 1; }
+        *o++ = 'e'; *o++ = ex < 0 ? '-' : '+';
+        int a = ex < 0 ? -ex : ex;
+        if (a >= 100) { *o++ = (char)('0' + a / 100); a %= 100; }
+        *o++ = (char)('0' + a / 10); *o++ = (char)('0' + a % 10);
+    }
+    return (int)(o - out);
+}
+
+// numpy.round(x, 6) on float32: rint(x * 1e6f) / 1e6f in float32
+inline float round6(float x) { return rintf(x * 1e6f) / 1e6f; }
+
+}  // namespace
+}  // namespace dsp
+
+using namespace dsp;
+
+extern "C" {
+
+int dsp_parse_features(const char* text, int64_t nbytes, int32_t is_final, int32_t seq_len, int32_t signal_len,
+                       int64_t max_sites, float* kmer, float* means, float* stds, float* lens, float* signals,
+                       int32_t* labels, int64_t* line_begin, int32_t* info_len, int32_t* kmer_off,
+                       int64_t* n_sites, int64_t* consumed, int32_t nthreads) {
+    DSP_REQUIRE(text && kmer && means && stds && lens && signals && labels && line_begin && info_len && kmer_off &&
+                n_sites && consumed, DSP_ERR_INVALID, "dsp_parse_features: null argument");
+    DSP_REQUIRE(seq_len >= 1 && signal_len >= 1 && max_sites >= 0 && nbytes >= 0, DSP_ERR_INVALID,
+                "dsp_parse_features: bad dimensions");
+    // pass 1: complete lines (line.strip(): surrounding white space does not belong to a field)
+    std::vector<int64_t> ends;
+    ends.reserve((size_t)(max_sites < (1 << 20) ? max_sites : (1 << 20)));
+    int64_t pos = 0, n = 0;
+    while (pos < nbytes && n < max_sites) {
+        const char* nl = (const char*)memchr(text + pos, '\n', (size_t)(nbytes - pos));
+        int64_t stop;
+        if (nl) stop = nl - text; else if (is_final) stop = nbytes; else break;
+        int64_t b = pos, e = stop;
+        while (b < e && is_space(text[b])) ++b;
+        while (e > b && is_space(text[e - 1])) --e;
+        pos = nl ? stop + 1 : nbytes;
+        if (b == e) {
+            // the reference dies on a blank line inside the file (IndexError); a trailing one is never read
+            bool only_space_left = true;
+            for (int64_t k = pos; k < nbytes; ++k) if (!is_space(text[k])) { only_space_left = false; break; }
+            DSP_REQUIRE(only_space_left && is_final, DSP_ERR_INVALID, "feature file: empty line at byte %lld", (long long)b);
+            pos = nbytes;
+            break;
+        }
+        line_begin[n] = b;
+        ends.push_back(e);
+        ++n;
+    }
+    ParseJob job{text, line_begin, ends.data(), seq_len, signal_len, kmer, means, stds, lens, signals, labels, info_len, kmer_off};
+    std::atomic<int64_t> bad_line{-1};
+    std::atomic<int> bad_col{0};
+    parallel_for(n, nthreads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const int col = parse_line(job, i);
+            if (col) {
+                int64_t expect = -1;
+                if (bad_line.compare_exchange_strong(expect, i)) bad_col = col;
+                return;
+            }
+        }
+    });
+    if (bad_line >= 0) {
+        if (bad_col == 13) set_error("feature file: line %lld (of this block) does not have 12 tab-separated columns", (long long)bad_line.load() + 1);
+        else set_error("feature file: line %lld (of this block), column %d is malformed for seq_len %d / signal_len %d",
+                       (long long)bad_line.load() + 1, bad_col.load(), seq_len, signal_len);
+        return DSP_ERR_INVALID;
+    }
+    *n_sites = n;
+    *consumed = pos;
+    return DSP_OK;
+}
+
+int dsp_format_calls(const char* text, const int64_t* line_begin, const int32_t* info_len, const int32_t* kmer_off,
+                     int32_t seq_len, const float* probs, const int32_t* labels, int64_t n,
+                     char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads) {
+    DSP_REQUIRE(text && line_begin && info_len && kmer_off && probs && labels && out && out_bytes, DSP_ERR_INVALID,
+                "dsp_format_calls: null argument");
+    const int c = seq_len / 2;                                    // call_modifications.py:181-184
+    const int lo5 = c - 2 > 0 ? c - 2 : 0, hi5 = c + 3 < seq_len ? c + 3 : seq_len;
+    struct Num { char s[2][20]; uint8_t len[2]; };
+    std::vector<Num> nums((size_t)n);
+    std::vector<int64_t> off((size_t)n + 1);
+    parallel_for(n, nthreads, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) {
+            const float p0 = probs[2 * i], p1 = probs[2 * i + 1];
+            const float p0n = round6(p0 / (p0 + p1));             // :177-179, float32 arithmetic
+            const float p1n = round6(1.0f - p0n);
+            nums[i].len[0] = (uint8_t)format_f32(p0n, nums[i].s[0]);
+            nums[i].len[1] = (uint8_t)format_f32(p1n, nums[i].s[1]);
+            char lab[16];
+            auto r = std::to_chars(lab, lab + 16, labels[i]);
+            off[i + 1] = info_len[i] + 1 + nums[i].len[0] + 1 + nums[i].len[1] + 1 + (r.ptr - lab) + 1 + (hi5 - lo5) + 1;
+        }
+    });
+    off[0] = 0;
+    for (int64_t i = 0; i < n; ++i) off[i + 1] += off[i];
+    *out_bytes = off[n];
+    DSP_REQUIRE(off[n] <= out_cap, DSP_ERR_NOMEM, "dsp_format_calls: output needs %lld bytes, buffer has %lld",
+                (long long)off[n], (long long)out_cap);
+    parallel_for(n, nthreads, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) {
+            char* o = out + off[i];
+            const char* line = text + line_begin[i];
+            memcpy(o, line, (size_t)info_len[i]); o += info_len[i]; *o++ = '\t';
+            memcpy(o, nums[i].s[0], nums[i].len[0]); o += nums[i].len[0]; *o++ = '\t';
+            memcpy(o, nums[i].s[1], nums[i].len[1]); o += nums[i].len[1]; *o++ = '\t';
+            o = std::to_chars(o, o + 16, labels[i]).ptr; *o++ = '\t';
+            memcpy(o, line + kmer_off[i] + lo5, (size_t)(hi5 - lo5)); o += hi5 - lo5;
+            *o++ = '\n';
+        }
+    });
+    return DSP_OK;
+}
+
+}  // extern "C"

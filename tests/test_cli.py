@@ -1,0 +1,68 @@
+"""call_mods / call_freq command line end to end on the GPU: feature file -> native parser ->
+pinned batches -> CUDA forward -> native formatter -> output file -> frequency table."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from deepsignal_plant_b200 import cli, feature_io, synthetic
+from deepsignal_plant_b200 import call_mods_freq as cf
+from oracle import model_oracle, freq_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def write_inputs(tmp_path, n, seed=41, gz=False):
+    feats = synthetic.make_features(n, 13, 16, seed=seed)
+    info = synthetic.make_sampleinfo(n, seed=seed)
+    labels = np.random.default_rng(seed).integers(0, 2, n)
+    path = str(tmp_path / ("features.tsv.gz" if gz else "features.tsv"))
+    opener = gzip.open if gz else open
+    with opener(path, "wt") as f:
+        for i in range(n):
+            f.write(feature_io.features_to_str(info[i], feats["kmer"][i], feats["base_means"][i], feats["base_stds"][i],
+                                               feats["base_signal_lens"][i], feats["signals"][i], labels[i]) + "\n")
+    torch.manual_seed(1234)
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    ref = ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True)
+    ckpt = str(tmp_path / "both_bilstm.b13_s16_epoch1.ckpt")
+    torch.save(ref.state_dict(), ckpt)                      # train.py:161-164: a bare state_dict
+    return path, ckpt, feats, info, {k: v.detach().numpy() for k, v in ref.state_dict().items()}
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_call_mods_cli_end_to_end(tmp_path, gz):
+    n = 3001
+    path, ckpt, feats, info, params = write_inputs(tmp_path, n, gz=gz)
+    out = str(tmp_path / "calls.tsv")
+    argv = ["call_mods", "-i", path, "-m", ckpt, "-o", out, "--max_batch", "1024", "--nproc", "4"] + (["--gzip"] if gz else [])
+    assert cli.main(argv) == 0
+    text = (gzip.open(out + ".gz", "rt") if gz else open(out)).read()
+    lines = text.splitlines()
+    assert len(lines) == n
+    # the oracle with ZERO initial states brackets what the Philox-state run may produce
+    cfg = model_oracle.make_cfg()
+    zeros = {g: (np.zeros((l * 2, n, h), np.float32),) * 2 for g, l, h in (("seq", 1, 128), ("signal", 1, 128), ("comb", 3, 256))}
+    want = model_oracle.forward(params, cfg, *(feats[k] for k in cases.FEATURE_KEYS), zeros)[1]
+    for i, line in enumerate(lines):
+        w = line.split("\t")
+        assert len(w) == 10 and "\t".join(w[:6]) == info[i]
+        p0, p1 = float(w[6]), float(w[7])
+        assert abs(p0 + p1 - 1.0) < 2e-6 and abs(p1 - want[i, 1]) < 0.05
+        assert w[8] == ("1" if p1 > p0 else "0") or abs(p1 - p0) < 2e-6
+        assert w[9] == "".join(feature_io.code2base_dna[int(c)] for c in feats["kmer"][i][4:9])
+    # call_freq on that output, against the oracle on the same lines
+    freq = str(tmp_path / "freq.tsv")
+    assert cli.main(["call_freq", "-i", out + (".gz" if gz else ""), "-o", freq, "--prob_cf", "0.0", "--sort"]) == 0
+    assert open(freq).read() == freq_oracle.render(freq_oracle.aggregate(lines, 0.0), True, False)
+
+
+def test_call_mods_cli_rejects_fast5_directory(tmp_path):
+    path, ckpt, *_ = write_inputs(tmp_path, 10)
+    with pytest.raises(ValueError, match="fast5"):
+        cli.main(["call_mods", "-i", str(tmp_path), "-m", ckpt, "-o", str(tmp_path / "o.tsv")])
+    with pytest.raises(ValueError, match="model_path"):
+        cli.main(["call_mods", "-i", path, "-m", str(tmp_path / "missing.ckpt"), "-o", str(tmp_path / "o.tsv")])

@@ -1,0 +1,120 @@
+"""Text boundary of call_mods: native feature-file parser and output formatter (host code in
+libdsp_b200, no GPU needed) against what the reference's reader / writer loop produce."""
+import gzip
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from deepsignal_plant_b200 import _native, feature_io, synthetic
+from deepsignal_plant_b200 import call_modifications as cm
+
+GOLD = cases.GOLD
+FEAT = cases.MANIFEST["features"]
+KEYS = ("kmer", "base_means", "base_stds", "base_signal_lens", "signals")
+
+
+def gold_arrays():
+    return np.load(os.path.join(GOLD, "features_small_parsed.npz"))
+
+
+@pytest.mark.parametrize("batch_sites", [4096, 50, 1])
+def test_parser_matches_reference_reader(batch_sites):
+    g = gold_arrays()
+    rd = feature_io.FeatureFileReader(os.path.join(GOLD, "features_small.tsv.gz"), FEAT["seq_len"], FEAT["signal_len"],
+                                      batch_sites=batch_sites, pinned=False, slots=2, nthreads=3)
+    got = {k: [] for k in KEYS + ("labels",)}
+    info = []
+    for b in rd:
+        assert 1 <= b.n <= batch_sites
+        for k, t in zip(KEYS, b.arrays()):
+            got[k].append(t.numpy().copy())
+        got["labels"].append(b.labels.numpy().copy())
+        info += b.sampleinfo()
+    assert len(info) == FEAT["n"] == rd.sites_read
+    assert hashlib.sha256("\n".join(info).encode()).hexdigest() == FEAT["sampleinfo_sha256"]
+    for k in got:
+        a = np.concatenate(got[k], 0)
+        assert a.dtype == g[k].dtype and a.shape == g[k].shape
+        assert a.tobytes() == g[k].tobytes(), k          # bit-identical to float32(float(text))
+
+
+def test_reference_list_view_and_text_digest():
+    text = gzip.open(os.path.join(GOLD, "features_small.tsv.gz"), "rb").read()
+    assert hashlib.sha256(text).hexdigest() == FEAT["text_sha256"]
+    b = next(iter(feature_io.FeatureFileReader(os.path.join(GOLD, "features_small.tsv.gz"), 13, 16, pinned=False)))
+    info, kmers, means, stds, lens, sig, labels = b.as_reference_lists()
+    first = text.split(b"\n")[0].decode().split("\t")
+    assert info[0] == "\t".join(first[:6])
+    assert kmers[0] == [cm.base2code_dna[c] for c in first[6]] and lens[0] == [int(x) for x in first[9].split(",")]
+    assert labels[0] == int(first[11]) and len(sig[0]) == 13 and len(sig[0][0]) == 16
+
+
+@pytest.mark.parametrize("bad", ["too\tfew\tcolumns\n",
+                                 "c\t1\t+\t1\tr\tt\tACGTACGTACGTA\t" + ",".join(["0.1"] * 12) + "\t" + ",".join(["0.1"] * 13) + "\t"
+                                 + ",".join(["3"] * 13) + "\t" + ";".join([",".join(["0"] * 16)] * 13) + "\t1\n",     # 12 means
+                                 "c\t1\t+\t1\tr\tt\tACGTACGTACGTX\t" + ",".join(["0.1"] * 13) + "\t" + ",".join(["0.1"] * 13) + "\t"
+                                 + ",".join(["3"] * 13) + "\t" + ";".join([",".join(["0"] * 16)] * 13) + "\t1\n"])    # base X
+def test_malformed_lines_fail_loudly(tmp_path, bad):
+    p = tmp_path / "bad.tsv"
+    p.write_text(bad)
+    with pytest.raises(_native.DspError, match="feature file"):
+        list(feature_io.FeatureFileReader(str(p), 13, 16, pinned=False))
+
+
+def test_byte_range_shards_cover_the_file_once(tmp_path):
+    text = gzip.open(os.path.join(GOLD, "features_small.tsv.gz"), "rb").read()
+    p = tmp_path / "f.tsv"
+    p.write_bytes(text)
+    size = len(text)
+    for world in (1, 2, 3, 7):
+        info = []
+        for r in range(world):
+            rng = (size * r // world, size * (r + 1) // world)
+            for b in feature_io.FeatureFileReader(str(p), 13, 16, batch_sites=64, pinned=False, byte_range=rng):
+                info += b.sampleinfo()
+        assert hashlib.sha256("\n".join(info).encode()).hexdigest() == FEAT["sampleinfo_sha256"], world
+    with pytest.raises(ValueError):
+        feature_io.FeatureFileReader(os.path.join(GOLD, "features_small.tsv.gz"), 13, 16, byte_range=(0, 10))
+
+
+def test_formatter_reproduces_reference_call_lines(tmp_path):
+    # the reference's _call_mods output (tests/golden/callmods_77.tsv.gz) from its own probabilities
+    e = cases.MANIFEST["callmods"]
+    n = 700
+    feats = synthetic.make_features(e["n"], 13, 16, seed=e["feature_seed"])
+    info = synthetic.make_sampleinfo(e["n"], seed=e["feature_seed"])
+    p = tmp_path / "feat.tsv"
+    with open(p, "w") as f:
+        for i in range(n):
+            f.write(feature_io.features_to_str(info[i], feats["kmer"][i], feats["base_means"][i], feats["base_stds"][i],
+                                               feats["base_signal_lens"][i], feats["signals"][i], 0) + "\n")
+    probs = np.load(os.path.join(GOLD, "callmods_%d_probs.npz" % e["rng_seed"]))["probs"][:n]
+    gold = cases.read_gz("callmods_%d.tsv.gz" % e["rng_seed"]).splitlines()[:n]
+    out = b""
+    k = 0
+    for b in feature_io.FeatureFileReader(str(p), 13, 16, batch_sites=256, pinned=False):
+        pr = probs[k:k + b.n]
+        out += feature_io.format_calls(b, pr, pr.argmax(1).astype(np.int32), nthreads=3)
+        k += b.n
+    assert out.decode().splitlines() == gold
+
+
+def test_float32_text_matches_numpy_str():
+    # str(numpy.float32) for the rounded, renormalised probabilities (call_modifications.py:177-188)
+    rng = np.random.default_rng(3)
+    p0 = np.concatenate([rng.random(20000), 10.0 ** rng.uniform(-9, -2, 20000), [0.0, 1.0, 0.5, 1e-6, 5.6e-05, 0.9999995]]).astype(np.float32)
+    probs = np.stack([p0, (1 - p0).astype(np.float32)], 1)
+    n = len(p0)
+    line = b"c\t1\t+\t1\tr\tt\tACGTACGTACGTA\tx\n"
+    b = feature_io.FeatureBatch()
+    b.n, b.seq_len, b.text = n, 13, line
+    b.line_begin, b.info_len, b.kmer_off = np.zeros(n, np.int64), np.full(n, 11, np.int32), np.full(n, 12, np.int32)
+    got = feature_io.format_calls(b, probs, np.zeros(n, np.int32)).decode().splitlines()
+    p0n, p1n = cm.normalise_probs(probs)
+    for i in range(n):
+        w = got[i].split("\t")
+        assert w[6] == str(p0n[i]) and w[7] == str(p1n[i]), (i, w, p0n[i], p1n[i])
+        assert w[8] == "0" and w[9] == "ACGTA"          # kmer[c-2:c+3], c = 6

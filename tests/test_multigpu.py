@@ -33,3 +33,30 @@ def test_freq_exchange_over_nccl_is_bit_exact():
 def test_bench_two_ranks_weak_scaling_line():
     out = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "20", "--warmup", "3", port=29534)
     assert out["n_gpus"] == 2 and out["scaling"] == "weak" and out["value"] > 0 and out["gpu_launches"] > 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_call_mods_cli_two_ranks_keeps_file_order(tmp_path):
+    import numpy as np
+    from deepsignal_plant_b200 import feature_io, synthetic
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    n = 5000
+    feats = synthetic.make_features(n, 13, 16, seed=43)
+    info = synthetic.make_sampleinfo(n, seed=43)
+    path = str(tmp_path / "features.tsv")
+    with open(path, "w") as f:
+        for i in range(n):
+            f.write(feature_io.features_to_str(info[i], feats["kmer"][i], feats["base_means"][i], feats["base_stds"][i],
+                                               feats["base_signal_lens"][i], feats["signals"][i], 0) + "\n")
+    torch.manual_seed(1234)
+    ckpt = str(tmp_path / "m.ckpt")
+    torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
+    out = str(tmp_path / "calls.tsv")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", "-m", "deepsignal_plant_b200", "call_mods", "-i", path, "-m", ckpt, "-o", out,
+           "--max_batch", "1024"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    lines = open(out).read().splitlines()
+    assert len(lines) == n and ["\t".join(l.split("\t")[:6]) for l in lines] == info
+    assert not [p for p in os.listdir(tmp_path) if ".part" in p]

@@ -57,3 +57,16 @@ def test_freq_oracle_matches_reference_bytes(name, freq_inputs):
     e = cases.MANIFEST["freq"][name]
     table = freq_oracle.aggregate(freq_inputs[e["input"]], e["prob_cf"])
     assert freq_oracle.render(table, e["sort"], e["bed"]) == cases.read_gz(name + ".txt.gz")
+
+
+def test_features_oracle_matches_reference_reader():
+    import gzip
+    import os
+    from oracle import features_oracle
+    lines = gzip.open(os.path.join(cases.GOLD, "features_small.tsv.gz"), "rt").read().splitlines()
+    g = np.load(os.path.join(cases.GOLD, "features_small_parsed.npz"))
+    info, kmers, means, stds, lens, sig, labels = features_oracle.read_features(lines)
+    for got, key, dt in ((kmers, "kmer", np.float32), (means, "base_means", np.float32), (stds, "base_stds", np.float32),
+                         (lens, "base_signal_lens", np.float32), (sig, "signals", np.float32), (labels, "labels", np.int32)):
+        assert np.asarray(got, dtype=dt).tobytes() == g[key].tobytes(), key
+    assert features_oracle.batch_sizes(lines, cases.MANIFEST["features"]["f5_batch_size"]) == g["batch_sizes"].tolist()
