@@ -210,9 +210,12 @@ def main():
     _native.check(L.dsp_get_timing(model._handle, 1, C.byref(t), C.byref(cnt)))
     kern_ms, kern_launches = float(t.value), int(cnt.value)
     class_ms = {}
-    for cls, name in ((0, "assemble"), (1, "recurrent"), (2, "fc"), (3, "head")):
+    for cls, name in ((0, "assemble"), (1, "recurrent_comb"), (4, "recurrent_branch"), (2, "fc"), (3, "head")):
         _native.check(L.dsp_get_timing(model._handle, cls, C.byref(t), C.byref(cnt)))
         class_ms[name] = round(float(t.value), 4)
+        if cls == 4:
+            kern_ms += float(t.value)
+            kern_launches += int(cnt.value)
     _native.check(L.dsp_set_timing(model._handle, 0))
 
     # ---- e2e: host buffers through the public host API, H2D + D2H inside ----------------

@@ -54,6 +54,16 @@ constexpr uint16_t PAIR_MASK = 3;                   // both CTAs of the pair
 #ifndef DSP_POLY_MASK
 #define DSP_POLY_MASK 0
 #endif
+// The two branch layers (hidden 128, K = 16 + 128) are the exception: their MMAs are tiny, the SM runs
+// far below the power cap and the MUFU pipe is what bounds them, so they get their own mask.
+#ifndef DSP_POLY_MASK_BRANCH
+#define DSP_POLY_MASK_BRANCH 3
+#endif
+// One reciprocal instead of two in the cell update (see lstm_cell2): fewer MUFU ops and, measured,
+// ~2 % more sites/s at the power cap (profiles/r01_run12_epilogue_variants2.log).  0 = separate form.
+#ifndef DSP_MERGE_RCP
+#define DSP_MERGE_RCP 1
+#endif
 
 struct LayerParams {
     const uint8_t* x_img;      // [tiles][T][KSX] slabs
@@ -151,7 +161,7 @@ __device__ __forceinline__ void lstm_cell2(float2 ai, float2 af, float2 ag, floa
     h = fma2(add2(ai, add2(ag, ao)), make_float2(1e-2f, 1e-2f), mul2(c, make_float2(1e-3f, 1e-3f)));
     return;
 #endif
-#ifdef DSP_MERGE_RCP
+#if DSP_MERGE_RCP
     constexpr bool CLAMP_IF = true;
 #else
     constexpr bool CLAMP_IF = false;
@@ -160,7 +170,7 @@ __device__ __forceinline__ void lstm_cell2(float2 ai, float2 af, float2 ag, floa
     const float2 ef = exp2_pair<((PM >> 3) & 1) != 0, CLAMP_IF>(af);
     const float2 eg = exp2_pair<(PM & 1) != 0, true>(ag);
     const float2 eo = exp2_pair<((PM >> 4) & 1) != 0, false>(ao);
-#ifdef DSP_MERGE_RCP
+#if DSP_MERGE_RCP
     // c' = [c (1+ei)(1+eg) + (1-eg)(1+ef)] / [(1+ef)(1+ei)(1+eg)]: one reciprocal instead of two
     // (needs bounded ei, ef: callers of this variant clamp them through HI_CLAMP below)
     const float2 F = add2(ef, ONE);
@@ -583,7 +593,7 @@ layer_kernel(const LayerParams p) {
                             const float2 af = add2(make_float2(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3])), make_float2(b0.z, b0.w));
                             const float2 ag = add2(make_float2(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5])), make_float2(b1.x, b1.y));
                             const float2 ao = add2(make_float2(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7])), make_float2(b1.z, b1.w));
-                            lstm_cell2<DSP_POLY_MASK>(ai, af, ag, ao, c2[ch][part * 2 + qq], h2[part * 2 + qq]);
+                            lstm_cell2<(H == 128) ? DSP_POLY_MASK_BRANCH : DSP_POLY_MASK>(ai, af, ag, ao, c2[ch][part * 2 + qq], h2[part * 2 + qq]);
                         }
                     }
                     uint32_t pk[UPT / 2];
@@ -941,7 +951,7 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
             p.y_img = head_tc ? s->hfin_img : s->ybuf[l & 1]; p.hfinal = (final_layer && !head_tc) ? s->hfinal : nullptr;
             p.n = n; p.T = T; p.xk16 = pk->xk16; p.y_slabs = 2 * hid / 64; p.y_col_off = 0;
             p.write_y = final_layer ? (head_tc ? 2 : 0) : 1;
-            Span sp(m, 1, st);
+            Span sp(m, is_comb ? 1 : 4, st);
             int rc = launch_lstm(m, pk->KSX, hid, p, tiles, st);
             if (rc) return rc;
             x = s->ybuf[l & 1];

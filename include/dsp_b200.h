@@ -131,7 +131,8 @@ int dsp_forward_host_wait(dsp_handle h, int64_t ticket);
 int64_t dsp_launch_count(dsp_handle h);
 /* Milliseconds (CUDA events on the launching stream) spent in kernels of class `which`
  * during the last dsp_forward when timing was enabled with dsp_set_timing(h, 1):
- * 0 = feature assembly/state init, 1 = recurrent layers, 2 = per-timestep fc, 3 = head.
+ * 0 = feature assembly/state init, 1 = recurrent layers (lstm_comb; all LSTM layers on the fp32 path),
+ * 2 = per-timestep fc, 3 = head, 4 = branch recurrent layers (lstm_seq / lstm_signal, fp16 path).
  * Timing inserts event records only; it never synchronises inside dsp_forward. */
 int dsp_set_timing(dsp_handle h, int enable);
 int dsp_get_timing(dsp_handle h, int which, float* ms, int64_t* launches);
