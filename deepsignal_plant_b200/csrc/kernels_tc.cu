@@ -571,29 +571,33 @@ layer_kernel(const LayerParams p) {
                     tc_fence_after();
                     const int u0 = ch * 32 + sl * UPT;
                     float2 h2[UPT / 2];
+                    // PW accumulator columns (PW/8 unit pairs) are in flight per thread at a time: the whole
+                    // 32-column slice where registers allow (hidden 128: 32 cell-state registers), half otherwise
+                    constexpr int PW = (H == 128) ? 32 : 16;
 #pragma unroll
-                    for (int part = 0; part < CPT / 16; ++part) {
-                        uint32_t v[16];
-                        tmem_ld16(t_acc + buf * 128u + lane_addr + (uint32_t)(sl * CPT + part * 16), v);
-                        // biases of this part's 4 units (warp-wide broadcast reads) while the TMEM load is in flight
-                        float4 bq[4];
+                    for (int part = 0; part < CPT / PW; ++part) {
+                        uint32_t v[PW];
+                        if constexpr (PW == 32) tmem_ld32(t_acc + buf * 128u + lane_addr + (uint32_t)(sl * CPT), reinterpret_cast<uint32_t(&)[32]>(v));
+                        else tmem_ld16(t_acc + buf * 128u + lane_addr + (uint32_t)(sl * CPT + part * 16), reinterpret_cast<uint32_t(&)[16]>(v));
+                        // biases of this part's units (warp-wide broadcast reads) while the TMEM load is in flight
+                        float4 bq[PW / 4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) bq[i] = lds128(s_bias_u32 + (uint32_t)((ch * 128 + part * 16 + i * 4) * 4));
+                        for (int i = 0; i < PW / 4; ++i) bq[i] = lds128(s_bias_u32 + (uint32_t)((ch * 128 + part * PW + i * 4) * 4));
                         tmem_ld_wait();
-                        if (part == CPT / 16 - 1) {
+                        if (part == CPT / PW - 1) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(r_accempty + 8 * buf);
                         }
 #pragma unroll
-                        for (int qq = 0; qq < 2; ++qq) {
+                        for (int qq = 0; qq < PW / 8; ++qq) {
                             // columns of one unit pair: i i' f f' g g' o o'
                             const float4 b0 = bq[2 * qq], b1 = bq[2 * qq + 1];
                             const float2 ai = add2(make_float2(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1])), make_float2(b0.x, b0.y));
                             const float2 af = add2(make_float2(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3])), make_float2(b0.z, b0.w));
                             const float2 ag = add2(make_float2(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5])), make_float2(b1.x, b1.y));
                             const float2 ao = add2(make_float2(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7])), make_float2(b1.z, b1.w));
-                            lstm_cell2<(H == 128) ? DSP_POLY_MASK_BRANCH : DSP_POLY_MASK>(ai, af, ag, ao, c2[ch][part * 2 + qq], h2[part * 2 + qq]);
+                            lstm_cell2<(H == 128) ? DSP_POLY_MASK_BRANCH : DSP_POLY_MASK>(ai, af, ag, ao, c2[ch][part * (PW / 8) + qq], h2[part * (PW / 8) + qq]);
                         }
                     }
                     uint32_t pk[UPT / 2];
