@@ -26,12 +26,24 @@ import numpy as np  # noqa: E402
 METRIC = "classified sites/sec (ModelBiLSTM both_bilstm bn13_sn16 hidden 256)"
 UNIT = "sites/s"
 BATCH = 65536
-FLOP_PER_SITE = 118447104            # SURVEY.md section 8d (algorithmic, 2 x MAC)
-# recurrent layers only (lstm_seq + lstm_signal + 3 x lstm_comb), the dominant kernel class
-FLOP_PER_SITE_RECURRENT = 2 * (2 * 13 * 512 * (7 + 128) + 2 * 13 * 512 * (16 + 128)
-                               + 2 * 13 * 1024 * (256 + 256) + 2 * 2 * 13 * 1024 * (512 + 256))
-IN_BYTES_PER_SITE = 4 * (4 * 13 + 13 * 16)
 OUT_BYTES_PER_SITE = 4 * 2 * 2 + 4
+
+
+def flops_per_site(module="both_bilstm", T=13, S=16, H=256, E=4, layers1=3, C=2):
+    """Algorithmic FLOPs (2 x MAC, no padding) of one site: (whole forward, recurrent layers only).
+    both_bilstm 13x16 -> 118 447 104."""
+    def lstm(K, Hh):
+        return 2 * T * 4 * Hh * (K + Hh)
+    hs = H // 2 if module == "both_bilstm" else (H if module == "seq_bilstm" else 0)
+    hg = H - H // 2 if module == "both_bilstm" else (H if module == "signal_bilstm" else 0)
+    rec = (lstm(E + 3, hs) if hs else 0) + (lstm(S, hg) if hg else 0) + lstm(H, H) + (layers1 - 1) * lstm(2 * H, H)
+    dense = T * 2 * hs * hs + T * 2 * hg * hg + 2 * H * H + H * C
+    return 2 * (rec + dense), 2 * rec
+
+
+FLOP_PER_SITE, FLOP_PER_SITE_RECURRENT = flops_per_site()
+assert FLOP_PER_SITE == 118447104
+IN_BYTES_PER_SITE = 4 * (4 * 13 + 13 * 16)
 
 
 def peaks():
@@ -41,6 +53,18 @@ def peaks():
         return dict(tflops=float(d["bf16_tflops_sustained"]), tflops_burst=float(d["bf16_tflops"]),
                     hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained bf16)")
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def traffic_of_dominant_kernel(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (lstm_comb layer 1,
+    layer_kernel<8,256,LSTM>) from the committed `ncu --set full` capture, scaled to this batch;
+    None when no capture is recorded (profiles/roofline_traffic.json says which run it came from)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"bytes_per_launch": d["dram_bytes_per_site"] * batch, "unit": "B", "kernel": d["kernel"], "source": d["source"],
+            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_site"] * batch}
 
 
 class ClockSampler(threading.Thread):
@@ -79,11 +103,11 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
 
 
-def make_pool(n_buffers, batch, seed=0):
+def make_pool(n_buffers, batch, seed=0, T=13, S=16):
     """`n_buffers` distinct batches: one generated pool, rolled copies (distinct bytes, so the
     cycled inputs exceed L2: 4 x 68 MB > 126 MB)."""
     from deepsignal_plant_b200 import synthetic
-    base = synthetic.make_features(batch, 13, 16, seed=seed)
+    base = synthetic.make_features(batch, T, S, seed=seed)
     keys = ("kmer", "base_means", "base_stds", "base_signal_lens", "signals")
     return [tuple(np.ascontiguousarray(np.roll(base[k], 977 * b, axis=0)) for k in keys) for b in range(n_buffers)]
 
@@ -146,6 +170,10 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--buffers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # BASELINE.json configs[3]: the other model variants (not the headline line)
+    ap.add_argument("--module", default="both_bilstm", choices=["both_bilstm", "seq_bilstm", "signal_bilstm"])
+    ap.add_argument("--seq_len", type=int, default=13)
+    ap.add_argument("--signal_len", type=int, default=16)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,9 +200,13 @@ def main():
     W = max(args.warmup, 3)
 
     torch.manual_seed(1234)
-    model = ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True, module="both_bilstm", device=local,
+    T_, S_ = args.seq_len, args.signal_len
+    flop_site, flop_rec = flops_per_site(args.module, T_, S_)
+    in_bytes_site = 4 * ((4 * T_ if args.module != "signal_bilstm" else 0) + (T_ * S_ if args.module != "seq_bilstm" else 0))
+    headline = (args.module, T_, S_) == ("both_bilstm", 13, 16)
+    model = ModelBiLSTM(T_, S_, 3, 1, 2, 0, 256, 16, 4, True, True, module=args.module, device=local,
                         precision=args.precision, max_batch=args.batch, seed=rank).cuda(local).eval()
-    pool = make_pool(args.buffers, args.batch, seed=rank)
+    pool = make_pool(args.buffers, args.batch, seed=rank, T=T_, S=S_)
     dev_pool = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in pool]
     pin_pool = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in pool]
 
@@ -252,22 +284,23 @@ def main():
     e2e_value = world * args.batch * e2e_steps / (e2e_ms * 1e-3)
 
     pk = peaks()
-    achieved = (FLOP_PER_SITE_RECURRENT * args.batch / (kern_ms * 1e-3) / 1e12) if kern_ms > 0 else None
+    achieved = (flop_rec * args.batch / (kern_ms * 1e-3) / 1e12) if kern_ms > 0 else None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "metric": METRIC if headline else METRIC.replace("both_bilstm bn13_sn16", "%s bn%d_sn%d" % (args.module, T_, S_)), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate" if args.precision == "fp16" else "f32", "data": "synthetic",
-        "config": {"workload": "both_bilstm bn13_sn16 h256 inference, batch 65536 (BASELINE.json configs[1]), "
-                               "random-init weights seed 1234, in-kernel Philox initial states",
+        "config": {"workload": ("both_bilstm bn13_sn16 h256 inference, batch 65536 (BASELINE.json configs[1]), " if headline else
+                                "%s bn%d_sn%d h256 inference, batch %d (BASELINE.json configs[3] variant), " % (args.module, T_, S_, args.batch))
+                               + "random-init weights seed 1234, in-kernel Philox initial states",
                    "batch": args.batch, "precision": args.precision,
-                   "l2": "%d distinct input batches cycled (%.0f MB > L2)" % (args.buffers, args.buffers * args.batch * IN_BYTES_PER_SITE / 1e6),
+                   "l2": "%d distinct input batches cycled (%.0f MB > L2)" % (args.buffers, args.buffers * args.batch * in_bytes_site / 1e6),
                    "parallelism": "site-batch shards, one process per GPU, no collective"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": (achieved / pk["tflops"]) if achieved else None, "traffic": None,
+                     "frac": (achieved / pk["tflops"]) if achieved else None, "traffic": traffic_of_dominant_kernel(args.batch) if headline else None,
                      "kernel": "recurrent BiLSTM layer kernels (%d launches/step, %.3f ms/step)" % (kern_launches, kern_ms),
                      "peak_source": pk["source"], "last_step_kernel_ms": class_ms,
-                     "whole_step_frac": value / world * FLOP_PER_SITE / 1e12 / pk["tflops"]},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": args.batch * IN_BYTES_PER_SITE,
+                     "whole_step_frac": value / world * flop_site / 1e12 / pk["tflops"], "flop_per_site": flop_site},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": args.batch * in_bytes_site,
                 "d2h_bytes_per_step": args.batch * OUT_BYTES_PER_SITE, "api": "ModelBiLSTM.submit_host/wait_host (dsp_forward_host_submit), pinned host buffers in and out, 2 batches in flight"},
         "gpu_launches": launches, "clocks": clocks,
     }

@@ -61,6 +61,9 @@ constexpr uint16_t PAIR_MASK = 3;                   // both CTAs of the pair
 #endif
 // One reciprocal instead of two in the cell update (see lstm_cell2): fewer MUFU ops and, measured,
 // ~2 % more sites/s at the power cap (profiles/r01_run12_epilogue_variants2.log).  0 = separate form.
+#ifndef DSP_DIR_INTERLEAVE
+#define DSP_DIR_INTERLEAVE 1
+#endif
 #ifndef DSP_MERGE_RCP
 #define DSP_MERGE_RCP 1
 #endif
@@ -244,7 +247,14 @@ layer_kernel(const LayerParams p) {
     const uint32_t b_hready = b_accfull + 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#if DSP_DIR_INTERLEAVE
+    // block order: (tile pair, direction, rank in pair) -- both directions of a tile run in the same wave,
+    // so the second read of the layer's input image mostly hits L2
+    const int dir = IS_FC ? 0 : (int)((blockIdx.x >> 1) & 1u);
+    const int tile = IS_FC ? (int)blockIdx.x : (int)(((blockIdx.x >> 2) << 1) | (blockIdx.x & 1u));
+#else
     const int tile = blockIdx.x, dir = IS_FC ? 0 : blockIdx.y;
+#endif
     const int T = p.T;
     const uint32_t crank = cluster_ctarank();              // 0 = leader
 
@@ -744,7 +754,12 @@ int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st)
     auto kern = layer_kernel<KSX, H, MODE, NOUT>;
     DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)((tiles + 1) / 2 * 2), MODE != MODE_LSTM ? 1 : 2);   // CTA pairs: the workspace is padded too
+    const unsigned tiles2 = (unsigned)((tiles + 1) / 2 * 2);                          // CTA pairs: the workspace is padded too
+#if DSP_DIR_INTERLEAVE
+    cfg.gridDim = dim3(MODE != MODE_LSTM ? tiles2 : 2 * tiles2, 1);
+#else
+    cfg.gridDim = dim3(tiles2, MODE != MODE_LSTM ? 1 : 2);
+#endif
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
