@@ -17,7 +17,7 @@ SYMBOLS = (
     "dsp_pack_weights", "dsp_forward", "dsp_forward_host", "dsp_forward_host_submit",
     "dsp_forward_host_wait", "dsp_launch_count",
     "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate", "dsp_selftest",
-    "dsp_parse_features", "dsp_format_calls",
+    "dsp_parse_features", "dsp_format_calls", "dsp_freq_release_cache",
 )
 
 MODULES = {"both_bilstm": 0, "seq_bilstm": 1, "signal_bilstm": 2}

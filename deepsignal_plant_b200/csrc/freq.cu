@@ -13,21 +13,44 @@
 // first appearance.
 #include "common.cuh"
 #include <cub/cub.cuh>
+#include <mutex>
 
 namespace dsp {
 namespace {
 
+// Scratch memory comes from a small per-process cache of device blocks (grow-only, best fit):
+// a call makes ~20 allocations, and cudaMalloc/cudaFree around every call cost several times the
+// kernels themselves.  dsp_freq_release_cache() returns the blocks to the driver.
+struct Block { void* p; size_t bytes; int device; bool busy; };
+std::vector<Block> g_blocks;
+std::mutex g_blocks_mu;
+
 struct Scratch {
-    std::vector<void*> ptrs;
+    std::vector<size_t> held;
     cudaStream_t st;
-    explicit Scratch(cudaStream_t s) : st(s) {}
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    int device;
+    Scratch(cudaStream_t s, int dev) : st(s), device(dev) {}
+    ~Scratch() {
+        std::lock_guard<std::mutex> lk(g_blocks_mu);
+        for (size_t i : held) g_blocks[i].busy = false;
+    }
     template <typename T> int alloc(T** p, size_t count) {
-        void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
-        if (e != cudaSuccess) { set_error("dsp_freq_aggregate: cudaMalloc failed: %s", cudaGetErrorString(e)); return DSP_ERR_NOMEM; }
-        ptrs.push_back(q);
-        *p = (T*)q;
+        const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+        std::lock_guard<std::mutex> lk(g_blocks_mu);
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < g_blocks.size(); ++i)
+            if (!g_blocks[i].busy && g_blocks[i].device == device && g_blocks[i].bytes >= bytes &&
+                (best == (size_t)-1 || g_blocks[i].bytes < g_blocks[best].bytes)) best = i;
+        if (best == (size_t)-1 || g_blocks[best].bytes > 2 * bytes + (1 << 20)) {
+            void* q = nullptr;
+            cudaError_t e = cudaMalloc(&q, bytes);
+            if (e != cudaSuccess) { set_error("dsp_freq_aggregate: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return DSP_ERR_NOMEM; }
+            g_blocks.push_back({q, bytes, device, false});
+            best = g_blocks.size() - 1;
+        }
+        g_blocks[best].busy = true;
+        held.push_back(best);
+        *p = (T*)g_blocks[best].p;
         return DSP_OK;
     }
 };
@@ -123,7 +146,7 @@ extern "C" int dsp_freq_aggregate(int device, const uint64_t* key, const double*
     if (prev != device) cudaSetDevice(device);
     struct Restore { int p, d; ~Restore() { if (p != d && p >= 0) cudaSetDevice(p); } } restore{prev, device};
     cudaStream_t st = (cudaStream_t)stream;
-    Scratch sc(st);
+    Scratch sc(st, device);
     int rc;
 
     // 1. callable filter -> compacted record indices (file order preserved)
@@ -200,5 +223,21 @@ extern "C" int dsp_freq_aggregate(int device, const uint64_t* key, const double*
     DSP_CUDA(cudaGetLastError());
     DSP_CUDA(cudaStreamSynchronize(st));
     *n_sites_host = nseg;
+    return DSP_OK;
+}
+
+extern "C" int dsp_freq_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_blocks_mu);
+    std::vector<Block> keep;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (Block& b : g_blocks) {
+        if (b.busy) { keep.push_back(b); continue; }
+        cudaSetDevice(b.device);
+        cudaFree(b.p);
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    g_blocks.swap(keep);
+    cudaGetLastError();
     return DSP_OK;
 }

@@ -156,6 +156,9 @@ int dsp_freq_aggregate(int device, const uint64_t* key, const double* p0, const 
                        int32_t* out_met, int32_t* out_unmet, int32_t* out_cov,
                        int64_t* n_sites_host, void* stream);
 
+/* dsp_freq_aggregate keeps its scratch device memory cached between calls; this frees it. */
+int dsp_freq_release_cache(void);
+
 /* ---- text boundary of call_mods (host code, HOST pointers) ---------------------------------
  * dsp_parse_features: _read_features_file (call_modifications.py:55-127) for a block of the
  * feature file written by `deepsignal_plant extract` (12 tab-separated columns,
