@@ -652,6 +652,297 @@ layer_kernel(const LayerParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Branch layers of both_bilstm (lstm_seq / lstm_signal: hidden 128, K = 16 + 128).  Their MMAs are
+// tiny, so a single (tile, direction) recurrence leaves the SM waiting on its own dependency chain
+// (MMA -> gate math -> h -> MMA) most of the time.  Here a CTA pair runs BOTH directions of its two
+// tiles as two independent chains that fill each other's bubbles: 64-column chunks (16 hidden
+// units) so that two chains fit in TMEM (per chain 2 x 64 accumulator columns + 2 x 64 h columns),
+// 8 epilogue warps per chain, one MMA issuer alternating between the chains.  Everything else
+// (CTA pair, half-operand staging, barrier protocol) is as in layer_kernel.
+constexpr int BR_H = 128, BR_NW = 64, BR_NCH = BR_H / 16, BR_KSH = BR_H / 64;
+constexpr int QSLAB_BYTES = 32 * SLAB_ROW_BYTES;          // 4 KB: one CTA's share (32 rows) of a 64-column B slab
+constexpr int BR_STG = 4, BR_NST = 6;                     // ring: 6 stages of 16 KB
+
+template <int KSX>
+__global__ void __launch_bounds__(NTHREADS, 1)
+branch_kernel(const LayerParams p) {
+    constexpr int KS = KSX + BR_KSH;
+    constexpr int PAIR_UNITS = 4 * KSX + 4 * BR_KSH;      // X(0,c) X(0,c+1) X(1,c) X(1,c+1) H(0,c) H(0,c+1) H(1,c) H(1,c+1)
+    constexpr int W_STEP = (BR_NCH / 2) * PAIR_UNITS;     // ring units streamed per step
+    constexpr int NBIAS = 2 * BR_NCH * BR_NW;
+    constexpr uint32_t IDESC = make_idesc_f16(256, BR_NW);
+    static_assert(W_STEP % BR_STG == 0 && KS * 2 == PAIR_UNITS / 2, "stream layout");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_x = smem;                                   // [dir][KSX] slabs
+    uint8_t* s_w = smem + (size_t)2 * KSX * SLAB_BYTES;
+    float* s_bias = reinterpret_cast<float*>(s_w + (size_t)BR_NST * BR_STG * QSLAB_BYTES);
+    __shared__ __align__(8) uint64_t bars[2 * BR_NST + 4 * KSX + 10];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t b_wfull = smem_u32(&bars[0]), b_wempty = smem_u32(&bars[BR_NST]);
+    const uint32_t b_xfull = smem_u32(&bars[2 * BR_NST]), b_xempty = b_xfull + 8 * 2 * KSX;       // [dir][KSX]
+    const uint32_t b_accfull = b_xempty + 8 * 2 * KSX, b_accempty = b_accfull + 32;               // [dir][2]
+    const uint32_t b_hready = b_accempty + 32;                                                  // [dir]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int T = p.T;
+    const uint32_t crank = cluster_ctarank();
+
+    if (tid == 0) {
+        const uint32_t both = crank == 0 ? 2u : 1u;
+        for (int i = 0; i < BR_NST; ++i) { mbar_init(b_wfull + 8 * i, both); mbar_init(b_wempty + 8 * i, 1); }
+        for (int i = 0; i < 2 * KSX; ++i) { mbar_init(b_xfull + 8 * i, both); mbar_init(b_xempty + 8 * i, 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, EPI_WARPS); }   // 8 warps x 2 CTAs
+        for (int i = 0; i < 2; ++i) mbar_init(b_hready + 8 * i, EPI_WARPS);
+        mbar_fence_init();
+    }
+    if (warp == 3) tmem_alloc_pair(smem_u32(&tmem_base_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    // chain d: accumulators at d*128 + {0, 64}, h buffers at 256 + d*128 + {0, 64}
+    auto t_acc = [&](int d, int e) -> uint32_t { return tmem + (uint32_t)(d * 128 + e * 64); };
+    auto t_h = [&](int d, int b) -> uint32_t { return tmem + 256u + (uint32_t)(d * 128 + b * 64); };
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (warp == 0) {
+            if (elect_one()) {
+                const uint8_t* wsrc = p.w_img + (size_t)crank * W_STEP * QSLAB_BYTES;
+                uint32_t stage = 0, phase = 0;
+                for (int step = 0; step < T; ++step) {
+                    const uint8_t* src = wsrc;
+                    for (int s = 0; s < W_STEP; s += BR_STG) {
+                        mbar_wait(b_wempty + 8 * stage, phase ^ 1);
+                        mbar_arrive_expect_tx(b_wfull + 8 * stage, BR_STG * QSLAB_BYTES);
+                        bulk_g2s(smem_u32(s_w + (size_t)stage * BR_STG * QSLAB_BYTES), src, BR_STG * QSLAB_BYTES, b_wfull + 8 * stage);
+                        src += (size_t)BR_STG * QSLAB_BYTES;
+                        if (++stage == BR_NST) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 2) {
+            if (elect_one()) {
+                for (int step = 0; step < T; ++step)
+                    for (int d = 0; d < 2; ++d) {
+                        const int t = d ? (T - 1 - step) : step;
+                        const uint8_t* xsrc = p.x_img + ((size_t)tile * T + t) * KSX * SLAB_BYTES;
+                        for (int j = 0; j < KSX; ++j) {
+                            const uint32_t o = 8u * (uint32_t)(d * KSX + j);
+                            mbar_wait(b_xempty + o, (step & 1) ^ 1);
+                            mbar_arrive_expect_tx(b_xfull + o, SLAB_BYTES);
+                            bulk_g2s(smem_u32(s_x + (size_t)(d * KSX + j) * SLAB_BYTES), xsrc + (size_t)j * SLAB_BYTES, SLAB_BYTES, b_xfull + o);
+                        }
+                    }
+            }
+        } else if (warp == 1 && crank != 0) {
+            const uint32_t r_wfull = mapa_u32(b_wfull, 0), r_xfull = mapa_u32(b_xfull, 0);
+            uint32_t stage = 0, phase = 0;
+            for (int step = 0; step < T; ++step) {
+                for (int i = 0; i < 2 * KSX; ++i) {
+                    mbar_wait(b_xfull + 8 * i, step & 1);
+                    if (lane == 0) mbar_arrive_cluster(r_xfull + 8 * i);
+                }
+                for (int s = 0; s < W_STEP; s += BR_STG) {
+                    mbar_wait(b_wfull + 8 * stage, phase);
+                    if (lane == 0) mbar_arrive_cluster(r_wfull + 8 * stage);
+                    if (++stage == BR_NST) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            const bool leader = elect_one();
+            const uint32_t a_lo0 = smem_desc_lo(smem_u32(s_x)), b_lo0 = smem_desc_lo(smem_u32(s_w));
+            const int xk16 = p.xk16;
+            uint32_t stage = 0, phase = 0, in_stage = 0;
+            auto w_acquire = [&]() -> uint32_t {
+                if (in_stage == 0) { mbar_wait_cluster(b_wfull + 8 * stage, phase); tc_fence_after(); }
+                return b_lo0 + (stage * BR_STG + in_stage) * (uint32_t)(QSLAB_BYTES >> 4);
+            };
+            auto w_release = [&]() {
+                if (++in_stage == BR_STG) {
+                    if (leader) mma2_commit(b_wempty + 8 * stage, PAIR_MASK);
+                    in_stage = 0;
+                    if (++stage == BR_NST) { stage = 0; phase ^= 1; }
+                }
+                __syncwarp();
+            };
+            for (int step = 0; step < T; ++step) {
+                if (step == 0) { mbar_wait_cluster(b_hready, 0); mbar_wait_cluster(b_hready + 8, 0); }   // c0 staged in the accumulators
+                for (int pr = 0; pr < BR_NCH / 2; ++pr) {
+                    const uint32_t use = (uint32_t)(step * (BR_NCH / 2) + pr);
+#pragma unroll
+                    for (int d = 0; d < 2; ++d)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            mbar_wait_cluster(b_accempty + 8 * (d * 2 + e), (use & 1u) ^ 1u);
+                            tc_fence_after();
+#pragma unroll
+                            for (int j = 0; j < KSX; ++j) {
+                                const uint32_t xo = 8u * (uint32_t)(d * KSX + j);
+                                if (pr == 0 && e == 0) { mbar_wait_cluster(b_xfull + xo, step & 1); tc_fence_after(); }
+                                const uint32_t bl = w_acquire();
+                                if (leader) {
+                                    const uint32_t al = a_lo0 + (uint32_t)(d * KSX + j) * (SLAB_BYTES >> 4);
+                                    const int nk = (KSX * 4 == xk16) ? 4 : min(4, xk16 - 4 * j);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        if (k < nk) {
+                                            if (j == 0 && k == 0) mma2_ss_lo<0>(t_acc(d, e), al, bl, IDESC);
+                                            else mma2_ss_lo<1>(t_acc(d, e), al + k * 2, bl + k * 2, IDESC);
+                                        }
+                                    }
+                                    if (pr == BR_NCH / 2 - 1 && e == 1) mma2_commit(b_xempty + xo, PAIR_MASK);
+                                }
+                                w_release();
+                            }
+                        }
+#pragma unroll
+                    for (int d = 0; d < 2; ++d) {
+                        if (pr == 0) { mbar_wait_cluster(b_hready + 8 * d, step & 1); tc_fence_after(); }
+                        const uint32_t a_t = t_h(d, step & 1);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+#pragma unroll
+                            for (int j = 0; j < BR_KSH; ++j) {
+                                const uint32_t bl = w_acquire();
+                                if (leader) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        mma2_ts_lo<1>(t_acc(d, e), a_t + (uint32_t)(j * 32 + k * 8), bl + k * 2, IDESC);
+                                }
+                                w_release();
+                            }
+                            if (leader) mma2_commit(b_accfull + 8 * (d * 2 + e), PAIR_MASK);
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        const int ew = warp - 4;
+        const int d = ew >> 3;                       // chain = direction
+        const int q = warp & 3;                      // TMEM lane quarter
+        const int half = (ew >> 2) & 1;              // which 32 of the chunk's 64 columns (8 hidden units)
+        const int row = q * 32 + lane;
+        const int64_t site = (int64_t)tile * TILE + row;
+        const bool valid = site < p.n;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t r_accempty = mapa_u32(b_accempty, 0) + 16u * (uint32_t)d, r_hready = mapa_u32(b_hready, 0) + 8u * (uint32_t)d;
+        const uint32_t b_myfull = b_accfull + 16u * (uint32_t)d;
+
+        for (int i = tid - 128; i < NBIAS; i += EPI_WARPS * 32) s_bias[i] = p.bias[i];
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+
+        constexpr int UPT = 8;
+        float2 c2[BR_NCH][UPT / 2];
+        if (p.h0 == nullptr) {
+            const uint64_t gs = (uint64_t)(p.site_base + site);
+            const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+            const uint32_t slot0 = (p.rng_slot + (uint32_t)d) << 16;
+            const uint32_t t_stage = t_acc(d, 0) + lane_addr + (uint32_t)(half * BR_NCH * UPT);   // this chain's 128 accumulator columns
+#pragma unroll 1
+            for (int i = 0; i < BR_NCH * (UPT / 4); ++i) {
+                const int unit = (i >> 1) * 16 + half * UPT + (i & 1) * 4;
+                const uint32_t slot = slot0 | (uint32_t)(unit >> 2);
+                const float4 hq = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot, p.rng_call, k0, k1);
+                const float4 cv = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot | 0x8000u, p.rng_call, k0, k1);
+                tmem_st2(t_h(d, 0) + lane_addr + (uint32_t)(unit >> 1), pack_half2(hq.x, hq.y), pack_half2(hq.z, hq.w));
+                tmem_st4(t_stage + (uint32_t)(i * 4), __float_as_uint(cv.x), __float_as_uint(cv.y), __float_as_uint(cv.z),
+                         __float_as_uint(cv.w));
+            }
+            tmem_st_wait();
+#pragma unroll
+            for (int ch = 0; ch < BR_NCH; ++ch) {
+                uint32_t v[8];
+                tmem_ld8(t_stage + (uint32_t)(ch * UPT), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < UPT / 2; ++j) c2[ch][j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            }
+        } else {
+            const float* h0 = p.h0 + (size_t)d * p.state_dir_stride + (size_t)site * BR_H;
+            const float* c0 = p.c0 + (size_t)d * p.state_dir_stride + (size_t)site * BR_H;
+#pragma unroll
+            for (int ch = 0; ch < BR_NCH; ++ch) {
+                const int u0 = ch * 16 + half * UPT;
+                float4 cv0 = make_float4(0.f, 0.f, 0.f, 0.f), cv1 = cv0, hq0 = cv0, hq1 = cv0;
+                if (valid) {
+                    cv0 = *reinterpret_cast<const float4*>(c0 + u0); cv1 = *reinterpret_cast<const float4*>(c0 + u0 + 4);
+                    hq0 = *reinterpret_cast<const float4*>(h0 + u0); hq1 = *reinterpret_cast<const float4*>(h0 + u0 + 4);
+                }
+                c2[ch][0] = make_float2(cv0.x, cv0.y); c2[ch][1] = make_float2(cv0.z, cv0.w);
+                c2[ch][2] = make_float2(cv1.x, cv1.y); c2[ch][3] = make_float2(cv1.z, cv1.w);
+                tmem_st4(t_h(d, 0) + lane_addr + (uint32_t)(u0 >> 1), pack_half2(hq0.x, hq0.y), pack_half2(hq0.z, hq0.w),
+                         pack_half2(hq1.x, hq1.y), pack_half2(hq1.z, hq1.w));
+            }
+            tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(r_hready);
+        const uint32_t s_bias_u32 = smem_u32(s_bias) + (uint32_t)((d * BR_NCH * BR_NW + half * 32) * 4);
+        for (int step = 0; step < T; ++step) {
+            const int t = d ? (T - 1 - step) : step;
+            uint8_t* ybase = p.y_img + ((size_t)tile * T + t) * p.y_slabs * SLAB_BYTES + row * SLAB_ROW_BYTES;
+            const uint32_t t_hnext = t_h(d, (step + 1) & 1) + lane_addr;
+#pragma unroll
+            for (int ch = 0; ch < BR_NCH; ++ch) {
+                const int e = ch & 1;
+                const uint32_t use = (uint32_t)(step * (BR_NCH / 2) + (ch >> 1));
+                mbar_wait(b_myfull + 8 * e, use & 1u);
+                tc_fence_after();
+                const int u0 = ch * 16 + half * UPT;
+                float2 h2[UPT / 2];
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    uint32_t v[16];
+                    tmem_ld16(t_acc(d, e) + lane_addr + (uint32_t)(half * 32 + part * 16), v);
+                    float4 bq[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) bq[i] = lds128(s_bias_u32 + (uint32_t)((ch * BR_NW + part * 16 + i * 4) * 4));
+                    tmem_ld_wait();
+                    if (part == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(r_accempty + 8 * e);
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const float4 b0 = bq[2 * qq], b1 = bq[2 * qq + 1];
+                        const float2 ai = add2(make_float2(__uint_as_float(v[qq * 8 + 0]), __uint_as_float(v[qq * 8 + 1])), make_float2(b0.x, b0.y));
+                        const float2 af = add2(make_float2(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3])), make_float2(b0.z, b0.w));
+                        const float2 ag = add2(make_float2(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5])), make_float2(b1.x, b1.y));
+                        const float2 ao = add2(make_float2(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7])), make_float2(b1.z, b1.w));
+                        lstm_cell2<DSP_POLY_MASK_BRANCH>(ai, af, ag, ao, c2[ch][part * 2 + qq], h2[part * 2 + qq]);
+                    }
+                }
+                uint32_t pk[UPT / 2];
+#pragma unroll
+                for (int j = 0; j < UPT / 2; ++j) pk[j] = pack_half2(h2[j].x, h2[j].y);
+                tmem_st4(t_hnext + (uint32_t)(u0 >> 1), pk[0], pk[1], pk[2], pk[3]);
+                const int col = d * BR_H + u0;                             // multiple of 8
+                uint8_t* yslab = ybase + (size_t)(col >> 6) * SLAB_BYTES;
+                *reinterpret_cast<uint4*>(yslab + ((((col & 63) >> 3) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(r_hready);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 3) tmem_dealloc_pair(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Feature assembly into slab images (models.py:182-195): per (site, t) one row of
 // [embed(kmer) | mean | std | len | 0...] (seq) and of the signal rectangle (signal), FP16.
 __global__ void prep_images_kernel(const float* __restrict__ kmer, const float* __restrict__ means,
@@ -713,6 +1004,9 @@ struct TcLstmPack {
     uint8_t* w_img = nullptr;   // [2][2][NCH*KS] half slabs
     float* bias = nullptr;      // [2][NCH*128], scaled like the weights
     int KSX = 0, xk16 = 0;
+    // hidden-128 layers also carry the branch_kernel layout (both directions in one stream, 64-column chunks)
+    uint8_t* w_img_dual = nullptr;
+    float* bias_dual = nullptr;
 };
 struct TcDensePack {
     uint8_t* w_img = nullptr;   // [2][NCH*KS] (x passes for the head) half slabs
@@ -760,6 +1054,26 @@ int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st)
 #else
     cfg.gridDim = dim3(tiles2, MODE != MODE_LSTM ? 1 : 2);
 #endif
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DSP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    m->launches++;
+    return DSP_OK;
+}
+
+template <int KSX>
+int launch_branch(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
+    const size_t smem = (size_t)2 * KSX * SLAB_BYTES + (size_t)BR_NST * BR_STG * QSLAB_BYTES + (size_t)2 * BR_NCH * BR_NW * sizeof(float) + 1024;
+    auto kern = branch_kernel<KSX>;
+    DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((tiles + 1) / 2 * 2), 1);
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -845,11 +1159,42 @@ int tc_pack_lstm_layer(Model* m, LstmLayer& L,
     s->lstm_packs.push_back(pk);
     pk->KSX = KSX;
     pk->xk16 = (K + 15) / 16;
+    const float* wih[2] = {wih0, wih1}; const float* whh[2] = {whh0, whh1};
+    const float* bih[2] = {bih0, bih1}; const float* bhh[2] = {bhh0, bhh1};
+    if (H == BR_H && KSX == 1) {
+        // branch_kernel: [rank][stream unit][32 rows x 128 B]; per chunk pair (c, c+1) the stream is
+        // X(0,c) X(0,c+1) X(1,c) X(1,c+1) H(0,c) H(0,c+1) H(1,c) H(1,c+1) (first index = direction)
+        const int pair_units = 4 * KSX + 4 * KSH;
+        const size_t per_rank = (size_t)(BR_NCH / 2) * pair_units;
+        std::vector<uint8_t> img((size_t)2 * per_rank * QSLAB_BYTES, 0);
+        std::vector<float> bias((size_t)2 * BR_NCH * BR_NW);
+        auto put = [&](int rank, size_t unit, int row, int k, float v) {
+            __half h = __float2half_rn(v);
+            memcpy(&img[((size_t)rank * per_rank + unit) * QSLAB_BYTES + slab_offset_bytes((uint32_t)row, (uint32_t)k)], &h, 2);
+        };
+        for (int d = 0; d < 2; ++d)
+            for (int ch = 0; ch < BR_NCH; ++ch) {
+                const size_t pair_base = (size_t)(ch >> 1) * pair_units;
+                const size_t sx = pair_base + (size_t)(d * 2 + (ch & 1)) * KSX, sh = pair_base + 4 * KSX + (size_t)(d * 2 + (ch & 1)) * KSH;
+                for (int n = 0; n < BR_NW; ++n) {
+                    const int g = (n >> 1) & 3;
+                    const int unit = ch * 16 + (n >> 3) * 2 + (n & 1);
+                    const int wrow = g * H + unit;
+                    const float scale = (g == 2) ? -2.f * LOG2E : -LOG2E;
+                    bias[((size_t)d * BR_NCH + ch) * BR_NW + n] = scale * (bih[d][wrow] + bhh[d][wrow]);
+                    for (int k = 0; k < K; ++k) put(n >> 5, sx + (k >> 6), n & 31, k & 63, scale * wih[d][(size_t)wrow * K + k]);
+                    for (int k = 0; k < H; ++k) put(n >> 5, sh + (k >> 6), n & 31, k & 63, scale * whh[d][(size_t)wrow * H + k]);
+                }
+            }
+        int rc;
+        if ((rc = tc_alloc(m, (void**)&pk->w_img_dual, img.size()))) return rc;
+        if ((rc = tc_alloc(m, (void**)&pk->bias_dual, bias.size() * sizeof(float)))) return rc;
+        DSP_CUDA(cudaMemcpy(pk->w_img_dual, img.data(), img.size(), cudaMemcpyHostToDevice));
+        DSP_CUDA(cudaMemcpy(pk->bias_dual, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     const size_t per_rank = (size_t)NCH * KS;                       // half slabs per (dir, rank)
     std::vector<uint8_t> img((size_t)2 * 2 * per_rank * HSLAB_BYTES, 0);
     std::vector<float> bias((size_t)2 * NCH * 128);
-    const float* wih[2] = {wih0, wih1}; const float* whh[2] = {whh0, whh1};
-    const float* bih[2] = {bih0, bih1}; const float* bhh[2] = {bhh0, bhh1};
     for (int d = 0; d < 2; ++d)
         for (int ch = 0; ch < NCH; ++ch) {
             // stream order of a chunk pair (c, c+1): X(c) X(c+1) H(c) H(c+1)
@@ -971,7 +1316,19 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
             p.n = n; p.T = T; p.xk16 = pk->xk16; p.y_slabs = 2 * hid / 64; p.y_col_off = 0;
             p.write_y = final_layer ? (head_tc ? 2 : 0) : 1;
             Span sp(m, is_comb ? 1 : 4, st);
-            int rc = launch_lstm(m, pk->KSX, hid, p, tiles, st);
+            // Two ways to run a hidden-128 layer: one CTA pair per (tile pair, direction), or both directions
+            // as two chains of one CTA pair (branch_kernel: ~1.8x the time per CTA for 2x the work).  Pick
+            // by whole waves: 2 x tiles CTAs of cost 1 against tiles CTAs of cost 1.8.
+            bool dual = pk->w_img_dual != nullptr;
+            if (dual) {
+                const int64_t sms = m->n_sm > 0 ? m->n_sm : 148;
+                const double single_cost = (double)((2 * tiles + sms - 1) / sms);
+                const double dual_cost = 1.8 * (double)((tiles + sms - 1) / sms);
+                dual = dual_cost < single_cost;
+                if (const char* e = getenv("DSP_B200_BRANCH_DUAL")) dual = atoi(e) != 0;
+            }
+            if (dual) { p.w_img = pk->w_img_dual; p.bias = pk->bias_dual; }
+            int rc = dual ? launch_branch<1>(m, p, tiles, st) : launch_lstm(m, pk->KSX, hid, p, tiles, st);
             if (rc) return rc;
             x = s->ybuf[l & 1];
         }

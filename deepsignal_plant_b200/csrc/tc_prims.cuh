@@ -230,6 +230,11 @@ __device__ __forceinline__ float4 lds128(uint32_t smem_addr) {
 }
 
 // ---- packed fp32 pairs (FADD2 / FMUL2 / FFMA2): one issue slot for two lanes of work ----------------
+#ifdef DSP_NO_PACK   // measurement build: scalar FADD/FMUL/FFMA (either FMA pipe) instead of the packed forms (heavy pipe only)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     float2 d;
     asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
@@ -251,6 +256,7 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
         : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return d;
 }
+#endif
 
 // ---- TMEM <-> registers (32 lanes x 32-bit, N consecutive columns per thread) -----------------------
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {

@@ -12,7 +12,7 @@ if [ "$2" != "quick" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 27 -c 27 --csv \
       --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench_$TAG.log 2>&1
   # full capture of one step's layer kernels (smaller batch keeps the replays short)
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:layer_kernel -s 24 -c 8 \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:layer_kernel|branch_kernel" -s 24 -c 8 \
       -o $OUT/prof_$TAG -f python bench.py --steps 1 --warmup 3 --batch 37888 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
   ls -la $OUT | tail -8
 fi
