@@ -4,8 +4,8 @@ Mirrors ``deepsignal_plant/call_mods_freq.py`` of the reference:
 
 * ``calculate_mods_frequency(mods_files, prob_cf, contig_name=None)`` (``:29-74``)
 * ``write_sitekey2stats(sitekey2stats, result_file, is_sort, is_bed, is_gzip)`` (``:77-122``)
-* ``call_mods_frequency_to_file(args)`` (``:218-296``; the ``--contigs/--nproc`` per-contig
-  multiprocess split is not reproduced -- one GPU pass handles all contigs)
+* ``call_mods_frequency_to_file(args)`` (``:218-296``), including the ``--contigs`` per-contig mode
+  (``:154-215,262-295``; same rows and order, one GPU pass instead of temp files + ``--nproc`` workers)
 
 and ``utils/txt_formater.py`` (``ModRecord`` parsing rules, ``SiteStats`` attributes,
 ``split_key``).  The text is parsed into columns on the host, the segmented reduction --
@@ -399,8 +399,58 @@ def aggregate_records_distributed(keys, p0, p1, label, gidx, prob_cf, sort_by_ke
             m[:, 4].astype(np.int32), m[:, 5].astype(np.int32), m[:, 6].astype(np.int32))
 
 
+def _get_contignams_from_genome_fasta(genomefa):
+    """``call_mods_freq.py:130-137``."""
+    contigs = []
+    with open(genomefa, "r") as rf:
+        for line in rf:
+            if line.startswith(">"):
+                contigs.append(line.strip()[1:].split(" ")[0])
+    return contigs
+
+
+def _is_file_a_genome_fasta(contigfile):
+    """``call_mods_freq.py:140-147``."""
+    with open(contigfile, "r") as rf:
+        for line in rf:
+            if line.startswith("#"):
+                continue
+            elif line.startswith(">"):
+                return True
+    return False
+
+
+def parse_contigs_arg(contigs):
+    """``--contigs`` (``call_mods_freq.py:243-254``): a genome FASTA (names in file order), a file of
+    names or a comma-separated string (both: sorted set)."""
+    if contigs is None:
+        return None
+    if os.path.isfile(contigs):
+        if contigs.endswith((".fa", ".fasta", ".fna")) or _is_file_a_genome_fasta(contigs):
+            return _get_contignams_from_genome_fasta(contigs)
+        with open(contigs, "r") as rf:
+            return sorted(set(rf.read().splitlines()))
+    return sorted(set(contigs.strip().split(",")))
+
+
+def order_by_contig(table, contigs, is_sort):
+    """Row order of the reference's per-contig mode (``call_mods_freq.py:175-215``): every contig is
+    aggregated and written on its own -- rows in first-appearance order, or by position with
+    ``--sort`` -- and the per-contig files are concatenated in sorted FILE-NAME order, i.e. by
+    ``contig + "."`` (the name is followed by ``.<uuid>`` in ``_call_and_write_modsfreq_process``)."""
+    rank = {c: i for i, c in enumerate(sorted(set(contigs), key=lambda c: c + "."))}
+    r = np.fromiter((rank[c] for c in table.chrom.tolist()), dtype=np.int64, count=len(table))
+    if is_sort:
+        order = np.lexsort((table.pos, r))
+    else:
+        order = np.argsort(r, kind="stable")          # insertion order inside a contig
+    return table.reorder(order)
+
+
 def call_mods_frequency_to_file(args):
-    """``call_mods_freq.py:218-296``: collect files, aggregate, write."""
+    """``call_mods_freq.py:218-296``: collect files, aggregate, write.  With ``--contigs`` only the
+    listed contigs are used and the rows come out contig by contig like the reference's per-contig
+    mode (its temp files and ``--nproc`` worker processes are replaced by one GPU pass)."""
     print("[main]call_freq starts..")
     start = time.time()
     mods_files = []
@@ -415,8 +465,20 @@ def call_mods_frequency_to_file(args):
         else:
             raise ValueError("--input_path is not a file or a directory!")
     print("get {} input file(s)..".format(len(mods_files)))
-    print("read the input files..")
-    sites_stats = calculate_mods_frequency(mods_files, args.prob_cf)
-    print("write the result..")
-    write_sitekey2stats(sites_stats, args.result_file, args.sort, args.bed, args.gzip)
+    contigs = parse_contigs_arg(getattr(args, "contigs", None))
+    if contigs is None:
+        print("read the input files..")
+        sites_stats = calculate_mods_frequency(mods_files, args.prob_cf)
+        print("write the result..")
+        write_sitekey2stats(sites_stats, args.result_file, args.sort, args.bed, args.gzip)
+    else:
+        print("start processing {} contigs..".format(len(contigs)))
+        rec = Records.concat([read_mods_file(f) for f in mods_files])
+        wanted = set(contigs)
+        keep = np.fromiter((c in wanted for c in rec.chrom.tolist()), dtype=bool, count=len(rec))
+        rec = Records(*(getattr(rec, f)[keep] for f in ("chrom", "pos", "strand", "pos_in_strand", "p0", "p1", "label", "kmer")))
+        table = aggregate_records(rec, args.prob_cf)
+        print("{} of {} calls used for {} contigs..".format(table.n_used, len(rec), len(contigs)))
+        table = order_by_contig(table, contigs, args.sort)
+        write_sitekey2stats(table, args.result_file, False, args.bed, args.gzip)
     print("[main]call_freq costs %.1f seconds.." % (time.time() - start))

@@ -61,6 +61,10 @@ constexpr uint16_t PAIR_MASK = 3;                   // both CTAs of the pair
 #endif
 // One reciprocal instead of two in the cell update (see lstm_cell2): fewer MUFU ops and, measured,
 // ~2 % more sites/s at the power cap (profiles/r01_run12_epilogue_variants2.log).  0 = separate form.
+// lstm_comb layer 0 (K = 256 + 256) sits between the two regimes.
+#ifndef DSP_POLY_MASK_L0
+#define DSP_POLY_MASK_L0 DSP_POLY_MASK
+#endif
 #ifndef DSP_DIR_INTERLEAVE
 #define DSP_DIR_INTERLEAVE 1
 #endif
@@ -607,7 +611,7 @@ layer_kernel(const LayerParams p) {
                             const float2 af = add2(make_float2(__uint_as_float(v[qq * 8 + 2]), __uint_as_float(v[qq * 8 + 3])), make_float2(b0.z, b0.w));
                             const float2 ag = add2(make_float2(__uint_as_float(v[qq * 8 + 4]), __uint_as_float(v[qq * 8 + 5])), make_float2(b1.x, b1.y));
                             const float2 ao = add2(make_float2(__uint_as_float(v[qq * 8 + 6]), __uint_as_float(v[qq * 8 + 7])), make_float2(b1.z, b1.w));
-                            lstm_cell2<(H == 128) ? DSP_POLY_MASK_BRANCH : DSP_POLY_MASK>(ai, af, ag, ao, c2[ch][part * (PW / 8) + qq], h2[part * (PW / 8) + qq]);
+                            lstm_cell2<(H == 128) ? DSP_POLY_MASK_BRANCH : (KSX == 4 ? DSP_POLY_MASK_L0 : DSP_POLY_MASK)>(ai, af, ag, ao, c2[ch][part * (PW / 8) + qq], h2[part * (PW / 8) + qq]);
                         }
                     }
                     uint32_t pk[UPT / 2];

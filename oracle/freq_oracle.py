@@ -64,3 +64,16 @@ def render(table, is_sort=False, is_bed=False):
             out.append("%s\t%d\t%s\t%d\t%.3f\t%.3f\t%d\t%d\t%d\t%.4f\t%s\n" % (
                 chrom, pos, strand, pis, s0, s1, met, unmet, cov, rmet, kmer))
     return "".join(out)
+
+
+def render_by_contig(lines, contigs, prob_cf=0.0, is_sort=False, is_bed=False):
+    """Per-contig mode (``call_mods_freq.py:154-215,262-295``): one aggregation per contig, results
+    concatenated in sorted temp-file-name order (``<result>.<contig>.<uuid>``, i.e. by contig + ".");
+    contigs without records produce nothing."""
+    lines = list(lines)
+    out = []
+    for contig in sorted(set(contigs), key=lambda c: c + "."):
+        table = aggregate(lines, prob_cf, contig)
+        if table:
+            out.append(render(table, is_sort, is_bed))
+    return "".join(out)

@@ -193,3 +193,38 @@ def test_gpu_freq_large_random_property():
     order = np.argsort(chrom, kind="stable")
     k2, _, s0b, s1b, *_ = cf._aggregate_device(keys[order], p0[order], p1[order], label[order], 0.2, True, 0)
     assert (k2 == k).all() and (s0b == s0).all() and (s1b == s1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["names", "names_sorted_bed", "fasta"])
+def test_gpu_call_freq_contigs_mode_matches_reference_bytes(name, tmp_path):
+    # `call_freq --contigs` (call_mods_freq.py:262-295) through the command line
+    from deepsignal_plant_b200 import cli
+    m = cases.MANIFEST["freq_contigs"]
+    e = m[name]
+    lines = synthetic.make_callmods_records(m["input"]["n"], n_chrom=m["input"]["n_chrom"], n_pos=m["input"]["n_pos"], seed=m["input"]["seed"])
+    a, b = tmp_path / "a.tsv", tmp_path / "b.tsv.gz"
+    a.write_text("\n".join(lines[:9000]) + "\n")
+    with gzip.open(b, "wt") as f:
+        f.write("\n".join(lines[9000:]) + "\n")
+    contigs = e["contigs"]
+    if contigs is None:
+        fa = tmp_path / "genome.fa"
+        fa.write_text(m["fasta_text"])
+        contigs = str(fa)
+    out = tmp_path / "freq.txt"
+    argv = ["call_freq", "-i", str(a), "-i", str(b), "-o", str(out), "--prob_cf", str(e["prob_cf"]), "--contigs", contigs, "--nproc", "2"]
+    argv += (["--sort"] if e["sort"] else []) + (["--bed"] if e["bed"] else [])
+    assert cli.main(argv) == 0
+    assert out.read_text() == cases.read_gz("freq_contigs_%s.txt.gz" % name)
+
+
+def test_contig_argument_forms(tmp_path):
+    assert cf.parse_contigs_arg(None) is None
+    assert cf.parse_contigs_arg("chr3,chr10,chr1,chr3") == ["chr1", "chr10", "chr3"]
+    names = tmp_path / "names.txt"
+    names.write_text("chrB\nchrA\nchrB\n")
+    assert cf.parse_contigs_arg(str(names)) == ["chrA", "chrB"]
+    fa = tmp_path / "g.fasta"
+    fa.write_text(">chr9 desc\nAC\n>chr2\nGT\n")
+    assert cf.parse_contigs_arg(str(fa)) == ["chr9", "chr2"]

@@ -70,3 +70,12 @@ def test_features_oracle_matches_reference_reader():
                          (lens, "base_signal_lens", np.float32), (sig, "signals", np.float32), (labels, "labels", np.int32)):
         assert np.asarray(got, dtype=dt).tobytes() == g[key].tobytes(), key
     assert features_oracle.batch_sizes(lines, cases.MANIFEST["features"]["f5_batch_size"]) == g["batch_sizes"].tolist()
+
+
+@pytest.mark.parametrize("name", ["names", "names_sorted_bed", "fasta"])
+def test_freq_oracle_contigs_mode_matches_reference(name):
+    m = cases.MANIFEST["freq_contigs"]
+    e = m[name]
+    lines = synthetic.make_callmods_records(m["input"]["n"], n_chrom=m["input"]["n_chrom"], n_pos=m["input"]["n_pos"], seed=m["input"]["seed"])
+    contigs = e["contigs"].split(",") if e["contigs"] else [l[1:].split(" ")[0] for l in m["fasta_text"].splitlines() if l.startswith(">")]
+    assert freq_oracle.render_by_contig(lines, contigs, e["prob_cf"], e["sort"], e["bed"]) == cases.read_gz("freq_contigs_%s.txt.gz" % name)
