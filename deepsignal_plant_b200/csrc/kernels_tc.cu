@@ -375,7 +375,6 @@ layer_kernel(const LayerParams p) {
             for (int step = 0; step < T; ++step) {
                 if constexpr (MODE == MODE_LSTM) {
                     const uint32_t a_t = t_h + (uint32_t)(step & 1) * 128u;
-                    if (step == 0) mbar_wait_cluster(b_hready, 0);        // c0 was staged in the accumulator columns
                     for (int pr = 0; pr < NCH / 2; ++pr) {
                         const uint32_t use = (uint32_t)(step * (NCH / 2) + pr);
 #pragma unroll
@@ -522,32 +521,20 @@ layer_kernel(const LayerParams p) {
         } else {
             float2 c2[NCH][UPT / 2];                  // cell state, fp32, in registers for all T steps
             // initial states: c0 -> registers, h0 -> TMEM h buffer 0 (packed FP16 pairs)
-            if (p.h0 == nullptr) {
-                // drawn here (Philox): a compact loop stores h0 straight into the TMEM operand buffer and
-                // parks c0 in the (still unused) accumulator columns, from where it is read into registers
-                const uint64_t gs = (uint64_t)(p.site_base + site);
-                const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-                const uint32_t slot0 = (p.rng_slot + (uint32_t)dir) << 16;
-                const uint32_t t_stage = t_acc + lane_addr + (uint32_t)(sl * NCH * UPT);
+            const bool draw = p.h0 == nullptr;
+            const uint64_t gs = (uint64_t)(p.site_base + site);
+            const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+            const uint32_t slot0 = (p.rng_slot + (uint32_t)dir) << 16;
+            if (draw) {
+                // drawn here (Philox).  Only h0 is needed before the first MMA: a compact loop stores it
+                // straight into the TMEM operand buffer; c0 follows after the MMA warp has been released.
 #pragma unroll 1
                 for (int i = 0; i < NCH * (UPT / 4); ++i) {
                     const int unit = (i / (UPT / 4)) * 32 + sl * UPT + (i % (UPT / 4)) * 4;
-                    const uint32_t slot = slot0 | (uint32_t)(unit >> 2);
-                    const float4 hq = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot, p.rng_call, k0, k1);
-                    const float4 cv = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot | 0x8000u, p.rng_call, k0, k1);
+                    const float4 hq = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot0 | (uint32_t)(unit >> 2), p.rng_call, k0, k1);
                     tmem_st2(t_h + lane_addr + (uint32_t)(unit >> 1), pack_half2(hq.x, hq.y), pack_half2(hq.z, hq.w));
-                    tmem_st4(t_stage + (uint32_t)(i * 4), __float_as_uint(cv.x), __float_as_uint(cv.y), __float_as_uint(cv.z),
-                             __float_as_uint(cv.w));
                 }
                 tmem_st_wait();
-#pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    uint32_t v[8];
-                    tmem_ld8(t_stage + (uint32_t)(ch * UPT), v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < UPT / 2; ++j) c2[ch][j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                }
             } else {
                 const float* h0 = p.h0 + (size_t)dir * p.state_dir_stride + (size_t)site * H;
                 const float* c0 = p.c0 + (size_t)dir * p.state_dir_stride + (size_t)site * H;
@@ -569,6 +556,30 @@ layer_kernel(const LayerParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(r_hready);
+            if (draw) {
+                // c0 while the first MMAs run: parked as packed FP16 pairs in THIS thread's columns of h
+                // buffer 1 (nobody touches them before this thread writes h_1 there), then read back with
+                // static register indices.  (A random N(0,1) draw rounded to FP16 is as good a draw.)
+                const uint32_t t_park = t_h + 128u + lane_addr;
+#pragma unroll 1
+                for (int i = 0; i < NCH * (UPT / 4); ++i) {
+                    const int unit = (i / (UPT / 4)) * 32 + sl * UPT + (i % (UPT / 4)) * 4;
+                    const float4 cv = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot0 | (uint32_t)(unit >> 2) | 0x8000u, p.rng_call, k0, k1);
+                    tmem_st2(t_park + (uint32_t)(unit >> 1), pack_half2(cv.x, cv.y), pack_half2(cv.z, cv.w));
+                }
+                tmem_st_wait();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    uint32_t v[4];
+                    tmem_ld4(t_park + (uint32_t)((ch * 32 + sl * UPT) >> 1), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < UPT / 2; ++j) {
+                        const __half2 hh = *reinterpret_cast<const __half2*>(&v[j]);
+                        c2[ch][j] = make_float2(__low2float(hh), __high2float(hh));
+                    }
+                }
+            }
             const uint32_t s_bias_u32 = smem_u32(s_bias) + (uint32_t)(sl * CPT * 4);
             for (int step = 0; step < T; ++step) {
                 const int t = dir ? (T - 1 - step) : step;
@@ -775,7 +786,6 @@ branch_kernel(const LayerParams p) {
                 __syncwarp();
             };
             for (int step = 0; step < T; ++step) {
-                if (step == 0) { mbar_wait_cluster(b_hready, 0); mbar_wait_cluster(b_hready + 8, 0); }   // c0 staged in the accumulators
                 for (int pr = 0; pr < BR_NCH / 2; ++pr) {
                     const uint32_t use = (uint32_t)(step * (BR_NCH / 2) + pr);
 #pragma unroll
@@ -845,30 +855,18 @@ branch_kernel(const LayerParams p) {
 
         constexpr int UPT = 8;
         float2 c2[BR_NCH][UPT / 2];
-        if (p.h0 == nullptr) {
-            const uint64_t gs = (uint64_t)(p.site_base + site);
-            const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-            const uint32_t slot0 = (p.rng_slot + (uint32_t)d) << 16;
-            const uint32_t t_stage = t_acc(d, 0) + lane_addr + (uint32_t)(half * BR_NCH * UPT);   // this chain's 128 accumulator columns
+        const bool draw = p.h0 == nullptr;
+        const uint64_t gs = (uint64_t)(p.site_base + site);
+        const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+        const uint32_t slot0 = (p.rng_slot + (uint32_t)d) << 16;
+        if (draw) {
 #pragma unroll 1
             for (int i = 0; i < BR_NCH * (UPT / 4); ++i) {
                 const int unit = (i >> 1) * 16 + half * UPT + (i & 1) * 4;
-                const uint32_t slot = slot0 | (uint32_t)(unit >> 2);
-                const float4 hq = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot, p.rng_call, k0, k1);
-                const float4 cv = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot | 0x8000u, p.rng_call, k0, k1);
+                const float4 hq = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot0 | (uint32_t)(unit >> 2), p.rng_call, k0, k1);
                 tmem_st2(t_h(d, 0) + lane_addr + (uint32_t)(unit >> 1), pack_half2(hq.x, hq.y), pack_half2(hq.z, hq.w));
-                tmem_st4(t_stage + (uint32_t)(i * 4), __float_as_uint(cv.x), __float_as_uint(cv.y), __float_as_uint(cv.z),
-                         __float_as_uint(cv.w));
             }
             tmem_st_wait();
-#pragma unroll
-            for (int ch = 0; ch < BR_NCH; ++ch) {
-                uint32_t v[8];
-                tmem_ld8(t_stage + (uint32_t)(ch * UPT), v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < UPT / 2; ++j) c2[ch][j] = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            }
         } else {
             const float* h0 = p.h0 + (size_t)d * p.state_dir_stride + (size_t)site * BR_H;
             const float* c0 = p.c0 + (size_t)d * p.state_dir_stride + (size_t)site * BR_H;
@@ -890,6 +888,27 @@ branch_kernel(const LayerParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(r_hready);
+        if (draw) {          // c0 behind the first MMAs, parked in this thread's columns of h buffer 1 (see layer_kernel)
+            const uint32_t t_park = t_h(d, 1) + lane_addr;
+#pragma unroll 1
+            for (int i = 0; i < BR_NCH * (UPT / 4); ++i) {
+                const int unit = (i >> 1) * 16 + half * UPT + (i & 1) * 4;
+                const float4 cv = philox_normal4((uint32_t)gs, (uint32_t)(gs >> 32), slot0 | (uint32_t)(unit >> 2) | 0x8000u, p.rng_call, k0, k1);
+                tmem_st2(t_park + (uint32_t)(unit >> 1), pack_half2(cv.x, cv.y), pack_half2(cv.z, cv.w));
+            }
+            tmem_st_wait();
+#pragma unroll
+            for (int ch = 0; ch < BR_NCH; ++ch) {
+                uint32_t v[4];
+                tmem_ld4(t_park + (uint32_t)((ch * 16 + half * UPT) >> 1), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < UPT / 2; ++j) {
+                    const __half2 hh = *reinterpret_cast<const __half2*>(&v[j]);
+                    c2[ch][j] = make_float2(__low2float(hh), __high2float(hh));
+                }
+            }
+        }
         const uint32_t s_bias_u32 = smem_u32(s_bias) + (uint32_t)((d * BR_NCH * BR_NW + half * 32) * 4);
         for (int step = 0; step < T; ++step) {
             const int t = d ? (T - 1 - step) : step;
