@@ -277,6 +277,7 @@ layer_kernel(const LayerParams p) {
     cluster_sync_all();                          // the peer's barriers exist before anything lands on them
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    griddep_launch_dependents();                 // the next kernel of the stream may take SMs as this grid drains
     const uint32_t t_acc = tmem;                 // two accumulators: columns [0,128) and [128,256)
     const uint32_t t_h = tmem + 256;             // two h buffers of H/2 columns at +0 and +128
 
@@ -303,6 +304,7 @@ layer_kernel(const LayerParams p) {
         } else if (warp == 2) {
             // ---- x_t slab producer ------------------------------------------------------------
             if (elect_one()) {
+                griddep_wait();              // the layer input is the previous kernel's output
                 for (int step = 0; step < T; ++step) {
                     const int t = dir ? (T - 1 - step) : step;
                     // MODE_HEAD: pass 0 and 2 read the hi image, pass 1 the lo image of [h_fwd | h_bwd]
@@ -719,6 +721,7 @@ branch_kernel(const LayerParams p) {
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    griddep_launch_dependents();
     // chain d: accumulators at d*128 + {0, 64}, h buffers at 256 + d*128 + {0, 64}
     auto t_acc = [&](int d, int e) -> uint32_t { return tmem + (uint32_t)(d * 128 + e * 64); };
     auto t_h = [&](int d, int b) -> uint32_t { return tmem + 256u + (uint32_t)(d * 128 + b * 64); };
@@ -742,6 +745,7 @@ branch_kernel(const LayerParams p) {
             }
         } else if (warp == 2) {
             if (elect_one()) {
+                griddep_wait();              // the layer input is the previous kernel's output
                 for (int step = 0; step < T; ++step)
                     for (int d = 0; d < 2; ++d) {
                         const int t = d ? (T - 1 - step) : step;
@@ -1063,6 +1067,9 @@ int tc_alloc(Model* m, void** p, size_t bytes) {
     return DSP_OK;
 }
 
+// programmatic dependent launch between the layer kernels of a forward (DSP_B200_PDL=0 turns it off)
+bool g_pdl = true;
+
 template <int KSX, int H, int MODE, int NOUT>
 int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
     constexpr int NCH = MODE != MODE_LSTM ? NOUT / 128 : H / 32;
@@ -1080,11 +1087,13 @@ int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st)
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_pdl ? 2 : 1;
     DSP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     m->launches++;
     return DSP_OK;
@@ -1100,11 +1109,13 @@ int launch_branch(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_pdl ? 2 : 1;
     DSP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     m->launches++;
     return DSP_OK;
@@ -1141,6 +1152,7 @@ int tc_create(Model* m) {
                 "DSP_PRECISION_FP16 supports signal_len <= 64 and <= 16 sequence features per base");
     TcState* s = new TcState();
     m->tc_state = s;
+    if (const char* e = getenv("DSP_B200_PDL")) g_pdl = atoi(e) != 0;
     s->tiles = ((m->cap + TILE - 1) / TILE + 1) / 2 * 2;     // whole CTA pairs
     const size_t per_tile_t = (size_t)s->tiles * c.seq_len * SLAB_BYTES;
     int rc;

@@ -80,6 +80,12 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start
+// (prologue, TMEM allocation, initial-state draws) while the previous kernel of the stream drains;
+// griddep_wait() blocks until that kernel has completed and its writes are visible.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- proxy / tcgen05 fences ----------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
