@@ -1013,10 +1013,21 @@ __global__ void prep_images_kernel(const float* __restrict__ kmer, const float* 
         const float* src = signals + (site * T + t) * S;
         uint8_t* dst = xsig_img + slab + row * SLAB_ROW_BYTES;
         const int nchunk = ((S + 15) / 16) * 2;
+        const bool vec = (S & 3) == 0;               // rows of the signal rectangle are 16-byte aligned: 128-bit loads
         for (int chunk = 0; chunk < nchunk; ++chunk) {
             float f[8];
+            if (vec) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const int k = chunk * 8 + i; f[i] = (valid && k < S) ? src[k] : 0.f; }
+                for (int h4 = 0; h4 < 2; ++h4) {
+                    const int k = chunk * 8 + h4 * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid && k < S) v = __ldg(reinterpret_cast<const float4*>(src + k));
+                    f[h4 * 4] = v.x; f[h4 * 4 + 1] = v.y; f[h4 * 4 + 2] = v.z; f[h4 * 4 + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int k = chunk * 8 + i; f[i] = (valid && k < S) ? src[k] : 0.f; }
+            }
             uint4 o;
             o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]); o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
             *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = o;
