@@ -113,22 +113,21 @@ def make_pool(n_buffers, batch, seed=0, T=13, S=16):
 
 
 def cpu_baseline_run(sites, threads):
-    """The numpy oracle port of the reference forward on host cores (oracle/ as checker /
-    baseline only).  Returns sites/s."""
+    """The reference's CPU path on the host cores: its forward restated on torch's own CPU operators
+    (oracle/torch_oracle.py: nn.LSTM -> oneDNN, nn.Linear, softmax), driven like `_call_mods` drives
+    it -- batches of 512 (the reference's default --batch_size), fresh torch.randn states per batch,
+    argmax.  oracle/ is used here as the baseline only.  Returns (sites/s, seconds)."""
     import torch
     from deepsignal_plant_b200 import synthetic
     from deepsignal_plant_b200.models import ModelBiLSTM
-    from oracle import model_oracle
+    from oracle import model_oracle, torch_oracle
+    torch.set_num_threads(threads)
     cfg = model_oracle.make_cfg()
     torch.manual_seed(1234)
-    params = {k: v.detach().numpy() for k, v in ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict().items()}
-    feats = synthetic.make_features(sites, 13, 16, seed=0)
-    states = synthetic.make_states(cfg, sites, seed=4321)
-    keys = ("kmer", "base_means", "base_stds", "base_signal_lens", "signals")
+    sd = {k: v.detach().clone() for k, v in ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict().items()}
+    feats = {k: torch.from_numpy(v) for k, v in synthetic.make_features(sites, 13, 16, seed=0).items()}
     t0 = time.perf_counter()
-    for s in range(0, sites, 512):            # the reference's default --batch_size 512
-        sub = {g: tuple(x[:, s:s + 512] for x in hc) for g, hc in states.items()}
-        model_oracle.forward(params, cfg, *(feats[k][s:s + 512] for k in keys), sub)
+    torch_oracle.call_mods_batches(sd, cfg, feats, 512)
     dt = time.perf_counter() - t0
     return sites / dt, dt
 
@@ -137,7 +136,8 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 4096
+    # bounded sample per step: the whole run (K steps) stays around a minute at ~2 k sites/s
+    sample = int(min(8192, max(512, (120000 // max(args.steps, 1)) // 512 * 512)))
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_baseline_run(512, cores)
     vals = []
@@ -151,10 +151,10 @@ def reference_arm(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "both_bilstm bn13_sn16 h256 inference, batch 65536 (config 2)",
-                       "note": "reference CPU path restated in numpy (oracle port; the reference is pure Python/torch "
-                               "and /root/reference does not travel); each step = %d-site sample in batches of 512" % sample},
+                       "note": "reference CPU path: its forward restated on the same torch CPU operators (oracle/torch_oracle.py; "
+                               "/root/reference itself does not travel); each step = %d-site sample in batches of 512" % sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d sites per step, batch 512, numpy fp32 (threaded BLAS)" % sample},
+                             "sample": "%d sites per step, batch 512, torch CPU fp32 (oneDNN LSTM), %d threads" % (sample, cores)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -181,8 +181,6 @@ def main():
     if args.steps is None:
         args.steps = 100 if args.precision == "fp16" else 4
     if args.impl == "reference":
-        if args.steps > 8:
-            args.steps = 8
         reference_arm(args, rank, world)
         return
 
@@ -311,7 +309,7 @@ def main():
             sample = 8192
             v, dt = cpu_baseline_run(sample, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d sites, batch 512, numpy fp32 oracle (threaded BLAS), %.1f s" % (sample, dt)}
+                                    "sample": "%d sites, batch 512, torch CPU fp32 restatement of the reference forward, %d threads, %.1f s" % (sample, cores, dt)}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -79,3 +79,17 @@ def test_freq_oracle_contigs_mode_matches_reference(name):
     lines = synthetic.make_callmods_records(m["input"]["n"], n_chrom=m["input"]["n_chrom"], n_pos=m["input"]["n_pos"], seed=m["input"]["seed"])
     contigs = e["contigs"].split(",") if e["contigs"] else [l[1:].split(" ")[0] for l in m["fasta_text"].splitlines() if l.startswith(">")]
     assert freq_oracle.render_by_contig(lines, contigs, e["prob_cf"], e["sort"], e["bed"]) == cases.read_gz("freq_contigs_%s.txt.gz" % name)
+
+
+@pytest.mark.parametrize("name", ["both_13_16_s1", "seq_13_16_s1234", "signal_13_16_s1234", "both_small_odd", "seq_nobase", "both_nolen_c3"])
+def test_torch_cpu_oracle_matches_reference_fixtures(name):
+    # the CPU baseline of bench.py runs this restatement: same torch CPU operators as the reference
+    import torch
+    from oracle import torch_oracle
+    case = cases.load_case(name)
+    n = min(case["entry"]["n"], 2048)
+    case = cases.slice_case(case, n)
+    sd = {k: torch.from_numpy(v) for k, v in case["params"].items()}
+    states = {g: tuple(torch.from_numpy(np.ascontiguousarray(x)) for x in hc) for g, hc in case["states"].items()}
+    logits, probs = torch_oracle.forward(sd, case["cfg"], *(torch.from_numpy(case["feats"][k]) for k in cases.FEATURE_KEYS), states)
+    assert np.abs(probs.numpy() - case["probs"]).max() < 2e-6 and np.abs(logits.numpy() - case["logits"]).max() < 2e-5
