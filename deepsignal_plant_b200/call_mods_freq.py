@@ -311,36 +311,29 @@ def owner_of_key(keys, world):
     return (h % np.uint64(world)).astype(np.int64)
 
 
-def exchange_rows(rows, dest, world, rank, dev, group=None):
-    """Variable-size all-to-all of int64 rows: row i goes to rank dest[i]; rows bound for the
-    same rank keep their order; the result concatenates what source ranks 0..world-1 sent,
-    in rank order.  One ``batch_isend_irecv`` = NCCL grouped send/recv over NVLink on GPUs
-    (gloo in the CPU tests)."""
+def owner_of_key_t(keys, world):
+    """``owner_of_key`` on an int64 torch tensor (any device): the same 31-bit hash, computed with
+    wrapping int64 arithmetic (arithmetic shift + mask = logical shift)."""
+    h = (keys * (-7046029254386353131)) >> 33            # 0x9E3779B97F4A7C15 as a signed 64-bit constant
+    return (h & 0x7FFFFFFF) % world
+
+
+def exchange_rows(rows, dest, world, group=None):
+    """Variable-size all-to-all of int64 rows that stay on their device: row i of ``rows`` (m, w) goes
+    to rank ``dest[i]``; rows bound for the same rank keep their order; the result concatenates what
+    source ranks 0..world-1 sent, in rank order.  One ``all_to_all_single`` with split sizes = NCCL
+    send/recv over NVLink on GPUs (gloo in the CPU tests)."""
     import torch
     import torch.distributed as dist
-    order = np.argsort(dest, kind="stable")
-    counts = np.bincount(dest, minlength=world).astype(np.int64)
-    send = torch.from_numpy(np.ascontiguousarray(rows[order])).to(dev)
-    t_counts = torch.from_numpy(counts).to(dev)
-    all_counts = [torch.empty_like(t_counts) for _ in range(world)]
-    dist.all_gather(all_counts, t_counts, group=group)
-    recv_counts = [int(c[rank]) for c in all_counts]
-    width = rows.shape[1]
-    recv = [torch.empty((c, width), dtype=torch.int64, device=dev) for c in recv_counts]
-    offs = np.concatenate([[0], np.cumsum(counts)])
-    ops = []
-    for r in range(world):
-        if r == rank:
-            recv[r].copy_(send[offs[r]:offs[r + 1]])
-            continue
-        if counts[r]:
-            ops.append(dist.P2POp(dist.isend, send[offs[r]:offs[r + 1]].contiguous(), r, group=group))
-        if recv_counts[r]:
-            ops.append(dist.P2POp(dist.irecv, recv[r], r, group=group))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    return torch.cat(recv, 0)
+    order = torch.sort(dest, stable=True).indices
+    counts = torch.bincount(dest, minlength=world)
+    send = rows[order].contiguous()
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts, group=group)
+    in_splits, out_splits = counts.tolist(), recv_counts.tolist()
+    recv = rows.new_empty((int(sum(out_splits)), rows.shape[1]))
+    dist.all_to_all_single(recv, send, out_splits, in_splits, group=group)
+    return recv
 
 
 def _gpu_local_aggregate(got, prob_cf, dev):
@@ -358,43 +351,54 @@ def _gpu_local_aggregate(got, prob_cf, dev):
                         met.to(torch.int64), unmet.to(torch.int64), cov.to(torch.int64)], dim=1)
 
 
-def aggregate_records_distributed(keys, p0, p1, label, gidx, prob_cf, sort_by_key=False, device=None,
-                                  group=None, local_aggregate=None):
-    """Multi-GPU ``calculate_mods_frequency``.  Every rank passes ITS contiguous shard of the
-    records in file order (numpy columns; ``gidx`` = global record index, ascending across
-    ranks).  Callable records are routed to ``owner_of_key`` with one variable-size
-    all-to-all, so all records of a site reach one rank in ascending global order and the
-    float64 sums are the reference's bit for bit (no partial-sum merge: float64 addition is
-    order sensitive).  Each rank aggregates its keys with ``dsp_freq_aggregate``; the
-    per-site rows are collected on rank 0 and ordered by first callable appearance (dict
-    insertion order) or by key.  Returns on rank 0 a tuple of numpy arrays (key uint64,
-    first_gidx, s0, s1, met, unmet, cov); ``None`` elsewhere.
-
-    ``local_aggregate(rows, prob_cf) -> rows7`` replaces the GPU step in the CPU (gloo) tests."""
+def aggregate_tensors_distributed(key, p0, p1, label, gidx, prob_cf, sort_by_key=False, group=None, local_aggregate=None):
+    """Multi-GPU ``calculate_mods_frequency`` on tensors that are already on this rank's device
+    (int64 keys, float64 probabilities, int32 labels, int64 global record indices of THIS rank's
+    contiguous shard, file order).  Callable records are routed to ``owner_of_key_t`` with one
+    variable-size all-to-all, so all records of a site reach one rank in ascending global order and
+    the float64 sums are the reference's bit for bit (no partial-sum merge: float64 addition is
+    order sensitive).  Each rank aggregates its keys with ``dsp_freq_aggregate``; the per-site rows
+    are collected on rank 0 and ordered by first callable appearance (dict insertion order) or by
+    key.  Nothing but split sizes visits the host.  Returns on rank 0 an (s, 7) int64 tensor
+    [key, first_gidx, s0 bits, s1 bits, met, unmet, cov]; ``None`` elsewhere."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    dev = torch.device("cuda", device) if device is not None else torch.device("cpu")
-    keep = ~(np.abs(p0 - p1) < prob_cf)                   # txt_formater.py:23-26, before the exchange
-    keys, p0, p1, label, gidx = keys[keep], p0[keep], p1[keep], label[keep], gidx[keep]
-    rows = np.stack([keys.view(np.int64), np.ascontiguousarray(p0).view(np.int64),
-                     np.ascontiguousarray(p1).view(np.int64), label.astype(np.int64), gidx.astype(np.int64)], axis=1)
-    got = exchange_rows(rows, owner_of_key(keys, world), world, rank, dev, group)
+    dev = key.device
+    keep = ~((p0 - p1).abs() < prob_cf)                   # txt_formater.py:23-26, before the exchange
+    rows = torch.stack([key, p0.view(torch.int64), p1.view(torch.int64), label.to(torch.int64), gidx], dim=1)[keep]
+    got = exchange_rows(rows, owner_of_key_t(rows[:, 0], world), world, group)
     if local_aggregate is None:
-        if device is None:
+        if dev.type != "cuda":
             raise RuntimeError("call_freq aggregation needs a CUDA device; there is no CPU path")
         with torch.cuda.device(dev):
             mine = _gpu_local_aggregate(got, prob_cf, dev)
     else:
         mine = torch.from_numpy(np.ascontiguousarray(local_aggregate(got.cpu().numpy(), prob_cf))).to(dev)
-    mine_np = mine.cpu().numpy()
-    merged = exchange_rows(mine_np, np.zeros(mine_np.shape[0], np.int64), world, rank, dev, group)
+    merged = exchange_rows(mine, torch.zeros(mine.shape[0], dtype=torch.int64, device=dev), world, group)
     if rank != 0:
         return None
-    m = merged.cpu().numpy()
-    order = np.argsort(m[:, 0].view(np.uint64), kind="stable") if sort_by_key else np.argsort(m[:, 1], kind="stable")
-    m = m[order]
+    order = torch.sort(merged[:, 0] if sort_by_key else merged[:, 1], stable=True).indices
+    return merged[order]
+
+
+def aggregate_records_distributed(keys, p0, p1, label, gidx, prob_cf, sort_by_key=False, device=None,
+                                  group=None, local_aggregate=None):
+    """numpy front end of ``aggregate_tensors_distributed``: every rank passes ITS contiguous shard
+    of the records in file order (``gidx`` = global record index, ascending across ranks).  Returns
+    on rank 0 a tuple of numpy arrays (key uint64, first_gidx, s0, s1, met, unmet, cov); ``None``
+    elsewhere.  ``local_aggregate(rows, prob_cf) -> rows7`` replaces the GPU step in the CPU (gloo) tests."""
+    import torch
+    if device is None and local_aggregate is None:
+        raise RuntimeError("call_freq aggregation needs a CUDA device; there is no CPU path")
+    dev = torch.device("cuda", device) if device is not None else torch.device("cpu")
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt, copy=False)).to(dev)
+    m = aggregate_tensors_distributed(t(keys.view(np.int64), np.int64), t(p0, np.float64), t(p1, np.float64),
+                                      t(label, np.int32), t(gidx, np.int64), prob_cf, sort_by_key, group, local_aggregate)
+    if m is None:
+        return None
+    m = m.cpu().numpy()
     return (m[:, 0].copy().view(np.uint64), m[:, 1].copy(), m[:, 2].copy().view(np.float64), m[:, 3].copy().view(np.float64),
             m[:, 4].astype(np.int32), m[:, 5].astype(np.int32), m[:, 6].astype(np.int32))
 

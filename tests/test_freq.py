@@ -126,6 +126,14 @@ def test_distributed_exchange_gloo(world, prob_cf, sort_by_key):
         assert rec.chrom[first[i]] == chrom and rec.pos[first[i]] == pos
 
 
+def test_owner_hash_on_tensors_equals_numpy():
+    rng = np.random.default_rng(2)
+    keys = cf.make_keys(rng.integers(0, 200, 5000), rng.integers(0, 1 << 39, 5000))
+    for world in (1, 2, 3, 8):
+        got = cf.owner_of_key_t(torch.from_numpy(keys.view(np.int64)), world).numpy()
+        assert (got == cf.owner_of_key(keys, world)).all()
+
+
 def test_owner_of_key_is_balanced_and_deterministic():
     keys = cf.make_keys(np.repeat(np.arange(5), 1000), np.tile(np.arange(1000), 5))
     own = cf.owner_of_key(keys, 8)

@@ -30,34 +30,34 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rng = np.random.default_rng(7)
+    # the same seeded records on every rank, generated on the device; rank r keeps shard r (file order)
     n = args.records
-    chrom = rng.integers(0, 5, n)
-    pos = rng.integers(0, max(n // 20, 1), n)            # coverage ~20 per site over 5 chromosomes
-    keys = cf.make_keys(chrom, pos)
-    p1 = np.round(rng.random(n), 6)
-    p0 = np.round(1.0 - p1, 6)
-    label = (p1 > p0).astype(np.int32)
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    chrom = torch.randint(0, 5, (n,), device=dev, generator=g)
+    pos = torch.randint(0, max(n // 20, 1), (n,), device=dev, generator=g)      # coverage ~20 per site over 5 chromosomes
+    key = (chrom << cf.POS_BITS) | pos
+    p1 = torch.round(torch.rand(n, device=dev, generator=g, dtype=torch.float64) * 1e6) / 1e6
+    p0 = torch.round((1.0 - p1) * 1e6) / 1e6
+    label = (p1 > p0).to(torch.int32)
     lo, hi = rank * n // world, (rank + 1) * n // world
-    gidx = np.arange(lo, hi, dtype=np.int64)
-    for it in range(2):                                   # first pass warms NCCL / CUB up
+    gidx = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+    for it in range(3):                                   # first passes warm NCCL / CUB up
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = cf.aggregate_records_distributed(keys[lo:hi], p0[lo:hi], p1[lo:hi], label[lo:hi], gidx, args.prob_cf,
-                                               sort_by_key=True, device=local)
+        res = cf.aggregate_tensors_distributed(key[lo:hi], p0[lo:hi], p1[lo:hi], label[lo:hi], gidx, args.prob_cf, sort_by_key=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     if rank == 0:
-        want = cf._aggregate_device(keys, p0, p1, label, args.prob_cf, True, local)
-        k, first, s0, s1, met, unmet, cov = res
-        ok = (k.view(np.uint64) == want[0].view(np.uint64)).all() and (first == want[1]).all() \
-            and (s0.view(np.int64) == want[2].view(np.int64)).all() and (s1.view(np.int64) == want[3].view(np.int64)).all() \
-            and (met == want[4]).all() and (unmet == want[5]).all() and (cov == want[6]).all()
+        k, first, s0, s1, met, unmet, cov = cf._aggregate_tensors(key, p0, p1, label, args.prob_cf, True, dev)
+        want = torch.stack([k, first, s0.view(torch.int64), s1.view(torch.int64), met.long(), unmet.long(), cov.long()], 1)
+        ok = res.shape == want.shape and bool((res == want).all())
         print(json.dumps({"check": "freq multi-GPU == single-GPU, bit for bit", "ok": bool(ok), "world": world,
-                          "records": n, "sites": int(len(k)), "seconds": float(tt[0]),
+                          "records": n, "sites": int(res.shape[0]), "seconds": float(tt[0]),
                           "records_per_s": n / float(tt[0])}), flush=True)
         if not ok:
             sys.exit(1)
