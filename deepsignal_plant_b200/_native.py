@@ -67,9 +67,9 @@ def lib():
                                      vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
     L.dsp_selftest.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     i32 = C.c_int32
-    L.dsp_parse_features.argtypes = [vp, i64, i32, i32, i32, i64, fp, fp, fp, fp, fp, vp, vp, vp, vp,
+    L.dsp_parse_features.argtypes = [vp, i64, i32, i32, i32, i64, fp, fp, fp, fp, fp, vp, vp, i64, vp,
                                      C.POINTER(i64), C.POINTER(i64), i32]
-    L.dsp_format_calls.argtypes = [vp, vp, vp, vp, i32, fp, vp, i64, vp, i64, C.POINTER(i64), i32]
+    L.dsp_format_calls.argtypes = [vp, vp, fp, i32, fp, vp, i64, vp, i64, C.POINTER(i64), i32]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here means header and library disagree
     _lib = L

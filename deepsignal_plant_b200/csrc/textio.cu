@@ -34,11 +34,35 @@ int base_code(char ch) {
 
 inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
 
-// Python float(str): decimal -> nearest double; the float32 tensor then rounds the double
+// Python float(str): decimal -> nearest double; the float32 tensor then rounds the double.
+// Fast path (Clinger): up to 15 significant digits and no exponent -- what `extract` writes
+// (np.around(x, 6)) -- is an exact integer divided by an exact power of ten, one correctly rounded
+// operation; everything else goes through std::from_chars (also correctly rounded).
 bool parse_double(const char* b, const char* e, double* out) {
+    static const double P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                   1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
     while (b < e && is_space(*b)) ++b;
     while (e > b && is_space(e[-1])) --e;
-    if (b < e && *b == '+') ++b;
+    if (b >= e) return false;
+    {
+        const char* p = b;
+        bool neg = false;
+        if (*p == '-') { neg = true; ++p; } else if (*p == '+') ++p;
+        unsigned long long mant = 0;
+        int ndig = 0, frac = -1;
+        for (; p < e; ++p) {
+            const unsigned c = (unsigned)(*p - '0');
+            if (c <= 9) { mant = mant * 10 + c; ++ndig; if (frac >= 0) ++frac; }
+            else if (*p == '.' && frac < 0) frac = 0;
+            else break;
+        }
+        if (p == e && ndig >= 1 && ndig <= 15) {
+            const double v = (double)mant / P10[frac < 0 ? 0 : frac];
+            *out = neg ? -v : v;
+            return true;
+        }
+    }
+    if (*b == '+') ++b;
     if (b >= e) return false;
     auto r = std::from_chars(b, e, *out);
     if (r.ec == std::errc::result_out_of_range) { *out = (*b == '-') ? -HUGE_VAL : HUGE_VAL; return r.ptr == e; }   // float('1e999') == inf
@@ -69,7 +93,7 @@ bool split_exact(const char* b, const char* e, char sep, int count, F&& each) {
 
 struct ParseJob {
     const char* text; const int64_t* begin; const int64_t* end; int T, S;
-    float *kmer, *means, *stds, *lens, *signals; int32_t* labels; int32_t *info_len, *kmer_off;
+    float *kmer, *means, *stds, *lens, *signals; int32_t* labels; int32_t* info_len;
 };
 
 // returns 0 or the 1-based index of the offending column
@@ -84,7 +108,6 @@ int parse_line(const ParseJob& j, int64_t i) {
     f[12] = e + 1;
     const int T = j.T, S = j.S;
     j.info_len[i] = (int32_t)(f[6] - 1 - b);
-    j.kmer_off[i] = (int32_t)(f[6] - b);
     if (f[7] - 1 - f[6] != T) return 7;
     for (int t = 0; t < T; ++t) {
         const int code = base_code(f[6][t]);
@@ -168,15 +191,16 @@ extern "C" {
 
 int dsp_parse_features(const char* text, int64_t nbytes, int32_t is_final, int32_t seq_len, int32_t signal_len,
                        int64_t max_sites, float* kmer, float* means, float* stds, float* lens, float* signals,
-                       int32_t* labels, int64_t* line_begin, int32_t* info_len, int32_t* kmer_off,
+                       int32_t* labels, char* info_text, int64_t info_cap, int64_t* info_off,
                        int64_t* n_sites, int64_t* consumed, int32_t nthreads) {
-    DSP_REQUIRE(text && kmer && means && stds && lens && signals && labels && line_begin && info_len && kmer_off &&
+    DSP_REQUIRE(text && kmer && means && stds && lens && signals && labels && info_text && info_off &&
                 n_sites && consumed, DSP_ERR_INVALID, "dsp_parse_features: null argument");
     DSP_REQUIRE(seq_len >= 1 && signal_len >= 1 && max_sites >= 0 && nbytes >= 0, DSP_ERR_INVALID,
                 "dsp_parse_features: bad dimensions");
     // pass 1: complete lines (line.strip(): surrounding white space does not belong to a field)
-    std::vector<int64_t> ends;
-    ends.reserve((size_t)(max_sites < (1 << 20) ? max_sites : (1 << 20)));
+    std::vector<int64_t> begins, ends;
+    begins.reserve((size_t)(max_sites < (1 << 20) ? max_sites : (1 << 20)));
+    ends.reserve(begins.capacity());
     int64_t pos = 0, n = 0;
     while (pos < nbytes && n < max_sites) {
         const char* nl = (const char*)memchr(text + pos, '\n', (size_t)(nbytes - pos));
@@ -194,11 +218,12 @@ int dsp_parse_features(const char* text, int64_t nbytes, int32_t is_final, int32
             pos = nbytes;
             break;
         }
-        line_begin[n] = b;
+        begins.push_back(b);
         ends.push_back(e);
         ++n;
     }
-    ParseJob job{text, line_begin, ends.data(), seq_len, signal_len, kmer, means, stds, lens, signals, labels, info_len, kmer_off};
+    std::vector<int32_t> info_len((size_t)n);
+    ParseJob job{text, begins.data(), ends.data(), seq_len, signal_len, kmer, means, stds, lens, signals, labels, info_len.data()};
     std::atomic<int64_t> bad_line{-1};
     std::atomic<int> bad_col{0};
     parallel_for(n, nthreads, [&](int64_t lo, int64_t hi) {
@@ -217,16 +242,25 @@ int dsp_parse_features(const char* text, int64_t nbytes, int32_t is_final, int32
                        (long long)bad_line.load() + 1, bad_col.load(), seq_len, signal_len);
         return DSP_ERR_INVALID;
     }
+    // the first six columns of every line ("sampleinfo", :89), packed back to back
+    info_off[0] = 0;
+    for (int64_t i = 0; i < n; ++i) info_off[i + 1] = info_off[i] + info_len[i];
+    DSP_REQUIRE(info_off[n] <= info_cap, DSP_ERR_NOMEM, "dsp_parse_features: sample info needs %lld bytes, buffer has %lld",
+                (long long)info_off[n], (long long)info_cap);
+    parallel_for(n, nthreads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) memcpy(info_text + info_off[i], text + begins[i], (size_t)info_len[i]);
+    });
     *n_sites = n;
     *consumed = pos;
     return DSP_OK;
 }
 
-int dsp_format_calls(const char* text, const int64_t* line_begin, const int32_t* info_len, const int32_t* kmer_off,
-                     int32_t seq_len, const float* probs, const int32_t* labels, int64_t n,
+int dsp_format_calls(const char* info_text, const int64_t* info_off, const float* kmer, int32_t seq_len,
+                     const float* probs, const int32_t* labels, int64_t n,
                      char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads) {
-    DSP_REQUIRE(text && line_begin && info_len && kmer_off && probs && labels && out && out_bytes, DSP_ERR_INVALID,
+    DSP_REQUIRE(info_text && info_off && kmer && probs && labels && out && out_bytes, DSP_ERR_INVALID,
                 "dsp_format_calls: null argument");
+    static const char BASES[] = "ACGTNWSMKRYBVDHZ";              // code2base_dna (utils/process_utils.py:29)
     const int c = seq_len / 2;                                    // call_modifications.py:181-184
     const int lo5 = c - 2 > 0 ? c - 2 : 0, hi5 = c + 3 < seq_len ? c + 3 : seq_len;
     struct Num { char s[2][20]; uint8_t len[2]; };
@@ -241,7 +275,7 @@ int dsp_format_calls(const char* text, const int64_t* line_begin, const int32_t*
             nums[i].len[1] = (uint8_t)format_f32(p1n, nums[i].s[1]);
             char lab[16];
             auto r = std::to_chars(lab, lab + 16, labels[i]);
-            off[i + 1] = info_len[i] + 1 + nums[i].len[0] + 1 + nums[i].len[1] + 1 + (r.ptr - lab) + 1 + (hi5 - lo5) + 1;
+            off[i + 1] = (info_off[i + 1] - info_off[i]) + 1 + nums[i].len[0] + 1 + nums[i].len[1] + 1 + (r.ptr - lab) + 1 + (hi5 - lo5) + 1;
         }
     });
     off[0] = 0;
@@ -252,12 +286,12 @@ int dsp_format_calls(const char* text, const int64_t* line_begin, const int32_t*
     parallel_for(n, nthreads, [&](int64_t a, int64_t b) {
         for (int64_t i = a; i < b; ++i) {
             char* o = out + off[i];
-            const char* line = text + line_begin[i];
-            memcpy(o, line, (size_t)info_len[i]); o += info_len[i]; *o++ = '\t';
+            const int64_t il = info_off[i + 1] - info_off[i];
+            memcpy(o, info_text + info_off[i], (size_t)il); o += il; *o++ = '\t';
             memcpy(o, nums[i].s[0], nums[i].len[0]); o += nums[i].len[0]; *o++ = '\t';
             memcpy(o, nums[i].s[1], nums[i].len[1]); o += nums[i].len[1]; *o++ = '\t';
             o = std::to_chars(o, o + 16, labels[i]).ptr; *o++ = '\t';
-            memcpy(o, line + kmer_off[i] + lo5, (size_t)(hi5 - lo5)); o += hi5 - lo5;
+            for (int t = lo5; t < hi5; ++t) { const int code = (int)kmer[i * seq_len + t]; *o++ = BASES[code & 15]; }
             *o++ = '\n';
         }
     });

@@ -38,18 +38,21 @@ def features_to_str(sampleinfo, kmer_codes, means, stds, lens, signals, label):
 
 class FeatureBatch:
     """One parsed block of the feature file.  ``kmer`` ... ``signals`` are float32 torch tensors
-    (page-locked when ``pinned``) trimmed to ``n`` sites; ``labels`` int32; ``text`` keeps the
-    block's bytes alive for the output lines (sampleinfo columns and the k-mer are copied from it)."""
+    (page-locked when ``pinned``) trimmed to ``n`` sites; ``labels`` int32; ``info_text`` /
+    ``info_off`` hold the first six columns of every line packed back to back (the output lines
+    start with them).  Everything lives in a reader slot that is recycled after ``slots - 1``
+    further batches."""
     __slots__ = ("n", "kmer", "base_means", "base_stds", "base_signal_lens", "signals", "labels",
-                 "text", "line_begin", "info_len", "kmer_off", "seq_len", "slot")
+                 "info_text", "info_off", "seq_len", "slot")
 
     def arrays(self):
         return self.kmer, self.base_means, self.base_stds, self.base_signal_lens, self.signals
 
     def sampleinfo(self):
         """list of the tab-joined first six columns (``call_modifications.py:89``)."""
-        t = self.text
-        return [t[b:b + l].decode() for b, l in zip(self.line_begin[:self.n].tolist(), self.info_len[:self.n].tolist())]
+        off = self.info_off[:self.n + 1].tolist()
+        t = self.info_text[:off[-1]].tobytes()
+        return [t[a:b].decode() for a, b in zip(off[:-1], off[1:])]
 
     def as_reference_lists(self):
         """The 7-tuple of Python lists ``_read_features_file`` puts on its queue (``:103-104``)."""
@@ -80,9 +83,8 @@ class _Slot:
         self.kmer, self.means, self.stds, self.lens = (mk((cap, T), torch.float32) for _ in range(4))
         self.signals = mk((cap, T, S), torch.float32)
         self.labels = mk((cap,), torch.int32)
-        self.line_begin = np.empty(cap, np.int64)
-        self.info_len = np.empty(cap, np.int32)
-        self.kmer_off = np.empty(cap, np.int32)
+        self.info_off = np.empty(cap + 1, np.int64)
+        self.info_text = np.empty(cap * 96, np.uint8)         # grown on demand (DSP_ERR_NOMEM)
 
 
 class FeatureFileReader:
@@ -121,43 +123,63 @@ class FeatureFileReader:
                 start, end = shard_bounds(f, *self.byte_range)
                 f.seek(start)
                 remaining = end - start
-            buf = b""
+            if remaining is None and not self.path.endswith(".gz"):
+                remaining = os.path.getsize(self.path)              # known for plain files: never over-allocate
             eof = False
             est_line = 4 * self.T * 10 + self.T * self.S * 10       # refined after the first block
             k = 0
+            arr = bytearray(0)                                      # read buffer, reused; arr[:fill] is valid
+            fill = 0
             while True:
                 want = int(est_line * self.batch_sites * 1.05) + (1 << 16)
-                while not eof and len(buf) < want:
-                    ask = want - len(buf) if remaining is None else min(want - len(buf), remaining)
-                    chunk = f.read(ask) if ask > 0 else b""
-                    if not chunk:
+                if remaining is not None:
+                    want = min(want, fill + remaining + 1)
+                if len(arr) < want:                       # grow (calloc-backed: untouched pages cost nothing)
+                    bigger = bytearray(want)
+                    bigger[:fill] = arr[:fill]
+                    arr = bigger
+                mv = memoryview(arr)
+                while not eof and fill < want:
+                    ask = want - fill if remaining is None else min(want - fill, remaining)
+                    got = f.readinto(mv[fill:fill + ask]) if ask > 0 else 0
+                    if not got:
                         eof = True
                         break
                     if remaining is not None:
-                        remaining -= len(chunk)
-                    buf += chunk
-                if not buf or buf.isspace():
+                        remaining -= got
+                    fill += got
+                if fill == 0 or bytes(mv[:min(fill, 4096)]).isspace() and bytes(mv[:fill]).isspace():
                     return
                 s = self._slot(k % self.nslots)
                 n, used = C.c_int64(0), C.c_int64(0)
-                _native.check(L.dsp_parse_features(
-                    buf, len(buf), int(eof), self.T, self.S, self.batch_sites,
-                    s.kmer.data_ptr(), s.means.data_ptr(), s.stds.data_ptr(), s.lens.data_ptr(), s.signals.data_ptr(),
-                    s.labels.data_ptr(), s.line_begin.ctypes.data, s.info_len.ctypes.data, s.kmer_off.ctypes.data,
-                    C.byref(n), C.byref(used), self.nthreads), "dsp_parse_features(%s)" % self.path)
+                base = (C.c_char * len(arr)).from_buffer(arr)
+                while True:
+                    rc = L.dsp_parse_features(
+                        base, fill, int(eof), self.T, self.S, self.batch_sites,
+                        s.kmer.data_ptr(), s.means.data_ptr(), s.stds.data_ptr(), s.lens.data_ptr(), s.signals.data_ptr(),
+                        s.labels.data_ptr(), s.info_text.ctypes.data, s.info_text.size, s.info_off.ctypes.data,
+                        C.byref(n), C.byref(used), self.nthreads)
+                    if rc == 4 and s.info_text.size < fill:       # DSP_ERR_NOMEM: unusually long sample-info columns
+                        s.info_text = np.empty(min(fill, s.info_text.size * 4), np.uint8)
+                        continue
+                    _native.check(rc, "dsp_parse_features(%s)" % self.path)
+                    break
+                del base
                 n, used = int(n.value), int(used.value)
                 if n == 0:
                     if eof:
                         return
                     est_line *= 2                        # a line longer than the whole block: read more
+                    mv.release()
                     continue
                 b = FeatureBatch()
                 b.n, b.seq_len, b.slot = n, self.T, k % self.nslots
                 b.kmer, b.base_means, b.base_stds, b.base_signal_lens = s.kmer[:n], s.means[:n], s.stds[:n], s.lens[:n]
                 b.signals, b.labels = s.signals[:n], s.labels[:n]
-                b.text = buf[:used]
-                b.line_begin, b.info_len, b.kmer_off = s.line_begin, s.info_len, s.kmer_off
-                buf = buf[used:]
+                b.info_text, b.info_off = s.info_text, s.info_off
+                mv[:fill - used] = mv[used:fill]         # carry the (small) unparsed tail to the front
+                fill -= used
+                mv.release()
                 est_line = max(64, used // n)
                 self.sites_read += n
                 k += 1
@@ -174,11 +196,13 @@ def format_calls(batch, probs, labels, nthreads=None):
     lab = np.ascontiguousarray(np.asarray(labels, dtype=np.int32))
     if p.shape != (n, 2) or lab.shape != (n,):
         raise ValueError("format_calls: probs must be (n, 2) and labels (n,) for the batch's n = %d" % n)
-    cap = int(batch.info_len[:n].sum()) + n * (64 + batch.seq_len)
+    kmer = batch.kmer if isinstance(batch.kmer, np.ndarray) else batch.kmer.numpy()
+    kmer = np.ascontiguousarray(kmer[:n], dtype=np.float32)
+    cap = int(batch.info_off[n]) + n * (64 + batch.seq_len)
     out = C.create_string_buffer(cap)
     used = C.c_int64(0)
-    _native.check(L.dsp_format_calls(batch.text, batch.line_begin.ctypes.data, batch.info_len.ctypes.data,
-                                     batch.kmer_off.ctypes.data, batch.seq_len, p.ctypes.data, lab.ctypes.data, n,
+    _native.check(L.dsp_format_calls(batch.info_text.ctypes.data, batch.info_off.ctypes.data, kmer.ctypes.data,
+                                     batch.seq_len, p.ctypes.data, lab.ctypes.data, n,
                                      out, cap, C.byref(used), int(nthreads or min(16, os.cpu_count() or 1))),
                   "dsp_format_calls")
     return out.raw[:used.value]

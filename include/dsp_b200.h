@@ -164,29 +164,29 @@ int dsp_freq_release_cache(void);
  * feature file written by `deepsignal_plant extract` (12 tab-separated columns,
  * extract_features.py:381-395), parsed straight into caller buffers (typically page-locked,
  * then handed to dsp_forward_host_submit).  Only complete lines are consumed unless
- * is_final != 0; at most max_sites lines.  Per site i it also returns where its text lives:
- * line_begin[i] (byte offset in `text`), info_len[i] (length of the first six columns, the
- * "sampleinfo" the output line starts with, :89) and kmer_off[i] (offset of the k-mer column
- * within the line).  Numbers follow Python: float(x) to double, then float32; k-mer letters go
+ * is_final != 0; at most max_sites lines.  The first six columns of line i -- the "sampleinfo"
+ * its output line starts with (:89) -- are packed into info_text at
+ * [info_off[i], info_off[i+1]) (info_off has max_sites + 1 entries; DSP_ERR_NOMEM if info_cap
+ * is too small).  Numbers follow Python: float(x) to double, then float32; k-mer letters go
  * through base2code_dna (utils/process_utils.py:22-29).  Malformed lines fail with
  * DSP_ERR_INVALID (the reference raises).  *consumed = bytes of `text` used. */
 int dsp_parse_features(const char* text, int64_t nbytes, int32_t is_final,
                        int32_t seq_len, int32_t signal_len, int64_t max_sites,
                        float* kmer, float* base_means, float* base_stds, float* base_signal_lens,
                        float* signals, int32_t* labels,
-                       int64_t* line_begin, int32_t* info_len, int32_t* kmer_off,
+                       char* info_text, int64_t info_cap, int64_t* info_off,
                        int64_t* n_sites, int64_t* consumed, int32_t nthreads);
 
 /* dsp_format_calls: the per-site output loop of _call_mods (call_modifications.py:175-188):
  *   sampleinfo \t prob_0 \t prob_1 \t label \t 5-mer \n
  * with prob_0 = round(p0/(p0+p1), 6), prob_1 = round(1 - prob_0, 6) evaluated in float32 and
- * printed like str(numpy.float32).  probs is (n, 2) float32, labels (n) int32; text /
- * line_begin / info_len / kmer_off come from dsp_parse_features.  *out_bytes receives the size
- * needed; DSP_ERR_NOMEM if out_cap is too small. */
-int dsp_format_calls(const char* text, const int64_t* line_begin, const int32_t* info_len,
-                     const int32_t* kmer_off, int32_t seq_len, const float* probs,
-                     const int32_t* labels, int64_t n, char* out, int64_t out_cap,
-                     int64_t* out_bytes, int32_t nthreads);
+ * printed like str(numpy.float32); the 5-mer is kmer[c-2:c+3] of the (n, seq_len) float-coded
+ * k-mer array.  probs is (n, 2) float32, labels (n) int32; info_text / info_off come from
+ * dsp_parse_features.  *out_bytes receives the size needed; DSP_ERR_NOMEM if out_cap is too
+ * small. */
+int dsp_format_calls(const char* info_text, const int64_t* info_off, const float* kmer,
+                     int32_t seq_len, const float* probs, const int32_t* labels, int64_t n,
+                     char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads);
 
 /* Known-answer test of the tcgen05/TMEM/bulk-copy building blocks on `device`: a one-CTA
  * FP16 GEMM with FP32 accumulation checked against a double-precision host product.

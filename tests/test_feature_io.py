@@ -108,10 +108,12 @@ def test_float32_text_matches_numpy_str():
     p0 = np.concatenate([rng.random(20000), 10.0 ** rng.uniform(-9, -2, 20000), [0.0, 1.0, 0.5, 1e-6, 5.6e-05, 0.9999995]]).astype(np.float32)
     probs = np.stack([p0, (1 - p0).astype(np.float32)], 1)
     n = len(p0)
-    line = b"c\t1\t+\t1\tr\tt\tACGTACGTACGTA\tx\n"
+    info = b"c\t1\t+\t1\tr\tt"
     b = feature_io.FeatureBatch()
-    b.n, b.seq_len, b.text = n, 13, line
-    b.line_begin, b.info_len, b.kmer_off = np.zeros(n, np.int64), np.full(n, 11, np.int32), np.full(n, 12, np.int32)
+    b.n, b.seq_len = n, 13
+    b.info_text = np.frombuffer(info * n, dtype=np.uint8)
+    b.info_off = np.arange(n + 1, dtype=np.int64) * len(info)
+    b.kmer = np.tile(np.array([0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0], np.float32), (n, 1))     # ACGTACGTACGTA
     got = feature_io.format_calls(b, probs, np.zeros(n, np.int32)).decode().splitlines()
     p0n, p1n = cm.normalise_probs(probs)
     for i in range(n):
