@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""End-to-end `call_mods` command line on a large synthetic feature file: text -> native parser ->
+pinned batches -> CUDA forward -> native formatter -> output file.  Prints one JSON line.
+
+    python tools/bench_cli.py [--sites 1000000]"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from deepsignal_plant_b200 import cli, feature_io, synthetic  # noqa: E402
+from deepsignal_plant_b200.models import ModelBiLSTM  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sites", type=int, default=1_000_000)
+    ap.add_argument("--nproc", type=int, default=os.cpu_count() or 1)
+    a = ap.parse_args()
+    base_n = 8192
+    feats = synthetic.make_features(base_n, 13, 16, seed=1)
+    info = synthetic.make_sampleinfo(base_n, seed=1)
+    lines = [feature_io.features_to_str(info[i], feats["kmer"][i], feats["base_means"][i].astype(np.float64).round(6),
+                                        feats["base_stds"][i].astype(np.float64).round(6), feats["base_signal_lens"][i],
+                                        feats["signals"][i].astype(np.float64).round(6), 0) for i in range(base_n)]
+    block = ("\n".join(lines) + "\n").encode()
+    with tempfile.TemporaryDirectory() as tmp:
+        path, ckpt, out = os.path.join(tmp, "features.tsv"), os.path.join(tmp, "m.ckpt"), os.path.join(tmp, "calls.tsv")
+        reps = max(1, a.sites // base_n)
+        with open(path, "wb") as f:
+            for _ in range(reps):
+                f.write(block)
+        n = reps * base_n
+        torch.manual_seed(1234)
+        torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
+        argv = ["call_mods", "-i", path, "-m", ckpt, "-o", out, "--nproc", str(a.nproc)]
+        cli.main(argv)                                  # first run: page cache, CUDA context
+        t0 = time.perf_counter()
+        cli.main(argv)
+        dt = time.perf_counter() - t0
+        nout = sum(1 for _ in open(out, "rb"))
+        print(json.dumps({"metric": "call_mods command line, feature file -> calls file (sites/s, wall clock incl. model load)",
+                          "sites": n, "lines_written": nout, "seconds": dt, "value": n / dt, "unit": "sites/s",
+                          "input_bytes": os.path.getsize(path), "output_bytes": os.path.getsize(out), "host_threads": a.nproc}))
+
+
+if __name__ == "__main__":
+    main()
