@@ -65,6 +65,11 @@ constexpr uint16_t PAIR_MASK = 3;                   // both CTAs of the pair
 #ifndef DSP_POLY_MASK_L0
 #define DSP_POLY_MASK_L0 DSP_POLY_MASK
 #endif
+// Load the whole 32-column accumulator slice before the gate math in the hidden-256 layers too (frees
+// the accumulator earlier, costs registers): measured 2 % slower (profiles/r01_run25_pw32_all_layers.log).
+#ifndef DSP_PW32_ALL
+#define DSP_PW32_ALL 0
+#endif
 #ifndef DSP_DIR_INTERLEAVE
 #define DSP_DIR_INTERLEAVE 1
 #endif
@@ -600,7 +605,7 @@ layer_kernel(const LayerParams p) {
                     float2 h2[UPT / 2];
                     // PW accumulator columns (PW/8 unit pairs) are in flight per thread at a time: the whole
                     // 32-column slice where registers allow (hidden 128: 32 cell-state registers), half otherwise
-                    constexpr int PW = (H == 128) ? 32 : 16;
+                    constexpr int PW = (H == 128 || DSP_PW32_ALL) ? 32 : 16;
 #pragma unroll
                     for (int part = 0; part < CPT / PW; ++part) {
                         uint32_t v[PW];
