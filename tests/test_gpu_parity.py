@@ -61,6 +61,17 @@ def test_fp16_tensor_core_path_matches_reference(name):
     print("%s fp16: max|dprob|=%.2e agreement=%.5f" % (name, err, agree))
 
 
+@pytest.mark.parametrize("dual", ["0", "1"])
+def test_fp16_both_branch_kernels_match_reference(dual, monkeypatch):
+    # hidden-128 layers: one CTA pair per direction (layer_kernel) or both directions as two chains
+    # (branch_kernel); the library picks by wave cost, DSP_B200_BRANCH_DUAL forces either
+    monkeypatch.setenv("DSP_B200_BRANCH_DUAL", dual)
+    for name in ("both_13_16_s2", "both_17_20_s1234"):
+        case = cases.slice_case(cases.load_case(name), 3000)
+        logits, probs, labels, _ = run_case(case, "fp16")
+        check(case, logits, probs, labels, PROB_TOL, 0.9995)
+
+
 def test_fp16_ragged_batches_and_chunking():
     case = cases.load_case("both_13_16_s2")
     for n, mb in ((1, 4096), (127, 4096), (129, 4096), (1000, 256)):
