@@ -403,38 +403,23 @@ def aggregate_records_distributed(keys, p0, p1, label, gidx, prob_cf, sort_by_ke
             m[:, 4].astype(np.int32), m[:, 5].astype(np.int32), m[:, 6].astype(np.int32))
 
 
-def _get_contignams_from_genome_fasta(genomefa):
-    """``call_mods_freq.py:130-137``."""
-    contigs = []
-    with open(genomefa, "r") as rf:
-        for line in rf:
-            if line.startswith(">"):
-                contigs.append(line.strip()[1:].split(" ")[0])
-    return contigs
-
-
-def _is_file_a_genome_fasta(contigfile):
-    """``call_mods_freq.py:140-147``."""
-    with open(contigfile, "r") as rf:
-        for line in rf:
-            if line.startswith("#"):
-                continue
-            elif line.startswith(">"):
-                return True
-    return False
-
-
 def parse_contigs_arg(contigs):
-    """``--contigs`` (``call_mods_freq.py:243-254``): a genome FASTA (names in file order), a file of
-    names or a comma-separated string (both: sorted set)."""
+    """``--contigs`` (``call_mods_freq.py:243-254``): a genome FASTA -> record names in file order
+    (first word after ``>``); any other file -> its lines, de-duplicated and sorted; otherwise a
+    comma-separated string, de-duplicated and sorted.  A file counts as FASTA by extension
+    (.fa/.fasta/.fna) or when any of its lines starts with ``>`` (``:140-147``)."""
     if contigs is None:
         return None
-    if os.path.isfile(contigs):
-        if contigs.endswith((".fa", ".fasta", ".fna")) or _is_file_a_genome_fasta(contigs):
-            return _get_contignams_from_genome_fasta(contigs)
-        with open(contigs, "r") as rf:
-            return sorted(set(rf.read().splitlines()))
-    return sorted(set(contigs.strip().split(",")))
+    if not os.path.isfile(contigs):
+        return sorted(set(contigs.strip().split(",")))
+    with open(contigs, "r") as rf:
+        lines = rf.read().splitlines()
+    is_fasta = contigs.endswith((".fa", ".fasta", ".fna"))
+    if not is_fasta:
+        is_fasta = any(l.startswith(">") for l in lines)
+    if is_fasta:
+        return [l.strip()[1:].split(" ")[0] for l in lines if l.startswith(">")]
+    return sorted(set(lines))
 
 
 def order_by_contig(table, contigs, is_sort):
