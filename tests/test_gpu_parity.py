@@ -72,6 +72,41 @@ def test_fp16_both_branch_kernels_match_reference(dual, monkeypatch):
         check(case, logits, probs, labels, PROB_TOL, 0.9995)
 
 
+def test_fp16_full_batch_is_batching_and_order_invariant():
+    # BASELINE.json configs[1] batch (65 536 sites): size-independent properties of a per-site classifier
+    # with explicit states -- sites are independent (models.py:178-240 has no cross-site op), so splitting
+    # the batch or permuting the sites must give bit-identical probabilities; a 2 048-site sample is also
+    # checked against the oracle.
+    n = 65536
+    cfg = model_oracle.make_cfg()
+    feats = synthetic.make_features(n, 13, 16, seed=123)
+    states = synthetic.make_states(cfg, n, seed=321)
+    entry = cases.MANIFEST["forward"]["both_13_16_s1234"]
+    dev = torch.device("cuda:0")
+    model = cases.build_model(entry, precision="fp16", max_batch=n).cuda(0)
+
+    def run(idx):
+        f = {k: v[idx] for k, v in feats.items()}
+        st = {g: tuple(np.ascontiguousarray(x[:, idx]) for x in hc) for g, hc in states.items()}
+        cases.inject_states(model, st, dev)
+        _, probs = model(*(torch.from_numpy(np.ascontiguousarray(f[k])).to(dev) for k in cases.FEATURE_KEYS))
+        return probs.cpu().numpy(), model.last_labels.cpu().numpy()
+    full, labels = run(np.arange(n))
+    assert np.isfinite(full).all() and (labels == full.argmax(1)).all()
+    half_a, _ = run(np.arange(0, 30001))                   # ragged split, different tile alignment of every site after it
+    half_b, _ = run(np.arange(30001, n))
+    assert np.array_equal(np.concatenate([half_a, half_b]), full)
+    perm = np.random.default_rng(5).permutation(n)
+    shuffled, _ = run(perm)
+    assert np.array_equal(shuffled, full[perm])
+    sample = np.arange(0, n, 32)
+    params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    want = model_oracle.forward(params, cfg, *(feats[k][sample] for k in cases.FEATURE_KEYS),
+                                {g: tuple(x[:, sample] for x in hc) for g, hc in states.items()})[1]
+    assert np.abs(full[sample] - want).max() <= PROB_TOL
+    assert (full[sample].argmax(1) == want.argmax(1)).mean() >= 0.999
+
+
 def test_fp16_ragged_batches_and_chunking():
     case = cases.load_case("both_13_16_s2")
     for n, mb in ((1, 4096), (127, 4096), (129, 4096), (1000, 256)):
