@@ -282,6 +282,7 @@ int dsp_create(dsp_handle* out, const dsp_config* cfg) {
         }
     } while (0);
     if (rc) { dsp_destroy(m); return rc; }
+    m->n_workspace_allocs = m->device_allocs.size();
     *out = m;
     return DSP_OK;
 }
@@ -322,8 +323,15 @@ int dsp_pack_weights(dsp_handle h) {
     Model* m = h;
     DeviceGuard guard(m->cfg.device);
     const dsp_config& c = m->cfg;
-    // re-packing after a second load_state_dict: drop the previous arena
-    // (workspace pointers are kept; weights are re-uploaded into fresh allocations)
+    // re-packing after another load_state_dict: free the previous weight arena (the workspace stays)
+    if (m->device_allocs.size() > m->n_workspace_allocs) {
+        DSP_CUDA(cudaDeviceSynchronize());
+        for (size_t i = m->n_workspace_allocs; i < m->device_allocs.size(); ++i) cudaFree(m->device_allocs[i]);
+        m->device_allocs.resize(m->n_workspace_allocs);
+        tc_drop_packs(m);
+        m->embed = nullptr;
+        m->packed = false;
+    }
     int rc;
     const int H = c.hidden_size;
     if (has_seq(m)) {

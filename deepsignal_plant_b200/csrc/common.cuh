@@ -80,7 +80,8 @@ struct Model {
     float* comb_in = nullptr;               // (cap, T, hidden)
     float* states = nullptr;                // Philox-drawn initial states
     int64_t state_floats_per_site = 0;
-    std::vector<void*> device_allocs;
+    std::vector<void*> device_allocs;       // workspace first, then the packed-weight arena
+    size_t n_workspace_allocs = 0;          // device_allocs[0 .. n_workspace_allocs) survive a re-pack
 
     // host staging for dsp_forward_host
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;

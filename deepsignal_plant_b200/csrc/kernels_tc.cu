@@ -1198,6 +1198,16 @@ void tc_destroy(Model* m) {
     m->tc_state = nullptr;
 }
 
+void tc_drop_packs(Model* m) {
+    TcState* s = (TcState*)m->tc_state;
+    if (!s) return;
+    for (auto* p : s->lstm_packs) delete p;
+    for (auto* p : s->dense_packs) delete p;
+    s->lstm_packs.clear();
+    s->dense_packs.clear();
+    s->head_pack = nullptr;
+}
+
 int tc_pack_lstm_layer(Model* m, LstmLayer& L,
                        const float* wih0, const float* whh0, const float* bih0, const float* bhh0,
                        const float* wih1, const float* whh1, const float* bih1, const float* bhh1) {

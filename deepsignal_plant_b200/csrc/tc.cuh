@@ -14,6 +14,7 @@ int tc_pack_lstm_layer(Model* m, LstmLayer& L,
 int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b);
 int tc_pack_head(Model* m, DenseF32& fc1, const float* w, const float* b);
 int tc_finalize_pack(Model* m);
+void tc_drop_packs(Model* m);      // forget the packed layers before a re-pack (their device memory is freed by the caller)
 int tc_forward_chunk(Model* m, const float* kmer, const float* means, const float* stds, const float* lens,
                      const float* signals, const float* const* h0, const float* const* c0,
                      const int64_t* state_stride, uint64_t seed, uint64_t chunk_id, int64_t n,

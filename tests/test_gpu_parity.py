@@ -107,6 +107,26 @@ def test_fp16_full_batch_is_batching_and_order_invariant():
     assert (full[sample].argmax(1) == want.argmax(1)).mean() >= 0.999
 
 
+def test_repacking_after_load_state_dict_replaces_the_weights():
+    # call_modifications.py:219-223 loads a checkpoint into an already constructed model: the second
+    # pack must replace (and free) the first arena
+    a = cases.slice_case(cases.load_case("both_13_16_s1"), 1500)
+    b = cases.slice_case(cases.load_case("both_13_16_s2"), 1500)
+    dev = torch.device("cuda:0")
+    model = cases.build_model(a["entry"], precision="fp16").cuda(0)
+    for case in (a, b, a):
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in case["params"].items()})
+        cases.inject_states(model, case["states"], dev)
+        _, probs = model(*(torch.from_numpy(case["feats"][k]).to(dev) for k in cases.FEATURE_KEYS))
+        assert np.abs(probs.cpu().numpy() - case["probs"]).max() <= PROB_TOL
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(6):
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in b["params"].items()})
+        model(*(torch.from_numpy(b["feats"][k]).to(dev) for k in cases.FEATURE_KEYS))
+    torch.cuda.synchronize()
+    assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20          # no arena piles up
+
+
 def test_fp16_ragged_batches_and_chunking():
     case = cases.load_case("both_13_16_s2")
     for n, mb in ((1, 4096), (127, 4096), (129, 4096), (1000, 256)):
