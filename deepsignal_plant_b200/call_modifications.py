@@ -117,6 +117,98 @@ def _call_mods(features_batch, model, batch_size, device=0):
     return pred_str, accuracy, batch_num
 
 
+# ---- queue-based workers with the reference's names and protocol -----------------------------------
+# (call_modifications.py:55-127, 195-282).  `call_mods` below does not use them -- it streams pinned
+# batches -- but code written against the reference's worker functions keeps working: same arguments,
+# same queue items (7-tuples of Python lists, "kill" sentinel), same batch boundaries.
+
+class SimpleQueue:
+    """Minimal in-process queue with the methods the workers use (put/get/empty/qsize)."""
+
+    def __init__(self):
+        self._q = queue.Queue()
+
+    def put(self, x):
+        self._q.put(x)
+
+    def get(self):
+        return self._q.get()
+
+    def empty(self):
+        return self._q.empty()
+
+    def qsize(self):
+        return self._q.qsize()
+
+
+def _read_features_file(features_file, features_batch_q, f5_batch_size=10):
+    """``call_modifications.py:55-127``: parse the feature file (natively) and put batches of
+    ``f5_batch_size`` reads -- cut exactly where the reference cuts them, when the read id in column 5
+    has changed ``f5_batch_size`` times -- on the queue, then ``"kill"``."""
+    from . import feature_io
+    print("read_features process-{} starts".format(os.getpid()))
+    r_num, b_num = 0, 0
+    cur = [[], [], [], [], [], [], []]
+    readid_pre = None
+    reader = feature_io.FeatureFileReader(features_file, batch_sites=16384, pinned=False, slots=2,
+                                          seq_len=None, signal_len=None)
+    for blk in reader:
+        cols = blk.as_reference_lists()
+        for i, info in enumerate(cols[0]):
+            readid = info.split("\t")[4]
+            if readid_pre is not None and readid != readid_pre:
+                r_num += 1
+                if r_num % f5_batch_size == 0:
+                    features_batch_q.put(tuple(cur))
+                    cur = [[], [], [], [], [], [], []]
+                    b_num += 1
+            readid_pre = readid
+            for c, col in zip(cur, cols):
+                c.append(col[i])
+    r_num += 1
+    if len(cur[0]) > 0:
+        features_batch_q.put(tuple(cur))
+        b_num += 1
+    features_batch_q.put("kill")
+    print("read_features process-{} ending, read {} reads in {} f5-batches({})".format(os.getpid(), r_num, b_num,
+                                                                                       f5_batch_size))
+
+
+def _call_mods_q(model_path, features_batch_q, pred_str_q, success_file, args, device=0):
+    """``call_modifications.py:195-259``: build the model from ``args``, load the checkpoint, then call
+    every batch taken from ``features_batch_q`` until the ``"kill"`` sentinel (which is put back for
+    sibling workers, ``:241-245``)."""
+    print('call_mods process-{} starts'.format(os.getpid()))
+    args.model_path = model_path
+    model = load_model(args, device)
+    batch_num_total = 0
+    while True:
+        features_batch = features_batch_q.get()
+        if isinstance(features_batch, str) and features_batch == "kill":
+            features_batch_q.put("kill")
+            break
+        pred_str, accuracy, batch_num = _call_mods(features_batch, model, args.batch_size, device)
+        pred_str_q.put(pred_str)
+        batch_num_total += batch_num
+    print('call_mods process-{} ending, proceed {} feature-batches({})'.format(os.getpid(), batch_num_total,
+                                                                               args.batch_size))
+
+
+def _write_predstr_to_file(write_fp, predstr_q, is_gzip):
+    """``call_modifications.py:262-282``."""
+    print('write_process-{} starts'.format(os.getpid()))
+    if is_gzip and not write_fp.endswith(".gz"):
+        write_fp += ".gz"
+    with (gzip.open(write_fp, "wt") if is_gzip else open(write_fp, "w")) as wf:
+        while True:
+            pred_str = predstr_q.get()
+            if isinstance(pred_str, str) and pred_str == "kill":
+                break
+            wf.write("".join(line + "\n" for line in pred_str))
+            wf.flush()
+    print('write_process-{} finished'.format(os.getpid()))
+
+
 # ---- the call_mods pipeline over a feature file (call_modifications.py:195-282, 532-640) -----------
 
 def load_model(args, device=0):

@@ -76,6 +76,15 @@ def shard_bounds(f, lo, hi):
     return first_line_start_at_or_after(lo), first_line_start_at_or_after(hi)
 
 
+def sniff_shape(path):
+    """(seq_len, signal_len) of a feature file from its first line: k-mer length and samples per base."""
+    with (gzip.open(path, "rt") if path.endswith(".gz") else open(path, "r")) as f:
+        words = f.readline().strip().split("\t")
+    if len(words) < 12:
+        raise ValueError("%s does not look like a feature file (12 tab-separated columns)" % path)
+    return len(words[6]), len(words[10].split(";")[0].split(","))
+
+
 class _Slot:
     def __init__(self, cap, T, S, pinned):
         import torch
@@ -98,6 +107,8 @@ class FeatureFileReader:
     def __init__(self, path, seq_len=13, signal_len=16, batch_sites=65536, pinned=None, slots=4,
                  nthreads=None, byte_range=None):
         import torch
+        if seq_len is None or signal_len is None:            # take the shape from the first line, as the reference does
+            seq_len, signal_len = sniff_shape(path)
         self.path, self.T, self.S = path, int(seq_len), int(signal_len)
         self.batch_sites = int(batch_sites)
         self.pinned = torch.cuda.is_available() if pinned is None else bool(pinned)

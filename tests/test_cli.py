@@ -66,3 +66,19 @@ def test_call_mods_cli_rejects_fast5_directory(tmp_path):
         cli.main(["call_mods", "-i", str(tmp_path), "-m", ckpt, "-o", str(tmp_path / "o.tsv")])
     with pytest.raises(ValueError, match="model_path"):
         cli.main(["call_mods", "-i", path, "-m", str(tmp_path / "missing.ckpt"), "-o", str(tmp_path / "o.tsv")])
+
+
+def test_reference_worker_protocol(tmp_path):
+    # _read_features_file -> _call_mods_q -> _write_predstr_to_file with queues (call_modifications.py:587-626)
+    from deepsignal_plant_b200 import call_modifications as cm
+    n = 700
+    path, ckpt, feats, info, params = write_inputs(tmp_path, n)
+    args = cli.build_parser().parse_args(["call_mods", "-i", path, "-m", ckpt, "-o", str(tmp_path / "o.tsv"), "-b", "256"])
+    fq, pq = cm.SimpleQueue(), cm.SimpleQueue()
+    cm._read_features_file(path, fq, 3)
+    cm._call_mods_q(ckpt, fq, pq, None, args, 0)
+    pq.put("kill")
+    cm._write_predstr_to_file(str(tmp_path / "o.tsv"), pq, False)
+    lines = open(tmp_path / "o.tsv").read().splitlines()
+    assert len(lines) == n and ["\t".join(l.split("\t")[:6]) for l in lines] == info
+    assert fq.get() == "kill"

@@ -120,3 +120,30 @@ def test_float32_text_matches_numpy_str():
         w = got[i].split("\t")
         assert w[6] == str(p0n[i]) and w[7] == str(p1n[i]), (i, w, p0n[i], p1n[i])
         assert w[8] == "0" and w[9] == "ACGTA"          # kmer[c-2:c+3], c = 6
+
+
+def test_reference_style_reader_cuts_the_same_batches():
+    # _read_features_file (call_modifications.py:55-127): same queue items and batch boundaries
+    g = gold_arrays()
+    q = cm.SimpleQueue()
+    cm._read_features_file(os.path.join(GOLD, "features_small.tsv.gz"), q, FEAT["f5_batch_size"])
+    items = []
+    while not q.empty():
+        items.append(q.get())
+    assert items[-1] == "kill" and len(items) - 1 == FEAT["reference_batches"]
+    assert [len(b[0]) for b in items[:-1]] == g["batch_sizes"].tolist()
+    cat = lambda j, dt: np.concatenate([np.asarray(b[j], dtype=dt) for b in items[:-1]], 0)
+    for j, key, dt in ((1, "kmer", np.float32), (2, "base_means", np.float32), (3, "base_stds", np.float32),
+                       (4, "base_signal_lens", np.float32), (5, "signals", np.float32), (6, "labels", np.int32)):
+        assert cat(j, dt).tobytes() == g[key].tobytes(), key
+    assert isinstance(items[0][1][0][0], int) and isinstance(items[0][4][0][0], int) and isinstance(items[0][2][0][0], float)
+
+
+def test_writer_worker(tmp_path):
+    q = cm.SimpleQueue()
+    q.put(["a\t1", "b\t2"])
+    q.put(["c\t3"])
+    q.put("kill")
+    out = tmp_path / "o.tsv"
+    cm._write_predstr_to_file(str(out), q, True)
+    assert gzip.open(str(out) + ".gz", "rt").read() == "a\t1\nb\t2\nc\t3\n"
