@@ -262,6 +262,31 @@ def test_forward_host_pageable_and_ragged_chunks_fp16():
     assert (labels == probs.argmax(1)).all()
 
 
+@pytest.mark.parametrize("kw", [dict(num_classes=3, is_signallen=False), dict(is_base=False, num_layers1=2, num_layers2=2),
+                                dict(module="signal_bilstm", signal_len=32, seq_len=9)])
+def test_fp16_unusual_configurations_against_oracle(kw):
+    # shapes no fixture covers, on the tensor-core path: 3 classes, no signal-length / no base features,
+    # 2-layer branches (second branch layer has K = 256), long signal rows
+    a = dict(seq_len=13, signal_len=16, num_layers1=3, num_layers2=1, num_classes=2, hidden_size=256, vocab_size=16,
+             embedding_size=4, is_base=True, is_signallen=True, module="both_bilstm")
+    a.update(kw)
+    cfg = model_oracle.make_cfg(**a)
+    torch.manual_seed(17)
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    model = ModelBiLSTM(a["seq_len"], a["signal_len"], a["num_layers1"], a["num_layers2"], a["num_classes"], 0, 256, 16, 4,
+                        a["is_base"], a["is_signallen"], module=a["module"], precision="fp16").cuda(0).eval()
+    n = 1111
+    feats = synthetic.make_features(n, a["seq_len"], a["signal_len"], seed=17)
+    states = synthetic.make_states(cfg, n, seed=18)
+    params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    want = model_oracle.forward(params, cfg, *(feats[k] for k in cases.FEATURE_KEYS), states)[1]
+    cases.inject_states(model, states, torch.device("cuda:0"))
+    probs = model(*(torch.from_numpy(feats[k]).cuda(0) for k in cases.FEATURE_KEYS))[1].cpu().numpy()
+    assert probs.shape == want.shape and np.abs(probs - want).max() <= PROB_TOL
+    assert (probs.argmax(1) == want.argmax(1)).mean() >= 0.998
+    assert (model.last_labels.cpu().numpy() == probs.argmax(1)).all()
+
+
 def test_oracle_agrees_on_fresh_seed():
     # a case that is NOT in the fixtures: oracle and CUDA path on the same seeded inputs
     cfg = model_oracle.make_cfg(seq_len=11, signal_len=10, hidden_size=48, num_layers1=2)
