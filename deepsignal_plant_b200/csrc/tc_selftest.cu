@@ -191,6 +191,37 @@ mma_rate_kernel(const uint8_t* __restrict__ src, int iters, int mode, unsigned l
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- pipe-overlap probe ----------------------------------------------------------------------------
+// 16 warps per SM run `iters` iterations of 8 independent chains of: bit0 MUFU.EX2, bit1 packed FFMA2,
+// bit2 scalar FFMA (x2, same FLOPs as one FFMA2), bit3 MUFU.RCP.  Reports SM cycles per iteration per
+// warp-instruction slot, so that the cost of a mix can be compared with the sum / max of its parts.
+__global__ void __launch_bounds__(512, 1)
+pipe_probe_kernel(int iters, int mode, float seed, unsigned long long* __restrict__ cycles_out, float* __restrict__ sink) {
+    float2 a[8];
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = make_float2(seed + i, seed - i); e[i] = seed * 0.001f * (i + 1); }
+    const float2 m = make_float2(0.999f, 1.001f), c = make_float2(1e-3f, -1e-3f);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (mode & 1) e[i] = ex2_approx(e[i]);
+            if (mode & 8) e[i] = rcp_approx(e[i]);
+            if (mode & 2) a[i] = fma2(a[i], m, c);
+            if (mode & 4) { a[i].x = fmaf(a[i].x, m.x, c.x); a[i].y = fmaf(a[i].y, m.y, c.y); }
+        }
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += a[i].x + a[i].y + e[i];
+    if (acc == 12345.678f) sink[0] = acc;
+    if (threadIdx.x == 0) cycles_out[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
 void to_slabs(const std::vector<__half>& m, int rows, int K, std::vector<__half>& out) {
     const int KS = K / SLAB_K;
     out.assign((size_t)rows * K, __float2half(0.f));
@@ -217,8 +248,30 @@ extern "C" int dsp_selftest(int device, int which, double* max_abs_err) {
         return DSP_ERR_CUDA;
     }
     DSP_REQUIRE(device >= 0 && device < ndev, DSP_ERR_INVALID, "dsp_selftest: bad device");
-    DSP_REQUIRE((which >= 0 && which <= 3) || (which >= 100 && which < 228), DSP_ERR_INVALID, "dsp_selftest: unknown test %d", which);
+    DSP_REQUIRE((which >= 0 && which <= 3) || (which >= 100 && which < 228) || (which >= 300 && which < 316), DSP_ERR_INVALID,
+                "dsp_selftest: unknown test %d", which);
     DSP_CUDA(cudaSetDevice(device));
+    if (which >= 300) {
+        // pipe-overlap probe: returns SM cycles per loop iteration (8 chains x the selected instructions, 16 warps)
+        const int mode = which - 300, iters = 4000;
+        int nsm = 0;
+        DSP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+        unsigned long long* cyc; float* sink;
+        DSP_CUDA(cudaMalloc(&cyc, sizeof(unsigned long long) * nsm));
+        DSP_CUDA(cudaMalloc(&sink, sizeof(float)));
+        for (int rep = 0; rep < 2; ++rep) {
+            pipe_probe_kernel<<<nsm, 512>>>(iters, mode, 0.5f, cyc, sink);
+            DSP_CUDA(cudaGetLastError());
+            DSP_CUDA(cudaDeviceSynchronize());
+        }
+        std::vector<unsigned long long> h(nsm);
+        DSP_CUDA(cudaMemcpy(h.data(), cyc, sizeof(unsigned long long) * nsm, cudaMemcpyDeviceToHost));
+        cudaFree(cyc); cudaFree(sink);
+        double sum = 0;
+        for (auto v : h) sum += (double)v;
+        *max_abs_err = sum / nsm / (double)iters;
+        return DSP_OK;
+    }
     if (which >= 100) {
         // MMA rate probe: returns average SM cycles per tcgen05.mma over all SMs
         const int mode = which - 100, iters = 2000;
