@@ -306,7 +306,7 @@ def main():
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            sample = 8192
+            sample = 65536                  # one BASELINE batch: ~10-30 s of host work at 2-8 k sites/s
             v, dt = cpu_baseline_run(sample, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d sites, batch 512, torch CPU fp32 restatement of the reference forward, %d threads, %.1f s" % (sample, cores, dt)}
