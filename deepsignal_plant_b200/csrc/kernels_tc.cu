@@ -110,7 +110,10 @@ constexpr int HEAD_MAX_CLASSES = 8;
 // weight ring: NST stages of STG half slabs (one mbarrier pair per stage)
 template <int KSX, int MODE> struct RingCfg {
     static constexpr int STG = KSX >= 8 ? 2 : 4;
-    static constexpr int NST = KSX >= 8 ? (MODE == 2 ? 4 : 5) : 4;
+    static constexpr int NST = KSX >= 8 ? (MODE == 2 ? 4 : 5) : (MODE == 1 ? 2 : 4);
+    // x_t buffers: the per-timestep dense layers are HBM-bound streams of x_t, so where shared memory allows
+    // they double-buffer it (load of step t+1 overlaps the MMAs and stores of step t)
+    static constexpr int XB = (MODE == 1 && KSX <= 4) ? 2 : 1;
 };
 
 // Philox4x32-10 (Salmon et al., SC'11) + Box-Muller: four N(0,1) values per counter.  Used to
@@ -232,7 +235,8 @@ template <int KSX, int H, int MODE, int NOUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 layer_kernel(const LayerParams p) {
     constexpr bool IS_FC = MODE != MODE_LSTM;              // no recurrence: x part only
-    constexpr int STG = RingCfg<KSX, MODE>::STG, NST = RingCfg<KSX, MODE>::NST;
+    constexpr int STG = RingCfg<KSX, MODE>::STG, NST = RingCfg<KSX, MODE>::NST, XB = RingCfg<KSX, MODE>::XB;
+    constexpr int NXS = KSX * XB;                          // x slabs resident in shared memory
     constexpr int NCH = IS_FC ? NOUT / 128 : H / 32;       // 128-column chunks per step
     constexpr int KSH = IS_FC ? 0 : H / 64;                // h slabs (K of the recurrent part)
     constexpr int KS = KSX + KSH;
@@ -245,14 +249,14 @@ layer_kernel(const LayerParams p) {
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* s_x = smem;                                   // KSX slabs
-    uint8_t* s_w = smem + (size_t)KSX * SLAB_BYTES;        // NST ring stages of STG half slabs
+    uint8_t* s_x = smem;                                   // NXS slabs
+    uint8_t* s_w = smem + (size_t)NXS * SLAB_BYTES;        // NST ring stages of STG half slabs
     float* s_bias = reinterpret_cast<float*>(s_w + (size_t)NST * STG * HSLAB_BYTES);
-    __shared__ __align__(8) uint64_t bars[2 * NST + 2 * KSX + 5];
+    __shared__ __align__(8) uint64_t bars[2 * NST + 2 * NXS + 5];
     __shared__ uint32_t tmem_base_s;
     const uint32_t b_wfull = smem_u32(&bars[0]), b_wempty = smem_u32(&bars[NST]);
-    const uint32_t b_xfull = smem_u32(&bars[2 * NST]), b_xempty = smem_u32(&bars[2 * NST + KSX]);
-    const uint32_t b_accfull = smem_u32(&bars[2 * NST + 2 * KSX]), b_accempty = b_accfull + 16;
+    const uint32_t b_xfull = smem_u32(&bars[2 * NST]), b_xempty = smem_u32(&bars[2 * NST + NXS]);
+    const uint32_t b_accfull = smem_u32(&bars[2 * NST + 2 * NXS]), b_accempty = b_accfull + 16;
     const uint32_t b_hready = b_accfull + 32;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -271,7 +275,7 @@ layer_kernel(const LayerParams p) {
         // barriers the leader's MMA thread waits on collect one arrival per CTA
         const uint32_t both = crank == 0 ? 2u : 1u;
         for (int i = 0; i < NST; ++i) { mbar_init(b_wfull + 8 * i, both); mbar_init(b_wempty + 8 * i, 1); }
-        for (int i = 0; i < KSX; ++i) { mbar_init(b_xfull + 8 * i, both); mbar_init(b_xempty + 8 * i, 1); }
+        for (int i = 0; i < NXS; ++i) { mbar_init(b_xfull + 8 * i, both); mbar_init(b_xempty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(b_accfull + 8 * i, 1); mbar_init(b_accempty + 8 * i, 2 * EPI_WARPS); }
         mbar_init(b_hready, 2 * EPI_WARPS);
         mbar_fence_init();
@@ -316,10 +320,12 @@ layer_kernel(const LayerParams p) {
                     const uint8_t* xsrc = (MODE == MODE_HEAD)
                         ? p.x_img + ((size_t)tile * 2 + (step == 1 ? 1 : 0)) * KSX * SLAB_BYTES
                         : p.x_img + ((size_t)tile * T + t) * KSX * SLAB_BYTES;
+                    const int xbuf = step % XB, xround = step / XB;
                     for (int j = 0; j < KSX; ++j) {
-                        mbar_wait(b_xempty + 8 * j, (step & 1) ^ 1);
-                        mbar_arrive_expect_tx(b_xfull + 8 * j, SLAB_BYTES);
-                        bulk_g2s(smem_u32(s_x + (size_t)j * SLAB_BYTES), xsrc + (size_t)j * SLAB_BYTES, SLAB_BYTES, b_xfull + 8 * j);
+                        const int xi = xbuf * KSX + j;
+                        mbar_wait(b_xempty + 8 * xi, (xround & 1) ^ 1);
+                        mbar_arrive_expect_tx(b_xfull + 8 * xi, SLAB_BYTES);
+                        bulk_g2s(smem_u32(s_x + (size_t)xi * SLAB_BYTES), xsrc + (size_t)j * SLAB_BYTES, SLAB_BYTES, b_xfull + 8 * xi);
                     }
                 }
             }
@@ -329,8 +335,9 @@ layer_kernel(const LayerParams p) {
             uint32_t stage = 0, phase = 0;
             for (int step = 0; step < T; ++step) {
                 for (int j = 0; j < KSX; ++j) {
-                    mbar_wait(b_xfull + 8 * j, step & 1);
-                    if (lane == 0) mbar_arrive_cluster(r_xfull + 8 * j);
+                    const int xi = (step % XB) * KSX + j;
+                    mbar_wait(b_xfull + 8 * xi, (step / XB) & 1);
+                    if (lane == 0) mbar_arrive_cluster(r_xfull + 8 * xi);
                 }
                 for (int s = 0; s < W_STEP; s += STG) {
                     mbar_wait(b_wfull + 8 * stage, phase);
@@ -362,10 +369,11 @@ layer_kernel(const LayerParams p) {
             auto issue_x = [&](uint32_t acc, bool fresh, bool first_use, bool last_use, int step) {
 #pragma unroll
                 for (int j = 0; j < KSX; ++j) {
-                    if (first_use) { mbar_wait_cluster(b_xfull + 8 * j, step & 1); tc_fence_after(); }
+                    const int xi = (step % XB) * KSX + j;
+                    if (first_use) { mbar_wait_cluster(b_xfull + 8 * xi, (step / XB) & 1); tc_fence_after(); }
                     const uint32_t bl = w_acquire();
                     if (leader) {
-                        const uint32_t al = a_lo0 + (uint32_t)j * (SLAB_BYTES >> 4);
+                        const uint32_t al = a_lo0 + (uint32_t)xi * (SLAB_BYTES >> 4);
                         const int nk = (KSX * 4 == xk16) ? 4 : min(4, xk16 - 4 * j);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -374,7 +382,7 @@ layer_kernel(const LayerParams p) {
                                 else mma2_ss_lo<1>(acc, al + k * 2, bl + k * 2, IDESC);
                             }
                         }
-                        if (last_use) mma2_commit(b_xempty + 8 * j, PAIR_MASK);
+                        if (last_use) mma2_commit(b_xempty + 8 * xi, PAIR_MASK);
                     }
                     w_release();
                 }
@@ -1089,7 +1097,7 @@ bool g_pdl = true;
 template <int KSX, int H, int MODE, int NOUT>
 int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
     constexpr int NCH = MODE != MODE_LSTM ? NOUT / 128 : H / 32;
-    const size_t smem = (size_t)KSX * SLAB_BYTES + (size_t)RingCfg<KSX, MODE>::NST * RingCfg<KSX, MODE>::STG * HSLAB_BYTES
+    const size_t smem = (size_t)KSX * RingCfg<KSX, MODE>::XB * SLAB_BYTES + (size_t)RingCfg<KSX, MODE>::NST * RingCfg<KSX, MODE>::STG * HSLAB_BYTES
                         + (size_t)NCH * 128 * sizeof(float) + 1024;
     auto kern = layer_kernel<KSX, H, MODE, NOUT>;
     DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
