@@ -43,6 +43,14 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and "DSP_B200_LIB" not in os.environ:
+        # a source checkout that was never built: compile it (nvcc, sm_100a) rather than give up; this is the
+        # only automatic step -- there is still no CPU or PyTorch fallback if it fails
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:                                  # noqa: BLE001 -- reported below
+            raise DspError("libdsp_b200.so is not built and building it failed: %s" % e)
     if not os.path.exists(LIB_PATH):
         raise DspError(
             "libdsp_b200.so is not built (%s). Run `python -m deepsignal_plant_b200.build` "
