@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--buffers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--meas-skip-y", action="store_true",
+                    help="measurement only (INVALID as a result): after warm-up, skip the inter-layer activation stores")
     # BASELINE.json configs[3]: the other model variants (not the headline line)
     ap.add_argument("--module", default="both_bilstm", choices=["both_bilstm", "seq_bilstm", "signal_bilstm"])
     ap.add_argument("--seq_len", type=int, default=13)
@@ -219,6 +221,8 @@ def main():
     torch.cuda.synchronize()
     L = _native.lib()
 
+    if args.meas_skip_y:
+        os.environ["DSP_B200_MEAS_SKIP_Y"] = "1"
     # ---- timed region: inputs resident in HBM ------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:                       # one sampler per job: rank 0's GPU stands for the box
@@ -303,6 +307,8 @@ def main():
                 "d2h_bytes_per_step": args.batch * OUT_BYTES_PER_SITE, "api": "ModelBiLSTM.submit_host/wait_host (dsp_forward_host_submit), pinned host buffers in and out, 2 batches in flight"},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if args.meas_skip_y:
+        line["INVALID"] = "measurement run: activation stores skipped inside the timed region"
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1

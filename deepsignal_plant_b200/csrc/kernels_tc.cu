@@ -1384,6 +1384,9 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
             p.y_img = head_tc ? s->hfin_img : s->ybuf[l & 1]; p.hfinal = (final_layer && !head_tc) ? s->hfinal : nullptr;
             p.n = n; p.T = T; p.xk16 = pk->xk16; p.y_slabs = 2 * hid / 64; p.y_col_off = 0;
             p.write_y = final_layer ? (head_tc ? 2 : 0) : 1;
+            // measurement hook (bench.py --meas-skip-y): skip the inter-layer activation stores of the hidden-256
+            // layers once the images hold realistic data from earlier passes, to price those stores
+            if (p.write_y == 1 && hid == 256) { const char* e = getenv("DSP_B200_MEAS_SKIP_Y"); if (e && atoi(e)) p.write_y = 0; }
             Span sp(m, is_comb ? 1 : 4, st);
             // Two ways to run a hidden-128 layer: one CTA pair per (tile pair, direction), or both directions
             // as two chains of one CTA pair (branch_kernel: ~1.8x the time per CTA for 2x the work).  Pick
