@@ -1,0 +1,377 @@
+// Feature extraction from decoded re-squiggled reads:
+//   deepsignal_plant/extract_features.py  _rescale_signals (:276-277), _normalize_signals (:179-190),
+//   the per-site body of _extract_features (:343-372) and _get_signals_rect (:232-251).
+// HBM-bound integer/double work, bit-exact against numpy's float64 arithmetic:
+//   read_scale_kernel   one CTA per read: median and MAD of the rescaled samples by a block-wide radix
+//                       select over order-preserving 64-bit keys computed on the fly from the int16
+//                       samples (nothing is materialised; the read is walked 14 times out of L1/L2);
+//   site_features_kernel one thread per (site, base): normalise + round the base's samples on the fly,
+//                       numpy-order pairwise sums for mean/std, the 13 x 16 rectangle (centred zero pad, or
+//                       an ordered subsample -- caller-supplied offsets in parity mode, Philox selection
+//                       sampling otherwise), written straight into the five tensors dsp_forward takes.
+// Every double operation is an explicit round-to-nearest intrinsic so that nvcc cannot contract a
+// multiply and an add into an FMA (numpy does not).
+#include "common.cuh"
+#include <cub/block/block_scan.cuh>
+#include <cub/block/block_reduce.cuh>
+#include <math_constants.h>
+
+namespace dsp {
+namespace {
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_BITS = 11;
+constexpr int SEL_BINS = 1 << SEL_BITS;
+constexpr int BINS_PER_THREAD = SEL_BINS / SEL_THREADS;
+constexpr double MAD_C = 0.6744897501960817;   // scipy.stats.norm.ppf(3/4.), statsmodels.robust.mad's default c
+
+__device__ __forceinline__ uint64_t key_of(double v) {
+    const uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double value_of(uint64_t k) {
+    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// _rescale_signals: scaling * (raw + offset) in float64; a NaN scaling marks a read without channel
+// info (extract_features.py:313-315 leaves the DAC values as they are).
+struct Rescale {
+    double scaling, offset;
+    bool on;
+    __device__ __forceinline__ double operator()(int16_t r) const {
+        const double x = (double)r;
+        return on ? __dmul_rn(scaling, __dadd_rn(x, offset)) : x;
+    }
+};
+
+struct SelectShared {
+    int hist[SEL_BINS];
+    uint64_t prefix;
+    int64_t k;
+    typename cub::BlockScan<int, SEL_THREADS>::TempStorage scan;
+    union {
+        typename cub::BlockReduce<unsigned long long, SEL_THREADS>::TempStorage red_u;
+        typename cub::BlockReduce<int, SEL_THREADS>::TempStorage red_i;
+    } red;
+    uint64_t max_less;
+    int count_less;
+};
+
+// Key of the element of rank k (0-based) among keyfn(0..n-1): most-significant-digit radix select,
+// 11-bit digits, shared-memory histogram per pass.
+template <typename KeyFn>
+__device__ uint64_t block_select(SelectShared& sh, KeyFn keyfn, int64_t n, int64_t k) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { sh.prefix = 0; sh.k = k; }
+    int hi = 64;                                     // bits [hi, 64) of the answer are known (= sh.prefix)
+    while (hi > 0) {
+        const int width = hi >= SEL_BITS ? SEL_BITS : hi;
+        const int lo = hi - width;
+        for (int b = tid; b < SEL_BINS; b += SEL_THREADS) sh.hist[b] = 0;
+        __syncthreads();
+        const uint64_t prefix = sh.prefix;
+        for (int64_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
+            const int64_t i = i0 + tid;
+            bool in = i < n;
+            uint64_t key = 0;
+            if (in) {
+                key = keyfn(i);
+                in = hi == 64 || (key >> hi) == prefix;
+            }
+            const int bin = (int)((key >> lo) & ((1u << width) - 1));
+            // the high digits of neighbouring samples mostly agree: one atomic per warp when they all do
+            const unsigned act = __ballot_sync(0xffffffffu, in);
+            if (act == 0) continue;
+            const int leader = __ffs(act) - 1;
+            const int lbin = __shfl_sync(0xffffffffu, bin, leader);
+            const unsigned same = __ballot_sync(0xffffffffu, in && bin == lbin);
+            if (same == act) {
+                if ((tid & 31) == leader) atomicAdd(&sh.hist[lbin], __popc(act));
+            } else if (in) {
+                atomicAdd(&sh.hist[bin], 1);
+            }
+        }
+        __syncthreads();
+        int c[BINS_PER_THREAD], tsum = 0;
+#pragma unroll
+        for (int j = 0; j < BINS_PER_THREAD; ++j) { c[j] = sh.hist[tid * BINS_PER_THREAD + j]; tsum += c[j]; }
+        int before;
+        cub::BlockScan<int, SEL_THREADS>(sh.scan).ExclusiveSum(tsum, before);
+        const int64_t kk = sh.k;
+        __syncthreads();
+        if (kk >= before && kk < (int64_t)before + tsum) {   // exactly one thread
+            int64_t rem = kk - before;
+            int j = 0;
+            while (rem >= c[j]) { rem -= c[j]; ++j; }
+            sh.prefix = (prefix << width) | (uint64_t)(tid * BINS_PER_THREAD + j);
+            sh.k = rem;
+        }
+        __syncthreads();
+        hi = lo;
+    }
+    const uint64_t res = sh.prefix;
+    __syncthreads();                                 // the next select re-initialises sh.prefix
+    return res;
+}
+
+// numpy's median of an even count is the mean of the two middle order statistics: given the key of
+// rank k, the value of rank k-1 is either the same (ties) or the largest key below it.
+template <typename KeyFn>
+__device__ uint64_t block_rank_below(SelectShared& sh, KeyFn keyfn, int64_t n, int64_t k, uint64_t key_k) {
+    unsigned long long mx = 0;
+    int cnt = 0;
+    for (int64_t i = threadIdx.x; i < n; i += SEL_THREADS) {
+        const uint64_t key = keyfn(i);
+        if (key < key_k) { ++cnt; mx = key > mx ? key : mx; }
+    }
+    const unsigned long long bmx = cub::BlockReduce<unsigned long long, SEL_THREADS>(sh.red.red_u).Reduce(mx, cub::Max());
+    __syncthreads();
+    const int bcnt = cub::BlockReduce<int, SEL_THREADS>(sh.red.red_i).Sum(cnt);
+    if (threadIdx.x == 0) { sh.max_less = bmx; sh.count_less = bcnt; }
+    __syncthreads();
+    const uint64_t r = ((int64_t)sh.count_less <= k - 1) ? key_k : sh.max_less;
+    __syncthreads();
+    return r;
+}
+
+template <typename KeyFn>
+__device__ double block_median(SelectShared& sh, KeyFn keyfn, int64_t n) {
+    const int64_t k = n / 2;
+    const uint64_t key_hi = block_select(sh, keyfn, n, k);
+    if (n & 1) return value_of(key_hi);
+    const uint64_t key_lo = block_rank_below(sh, keyfn, n, k, key_hi);
+    // np.median -> np.mean of the two middle values: (lo + hi) / 2
+    return __ddiv_rn(__dadd_rn(value_of(key_lo), value_of(key_hi)), 2.0);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+read_scale_kernel(const int16_t* __restrict__ raw, const int64_t* __restrict__ raw_off,
+                  const double* __restrict__ scaling, const double* __restrict__ offset, int64_t n_reads,
+                  double* __restrict__ shift_out, double* __restrict__ scale_out) {
+    __shared__ SelectShared sh;
+    for (int64_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const int16_t* x = raw + raw_off[r];
+        const int64_t n = raw_off[r + 1] - raw_off[r];
+        if (n <= 0) {                                   // np.median of nothing is nan
+            if (threadIdx.x == 0) { shift_out[r] = CUDART_NAN; scale_out[r] = CUDART_NAN; }
+            continue;
+        }
+        Rescale f;
+        f.scaling = scaling[r]; f.offset = offset[r]; f.on = !(f.scaling != f.scaling);
+        const double med = block_median(sh, [&](int64_t i) { return key_of(f(x[i])); }, n);
+        // statsmodels.robust.mad: median(|a - median(a)| / c).  Dividing by the positive constant is
+        // monotone, so the order statistics are selected on |a - median| and divided afterwards.
+        auto dev_key = [&](int64_t i) { return key_of(fabs(__dsub_rn(f(x[i]), med))); };
+        const int64_t k = n / 2;
+        const uint64_t key_hi = block_select(sh, dev_key, n, k);
+        double mad;
+        if (n & 1) {
+            mad = __ddiv_rn(value_of(key_hi), MAD_C);
+        } else {
+            const uint64_t key_lo = block_rank_below(sh, dev_key, n, k, key_hi);
+            mad = __ddiv_rn(__dadd_rn(__ddiv_rn(value_of(key_lo), MAD_C), __ddiv_rn(value_of(key_hi), MAD_C)), 2.0);
+        }
+        if (threadIdx.x == 0) { shift_out[r] = med; scale_out[r] = mad; }
+        __syncthreads();
+    }
+}
+
+// np.around(v, 6): rint(v * 1e6) / 1e6 in float64
+__device__ __forceinline__ double around6(double v) { return __ddiv_rn(rint(__dmul_rn(v, 1e6)), 1e6); }
+
+// One base's samples as _normalize_signals leaves them: around((x - shift) / scale, 6), or around(x, 6)
+// when the scale is 0 (:186-189).
+struct NormSamples {
+    const int16_t* x;
+    Rescale f;
+    double shift, scale;
+    __device__ __forceinline__ double operator()(int64_t i) const {
+        const double v = f(x[i]);
+        return around6(scale == 0.0 ? v : __ddiv_rn(__dsub_rn(v, shift), scale));
+    }
+};
+
+// numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum) of elem(0..n-1):
+// n < 8 a running sum from 0; n <= 128 eight interleaved accumulators combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then the tail; larger n split at n/2 rounded down to a multiple of 8.
+template <typename Elem>
+__device__ double pairwise_leaf(Elem elem, int64_t off, int64_t n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, elem(off + i));
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = elem(off + j);
+    int64_t i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], elem(off + i + j));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, elem(off + i));
+    return res;
+}
+
+template <typename Elem>
+__device__ double pairwise_sum(Elem elem, int64_t n) {
+    if (n <= 128) return pairwise_leaf(elem, 0, n);
+    // explicit stack instead of recursion: frames are (offset, count, phase, left value)
+    constexpr int DEPTH = 40;
+    int64_t off_s[DEPTH], n_s[DEPTH];
+    double left_s[DEPTH];
+    int phase_s[DEPTH];
+    int sp = 0;
+    off_s[0] = 0; n_s[0] = n; phase_s[0] = 0; left_s[0] = 0.0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int64_t o = off_s[sp], c = n_s[sp];
+        if (phase_s[sp] == 0) {
+            if (c <= 128) { ret = pairwise_leaf(elem, o, c); --sp; continue; }
+            int64_t n2 = c / 2; n2 -= n2 % 8;
+            phase_s[sp] = 1;
+            ++sp; off_s[sp] = o; n_s[sp] = n2; phase_s[sp] = 0;
+        } else if (phase_s[sp] == 1) {
+            int64_t n2 = c / 2; n2 -= n2 % 8;
+            left_s[sp] = ret; phase_s[sp] = 2;
+            ++sp; off_s[sp] = o + n2; n_s[sp] = c - n2; phase_s[sp] = 0;
+        } else {
+            ret = __dadd_rn(left_s[sp], ret); --sp;
+        }
+    }
+    return ret;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): one 128-bit block per counter.
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__constant__ uint8_t c_base2code[256];
+
+struct SiteParams {
+    const int16_t* raw; const int64_t* raw_off; const double* scaling; const double* offset;
+    const int64_t* ev_start; const int64_t* ev_len; const uint8_t* ev_base;
+    const int32_t* site_read; const int64_t* site_ev; int64_t n_sites;
+    int T, S, round_stats;
+    const int32_t* drawn; uint64_t seed;
+    const double* shift; const double* scale;
+    float *kmer, *means, *stds, *lens, *signals;
+};
+
+__global__ void __launch_bounds__(256) site_features_kernel(SiteParams p) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.n_sites * p.T) return;
+    const int64_t site = idx / p.T;
+    const int j = (int)(idx - site * p.T);
+    const int32_t rd = p.site_read[site];
+    const int64_t ev = p.site_ev[site] - (p.T - 1) / 2 + j;
+    const int64_t n = p.ev_len[ev];
+    NormSamples v;
+    v.x = p.raw + p.raw_off[rd] + p.ev_start[ev];
+    v.f.scaling = p.scaling[rd]; v.f.offset = p.offset[rd]; v.f.on = !(v.f.scaling != v.f.scaling);
+    v.shift = p.shift[rd]; v.scale = p.scale[rd];
+
+    // np.mean / np.std of the slice (extract_features.py:363-364): sum / n, sqrt(sum((x - mean)^2) / n)
+    const double dn = (double)n;
+    double mean = __ddiv_rn(pairwise_sum(v, n), dn);
+    const double m0 = mean;
+    double sd = __dsqrt_rn(__ddiv_rn(pairwise_sum([&](int64_t i) { const double d = __dsub_rn(v(i), m0); return __dmul_rn(d, d); }, n), dn));
+    if (p.round_stats) { mean = around6(mean); sd = around6(sd); }   // _features_to_str, :388-389
+    p.kmer[idx] = (float)c_base2code[p.ev_base[ev]];
+    p.means[idx] = (float)mean;
+    p.stds[idx] = (float)sd;
+    p.lens[idx] = (float)n;
+
+    // _get_signals_rect (:232-251)
+    float* out = p.signals + idx * p.S;
+    const int S = p.S;
+    if (n <= S) {
+        const int left = (int)((S - n) / 2);
+        for (int s = 0; s < S; ++s) {
+            const int64_t i = s - left;
+            out[s] = (i >= 0 && i < n) ? (float)v(i) : 0.0f;
+        }
+    } else if (p.drawn) {                              // parity mode: replay the reference's random.sample offsets
+        const int32_t* d = p.drawn + idx * S;
+        for (int s = 0; s < S; ++s) out[s] = (float)v(d[s]);
+    } else {
+        // an ordered uniform S-subset by selection sampling (Knuth 3.4.2 S): sample i is taken with
+        // probability (still needed) / (still available); same distribution as sorted(random.sample(range(n), S))
+        int need = S, s = 0;
+        uint4 blk = make_uint4(0, 0, 0, 0);
+        for (int64_t i = 0; i < n && need > 0; ++i) {
+            if ((i & 3) == 0) blk = philox4x32((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(i >> 2), 0x65787472u,
+                                               (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+            const uint32_t u = (i & 3) == 0 ? blk.x : (i & 3) == 1 ? blk.y : (i & 3) == 2 ? blk.z : blk.w;
+            // u / 2^32 < need / (n - i)   <=>   u * (n - i) < need * 2^32
+            if ((uint64_t)u * (uint64_t)(n - i) < ((uint64_t)need << 32)) { out[s++] = (float)v(i); --need; }
+        }
+    }
+}
+
+const uint8_t kBase2Code[16] = {'A', 'C', 'G', 'T', 'N', 'W', 'S', 'M', 'K', 'R', 'Y', 'B', 'V', 'D', 'H', 'Z'};
+
+}  // namespace
+}  // namespace dsp
+
+using namespace dsp;
+
+extern "C" int dsp_extract_features(int device,
+                                    const int16_t* raw, const int64_t* raw_off, const double* scaling, const double* offset,
+                                    int64_t n_reads,
+                                    const int64_t* ev_start, const int64_t* ev_len, const uint8_t* ev_base,
+                                    const int32_t* site_read, const int64_t* site_ev, int64_t n_sites,
+                                    int32_t seq_len, int32_t signal_len, int32_t normalize_method, int32_t round_stats,
+                                    const int32_t* drawn, uint64_t seed,
+                                    double* read_shift, double* read_scale,
+                                    float* kmer, float* base_means, float* base_stds, float* base_signal_lens,
+                                    float* signals, void* stream) {
+    DSP_REQUIRE(n_reads >= 0 && n_sites >= 0, DSP_ERR_INVALID, "dsp_extract_features: negative count");
+    DSP_REQUIRE(seq_len > 0 && (seq_len & 1), DSP_ERR_INVALID, "kmer_len must be odd");
+    DSP_REQUIRE(signal_len > 0, DSP_ERR_INVALID, "dsp_extract_features: signal_len must be positive");
+    DSP_REQUIRE(normalize_method == 0, DSP_ERR_INVALID,
+                "dsp_extract_features: only normalize_method 0 ('mad', the reference's default) runs on the device");
+    DSP_REQUIRE(read_shift && read_scale, DSP_ERR_INVALID, "dsp_extract_features: read_shift / read_scale buffers are required");
+    DSP_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    static int table_device = -1;
+    if (table_device != device) {
+        uint8_t table[256];
+        for (int i = 0; i < 256; ++i) table[i] = 4;           // callers validate the alphabet; 'N' otherwise
+        for (int c = 0; c < 16; ++c) table[kBase2Code[c]] = (uint8_t)c;
+        DSP_CUDA(cudaMemcpyToSymbolAsync(c_base2code, table, sizeof(table), 0, cudaMemcpyHostToDevice, st));
+        DSP_CUDA(cudaStreamSynchronize(st));
+        table_device = device;
+    }
+    if (n_reads > 0) {
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        const int64_t grid = n_reads < (int64_t)n_sm * 4 ? n_reads : (int64_t)n_sm * 4;
+        read_scale_kernel<<<(unsigned)grid, SEL_THREADS, 0, st>>>(raw, raw_off, scaling, offset, n_reads, read_shift, read_scale);
+        DSP_CUDA(cudaGetLastError());
+    }
+    if (n_sites > 0) {
+        SiteParams p;
+        p.raw = raw; p.raw_off = raw_off; p.scaling = scaling; p.offset = offset;
+        p.ev_start = ev_start; p.ev_len = ev_len; p.ev_base = ev_base;
+        p.site_read = site_read; p.site_ev = site_ev; p.n_sites = n_sites;
+        p.T = seq_len; p.S = signal_len; p.round_stats = round_stats;
+        p.drawn = drawn; p.seed = seed; p.shift = read_shift; p.scale = read_scale;
+        p.kmer = kmer; p.means = base_means; p.stds = base_stds; p.lens = base_signal_lens; p.signals = signals;
+        const int64_t threads = n_sites * seq_len;
+        site_features_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p);
+        DSP_CUDA(cudaGetLastError());
+    }
+    return DSP_OK;
+}

@@ -1,0 +1,234 @@
+"""Feature extraction from decoded re-squiggled reads on the GPU (``dsp_extract_features``).
+
+Mirrors the numeric part of ``deepsignal_plant/extract_features.py`` of the reference:
+``_rescale_signals`` (``:276-277``), ``_normalize_signals`` (``:179-190``, method ``mad``), the per-site
+body of ``_extract_features`` (``:318-372``) and ``_get_signals_rect`` (``:232-251``), and hands the
+result over either in the reference's own shape (``_extract_features`` below returns the same
+12-tuples, ``:370-372``) or as the five device tensors ``ModelBiLSTM.forward`` takes, without the
+2.1 KB-per-site text detour of the feature file.
+
+What is NOT here: reading fast5 files.  h5py is absent in this image, so the entry points start at
+what ``_get_alignment_info_from_fast5`` / ``_get_label_raw`` / ``_get_scaling_of_a_read``
+(``:150-176,37-91,255-273``) return -- one dict per read (see ``pack_reads``).  A maintainer with h5py
+wraps those three accessors around ``pack_reads``; INTEGRATION.md shows the stub.
+
+The arithmetic runs in libdsp_b200 only; there is no CPU fallback (``pack_reads`` / ``find_sites`` are
+host-side index bookkeeping, not arithmetic).  ``normalize_method="zscore"`` is not implemented on the
+device and raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native
+
+base2code_dna = {'A': 0, 'C': 1, 'G': 2, 'T': 3, 'N': 4, 'W': 5, 'S': 6, 'M': 7, 'K': 8, 'R': 9,
+                 'Y': 10, 'B': 11, 'V': 12, 'D': 13, 'H': 14, 'Z': 15}
+iupac_alphabets = {'A': ['A'], 'T': ['T'], 'C': ['C'], 'G': ['G'], 'R': ['A', 'G'], 'M': ['A', 'C'],
+                   'S': ['C', 'G'], 'Y': ['C', 'T'], 'K': ['G', 'T'], 'W': ['A', 'T'], 'B': ['C', 'G', 'T'],
+                   'D': ['A', 'G', 'T'], 'H': ['A', 'C', 'T'], 'V': ['A', 'C', 'G'], 'N': ['A', 'C', 'G', 'T']}
+key_sep = "||"
+_ALPHABET = np.frombuffer(b"ACGTNWSMKRYBVDHZ", np.uint8)
+
+
+def get_motif_seqs(motifs, is_dna=True):
+    """``utils/process_utils.py:115-147``: expand comma-separated IUPAC motifs (DNA only here)."""
+    if not is_dna:
+        raise ValueError("only DNA motifs are supported")
+    out = []
+    for ori in motifs.strip().split(','):
+        seqs = ['']
+        for b in ori.strip().upper():
+            seqs = [s + x for s in seqs for x in iupac_alphabets[b]]
+        out += seqs
+    return out
+
+
+class ReadBatch:
+    """Flat arrays of a batch of decoded reads (host numpy; ``to_device`` uploads them once)."""
+
+    def __init__(self, reads):
+        n = len(reads)
+        self.n_reads = n
+        self.readname = [r["readname"] for r in reads]
+        self.strand = [r["strand"] for r in reads]
+        self.alignstrand = [r["alignstrand"] for r in reads]
+        self.chrom = [r["chrom"] for r in reads]
+        self.chrom_start = np.array([r["chrom_start"] for r in reads], np.int64)
+        self.raw_off = np.zeros(n + 1, np.int64)
+        self.ev_off = np.zeros(n + 1, np.int64)
+        for i, r in enumerate(reads):
+            self.raw_off[i + 1] = self.raw_off[i] + len(r["raw"])
+            self.ev_off[i + 1] = self.ev_off[i] + len(r["ev_len"])
+        cat = lambda key, dt: (np.concatenate([np.asarray(r[key]) for r in reads]).astype(dt, copy=False)
+                               if n else np.zeros(0, dt))
+        self.raw = cat("raw", np.int16)
+        self.ev_start = cat("ev_start", np.int64)
+        self.ev_len = cat("ev_len", np.int64)
+        self.ev_base = np.frombuffer("".join(r["ev_base"] for r in reads).encode("ascii"), np.uint8).copy()
+        # _get_scaling_of_a_read returns (None, None) when the channel info cannot be read (:271-273)
+        self.scaling = np.array([np.nan if r.get("scaling") is None else r["scaling"] for r in reads], np.float64)
+        self.offset = np.array([0.0 if r.get("scaling") is None else r["offset"] for r in reads], np.float64)
+        if self.ev_base.shape[0] != self.ev_len.shape[0] or self.ev_start.shape[0] != self.ev_len.shape[0]:
+            raise ValueError("event columns differ in length")         # the reference asserts (:87-88)
+        if not np.isin(self.ev_base, _ALPHABET).all():
+            bad = chr(int(self.ev_base[~np.isin(self.ev_base, _ALPHABET)][0]))
+            raise KeyError(bad)                                         # base2code_dna[x] in the reference
+        ev_read = np.repeat(np.arange(n), np.diff(self.ev_off))
+        if n and ((self.ev_start < 0).any() or (self.ev_len < 0).any()
+                  or (self.ev_start + self.ev_len > np.diff(self.raw_off)[ev_read]).any()):
+            raise ValueError("an event reaches outside its read's raw signal")
+        self._dev = None
+
+    def to_device(self, device):
+        if self._dev is None or self._dev["device"] != device:
+            up = lambda a: torch.from_numpy(a).to(device, non_blocking=False)
+            self._dev = dict(device=device, raw=up(self.raw), raw_off=up(self.raw_off), scaling=up(self.scaling),
+                             offset=up(self.offset), ev_start=up(self.ev_start), ev_len=up(self.ev_len),
+                             ev_base=up(self.ev_base))
+        return self._dev
+
+
+def pack_reads(reads):
+    """reads: list of dicts with readname, strand ('t'/'c'), alignstrand, chrom, chrom_start
+    (``_get_alignment_info_from_fast5``), raw (int16 DAC samples), ev_start (already shifted by
+    ``read_start_rel_to_raw``), ev_len, ev_base (``_get_label_raw``), scaling, offset
+    (``_get_scaling_of_a_read``; None = no channel info)."""
+    return reads if isinstance(reads, ReadBatch) else ReadBatch(reads)
+
+
+class Sites:
+    """Which (read, base) pairs to extract, and their coordinates (``:341-355``)."""
+    __slots__ = ("site_read", "site_ev", "pos", "pos_in_strand")
+
+    def __init__(self, site_read, site_ev, pos, pos_in_strand):
+        self.site_read, self.site_ev, self.pos, self.pos_in_strand = site_read, site_ev, pos, pos_in_strand
+
+    def __len__(self):
+        return int(self.site_read.shape[0])
+
+
+def find_sites(batch, motif_seqs, methyloc, chrom2len, kmer_len, positions=None, regioninfo=(None, None, None)):
+    """``get_refloc_of_methysite_in_motif`` (``utils/process_utils.py:97-112``) over every read of the
+    batch at once, then the reference's site filters in its order (``:341-355``): margin of
+    ``(kmer_len-1)//2`` bases, strand-aware position, region, position set.  Index bookkeeping only."""
+    if kmer_len % 2 == 0:
+        raise ValueError("kmer_len must be odd")
+    num_bases = (kmer_len - 1) // 2
+    motifs = sorted(set(motif_seqs))
+    mlen = len(motifs[0])
+    rg_chrom, rg_start, rg_end = regioninfo
+    nb = batch.ev_base.shape[0]
+    empty = Sites(np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64))
+    if nb < mlen:
+        return empty
+    hit = np.zeros(nb - mlen + 1, bool)
+    for m in motifs:
+        mb = np.frombuffer(m.encode("ascii"), np.uint8)
+        h = batch.ev_base[0:nb - mlen + 1] == mb[0]
+        for k in range(1, mlen):
+            h &= batch.ev_base[k:nb - mlen + 1 + k] == mb[k]
+        hit |= h
+    start = np.nonzero(hit)[0]
+    rd = np.searchsorted(batch.ev_off, start, side="right") - 1
+    rlen = np.diff(batch.ev_off)[rd]
+    loc0 = start - batch.ev_off[rd]
+    ok = loc0 + mlen <= rlen                                  # the motif must not run into the next read
+    loc = loc0 + methyloc
+    ok &= (loc >= num_bases) & (loc < rlen - num_bases)
+    rd, loc, rlen = rd[ok], loc[ok], rlen[ok]
+    cstart = batch.chrom_start[rd]
+    minus = np.array([s == '-' for s in batch.alignstrand], bool)[rd] if batch.n_reads else np.zeros(0, bool)
+    pos = np.where(minus, cstart + rlen - 1 - loc, cstart + loc)
+    if chrom2len is not None:
+        clen = np.array([chrom2len.get(c, -1) for c in batch.chrom], np.int64)[rd]
+        pis = np.where(clen < 0, -1, np.where(minus, clen - 1 - pos, pos))
+    else:
+        pis = np.full(pos.shape, -1, np.int64)
+    keep = np.ones(pos.shape, bool)
+    if rg_chrom is not None:
+        same = np.array([c == rg_chrom for c in batch.chrom], bool)[rd]
+        rs = cstart if rg_start is None else np.full(pos.shape, rg_start, np.int64)
+        re_ = cstart + rlen if rg_end is None else np.full(pos.shape, rg_end, np.int64)
+        keep &= same & ~((rs >= cstart + rlen) | (re_ <= cstart)) & (pos >= rs) & (pos < re_)
+    if positions is not None:
+        keep &= np.array([key_sep.join([batch.chrom[r], str(int(p)), batch.alignstrand[r]]) in positions
+                          for r, p in zip(rd, pos)], bool)
+    rd, loc, pos, pis = rd[keep], loc[keep], pos[keep], pis[keep]
+    return Sites(rd.astype(np.int32), (batch.ev_off[rd] + loc).astype(np.int64), pos.astype(np.int64), pis.astype(np.int64))
+
+
+def sampleinfo(batch, sites):
+    """The six leading columns of a feature / call_mods line (``call_modifications.py:312``)."""
+    return ["\t".join([batch.chrom[r], str(int(p)), batch.alignstrand[r], str(int(q)), batch.readname[r], batch.strand[r]])
+            for r, p, q in zip(sites.site_read, sites.pos, sites.pos_in_strand)]
+
+
+def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method="mad", round_stats=False,
+                    drawn=None, seed=0, device=None):
+    """Run ``dsp_extract_features``: -> dict of the five float32 CUDA tensors ``ModelBiLSTM.forward``
+    takes (``kmer, base_means, base_stds, base_signal_lens, signals``) plus ``read_shift`` /
+    ``read_scale`` (float64 per read: the median and MAD ``_normalize_signals`` used).
+    ``drawn``: optional (n_sites, kmer_len, signals_len) int32 subsample offsets to replay (parity)."""
+    if normalize_method != "mad":
+        raise NotImplementedError("normalize_method %r: only 'mad' (the reference's default) runs on the device"
+                                  % (normalize_method,))
+    if not torch.cuda.is_available():
+        raise _native.DspError("dsp_extract_features needs a CUDA device; there is no CPU fallback")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    L = _native.lib()
+    d = batch.to_device(device)
+    n = len(sites)
+    T, S = int(kmer_len), int(signals_len)
+    site_read = torch.from_numpy(sites.site_read).to(device)
+    site_ev = torch.from_numpy(sites.site_ev).to(device)
+    drawn_t = None
+    if drawn is not None:
+        drawn_t = torch.as_tensor(np.ascontiguousarray(drawn, np.int32)).to(device)
+        if tuple(drawn_t.shape) != (n, T, S):
+            raise ValueError("drawn must have shape (n_sites, kmer_len, signals_len)")
+    f32 = dict(dtype=torch.float32, device=device)
+    out = dict(kmer=torch.empty((n, T), **f32), base_means=torch.empty((n, T), **f32),
+               base_stds=torch.empty((n, T), **f32), base_signal_lens=torch.empty((n, T), **f32),
+               signals=torch.empty((n, T, S), **f32),
+               read_shift=torch.empty(batch.n_reads, dtype=torch.float64, device=device),
+               read_scale=torch.empty(batch.n_reads, dtype=torch.float64, device=device))
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+    with torch.cuda.device(device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = L.dsp_extract_features(
+            device.index, ptr(d["raw"]), C.c_void_p(d["raw_off"].data_ptr()), ptr(d["scaling"]), ptr(d["offset"]),
+            batch.n_reads, ptr(d["ev_start"]), ptr(d["ev_len"]), ptr(d["ev_base"]), ptr(site_read), ptr(site_ev), n,
+            T, S, 0, 1 if round_stats else 0, ptr(drawn_t), int(seed) & (2 ** 64 - 1),
+            C.c_void_p(out["read_shift"].data_ptr()), C.c_void_p(out["read_scale"].data_ptr()),
+            ptr(out["kmer"]), ptr(out["base_means"]), ptr(out["base_stds"]), ptr(out["base_signal_lens"]),
+            ptr(out["signals"]), C.c_void_p(st))
+    _native.check(rc, "dsp_extract_features")
+    return out
+
+
+def _extract_features(reads, normalize_method, motif_seqs, methyloc, chrom2len, kmer_len, signals_len,
+                      methy_label, positions, regioninfo, drawn=None, seed=0, device=None):
+    """The reference's ``_extract_features`` (``:280-378``) for decoded reads instead of fast5 paths:
+    -> (features_list, error) with the same 12-tuples
+    ``(chrom, pos, alignstrand, pos_in_strand, readname, strand, k_mer, signal_means, signal_stds,
+    signal_lens, k_signals_rect, methy_label)``.  Values are what the device produced in float32
+    (the precision every consumer -- ``FloatTensor`` -- reads them in)."""
+    batch = pack_reads(reads)
+    sites = find_sites(batch, motif_seqs, methyloc, chrom2len, kmer_len, positions, regioninfo)
+    if len(sites) == 0:
+        return [], 0
+    t = extract_tensors(batch, sites, kmer_len, signals_len, normalize_method, False, drawn, seed, device)
+    host = {k: t[k].cpu().numpy() for k in ("base_means", "base_stds", "base_signal_lens", "signals")}
+    num_bases = (kmer_len - 1) // 2
+    feats = []
+    for i in range(len(sites)):
+        r, ev = int(sites.site_read[i]), int(sites.site_ev[i])
+        k_mer = bytes(batch.ev_base[ev - num_bases:ev + num_bases + 1]).decode()
+        feats.append((batch.chrom[r], int(sites.pos[i]), batch.alignstrand[r], int(sites.pos_in_strand[i]),
+                      batch.readname[r], batch.strand[r], k_mer, list(host["base_means"][i]), list(host["base_stds"][i]),
+                      [int(x) for x in host["base_signal_lens"][i]], host["signals"][i].tolist(), methy_label))
+    return feats, 0

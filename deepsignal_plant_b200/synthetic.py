@@ -147,3 +147,51 @@ def make_callmods_records(n_records, n_chrom=5, n_pos=10000, seed=0, tie_fractio
             chrom[i], p, strand, pis, i // 25, str(p0n[i]), str(p1n[i]), label[i],
             "".join(bases[b] for b in kmers[i])))
     return lines
+
+
+def make_reads(n_reads, seed=0, mean_bases=400, mean_dwell=9.0, n_chrom=3, chrom_len=200000, long_every=7,
+               no_scaling_every=0):
+    """Synthetic re-squiggled reads, decoded the way ``_get_label_raw`` / ``_get_scaling_of_a_read``
+    (``extract_features.py:37-91,255-273``) hand them to ``_extract_features``: int16 DAC samples, the
+    channel's scaling / offset, and the tombo event table (start already shifted by
+    ``read_start_rel_to_raw``, length, base).  Dwell times are geometric-like with a heavy tail so that
+    bases shorter than, equal to and longer than the 16-sample rectangle all occur; every
+    ``long_every``-th read has a stalled stretch (dwell > 100 samples: numpy's pairwise summation
+    switches to its 8-accumulator and recursive forms there).  Returns a list of dicts."""
+    rng = np.random.default_rng(seed)
+    levels = rng.normal(0.0, 1.0, 4 ** 3)                       # a 3-mer pore model in normalised units
+    reads = []
+    for r in range(n_reads):
+        nb = int(max(30, rng.poisson(mean_bases)))
+        seq = rng.integers(0, 4, nb)
+        dwell = 1 + rng.geometric(1.0 / mean_dwell, nb) - 1
+        dwell = np.maximum(dwell, 1)
+        tail = rng.random(nb) < 0.04
+        dwell[tail] += rng.integers(8, 60, int(tail.sum()))
+        if long_every and r % long_every == 0:
+            j = rng.integers(0, nb, 3)
+            dwell[j] = rng.integers(110, 400, 3)
+        lead = int(rng.integers(0, 300))                         # read_start_rel_to_raw
+        trail = int(rng.integers(0, 200))
+        starts = lead + np.concatenate([[0], np.cumsum(dwell)[:-1]])
+        total = lead + int(dwell.sum()) + trail
+        ctx = np.zeros(nb, np.int64)
+        ctx[1:-1] = seq[:-2] * 16 + seq[1:-1] * 4 + seq[2:]
+        per_base = levels[ctx]
+        norm = np.repeat(per_base, dwell) + rng.normal(0, 0.25, int(dwell.sum()))
+        full = np.concatenate([rng.normal(0.5, 1.0, lead), norm, rng.normal(-0.3, 1.2, trail)])
+        scaling = float(rng.uniform(0.15, 0.2))
+        offset = float(rng.integers(-20, 30))
+        pa = 90.0 + 12.0 * full                                  # picoampere
+        raw = np.clip(np.rint(pa / scaling - offset), -32768, 32767).astype(np.int16)
+        assert raw.shape[0] == total
+        rd = dict(readname="read_%05d" % r, strand="t", alignstrand="+-"[int(rng.integers(0, 2))],
+                  chrom="chr%d" % int(rng.integers(1, n_chrom + 1)),
+                  chrom_start=int(rng.integers(0, chrom_len - nb)),
+                  raw=raw, scaling=np.float64(scaling), offset=np.float64(offset),
+                  ev_start=starts.astype(np.int64), ev_len=dwell.astype(np.int64),
+                  ev_base="".join("ACGT"[b] for b in seq))
+        if no_scaling_every and r % no_scaling_every == 1:
+            rd["scaling"], rd["offset"] = None, None
+        reads.append(rd)
+    return reads

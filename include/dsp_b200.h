@@ -188,6 +188,40 @@ int dsp_format_calls(const char* info_text, const int64_t* info_off, const float
                      int32_t seq_len, const float* probs, const int32_t* labels, int64_t n,
                      char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads);
 
+/* ---- feature extraction from decoded re-squiggled reads ----------------
+ * dsp_extract_features: the numeric body of _extract_features (extract_features.py:280-378) for a
+ * batch of reads whose fast5 content is already decoded into flat DEVICE arrays:
+ *   raw (int16 DAC samples of all reads, concatenated), raw_off (n_reads + 1 offsets into raw),
+ *   scaling / offset (per read, float64: _get_scaling_of_a_read, :255-273; a NaN scaling = no channel
+ *   info, samples used as they are, :313-315);
+ *   the tombo event tables of all reads, concatenated: ev_start (relative to the read's first raw
+ *   sample, read_start_rel_to_raw already added as :80 does), ev_len, ev_base (ASCII letters);
+ *   the sites to extract: site_read (read index) and site_ev (index of the site's own event in the
+ *   concatenated table; the seq_len events centred on it must belong to the same read, which is the
+ *   `num_bases <= loc < len - num_bases` rule of :341).
+ * Per read: _rescale_signals (:276-277) and _normalize_signals (:179-190) with normalize_method 0 =
+ * 'mad' (median / statsmodels.robust.mad, float64, then np.around(., 6)); their shift and scale are
+ * left in read_shift / read_scale (n_reads doubles each).  Per site and base: len, np.mean, np.std
+ * (float64, numpy's pairwise summation order) and the seq_len x signal_len rectangle of
+ * _get_signals_rect (:232-251), written as float32 into the five tensors dsp_forward takes
+ * (kmer = base2code_dna codes).  round_stats != 0 rounds means/stds to 6 decimals first, which is
+ * what the feature FILE carries (_features_to_str, :388-389); 0 is the direct fast5 route
+ * (call_modifications.py:309-318).  Bases with more than signal_len samples are subsampled in order:
+ * with `drawn` (n_sites x seq_len x signal_len int32 offsets, rows of other bases ignored) the given
+ * offsets are used -- the way to replay the reference's random.sample draws; with NULL an ordered
+ * uniform subset is drawn on the device from Philox4x32-10 keyed by (seed, site, base), which is what
+ * the reference does statistically.  Enqueues on `stream`; does not synchronise. */
+int dsp_extract_features(int device,
+                         const int16_t* raw, const int64_t* raw_off, const double* scaling, const double* offset,
+                         int64_t n_reads,
+                         const int64_t* ev_start, const int64_t* ev_len, const uint8_t* ev_base,
+                         const int32_t* site_read, const int64_t* site_ev, int64_t n_sites,
+                         int32_t seq_len, int32_t signal_len, int32_t normalize_method, int32_t round_stats,
+                         const int32_t* drawn, uint64_t seed,
+                         double* read_shift, double* read_scale,
+                         float* kmer, float* base_means, float* base_stds, float* base_signal_lens,
+                         float* signals, void* stream);
+
 /* Known-answer test of the tcgen05/TMEM/bulk-copy building blocks on `device`: a one-CTA
  * FP16 GEMM with FP32 accumulation checked against a double-precision host product.
  * which: 0,1 = both operands from shared memory; 2,3 = A operand staged in TMEM.

@@ -1,0 +1,255 @@
+"""Feature extraction from decoded reads: oracle and host bookkeeping vs the
+fixtures the reference's own ``_extract_features`` produced (CPU); ``dsp_extract_features`` vs the same
+fixtures and vs the oracle on fresh seeds, bit for bit (-m gpu)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from deepsignal_plant_b200 import _native, synthetic
+from deepsignal_plant_b200 import extract_features as ef
+from oracle import extract_oracle as eo
+
+EXTRACT_CASES = sorted(cases.MANIFEST["extract"])
+
+
+def load(name):
+    z = np.load(cases.GOLD + "/extract_%s.npz" % name)
+    reads = eo.unpack_reads(z)
+    K, S = int(z["kmer_len"]), int(z["signals_len"])
+    chrom2len = None if int(z["chrom_len"]) < 0 else {"chr%d" % c: int(z["chrom_len"]) for c in range(1, 4)}
+    return z, reads, K, S, chrom2len, eo.get_motif_seqs(str(z["motifs"])), int(z["mod_loc"])
+
+
+# ---------------------------------------------------------------------------- CPU: oracle + host logic
+@pytest.mark.parametrize("name", EXTRACT_CASES)
+def test_oracle_reproduces_reference_fixture(name):
+    z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
+    feats, drawn = eo.extract_features(reads, "mad", motif_seqs, mod_loc, chrom2len, K, S, 1,
+                                       rng=random.Random(int(z["random_seed"])))
+    assert len(feats) == cases.MANIFEST["extract"][name]["sites"] == len(z["info"])
+    assert ["\t".join([f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]]) for f in feats] == list(z["info"])
+    assert [f[6] for f in feats] == list(z["kmer"])
+    assert np.array_equal(np.array([f[7] for f in feats]), z["means"])          # float64, bit for bit
+    assert np.array_equal(np.array([f[8] for f in feats]), z["stds"])
+    assert np.array_equal(np.array([f[9] for f in feats]), z["lens"])
+    assert np.array_equal(np.array([f[10] for f in feats]), z["rect"])
+    assert np.array_equal(eo.drawn_to_array(drawn, K, S), z["drawn"])
+    assert (z["lens"] > S).sum() == cases.MANIFEST["extract"][name]["bases_longer_than_rect"] > 0
+    assert z["lens"].max() > 128                                                # numpy's recursive pairwise form is covered
+
+
+@pytest.mark.parametrize("name", EXTRACT_CASES)
+def test_feature_lines_of_the_fixture_round_trip(name):
+    # the lines the reference's _features_to_str wrote carry the 6-decimal means/stds: features_to_arrays(round_stats=True)
+    from oracle import features_oracle
+    z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
+    feats, _ = eo.extract_features(reads, "mad", motif_seqs, mod_loc, chrom2len, K, S, 1,
+                                   rng=random.Random(int(z["random_seed"])))
+    arr = eo.features_to_arrays(feats, round_stats=True)
+    info, kmers, means, stds, lens, sig, labels = features_oracle.read_features([str(x) for x in z["lines"]])
+    assert info == list(z["info"])
+    assert np.array_equal(np.asarray(kmers, np.float32), arr["kmer"])
+    assert np.array_equal(np.asarray(means, np.float32), arr["base_means"])
+    assert np.array_equal(np.asarray(stds, np.float32), arr["base_stds"])
+    assert np.array_equal(np.asarray(lens, np.float32), arr["base_signal_lens"])
+    assert np.array_equal(np.asarray(sig, np.float32), arr["signals"])
+
+
+@pytest.mark.parametrize("name", EXTRACT_CASES)
+def test_find_sites_and_sampleinfo_match_reference(name):
+    z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
+    batch = ef.pack_reads(reads)
+    assert sorted(ef.get_motif_seqs(str(z["motifs"]))) == sorted(motif_seqs)
+    sites = ef.find_sites(batch, motif_seqs, mod_loc, chrom2len, K)
+    assert ef.sampleinfo(batch, sites) == list(z["info"])
+    nb = (K - 1) // 2
+    assert [bytes(batch.ev_base[e - nb:e + nb + 1]).decode() for e in sites.site_ev] == list(z["kmer"])
+
+
+def test_find_sites_filters_match_oracle():
+    reads = synthetic.make_reads(25, seed=11, mean_bases=90)
+    chrom2len = {"chr1": 200000, "chr2": 200000}                      # chr3 missing -> pos_in_strand -1 (:331-335)
+    motif_seqs = eo.get_motif_seqs("CHG")
+    batch = ef.pack_reads(reads)
+    for mod_loc, K in ((0, 13), (2, 9)):
+        full, _ = eo.extract_features(reads, "mad", motif_seqs, mod_loc, chrom2len, K, 16, 1, rng=random.Random(1))
+        want = ["\t".join([f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]]) for f in full]
+        assert ef.sampleinfo(batch, ef.find_sites(batch, motif_seqs, mod_loc, chrom2len, K)) == want and len(want) > 50
+    full, _ = eo.extract_features(reads, "mad", motif_seqs, 0, chrom2len, 13, 16, 1, rng=random.Random(1))
+    some = full[len(full) // 2]
+    for region in (("chr2", None, None), (some[0], some[1] - 40, some[1] + 25), ("chrNone", None, None), (some[0], some[1], None)):
+        sub, _ = eo.extract_features(reads, "mad", motif_seqs, 0, chrom2len, 13, 16, 1, regioninfo=region, rng=random.Random(1))
+        got = ef.sampleinfo(batch, ef.find_sites(batch, motif_seqs, 0, chrom2len, 13, regioninfo=region))
+        assert got == ["\t".join([f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]]) for f in sub], region
+    positions = {"||".join([f[0], str(f[1]), f[2]]) for f in full[::3]}
+    sub, _ = eo.extract_features(reads, "mad", motif_seqs, 0, chrom2len, 13, 16, 1, positions=positions, rng=random.Random(1))
+    got = ef.sampleinfo(batch, ef.find_sites(batch, motif_seqs, 0, chrom2len, 13, positions=positions))
+    assert got == ["\t".join([f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]]) for f in sub] and 0 < len(got) < len(full)
+
+
+def test_host_argument_errors():
+    reads = synthetic.make_reads(3, seed=2, mean_bases=60)
+    batch = ef.pack_reads(reads)
+    with pytest.raises(ValueError, match="kmer_len must be odd"):
+        ef.find_sites(batch, ["CG"], 0, None, 12)
+    bad = dict(reads[0]); bad["ev_base"] = "x" + bad["ev_base"][1:]
+    with pytest.raises(KeyError):
+        ef.pack_reads([bad])
+    bad = dict(reads[0]); bad["ev_len"] = bad["ev_len"].copy(); bad["ev_len"][-1] += 10 ** 6
+    with pytest.raises(ValueError, match="outside"):
+        ef.pack_reads([bad])
+    sites = ef.find_sites(batch, ["CG"], 0, None, 13)
+    with pytest.raises(NotImplementedError):
+        ef.extract_tensors(batch, sites, normalize_method="zscore")
+    if not torch.cuda.is_available():
+        with pytest.raises(_native.DspError, match="no CPU fallback"):
+            ef.extract_tensors(batch, sites)
+
+
+# ---------------------------------------------------------------------------- GPU: bit-exact parity
+def _check_against(feats, drawn, batch, sites, K, S, round_stats):
+    want = eo.features_to_arrays(feats, round_stats=round_stats)
+    got = ef.extract_tensors(batch, sites, K, S, round_stats=round_stats, drawn=eo.drawn_to_array(drawn, K, S))
+    for k in ("kmer", "base_signal_lens", "base_means", "base_stds", "signals"):
+        g = got[k].cpu().numpy()
+        assert g.dtype == np.float32 and g.shape == want[k].shape, k
+        assert np.array_equal(g.view(np.uint32), want[k].view(np.uint32)), (k, np.abs(g - want[k]).max())
+    return got
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", EXTRACT_CASES)
+@pytest.mark.parametrize("round_stats", [False, True])
+def test_gpu_extract_matches_reference_fixture_bit_for_bit(name, round_stats):
+    z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
+    batch = ef.pack_reads(reads)
+    sites = ef.find_sites(batch, motif_seqs, mod_loc, chrom2len, K)
+    got = ef.extract_tensors(batch, sites, K, S, round_stats=round_stats, drawn=z["drawn"])
+    means, stds = (np.around(z["means"], 6), np.around(z["stds"], 6)) if round_stats else (z["means"], z["stds"])
+    eq = lambda a, b: np.array_equal(a.cpu().numpy().view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+    assert eq(got["base_means"], means) and eq(got["base_stds"], stds)
+    assert eq(got["base_signal_lens"], z["lens"]) and eq(got["signals"], z["rect"])
+    assert eq(got["kmer"], [[eo.base2code_dna[c] for c in k] for k in z["kmer"]])
+    # the per-read shift / scale _normalize_signals used, float64 bit for bit
+    for i, rd in enumerate(reads):
+        x = rd["raw"] if rd["scaling"] is None else eo.rescale_signals(rd["raw"], rd["scaling"], rd["offset"])
+        assert got["read_shift"][i].item() == float(np.median(x)) and got["read_scale"][i].item() == float(eo.mad(x))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,K,S,motifs", [(101, 13, 16, "CG"), (102, 17, 20, "CHH"), (103, 5, 8, "C"), (104, 13, 16, "CWG,CCG")])
+def test_gpu_extract_matches_oracle_on_fresh_reads(seed, K, S, motifs):
+    reads = synthetic.make_reads(60, seed=seed, mean_bases=220, long_every=4, no_scaling_every=5)
+    # edge reads: constant signal (MAD 0 -> samples kept as they are, :186-187), odd and even sample counts,
+    # two-sample events everywhere, a read with a negative scaling (monotone decreasing rescale)
+    flat = dict(reads[0]); flat["raw"] = np.full_like(flat["raw"], 431); flat["readname"] = "flat"
+    odd = dict(reads[1]); odd["raw"] = odd["raw"][:len(odd["raw"]) - (len(odd["raw"]) % 2 == 0)]
+    last = odd["ev_start"] + odd["ev_len"] <= len(odd["raw"])
+    odd["ev_start"], odd["ev_len"], odd["ev_base"] = odd["ev_start"][last], odd["ev_len"][last], "".join(np.array(list(odd["ev_base"]))[last])
+    odd["readname"] = "odd"
+    neg = dict(reads[2]); neg["scaling"] = np.float64(-0.173); neg["readname"] = "neg"
+    reads = reads + [flat, odd, neg]
+    assert len(odd["raw"]) % 2 == 1
+    motif_seqs = eo.get_motif_seqs(motifs)
+    chrom2len = {"chr%d" % c: 200000 for c in range(1, 4)}
+    batch = ef.pack_reads(reads)
+    sites = ef.find_sites(batch, motif_seqs, 0, chrom2len, K)
+    feats, drawn = eo.extract_features(reads, "mad", motif_seqs, 0, chrom2len, K, S, 1, rng=random.Random(seed))
+    assert len(feats) == len(sites) > 300
+    for round_stats in (False, True):
+        got = _check_against(feats, drawn, batch, sites, K, S, round_stats)
+    assert got["read_scale"][-3].item() == 0.0
+
+
+@pytest.mark.gpu
+def test_gpu_philox_subsample_is_an_ordered_uniform_subset():
+    K, S = 13, 16
+    reads = synthetic.make_reads(40, seed=7, mean_bases=200, mean_dwell=14.0, long_every=2)
+    motif_seqs = eo.get_motif_seqs("CG")
+    batch = ef.pack_reads(reads)
+    sites = ef.find_sites(batch, motif_seqs, 0, None, K)
+    feats, drawn = eo.extract_features(reads, "mad", motif_seqs, 0, None, K, S, 1, rng=random.Random(3))
+    want = eo.features_to_arrays(feats, round_stats=False)
+    a = ef.extract_tensors(batch, sites, K, S, seed=5)
+    b = ef.extract_tensors(batch, sites, K, S, seed=5)
+    c = ef.extract_tensors(batch, sites, K, S, seed=6)
+    sa, sb, sc = (t["signals"].cpu().numpy() for t in (a, b, c))
+    lens = want["base_signal_lens"]
+    short = lens <= S
+    assert np.array_equal(sa, sb)                                        # deterministic in the seed
+    assert np.array_equal(sa[short], want["signals"][short])             # nothing random about short bases
+    assert not np.array_equal(sa[~short], sc[~short])                    # another seed, another draw
+    for k in ("kmer", "base_means", "base_stds", "base_signal_lens"):
+        assert np.array_equal(a[k].cpu().numpy(), want[k])
+    # every long base: the row is a subsequence of the base's normalised samples (strictly increasing offsets)
+    norm = {}
+    picks, frac = 0, []
+    for i, f in enumerate(feats):
+        r = int(sites.site_read[i])
+        if r not in norm:
+            rd = reads[r]
+            x = rd["raw"] if rd["scaling"] is None else eo.rescale_signals(rd["raw"], rd["scaling"], rd["offset"])
+            norm[r] = eo.normalize_signals(x)
+        for j in range(K):
+            n = int(lens[i, j])
+            if n <= S:
+                continue
+            ev = int(sites.site_ev[i]) - (K - 1) // 2 + j
+            base = norm[r][batch.ev_start[ev]:batch.ev_start[ev] + n].astype(np.float32)
+            pos = -1
+            for v in sa[i, j]:
+                nxt = np.nonzero(base[pos + 1:] == v)[0]
+                assert nxt.size, (i, j)
+                pos = pos + 1 + int(nxt[0])
+                frac.append(pos / (n - 1))
+            picks += 1
+    assert picks > 100
+    # offsets of a uniform subset are uniform over the base: mean 1/2, and every decile is populated evenly
+    frac = np.array(frac)
+    assert abs(frac.mean() - 0.5) < 0.02
+    hist = np.histogram(frac, bins=10, range=(0, 1))[0] / frac.size
+    assert np.abs(hist - 0.1).max() < 0.03
+
+
+@pytest.mark.gpu
+def test_gpu_extracted_tensors_feed_the_classifier_like_oracle_features():
+    # extract -> ModelBiLSTM.forward without the feature-file detour == the same model on the oracle's features
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    K, S = 13, 16
+    reads = synthetic.make_reads(80, seed=21, mean_bases=300)
+    motif_seqs = eo.get_motif_seqs("CG")
+    batch = ef.pack_reads(reads)
+    sites = ef.find_sites(batch, motif_seqs, 0, None, K)
+    feats, drawn = eo.extract_features(reads, "mad", motif_seqs, 0, None, K, S, 1, rng=random.Random(9))
+    want = eo.features_to_arrays(feats, round_stats=False)
+    got = ef.extract_tensors(batch, sites, K, S, drawn=eo.drawn_to_array(drawn, K, S))
+    torch.manual_seed(1234)
+    model = ModelBiLSTM(K, S, seed=77).cuda().eval()
+    names = ("kmer", "base_means", "base_stds", "base_signal_lens", "signals")
+    with torch.no_grad():
+        model._calls = 0
+        l1, p1 = model(*[got[k] for k in names])
+        model._calls = 0
+        l2, p2 = model(*[torch.from_numpy(want[k]).cuda() for k in names])
+    assert len(sites) > 500 and torch.equal(p1, p2) and torch.equal(l1, l2)
+    f2, err = ef._extract_features(reads, "mad", motif_seqs, 0, None, K, S, 1, None, (None, None, None),
+                                   drawn=eo.drawn_to_array(drawn, K, S))
+    assert err == 0 and [f[:7] for f in f2] == [f[:7] for f in feats] and [f[9] for f in f2] == [f[9] for f in feats]
+    assert np.array_equal(np.array([f[10] for f in f2], np.float32), want["signals"])
+
+
+@pytest.mark.gpu
+def test_gpu_extract_empty_and_invalid():
+    reads = synthetic.make_reads(2, seed=3, mean_bases=40)
+    batch = ef.pack_reads(reads)
+    none = ef.find_sites(batch, ["ACGTACGTACGTAAAA"], 0, None, 13)
+    assert len(none) == 0
+    out = ef.extract_tensors(batch, none, 13, 16)
+    assert out["signals"].shape == (0, 13, 16) and torch.isfinite(out["read_shift"]).all()
+    L = _native.lib()
+    assert L.dsp_extract_features(0, None, None, None, None, 0, None, None, None, None, None, 0, 12, 16, 0, 0,
+                                  None, 0, None, None, None, None, None, None, None, None) == 1
+    assert b"odd" in L.dsp_last_error()
