@@ -23,6 +23,7 @@ constexpr int SEL_THREADS = 512;
 constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS;
 constexpr int BINS_PER_THREAD = SEL_BINS / SEL_THREADS;
+constexpr int HIST_BINS = 16384;                // DAC levels a read may span on the histogram path (64 KB)
 constexpr double MAD_C = 0.6744897501960817;   // scipy.stats.norm.ppf(3/4.), statsmodels.robust.mad's default c
 
 __device__ __forceinline__ uint64_t key_of(double v) {
@@ -58,10 +59,11 @@ struct SelectShared {
     int count_less;
 };
 
-// Key of the element of rank k (0-based) among keyfn(0..n-1): most-significant-digit radix select,
-// 11-bit digits, shared-memory histogram per pass.
-template <typename KeyFn>
-__device__ uint64_t block_select(SelectShared& sh, KeyFn keyfn, int64_t n, int64_t k) {
+// Key of the element of rank k (0-based) in the multiset {keyfn(i) repeated wfn(i) times, i < n_items}:
+// most-significant-digit radix select, 11-bit digits, shared-memory histogram per pass.  The items are
+// either the samples themselves (weight 1) or the bins of a per-read histogram of DAC values.
+template <typename KeyFn, typename WFn>
+__device__ uint64_t block_select(SelectShared& sh, KeyFn keyfn, WFn wfn, int64_t n_items, int64_t k) {
     const int tid = threadIdx.x;
     if (tid == 0) { sh.prefix = 0; sh.k = k; }
     int hi = 64;                                     // bits [hi, 64) of the answer are known (= sh.prefix)
@@ -71,25 +73,26 @@ __device__ uint64_t block_select(SelectShared& sh, KeyFn keyfn, int64_t n, int64
         for (int b = tid; b < SEL_BINS; b += SEL_THREADS) sh.hist[b] = 0;
         __syncthreads();
         const uint64_t prefix = sh.prefix;
-        for (int64_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
+        for (int64_t i0 = 0; i0 < n_items; i0 += SEL_THREADS) {
             const int64_t i = i0 + tid;
-            bool in = i < n;
+            int w = i < n_items ? wfn(i) : 0;
             uint64_t key = 0;
-            if (in) {
+            if (w > 0) {
                 key = keyfn(i);
-                in = hi == 64 || (key >> hi) == prefix;
+                if (hi != 64 && (key >> hi) != prefix) w = 0;
             }
             const int bin = (int)((key >> lo) & ((1u << width) - 1));
-            // the high digits of neighbouring samples mostly agree: one atomic per warp when they all do
-            const unsigned act = __ballot_sync(0xffffffffu, in);
+            // the high digits of neighbouring items mostly agree: one atomic per warp when they all do
+            const unsigned act = __ballot_sync(0xffffffffu, w > 0);
             if (act == 0) continue;
             const int leader = __ffs(act) - 1;
             const int lbin = __shfl_sync(0xffffffffu, bin, leader);
-            const unsigned same = __ballot_sync(0xffffffffu, in && bin == lbin);
+            const unsigned same = __ballot_sync(0xffffffffu, w > 0 && bin == lbin);
             if (same == act) {
-                if ((tid & 31) == leader) atomicAdd(&sh.hist[lbin], __popc(act));
-            } else if (in) {
-                atomicAdd(&sh.hist[bin], 1);
+                const int tot = __reduce_add_sync(0xffffffffu, w);
+                if ((tid & 31) == leader) atomicAdd(&sh.hist[lbin], tot);
+            } else if (w > 0) {
+                atomicAdd(&sh.hist[bin], w);
             }
         }
         __syncthreads();
@@ -117,13 +120,15 @@ __device__ uint64_t block_select(SelectShared& sh, KeyFn keyfn, int64_t n, int64
 
 // numpy's median of an even count is the mean of the two middle order statistics: given the key of
 // rank k, the value of rank k-1 is either the same (ties) or the largest key below it.
-template <typename KeyFn>
-__device__ uint64_t block_rank_below(SelectShared& sh, KeyFn keyfn, int64_t n, int64_t k, uint64_t key_k) {
+template <typename KeyFn, typename WFn>
+__device__ uint64_t block_rank_below(SelectShared& sh, KeyFn keyfn, WFn wfn, int64_t n_items, int64_t k, uint64_t key_k) {
     unsigned long long mx = 0;
     int cnt = 0;
-    for (int64_t i = threadIdx.x; i < n; i += SEL_THREADS) {
+    for (int64_t i = threadIdx.x; i < n_items; i += SEL_THREADS) {
+        const int w = wfn(i);
+        if (w <= 0) continue;
         const uint64_t key = keyfn(i);
-        if (key < key_k) { ++cnt; mx = key > mx ? key : mx; }
+        if (key < key_k) { cnt += w; mx = key > mx ? key : mx; }
     }
     const unsigned long long bmx = cub::BlockReduce<unsigned long long, SEL_THREADS>(sh.red.red_u).Reduce(mx, cub::Max());
     __syncthreads();
@@ -135,21 +140,51 @@ __device__ uint64_t block_rank_below(SelectShared& sh, KeyFn keyfn, int64_t n, i
     return r;
 }
 
-template <typename KeyFn>
-__device__ double block_median(SelectShared& sh, KeyFn keyfn, int64_t n) {
+// median (np.median: mean of the two middle values for an even count) of valfn over the weighted items,
+// then optionally divided by `div` element-wise before the mean (statsmodels' mad divides by c first)
+template <typename ValFn, typename WFn>
+__device__ double block_median(SelectShared& sh, ValFn valfn, WFn wfn, int64_t n_items, int64_t n, double div) {
+    auto keyfn = [&](int64_t i) { return key_of(valfn(i)); };
     const int64_t k = n / 2;
-    const uint64_t key_hi = block_select(sh, keyfn, n, k);
-    if (n & 1) return value_of(key_hi);
-    const uint64_t key_lo = block_rank_below(sh, keyfn, n, k, key_hi);
-    // np.median -> np.mean of the two middle values: (lo + hi) / 2
-    return __ddiv_rn(__dadd_rn(value_of(key_lo), value_of(key_hi)), 2.0);
+    const uint64_t key_hi = block_select(sh, keyfn, wfn, n_items, k);
+    const double v_hi = div == 1.0 ? value_of(key_hi) : __ddiv_rn(value_of(key_hi), div);
+    if (n & 1) return v_hi;
+    const uint64_t key_lo = block_rank_below(sh, keyfn, wfn, n_items, k, key_hi);
+    const double v_lo = div == 1.0 ? value_of(key_lo) : __ddiv_rn(value_of(key_lo), div);
+    return __ddiv_rn(__dadd_rn(v_lo, v_hi), 2.0);
 }
 
+// every sample of a read, 8 per 16-byte load once the pointer is aligned
+template <typename F>
+__device__ __forceinline__ void for_each_sample(const int16_t* __restrict__ x, int64_t n, F fn) {
+    const int tid = threadIdx.x;
+    int64_t head = (int64_t)(((16 - ((uintptr_t)x & 15)) & 15) >> 1);
+    if (head > n) head = n;
+    for (int64_t i = tid; i < head; i += SEL_THREADS) fn((int)x[i]);
+    const uint4* v = reinterpret_cast<const uint4*>(x + head);
+    const int64_t nv = (n - head) >> 3;
+    for (int64_t i = tid; i < nv; i += SEL_THREADS) {
+        const uint4 q = v[i];
+        fn((int)(int16_t)(q.x & 0xffff)); fn((int)(int16_t)(q.x >> 16));
+        fn((int)(int16_t)(q.y & 0xffff)); fn((int)(int16_t)(q.y >> 16));
+        fn((int)(int16_t)(q.z & 0xffff)); fn((int)(int16_t)(q.z >> 16));
+        fn((int)(int16_t)(q.w & 0xffff)); fn((int)(int16_t)(q.w >> 16));
+    }
+    for (int64_t i = head + (nv << 3) + tid; i < n; i += SEL_THREADS) fn((int)x[i]);
+}
+
+// One CTA per read.  Fast path (DAC values of the read span <= HIST_BINS levels, i.e. every real read):
+// two passes over the samples -- min/max, then a shared-memory histogram of the DAC values -- and both
+// medians are selected over the histogram bins (value of a bin = the rescaled level, weight = its count),
+// which is exact because equal DAC values give equal float64 values.  Otherwise the same selects run over
+// the samples themselves.
 __global__ void __launch_bounds__(SEL_THREADS)
 read_scale_kernel(const int16_t* __restrict__ raw, const int64_t* __restrict__ raw_off,
                   const double* __restrict__ scaling, const double* __restrict__ offset, int64_t n_reads,
                   double* __restrict__ shift_out, double* __restrict__ scale_out) {
     __shared__ SelectShared sh;
+    __shared__ int s_mn, s_mx;
+    extern __shared__ int level_count[];               // HIST_BINS
     for (int64_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
         const int16_t* x = raw + raw_off[r];
         const int64_t n = raw_off[r + 1] - raw_off[r];
@@ -159,18 +194,30 @@ read_scale_kernel(const int16_t* __restrict__ raw, const int64_t* __restrict__ r
         }
         Rescale f;
         f.scaling = scaling[r]; f.offset = offset[r]; f.on = !(f.scaling != f.scaling);
-        const double med = block_median(sh, [&](int64_t i) { return key_of(f(x[i])); }, n);
-        // statsmodels.robust.mad: median(|a - median(a)| / c).  Dividing by the positive constant is
-        // monotone, so the order statistics are selected on |a - median| and divided afterwards.
-        auto dev_key = [&](int64_t i) { return key_of(fabs(__dsub_rn(f(x[i]), med))); };
-        const int64_t k = n / 2;
-        const uint64_t key_hi = block_select(sh, dev_key, n, k);
-        double mad;
-        if (n & 1) {
-            mad = __ddiv_rn(value_of(key_hi), MAD_C);
+        int mn = 32767, mx = -32768;
+        for_each_sample(x, n, [&](int v) { mn = v < mn ? v : mn; mx = v > mx ? v : mx; });
+        mn = cub::BlockReduce<int, SEL_THREADS>(sh.red.red_i).Reduce(mn, cub::Min());
+        __syncthreads();
+        mx = cub::BlockReduce<int, SEL_THREADS>(sh.red.red_i).Reduce(mx, cub::Max());
+        if (threadIdx.x == 0) { s_mn = mn; s_mx = mx; }
+        __syncthreads();
+        mn = s_mn; mx = s_mx;
+        const int levels = mx - mn + 1;
+        double med, mad;
+        if (levels <= HIST_BINS) {
+            for (int b = threadIdx.x; b < levels; b += SEL_THREADS) level_count[b] = 0;
+            __syncthreads();
+            for_each_sample(x, n, [&](int v) { atomicAdd(&level_count[v - mn], 1); });
+            __syncthreads();
+            auto w = [&](int64_t i) { return level_count[i]; };
+            med = block_median(sh, [&](int64_t i) { return f((int16_t)(mn + (int)i)); }, w, levels, n, 1.0);
+            // statsmodels.robust.mad: median(|a - median(a)| / c).  Dividing by the positive constant is
+            // monotone, so the order statistics are selected on |a - median| and divided afterwards.
+            mad = block_median(sh, [&](int64_t i) { return fabs(__dsub_rn(f((int16_t)(mn + (int)i)), med)); }, w, levels, n, MAD_C);
         } else {
-            const uint64_t key_lo = block_rank_below(sh, dev_key, n, k, key_hi);
-            mad = __ddiv_rn(__dadd_rn(__ddiv_rn(value_of(key_lo), MAD_C), __ddiv_rn(value_of(key_hi), MAD_C)), 2.0);
+            auto w = [](int64_t) { return 1; };
+            med = block_median(sh, [&](int64_t i) { return f(x[i]); }, w, n, n, 1.0);
+            mad = block_median(sh, [&](int64_t i) { return fabs(__dsub_rn(f(x[i]), med)); }, w, n, n, MAD_C);
         }
         if (threadIdx.x == 0) { shift_out[r] = med; scale_out[r] = mad; }
         __syncthreads();
@@ -269,54 +316,110 @@ struct SiteParams {
     float *kmer, *means, *stds, *lens, *signals;
 };
 
-__global__ void __launch_bounds__(256) site_features_kernel(SiteParams p) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.n_sites * p.T) return;
-    const int64_t site = idx / p.T;
-    const int j = (int)(idx - site * p.T);
-    const int32_t rd = p.site_read[site];
-    const int64_t ev = p.site_ev[site] - (p.T - 1) / 2 + j;
-    const int64_t n = p.ev_len[ev];
-    NormSamples v;
-    v.x = p.raw + p.raw_off[rd] + p.ev_start[ev];
-    v.f.scaling = p.scaling[rd]; v.f.offset = p.offset[rd]; v.f.on = !(v.f.scaling != v.f.scaling);
-    v.shift = p.shift[rd]; v.scale = p.scale[rd];
+constexpr int SITE_WARPS = 8;                      // sites per CTA (one warp each)
+constexpr int WIN_MAX = 768;                       // samples of a site's window held in shared memory (6 KB per warp)
 
-    // np.mean / np.std of the slice (extract_features.py:363-364): sum / n, sqrt(sum((x - mean)^2) / n)
-    const double dn = (double)n;
-    double mean = __ddiv_rn(pairwise_sum(v, n), dn);
-    const double m0 = mean;
-    double sd = __dsqrt_rn(__ddiv_rn(pairwise_sum([&](int64_t i) { const double d = __dsub_rn(v(i), m0); return __dmul_rn(d, d); }, n), dn));
-    if (p.round_stats) { mean = around6(mean); sd = around6(sd); }   // _features_to_str, :388-389
-    p.kmer[idx] = (float)c_base2code[p.ev_base[ev]];
-    p.means[idx] = (float)mean;
-    p.stds[idx] = (float)sd;
-    p.lens[idx] = (float)n;
+// ordered uniform S-subset of 0..n-1 by selection sampling (Knuth 3.4.2 S): offset i is taken with
+// probability (still needed) / (still available) -- the distribution of sorted(random.sample(range(n), S))
+template <typename Put>
+__device__ __forceinline__ void draw_ordered_subset(int64_t n, int S, int64_t row, uint64_t seed, Put put) {
+    int need = S, s = 0;
+    uint4 blk = make_uint4(0, 0, 0, 0);
+    for (int64_t i = 0; i < n && need > 0; ++i) {
+        if ((i & 3) == 0) blk = philox4x32((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(i >> 2), 0x65787472u,
+                                           (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint32_t u = (i & 3) == 0 ? blk.x : (i & 3) == 1 ? blk.y : (i & 3) == 2 ? blk.z : blk.w;
+        // u / 2^32 < need / (n - i)   <=>   u * (n - i) < need * 2^32
+        if ((uint64_t)u * (uint64_t)(n - i) < ((uint64_t)need << 32)) { put(s++, i); --need; }
+    }
+}
 
-    // _get_signals_rect (:232-251)
-    float* out = p.signals + idx * p.S;
-    const int S = p.S;
-    if (n <= S) {
-        const int left = (int)((S - n) / 2);
-        for (int s = 0; s < S; ++s) {
-            const int64_t i = s - left;
-            out[s] = (i >= 0 && i < n) ? (float)v(i) : 0.0f;
+// One warp per site.  The seq_len events of a site are neighbours in the raw signal, so the warp first
+// normalises the whole window (lane-strided, coalesced, two float64 divisions per sample, each sample
+// once) into shared memory; lane j then owns base j: len, np.mean, np.std (numpy's pairwise order, read
+// from shared memory) and, for a base longer than the rectangle, its subsample offsets; finally all lanes
+// emit the T x S rectangle with coalesced stores.  A site whose window does not fit (a stalled base)
+// takes the same steps with the samples recomputed from the raw signal instead of read from the window.
+__global__ void __launch_bounds__(SITE_WARPS * 32) site_features_kernel(SiteParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int T = p.T, S = p.S;
+    const size_t per_warp = (size_t)WIN_MAX * 8 + (size_t)T * 16 + (((size_t)T * S * 2 + 15) & ~(size_t)15);
+    unsigned char* base = smem_raw + warp * per_warp;
+    double* win = reinterpret_cast<double*>(base);
+    int64_t* b_off = reinterpret_cast<int64_t*>(base + (size_t)WIN_MAX * 8);       // [T] first sample of base j (read-relative)
+    int64_t* b_len = b_off + T;                                                     // [T]
+    uint16_t* sel = reinterpret_cast<uint16_t*>(base + (size_t)WIN_MAX * 8 + (size_t)T * 16);   // [T][S] subsample offsets
+
+    for (int64_t site = (int64_t)blockIdx.x * SITE_WARPS + warp; site < p.n_sites; site += (int64_t)gridDim.x * SITE_WARPS) {
+        const int32_t rd = p.site_read[site];
+        const int64_t ev0 = p.site_ev[site] - (T - 1) / 2;
+        NormSamples v;
+        v.x = p.raw + p.raw_off[rd];
+        v.f.scaling = p.scaling[rd]; v.f.offset = p.offset[rd]; v.f.on = !(v.f.scaling != v.f.scaling);
+        v.shift = p.shift[rd]; v.scale = p.scale[rd];
+        int64_t st = 0x7fffffffffffffffll, en = 0, n = 0, off = 0;
+        if (lane < T) {
+            off = p.ev_start[ev0 + lane]; n = p.ev_len[ev0 + lane];
+            st = off; en = off + n;
+            b_off[lane] = off; b_len[lane] = n;
         }
-    } else if (p.drawn) {                              // parity mode: replay the reference's random.sample offsets
-        const int32_t* d = p.drawn + idx * S;
-        for (int s = 0; s < S; ++s) out[s] = (float)v(d[s]);
-    } else {
-        // an ordered uniform S-subset by selection sampling (Knuth 3.4.2 S): sample i is taken with
-        // probability (still needed) / (still available); same distribution as sorted(random.sample(range(n), S))
-        int need = S, s = 0;
-        uint4 blk = make_uint4(0, 0, 0, 0);
-        for (int64_t i = 0; i < n && need > 0; ++i) {
-            if ((i & 3) == 0) blk = philox4x32((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(i >> 2), 0x65787472u,
-                                               (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-            const uint32_t u = (i & 3) == 0 ? blk.x : (i & 3) == 1 ? blk.y : (i & 3) == 2 ? blk.z : blk.w;
-            // u / 2^32 < need / (n - i)   <=>   u * (n - i) < need * 2^32
-            if ((uint64_t)u * (uint64_t)(n - i) < ((uint64_t)need << 32)) { out[s++] = (float)v(i); --need; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int64_t a = __shfl_xor_sync(0xffffffffu, st, d), b = __shfl_xor_sync(0xffffffffu, en, d);
+            st = a < st ? a : st; en = b > en ? b : en;
         }
+        const int64_t wlen = en - st;
+        const bool windowed = wlen <= WIN_MAX;
+        if (windowed) for (int64_t i = lane; i < wlen; i += 32) win[i] = v(st + i);
+        __syncwarp();
+        const int64_t row = site * T + lane;
+        if (lane < T) {
+            // np.mean / np.std of the slice (extract_features.py:363-364): sum / n, sqrt(sum((x - mean)^2) / n)
+            const double dn = (double)n;
+            const double* a = win + (off - st);
+            double mean, sd;
+            if (windowed) {
+                mean = __ddiv_rn(pairwise_sum([&](int64_t i) { return a[i]; }, n), dn);
+                const double m0 = mean;
+                sd = __dsqrt_rn(__ddiv_rn(pairwise_sum([&](int64_t i) { const double d = __dsub_rn(a[i], m0); return __dmul_rn(d, d); }, n), dn));
+            } else {
+                mean = __ddiv_rn(pairwise_sum([&](int64_t i) { return v(off + i); }, n), dn);
+                const double m0 = mean;
+                sd = __dsqrt_rn(__ddiv_rn(pairwise_sum([&](int64_t i) { const double d = __dsub_rn(v(off + i), m0); return __dmul_rn(d, d); }, n), dn));
+            }
+            if (p.round_stats) { mean = around6(mean); sd = around6(sd); }   // _features_to_str, :388-389
+            p.kmer[row] = (float)c_base2code[p.ev_base[ev0 + lane]];
+            p.means[row] = (float)mean;
+            p.stds[row] = (float)sd;
+            p.lens[row] = (float)n;
+            if (n > S) {
+                if (!p.drawn) {
+                    if (n <= 65536) draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { sel[lane * S + s] = (uint16_t)i; });
+                    else draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { p.signals[row * S + s] = (float)v(off + i); });
+                }
+            }
+        }
+        __syncwarp();
+        // _get_signals_rect (:232-251): centred zero pad, or the ordered subsample
+        float* out = p.signals + site * T * S;
+        for (int e = lane; e < T * S; e += 32) {
+            const int j = e / S, sidx = e - j * S;
+            const int64_t nj = b_len[j];
+            int64_t i;
+            if (nj <= S) {
+                i = sidx - (S - nj) / 2;
+                if (i < 0 || i >= nj) { out[e] = 0.0f; continue; }
+            } else if (p.drawn) {
+                i = p.drawn[site * T * S + e];         // parity mode: replay the reference's random.sample offsets
+            } else if (nj <= 65536) {
+                i = sel[e];
+            } else {
+                continue;                              // written by the base's own lane above
+            }
+            out[e] = (float)(windowed ? win[b_off[j] - st + i] : v(b_off[j] + i));
+        }
+        __syncwarp();
     }
 }
 
@@ -339,7 +442,8 @@ extern "C" int dsp_extract_features(int device,
                                     float* signals, void* stream) {
     DSP_REQUIRE(n_reads >= 0 && n_sites >= 0, DSP_ERR_INVALID, "dsp_extract_features: negative count");
     DSP_REQUIRE(seq_len > 0 && (seq_len & 1), DSP_ERR_INVALID, "kmer_len must be odd");
-    DSP_REQUIRE(signal_len > 0, DSP_ERR_INVALID, "dsp_extract_features: signal_len must be positive");
+    DSP_REQUIRE(seq_len <= 31, DSP_ERR_INVALID, "dsp_extract_features: kmer_len must be at most 31 (one lane per base)");
+    DSP_REQUIRE(signal_len > 0 && signal_len <= 128, DSP_ERR_INVALID, "dsp_extract_features: signal_len must be in 1..128");
     DSP_REQUIRE(normalize_method == 0, DSP_ERR_INVALID,
                 "dsp_extract_features: only normalize_method 0 ('mad', the reference's default) runs on the device");
     DSP_REQUIRE(read_shift && read_scale, DSP_ERR_INVALID, "dsp_extract_features: read_shift / read_scale buffers are required");
@@ -357,8 +461,13 @@ extern "C" int dsp_extract_features(int device,
     if (n_reads > 0) {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-        const int64_t grid = n_reads < (int64_t)n_sm * 4 ? n_reads : (int64_t)n_sm * 4;
-        read_scale_kernel<<<(unsigned)grid, SEL_THREADS, 0, st>>>(raw, raw_off, scaling, offset, n_reads, read_shift, read_scale);
+        const int64_t grid = n_reads < (int64_t)n_sm * 3 ? n_reads : (int64_t)n_sm * 3;   // 3 CTAs of 72 KB per SM
+        static bool attr_set = false;
+        if (!attr_set) {
+            DSP_CUDA(cudaFuncSetAttribute(read_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_BINS * (int)sizeof(int)));
+            attr_set = true;
+        }
+        read_scale_kernel<<<(unsigned)grid, SEL_THREADS, HIST_BINS * sizeof(int), st>>>(raw, raw_off, scaling, offset, n_reads, read_shift, read_scale);
         DSP_CUDA(cudaGetLastError());
     }
     if (n_sites > 0) {
@@ -369,8 +478,18 @@ extern "C" int dsp_extract_features(int device,
         p.T = seq_len; p.S = signal_len; p.round_stats = round_stats;
         p.drawn = drawn; p.seed = seed; p.shift = read_shift; p.scale = read_scale;
         p.kmer = kmer; p.means = base_means; p.stds = base_stds; p.lens = base_signal_lens; p.signals = signals;
-        const int64_t threads = n_sites * seq_len;
-        site_features_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p);
+        const size_t per_warp = (size_t)WIN_MAX * 8 + (size_t)seq_len * 16 + (((size_t)seq_len * signal_len * 2 + 15) & ~(size_t)15);
+        const size_t smem = per_warp * SITE_WARPS;
+        static size_t smem_allowed = 48 * 1024;
+        if (smem > smem_allowed) {
+            DSP_CUDA(cudaFuncSetAttribute(site_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_allowed = smem;
+        }
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        int64_t grid = (n_sites + SITE_WARPS - 1) / SITE_WARPS;
+        if (grid > (int64_t)n_sm * 64) grid = (int64_t)n_sm * 64;
+        site_features_kernel<<<(unsigned)grid, SITE_WARPS * 32, smem, st>>>(p);
         DSP_CUDA(cudaGetLastError());
     }
     return DSP_OK;

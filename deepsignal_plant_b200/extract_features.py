@@ -102,13 +102,19 @@ def pack_reads(reads):
 
 class Sites:
     """Which (read, base) pairs to extract, and their coordinates (``:341-355``)."""
-    __slots__ = ("site_read", "site_ev", "pos", "pos_in_strand")
+    __slots__ = ("site_read", "site_ev", "pos", "pos_in_strand", "_dev")
 
     def __init__(self, site_read, site_ev, pos, pos_in_strand):
         self.site_read, self.site_ev, self.pos, self.pos_in_strand = site_read, site_ev, pos, pos_in_strand
+        self._dev = None
 
     def __len__(self):
         return int(self.site_read.shape[0])
+
+    def to_device(self, device):
+        if self._dev is None or self._dev[0] != device:
+            self._dev = (device, torch.from_numpy(self.site_read).to(device), torch.from_numpy(self.site_ev).to(device))
+        return self._dev[1], self._dev[2]
 
 
 def find_sites(batch, motif_seqs, methyloc, chrom2len, kmer_len, positions=None, regioninfo=(None, None, None)):
@@ -168,11 +174,12 @@ def sampleinfo(batch, sites):
 
 
 def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method="mad", round_stats=False,
-                    drawn=None, seed=0, device=None):
+                    drawn=None, seed=0, device=None, out=None):
     """Run ``dsp_extract_features``: -> dict of the five float32 CUDA tensors ``ModelBiLSTM.forward``
     takes (``kmer, base_means, base_stds, base_signal_lens, signals``) plus ``read_shift`` /
     ``read_scale`` (float64 per read: the median and MAD ``_normalize_signals`` used).
-    ``drawn``: optional (n_sites, kmer_len, signals_len) int32 subsample offsets to replay (parity)."""
+    ``drawn``: optional (n_sites, kmer_len, signals_len) int32 subsample offsets to replay (parity).
+    ``out``: a dict returned by an earlier call with the same shapes, to be overwritten (no allocation)."""
     if normalize_method != "mad":
         raise NotImplementedError("normalize_method %r: only 'mad' (the reference's default) runs on the device"
                                   % (normalize_method,))
@@ -183,19 +190,22 @@ def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method=
     d = batch.to_device(device)
     n = len(sites)
     T, S = int(kmer_len), int(signals_len)
-    site_read = torch.from_numpy(sites.site_read).to(device)
-    site_ev = torch.from_numpy(sites.site_ev).to(device)
+    site_read, site_ev = sites.to_device(device)
     drawn_t = None
     if drawn is not None:
         drawn_t = torch.as_tensor(np.ascontiguousarray(drawn, np.int32)).to(device)
         if tuple(drawn_t.shape) != (n, T, S):
             raise ValueError("drawn must have shape (n_sites, kmer_len, signals_len)")
     f32 = dict(dtype=torch.float32, device=device)
-    out = dict(kmer=torch.empty((n, T), **f32), base_means=torch.empty((n, T), **f32),
-               base_stds=torch.empty((n, T), **f32), base_signal_lens=torch.empty((n, T), **f32),
-               signals=torch.empty((n, T, S), **f32),
-               read_shift=torch.empty(batch.n_reads, dtype=torch.float64, device=device),
-               read_scale=torch.empty(batch.n_reads, dtype=torch.float64, device=device))
+    if out is None:
+        out = dict(kmer=torch.empty((n, T), **f32), base_means=torch.empty((n, T), **f32),
+                   base_stds=torch.empty((n, T), **f32), base_signal_lens=torch.empty((n, T), **f32),
+                   signals=torch.empty((n, T, S), **f32),
+                   read_shift=torch.empty(batch.n_reads, dtype=torch.float64, device=device),
+                   read_scale=torch.empty(batch.n_reads, dtype=torch.float64, device=device))
+    elif (tuple(out["signals"].shape) != (n, T, S) or out["read_shift"].shape[0] != batch.n_reads
+          or out["signals"].device != device):
+        raise ValueError("out does not match this batch")
     ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
     with torch.cuda.device(device):
         st = torch.cuda.current_stream().cuda_stream

@@ -150,14 +150,15 @@ def make_callmods_records(n_records, n_chrom=5, n_pos=10000, seed=0, tie_fractio
 
 
 def make_reads(n_reads, seed=0, mean_bases=400, mean_dwell=9.0, n_chrom=3, chrom_len=200000, long_every=7,
-               no_scaling_every=0):
+               no_scaling_every=0, stall_every=0):
     """Synthetic re-squiggled reads, decoded the way ``_get_label_raw`` / ``_get_scaling_of_a_read``
     (``extract_features.py:37-91,255-273``) hand them to ``_extract_features``: int16 DAC samples, the
     channel's scaling / offset, and the tombo event table (start already shifted by
     ``read_start_rel_to_raw``, length, base).  Dwell times are geometric-like with a heavy tail so that
     bases shorter than, equal to and longer than the 16-sample rectangle all occur; every
     ``long_every``-th read has a stalled stretch (dwell > 100 samples: numpy's pairwise summation
-    switches to its 8-accumulator and recursive forms there).  Returns a list of dicts."""
+    switches to its 8-accumulator and recursive forms there); ``stall_every`` adds a base of 900-2600 samples.
+    Returns a list of dicts."""
     rng = np.random.default_rng(seed)
     levels = rng.normal(0.0, 1.0, 4 ** 3)                       # a 3-mer pore model in normalised units
     reads = []
@@ -171,6 +172,8 @@ def make_reads(n_reads, seed=0, mean_bases=400, mean_dwell=9.0, n_chrom=3, chrom
         if long_every and r % long_every == 0:
             j = rng.integers(0, nb, 3)
             dwell[j] = rng.integers(110, 400, 3)
+        if stall_every and r % stall_every == 0:                 # a blocked pore: one base dwells for thousands of samples
+            dwell[int(rng.integers(10, nb - 10))] = int(rng.integers(900, 2600))
         lead = int(rng.integers(0, 300))                         # read_start_rel_to_raw
         trail = int(rng.integers(0, 200))
         starts = lead + np.concatenate([[0], np.cumsum(dwell)[:-1]])

@@ -142,7 +142,7 @@ def test_gpu_extract_matches_reference_fixture_bit_for_bit(name, round_stats):
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,K,S,motifs", [(101, 13, 16, "CG"), (102, 17, 20, "CHH"), (103, 5, 8, "C"), (104, 13, 16, "CWG,CCG")])
 def test_gpu_extract_matches_oracle_on_fresh_reads(seed, K, S, motifs):
-    reads = synthetic.make_reads(60, seed=seed, mean_bases=220, long_every=4, no_scaling_every=5)
+    reads = synthetic.make_reads(60, seed=seed, mean_bases=220, long_every=4, no_scaling_every=5, stall_every=6)
     # edge reads: constant signal (MAD 0 -> samples kept as they are, :186-187), odd and even sample counts,
     # two-sample events everywhere, a read with a negative scaling (monotone decreasing rescale)
     flat = dict(reads[0]); flat["raw"] = np.full_like(flat["raw"], 431); flat["readname"] = "flat"
@@ -151,7 +151,11 @@ def test_gpu_extract_matches_oracle_on_fresh_reads(seed, K, S, motifs):
     odd["ev_start"], odd["ev_len"], odd["ev_base"] = odd["ev_start"][last], odd["ev_len"][last], "".join(np.array(list(odd["ev_base"]))[last])
     odd["readname"] = "odd"
     neg = dict(reads[2]); neg["scaling"] = np.float64(-0.173); neg["readname"] = "neg"
-    reads = reads + [flat, odd, neg]
+    # DAC values spanning more levels than the per-read histogram holds: the select runs over the samples
+    wide = dict(reads[3]); wide["readname"] = "wide"
+    wide["raw"] = np.clip((wide["raw"].astype(np.int32) - int(np.median(wide["raw"]))) * 90, -32768, 32767).astype(np.int16)
+    assert int(wide["raw"].max()) - int(wide["raw"].min()) > 20000
+    reads = reads + [wide, flat, odd, neg]
     assert len(odd["raw"]) % 2 == 1
     motif_seqs = eo.get_motif_seqs(motifs)
     chrom2len = {"chr%d" % c: 200000 for c in range(1, 4)}
@@ -159,6 +163,8 @@ def test_gpu_extract_matches_oracle_on_fresh_reads(seed, K, S, motifs):
     sites = ef.find_sites(batch, motif_seqs, 0, chrom2len, K)
     feats, drawn = eo.extract_features(reads, "mad", motif_seqs, 0, chrom2len, K, S, 1, rng=random.Random(seed))
     assert len(feats) == len(sites) > 300
+    lens = np.array([f[9] for f in feats])
+    assert (lens.sum(1) > 768).sum() >= 5 and (lens.sum(1) <= 768).sum() > 200     # windowed and recomputing sites
     for round_stats in (False, True):
         got = _check_against(feats, drawn, batch, sites, K, S, round_stats)
     assert got["read_scale"][-3].item() == 0.0

