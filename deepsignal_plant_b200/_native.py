@@ -17,7 +17,7 @@ SYMBOLS = (
     "dsp_pack_weights", "dsp_forward", "dsp_forward_host", "dsp_forward_host_submit",
     "dsp_forward_host_wait", "dsp_launch_count",
     "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate", "dsp_selftest",
-    "dsp_parse_features", "dsp_format_calls", "dsp_freq_release_cache", "dsp_extract_features",
+    "dsp_parse_features", "dsp_format_calls", "dsp_freq_release_cache", "dsp_extract_features", "dsp_format_sampleinfo",
 )
 
 MODULES = {"both_bilstm": 0, "seq_bilstm": 1, "signal_bilstm": 2}
@@ -80,6 +80,7 @@ def lib():
     L.dsp_format_calls.argtypes = [vp, vp, fp, i32, fp, vp, i64, vp, i64, C.POINTER(i64), i32]
     L.dsp_extract_features.argtypes = [C.c_int, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32,
                                        vp, u64, vp, vp, fp, fp, fp, fp, fp, vp]
+    L.dsp_format_sampleinfo.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here means header and library disagree
     _lib = L

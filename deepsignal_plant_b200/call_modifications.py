@@ -285,6 +285,88 @@ def _shard_of_file(path, rank, world):
     return (size * rank // world, size * (rank + 1) // world)
 
 
+class _CallBatch:
+    """What ``feature_io.format_calls`` needs of a batch that never was text."""
+    __slots__ = ("n", "kmer", "info_text", "info_off", "seq_len")
+
+    def __init__(self, n, kmer, info_text, info_off, seq_len):
+        self.n, self.kmer, self.info_text, self.info_off, self.seq_len = n, kmer, info_text, info_off, seq_len
+
+
+def call_mods_from_reads(args, model, write, device=0):
+    """The fast5 branch of ``call_mods`` (``call_modifications.py:560-577``:
+    ``_read_features_from_fast5s`` -> ``_call_mods``, ``:285-323,361-443``) for reads that are already
+    decoded (``extract_features.save_reads`` archive; h5py is absent here): per chunk of reads, site
+    search on the host, ``dsp_extract_features`` -> ``dsp_forward`` on device tensors (features never
+    become text and never leave the GPU), then the usual output lines.  Returns (sites, chunks)."""
+    from . import extract_features as ef
+    from . import feature_io
+    prof = {"load": 0.0, "find_sites": 0.0, "launch": 0.0, "sampleinfo": 0.0, "format": 0.0}
+    tick = time.perf_counter
+    t0 = tick()
+    allreads = ef.load_reads(args.input_path)
+    prof["load"] = tick() - t0
+    motif_seqs = ef.get_motif_seqs(args.motifs, str2bool(getattr(args, "is_dna", "yes")))
+    chrom2len = ef.get_contig2len(args.reference_path) if getattr(args, "reference_path", None) else None
+    positions = ef._read_position_file(args.positions) if getattr(args, "positions", None) else None
+    regioninfo = ef.parse_region_str(getattr(args, "region", None))
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    lo_r, hi_r = allreads.n_reads * rank // world, allreads.n_reads * (rank + 1) // world      # contiguous read shard
+    dev = torch.device("cuda", device)
+    max_batch = int(getattr(args, "max_batch", 65536))
+    step = max(1, int(getattr(args, "f5_batch_size", 30)))
+    sites_total, chunks = 0, 0
+    pending = None
+
+    def flush(item):
+        b, probs, labels = item
+        t1 = tick()
+        write(feature_io.format_calls(b, probs.cpu().numpy(), labels.cpu().numpy()))
+        prof["format"] += tick() - t1
+
+    lo = lo_r
+    while lo < hi_r:
+        hi = min(lo + step, hi_r)
+        batch = allreads.slice(lo, hi)
+        lo = hi
+        t1 = tick()
+        sites = ef.find_sites(batch, motif_seqs, args.mod_loc, chrom2len, args.seq_len, positions, regioninfo)
+        prof["find_sites"] += tick() - t1
+        n = len(sites)
+        # --f5_batch_size only seeds the chunking: aim at one full model batch of sites per chunk
+        step = max(1, min(int(step * max_batch / max(n, 1)), 4 * step + 64))
+        if n == 0:
+            continue
+        t1 = tick()
+        t = ef.extract_tensors(batch, sites, args.seq_len, args.signal_len, args.normalize_method, False,
+                               seed=sites_total, device=dev)
+        kmer_host = None
+        outs = []
+        for a in range(0, n, max_batch):                       # the model's workspace holds max_batch sites
+            z = min(a + max_batch, n)
+            with torch.no_grad():
+                _, probs = model(t["kmer"][a:z], t["base_means"][a:z], t["base_stds"][a:z],
+                                 t["base_signal_lens"][a:z], t["signals"][a:z])
+            outs.append((probs, model.last_labels))
+        prof["launch"] += tick() - t1
+        t1 = tick()
+        info_text, info_off = ef.sampleinfo_packed(batch, sites)          # host work overlaps the kernels above
+        prof["sampleinfo"] += tick() - t1
+        kmer_host = t["kmer"].cpu().numpy()
+        if pending is not None:
+            flush(pending)
+        probs = outs[0][0] if len(outs) == 1 else torch.cat([o[0] for o in outs])
+        labels = outs[0][1] if len(outs) == 1 else torch.cat([o[1] for o in outs])
+        pending = (_CallBatch(n, kmer_host, info_text, info_off, args.seq_len), probs, labels)
+        sites_total += n
+        chunks += 1
+    if pending is not None:
+        flush(pending)
+    if os.environ.get("DSP_B200_PROFILE"):
+        print("call_mods_from_reads host seconds: " + ", ".join("%s %.3f" % kv for kv in prof.items()))
+    return sites_total, chunks
+
+
 def call_mods(args):
     """``call_modifications.py:532-640`` for a feature-file input: read -> call -> write, output
     lines in file order.  Under ``torchrun`` (one process per GPU, RANK/WORLD_SIZE set) every rank
@@ -311,6 +393,8 @@ def call_mods(args):
             dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     args.model_path = model_path
     model = load_model(args, device)
+    from_reads = input_path.endswith(".npz")                  # decoded reads instead of a feature file
+    args.input_path = input_path
 
     result_file = args.result_file
     if args.gzip and not result_file.endswith(".gz"):
@@ -329,6 +413,14 @@ def call_mods(args):
 
     wt = threading.Thread(target=writer, daemon=True)
     wt.start()
+    if from_reads:
+        sites, nb = call_mods_from_reads(args, model, wq.put, device)
+        wq.put(None)
+        wt.join()
+        print("call_mods rank {}: {} sites in {} read-batches".format(rank, sites, nb))
+        _merge_parts(result_file, rank, world)
+        print("[main] call_mods costs %.2f seconds.." % (time.time() - start))
+        return sites
     rq = queue.Queue(maxsize=2)
     reader = feature_io.FeatureFileReader(input_path, args.seq_len, args.signal_len,
                                           batch_sites=getattr(args, "max_batch", 65536), slots=6,
@@ -360,20 +452,26 @@ def call_mods(args):
     if err:
         raise err[0]
     print("call_mods rank {}: {} sites in {} feature-batches".format(rank, sites, nb))
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        if rank == 0:
-            with open(result_file, "wb") as out:
-                for r in range(world):
-                    part = "%s.part%05d" % (result_file, r)
-                    with open(part, "rb") as f:
-                        while True:
-                            blk = f.read(1 << 24)
-                            if not blk:
-                                break
-                            out.write(blk)
-                    os.remove(part)
-        dist.barrier()
+    _merge_parts(result_file, rank, world)
     print("[main] call_mods costs %.2f seconds.." % (time.time() - start))
     return sites
+
+
+def _merge_parts(result_file, rank, world):
+    """Rank 0 concatenates the per-rank parts in rank order (contiguous shards -> input order)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    dist.barrier()
+    if rank == 0:
+        with open(result_file, "wb") as out:
+            for r in range(world):
+                part = "%s.part%05d" % (result_file, r)
+                with open(part, "rb") as f:
+                    while True:
+                        blk = f.read(1 << 24)
+                        if not blk:
+                            break
+                        out.write(blk)
+                os.remove(part)
+    dist.barrier()

@@ -23,9 +23,19 @@ def build_parser():
 
     g = cm.add_argument_group("INPUT")
     g.add_argument("--input_path", "-i", action="store", type=str, required=True,
-                   help="a signal_feature file from `deepsignal_plant extract` (plain or .gz)")
+                   help="a signal_feature file from `deepsignal_plant extract` (plain or .gz), or a decoded-reads archive "
+                        "(.npz written by extract_features.save_reads) to extract and call in one pass")
     g.add_argument("--f5_batch_size", action="store", type=int, default=30, required=False,
-                   help="accepted for compatibility; batches are cut by site count here")
+                   help="reads per extraction chunk for a decoded-reads archive; feature files are cut by site count")
+    g = cm.add_argument_group("EXTRACTION (when --input_path is a decoded-reads .npz archive instead of a feature file)")
+    g.add_argument("--normalize_method", action="store", type=str, choices=["mad", "zscore"], default="mad", required=False)
+    g.add_argument("--motifs", action="store", type=str, required=False, default="CG")
+    g.add_argument("--mod_loc", action="store", type=int, required=False, default=0)
+    g.add_argument("--is_dna", action="store", type=str, required=False, default="yes")
+    g.add_argument("--reference_path", action="store", type=str, required=False, default=None,
+                   help="genome FASTA: contig lengths give the pos_in_strand column")
+    g.add_argument("--positions", action="store", type=str, required=False, default=None)
+    g.add_argument("--region", action="store", type=str, required=False, default=None)
     g = cm.add_argument_group("CALL")
     g.add_argument("--model_path", "-m", action="store", type=str, required=True, help="file path of the trained model (.ckpt)")
     g.add_argument("--model_type", type=str, default="both_bilstm", choices=["both_bilstm", "seq_bilstm", "signal_bilstm"])

@@ -298,4 +298,44 @@ int dsp_format_calls(const char* info_text, const int64_t* info_off, const float
     return DSP_OK;
 }
 
+// The six sample-info columns of sites extracted on the device (call_modifications.py:312:
+// chrom \t pos \t alignstrand \t pos_in_strand \t readname \t strand), packed back to back in the layout
+// dsp_parse_features produces and dsp_format_calls consumes.  Per READ: chrom and readname as packed text +
+// offsets, alignstrand and strand as one character each; per SITE: read index, pos, pos_in_strand.
+int dsp_format_sampleinfo(const char* chrom_text, const int64_t* chrom_off, const char* name_text, const int64_t* name_off,
+                          const char* alignstrand, const char* strand,
+                          const int32_t* site_read, const int64_t* pos, const int64_t* pos_in_strand, int64_t n,
+                          char* info_text, int64_t info_cap, int64_t* info_off, int32_t nthreads) {
+    DSP_REQUIRE(n >= 0 && info_off, DSP_ERR_INVALID, "dsp_format_sampleinfo: bad argument");
+    info_off[0] = 0;
+    if (n == 0) return DSP_OK;
+    DSP_REQUIRE(chrom_text && chrom_off && name_text && name_off && alignstrand && strand && site_read && pos &&
+                pos_in_strand && info_text, DSP_ERR_INVALID, "dsp_format_sampleinfo: null argument");
+    auto digits = [](int64_t v) { int d = v < 0 ? 2 : 1; uint64_t u = v < 0 ? (uint64_t)(-(v + 1)) + 1 : (uint64_t)v; while (u >= 10) { u /= 10; ++d; } return d; };
+    parallel_for(n, nthreads, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) {
+            const int32_t r = site_read[i];
+            info_off[i + 1] = (chrom_off[r + 1] - chrom_off[r]) + 1 + digits(pos[i]) + 1 + 1 + 1 + digits(pos_in_strand[i]) + 1 +
+                              (name_off[r + 1] - name_off[r]) + 1 + 1;
+        }
+    });
+    for (int64_t i = 0; i < n; ++i) info_off[i + 1] += info_off[i];
+    DSP_REQUIRE(info_off[n] <= info_cap, DSP_ERR_NOMEM, "dsp_format_sampleinfo: output needs %lld bytes, buffer has %lld",
+                (long long)info_off[n], (long long)info_cap);
+    parallel_for(n, nthreads, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; ++i) {
+            const int32_t r = site_read[i];
+            char* o = info_text + info_off[i];
+            const int64_t cl = chrom_off[r + 1] - chrom_off[r], nl = name_off[r + 1] - name_off[r];
+            memcpy(o, chrom_text + chrom_off[r], (size_t)cl); o += cl; *o++ = '\t';
+            o = std::to_chars(o, o + 24, (long long)pos[i]).ptr; *o++ = '\t';
+            *o++ = alignstrand[r]; *o++ = '\t';
+            o = std::to_chars(o, o + 24, (long long)pos_in_strand[i]).ptr; *o++ = '\t';
+            memcpy(o, name_text + name_off[r], (size_t)nl); o += nl; *o++ = '\t';
+            *o++ = strand[r];
+        }
+    });
+    return DSP_OK;
+}
+
 }  // extern "C"

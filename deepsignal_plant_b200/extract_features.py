@@ -72,6 +72,11 @@ class ReadBatch:
         # _get_scaling_of_a_read returns (None, None) when the channel info cannot be read (:271-273)
         self.scaling = np.array([np.nan if r.get("scaling") is None else r["scaling"] for r in reads], np.float64)
         self.offset = np.array([0.0 if r.get("scaling") is None else r["offset"] for r in reads], np.float64)
+        self._dev = None
+        self._validate()
+
+    def _validate(self):
+        n = self.n_reads
         if self.ev_base.shape[0] != self.ev_len.shape[0] or self.ev_start.shape[0] != self.ev_len.shape[0]:
             raise ValueError("event columns differ in length")         # the reference asserts (:87-88)
         if not np.isin(self.ev_base, _ALPHABET).all():
@@ -81,15 +86,109 @@ class ReadBatch:
         if n and ((self.ev_start < 0).any() or (self.ev_len < 0).any()
                   or (self.ev_start + self.ev_len > np.diff(self.raw_off)[ev_read]).any()):
             raise ValueError("an event reaches outside its read's raw signal")
-        self._dev = None
+
+    # ---- the archive form: flat arrays in an .npz (what a fast5 decoder writes once; see save_reads)
+    ARCHIVE_KEYS = ("raw", "raw_off", "ev_off", "scaling", "offset", "ev_start", "ev_len", "ev_base",
+                    "readname", "strand", "alignstrand", "chrom", "chrom_start")
+
+    def arrays(self):
+        return dict(raw=self.raw, raw_off=self.raw_off, ev_off=self.ev_off, scaling=self.scaling, offset=self.offset,
+                    ev_start=self.ev_start, ev_len=self.ev_len, ev_base=self.ev_base,
+                    readname=np.array(self.readname), strand=np.array(self.strand),
+                    alignstrand=np.array(self.alignstrand), chrom=np.array(self.chrom), chrom_start=self.chrom_start)
+
+    def slice(self, lo, hi):
+        """Reads [lo, hi) as a batch of their own (views of the flat arrays, offsets rebased)."""
+        b = object.__new__(ReadBatch)
+        a, z = int(self.raw_off[lo]), int(self.raw_off[hi])
+        c, d = int(self.ev_off[lo]), int(self.ev_off[hi])
+        b.n_reads = hi - lo
+        for k in ("readname", "strand", "alignstrand", "chrom"):
+            setattr(b, k, getattr(self, k)[lo:hi])
+        b.chrom_start, b.scaling, b.offset = self.chrom_start[lo:hi], self.scaling[lo:hi], self.offset[lo:hi]
+        b.raw_off, b.ev_off = self.raw_off[lo:hi + 1] - a, self.ev_off[lo:hi + 1] - c
+        b.raw, b.ev_start, b.ev_len, b.ev_base = self.raw[a:z], self.ev_start[c:d], self.ev_len[c:d], self.ev_base[c:d]
+        b._dev = None
+        return b
 
     def to_device(self, device):
         if self._dev is None or self._dev["device"] != device:
-            up = lambda a: torch.from_numpy(a).to(device, non_blocking=False)
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
             self._dev = dict(device=device, raw=up(self.raw), raw_off=up(self.raw_off), scaling=up(self.scaling),
                              offset=up(self.offset), ev_start=up(self.ev_start), ev_len=up(self.ev_len),
                              ev_base=up(self.ev_base))
         return self._dev
+
+
+def save_reads(path, reads):
+    """Write decoded reads as an .npz archive of flat arrays (``ReadBatch.ARCHIVE_KEYS``): the input
+    ``call_mods --input_path reads.npz`` takes in place of a fast5 directory."""
+    np.savez(path, **pack_reads(reads).arrays())
+
+
+def load_reads(path):
+    """-> ReadBatch straight from the archive's flat arrays (no per-read objects)."""
+    z = np.load(path)
+    missing = [k for k in ReadBatch.ARCHIVE_KEYS if k not in z.files]
+    if missing:
+        raise ValueError("%s is not a decoded-reads archive (missing %s)" % (path, ", ".join(missing)))
+    b = object.__new__(ReadBatch)
+    b.n_reads = int(z["readname"].shape[0])
+    for k in ("readname", "strand", "alignstrand", "chrom"):
+        setattr(b, k, z[k].tolist())
+    b.chrom_start = z["chrom_start"].astype(np.int64, copy=False)
+    b.raw_off, b.ev_off = z["raw_off"].astype(np.int64, copy=False), z["ev_off"].astype(np.int64, copy=False)
+    b.raw = z["raw"].astype(np.int16, copy=False)
+    b.ev_start, b.ev_len = z["ev_start"].astype(np.int64, copy=False), z["ev_len"].astype(np.int64, copy=False)
+    b.ev_base = z["ev_base"].astype(np.uint8, copy=False)
+    b.scaling, b.offset = z["scaling"].astype(np.float64, copy=False), z["offset"].astype(np.float64, copy=False)
+    b._dev = None
+    b._validate()
+    return b
+
+
+def _read_position_file(position_file):
+    """``extract_features.py:519-528``: set of ``chrom||pos||strand`` keys."""
+    positions = set()
+    with open(position_file, "r") as rf:
+        for line in rf:
+            words = line.strip().split("\t")
+            if len(words) < 3:
+                raise ValueError("--position file in wrong format. "
+                                 "If you didn't use Tab as delimiter, Please do.")
+            positions.add(key_sep.join(words[:3]))
+    return positions
+
+
+def parse_region_str(regionstr):
+    """``utils/process_utils.py:163-187``: ``chrom:start-end`` | ``chrom:start`` | ``chrom`` (0-based, half-open)."""
+    try:
+        if regionstr is None:
+            return None, None, None
+        if ":" in regionstr:
+            chrom, se = regionstr.strip().split(":")
+            if "-" in se:
+                s_, e_ = se.split("-")
+                return chrom, int(s_), int(e_)
+            return chrom, int(se), None
+        return regionstr.strip(), None, None
+    except Exception:
+        raise ValueError("--region not set right!")
+
+
+def get_contig2len(ref_path):
+    """``utils/ref_reader.py:7-30``: contig name (up to the first blank) -> sequence length of a FASTA."""
+    chrom2len, name, n = {}, "", 0
+    with open(ref_path, "r") as rf:
+        for line in rf:
+            if line.startswith(">"):
+                if name != "" and n:
+                    chrom2len[name] = n
+                name, n = line.strip()[1:].split(" ")[0], 0
+            else:
+                n += len(line.strip())
+    chrom2len[name] = n
+    return chrom2len
 
 
 def pack_reads(reads):
@@ -171,6 +270,36 @@ def sampleinfo(batch, sites):
     """The six leading columns of a feature / call_mods line (``call_modifications.py:312``)."""
     return ["\t".join([batch.chrom[r], str(int(p)), batch.alignstrand[r], str(int(q)), batch.readname[r], batch.strand[r]])
             for r, p, q in zip(sites.site_read, sites.pos, sites.pos_in_strand)]
+
+
+def _packed_strings(xs):
+    off = np.zeros(len(xs) + 1, np.int64)
+    np.cumsum([len(x) for x in xs], out=off[1:])
+    return np.frombuffer("".join(xs).encode("ascii"), np.uint8), off
+
+
+def sampleinfo_packed(batch, sites, nthreads=None):
+    """The same six columns packed back to back for ``dsp_format_calls``: (uint8 text, int64 offsets),
+    written by ``dsp_format_sampleinfo`` (host threads)."""
+    import os
+    n = len(sites)
+    if any(len(x) != 1 for x in batch.alignstrand) or any(len(x) != 1 for x in batch.strand):
+        raise ValueError("alignstrand / strand must be single characters ('+'/'-', 't'/'c')")
+    L = _native.lib()
+    ctext, coff = _packed_strings(batch.chrom)
+    ntext, noff = _packed_strings(batch.readname)
+    astr = np.frombuffer("".join(batch.alignstrand).encode("ascii"), np.uint8)
+    sstr = np.frombuffer("".join(batch.strand).encode("ascii"), np.uint8)
+    per_read = (np.diff(coff) + np.diff(noff))[sites.site_read].sum() if n else 0
+    cap = int(per_read) + n * 48
+    text = np.empty(max(cap, 1), np.uint8)
+    off = np.zeros(n + 1, np.int64)
+    sr, pos, pis = (np.ascontiguousarray(a) for a in (sites.site_read, sites.pos, sites.pos_in_strand))
+    p = lambda a: a.ctypes.data
+    _native.check(L.dsp_format_sampleinfo(p(ctext), p(coff), p(ntext), p(noff), p(astr), p(sstr), p(sr), p(pos), p(pis), n,
+                                          p(text), cap, p(off), int(nthreads or min(16, os.cpu_count() or 1))),
+                  "dsp_format_sampleinfo")
+    return text[:int(off[n])], off
 
 
 def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method="mad", round_stats=False,

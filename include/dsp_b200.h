@@ -188,6 +188,18 @@ int dsp_format_calls(const char* info_text, const int64_t* info_off, const float
                      int32_t seq_len, const float* probs, const int32_t* labels, int64_t n,
                      char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads);
 
+/* The sample-info columns of sites extracted by dsp_extract_features, i.e. what
+ * _read_features_from_fast5s joins per site (call_modifications.py:312):
+ *   chrom \t pos \t alignstrand \t pos_in_strand \t readname \t strand
+ * packed into info_text / info_off exactly as dsp_parse_features leaves them (n + 1 offsets), ready
+ * for dsp_format_calls.  HOST pointers.  Per read r: chrom = chrom_text[chrom_off[r] .. chrom_off[r+1]),
+ * readname likewise, alignstrand[r] and strand[r] one character each ('+'/'-', 't'/'c'); per site:
+ * site_read, pos, pos_in_strand.  DSP_ERR_NOMEM if info_cap is too small. */
+int dsp_format_sampleinfo(const char* chrom_text, const int64_t* chrom_off, const char* name_text, const int64_t* name_off,
+                          const char* alignstrand, const char* strand,
+                          const int32_t* site_read, const int64_t* pos, const int64_t* pos_in_strand, int64_t n,
+                          char* info_text, int64_t info_cap, int64_t* info_off, int32_t nthreads);
+
 /* ---- feature extraction from decoded re-squiggled reads ----------------
  * dsp_extract_features: the numeric body of _extract_features (extract_features.py:280-378) for a
  * batch of reads whose fast5 content is already decoded into flat DEVICE arrays:

@@ -90,6 +90,37 @@ def test_find_sites_filters_match_oracle():
     assert got == ["\t".join([f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]]) for f in sub] and 0 < len(got) < len(full)
 
 
+def test_sampleinfo_native_formatter_and_archive_round_trip(tmp_path):
+    reads = synthetic.make_reads(9, seed=4, mean_bases=150)
+    reads[2]["chrom_start"] = 0
+    batch = ef.pack_reads(reads)
+    for chrom2len in (None, {"chr1": 200000, "chr3": 123456789012}):
+        sites = ef.find_sites(batch, ["CG"], 0, chrom2len, 13)
+        text, off = ef.sampleinfo_packed(batch, sites, nthreads=3)
+        want = ef.sampleinfo(batch, sites)
+        assert [text[off[i]:off[i + 1]].tobytes().decode() for i in range(len(sites))] == want and len(want) > 20
+    none = ef.find_sites(batch, ["ACGTACGTACGTTTTT"], 0, None, 13)
+    text, off = ef.sampleinfo_packed(batch, none)
+    assert text.size == 0 and off.tolist() == [0]
+    path = str(tmp_path / "reads.npz")
+    ef.save_reads(path, reads)
+    again = ef.load_reads(path)
+    for k, v in batch.arrays().items():
+        assert np.array_equal(v, again.arrays()[k]), k
+    part = again.slice(3, 7)
+    sub = ef.find_sites(part, ["CG"], 0, None, 13)
+    full = ef.find_sites(batch, ["CG"], 0, None, 13)
+    keep = (full.site_read >= 3) & (full.site_read < 7)
+    assert ef.sampleinfo(part, sub) == [x for x, k in zip(ef.sampleinfo(batch, full), keep) if k]
+    np.savez(str(tmp_path / "bad.npz"), raw=np.zeros(3, np.int16))
+    with pytest.raises(ValueError, match="not a decoded-reads archive"):
+        ef.load_reads(str(tmp_path / "bad.npz"))
+    assert ef.parse_region_str("chr1:5-9") == ("chr1", 5, 9) and ef.parse_region_str("chr1:5") == ("chr1", 5, None)
+    assert ef.parse_region_str("chr1") == ("chr1", None, None) and ef.parse_region_str(None) == (None, None, None)
+    with pytest.raises(ValueError, match="--region not set right"):
+        ef.parse_region_str("chr1:a-b")
+
+
 def test_host_argument_errors():
     reads = synthetic.make_reads(3, seed=2, mean_bases=60)
     batch = ef.pack_reads(reads)
@@ -259,3 +290,56 @@ def test_gpu_extract_empty_and_invalid():
     assert L.dsp_extract_features(0, None, None, None, None, 0, None, None, None, None, None, 0, 12, 16, 0, 0,
                                   None, 0, None, None, None, None, None, None, None, None) == 1
     assert b"odd" in L.dsp_last_error()
+
+
+@pytest.mark.gpu
+def test_gpu_call_mods_from_a_decoded_reads_archive(tmp_path):
+    # `call_mods -i reads.npz`: extract + classify in one pass, features never become text
+    from deepsignal_plant_b200 import cli, feature_io
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    from oracle import model_oracle
+    K, S = 13, 16
+    reads = synthetic.make_reads(45, seed=33, mean_bases=400, long_every=5)
+    arch = str(tmp_path / "reads.npz")
+    ef.save_reads(arch, reads)
+    fasta = str(tmp_path / "genome.fa")
+    with open(fasta, "w") as f:
+        for c in (1, 2, 3):
+            f.write(">chr%d some description\n" % c + ("ACGT" * 25 + "\n") * 2000)
+    torch.manual_seed(1234)
+    ref = ModelBiLSTM(K, S, 3, 1, 2, 0, 256, 16, 4, True, True)
+    ckpt = str(tmp_path / "m.ckpt")
+    torch.save(ref.state_dict(), ckpt)
+    params = {k: v.detach().numpy() for k, v in ref.state_dict().items()}
+    out = str(tmp_path / "calls.tsv")
+    argv = ["call_mods", "-i", arch, "-m", ckpt, "-o", out, "--max_batch", "512", "--f5_batch_size", "4",
+            "--motifs", "CG", "--reference_path", fasta]
+    assert cli.main(argv) == 0
+    lines = open(out).read().splitlines()
+    motif_seqs = eo.get_motif_seqs("CG")
+    feats, _ = eo.extract_features(reads, "mad", motif_seqs, 0, {"chr%d" % c: 200000 for c in (1, 2, 3)}, K, S, 1,
+                                   rng=random.Random(0))
+    n = len(feats)
+    assert len(lines) == n > 1000
+    arr = eo.features_to_arrays(feats, round_stats=False)
+    cfg = model_oracle.make_cfg()
+    zeros = {g: (np.zeros((l * 2, n, h), np.float32),) * 2 for g, l, h in (("seq", 1, 128), ("signal", 1, 128), ("comb", 3, 256))}
+    want = model_oracle.forward(params, cfg, *(arr[k] for k in cases.FEATURE_KEYS), zeros)[1]
+    for i, line in enumerate(lines):
+        w = line.split("\t")
+        f = feats[i]
+        assert len(w) == 10 and w[:6] == [f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]]
+        p0, p1 = float(w[6]), float(w[7])
+        assert abs(p0 + p1 - 1.0) < 2e-6 and abs(p1 - want[i, 1]) < 0.05
+        assert w[8] == ("1" if p1 > p0 else "0") or abs(p1 - p0) < 2e-6
+        assert w[9] == f[6][4:9]
+    # region + positions filters reach the extraction
+    some = feats[n // 2]
+    pos_file = str(tmp_path / "pos.tsv")
+    with open(pos_file, "w") as pf:
+        for f in feats[::2]:
+            pf.write("%s\t%d\t%s\n" % (f[0], f[1], f[2]))
+    out2 = str(tmp_path / "calls2.tsv")
+    assert cli.main(argv[:6] + [out2] + argv[7:] + ["--positions", pos_file, "--region", some[0]]) == 0
+    got = ["\t".join(l.split("\t")[:3]) for l in open(out2).read().splitlines()]
+    assert got == ["\t".join([f[0], str(f[1]), f[2]]) for f in feats[::2] if f[0] == some[0]] and len(got) > 50
