@@ -319,8 +319,10 @@ def call_mods_from_reads(args, model, write, device=0):
     pending = None
 
     def flush(item):
+        # collecting chunk i-1 after chunk i is enqueued: its device->host reads do not stall the launches
         b, probs, labels = item
         t1 = tick()
+        b.kmer = b.kmer.cpu().numpy()
         write(feature_io.format_calls(b, probs.cpu().numpy(), labels.cpu().numpy()))
         prof["format"] += tick() - t1
 
@@ -340,7 +342,6 @@ def call_mods_from_reads(args, model, write, device=0):
         t1 = tick()
         t = ef.extract_tensors(batch, sites, args.seq_len, args.signal_len, args.normalize_method, False,
                                seed=sites_total, device=dev)
-        kmer_host = None
         outs = []
         for a in range(0, n, max_batch):                       # the model's workspace holds max_batch sites
             z = min(a + max_batch, n)
@@ -352,12 +353,11 @@ def call_mods_from_reads(args, model, write, device=0):
         t1 = tick()
         info_text, info_off = ef.sampleinfo_packed(batch, sites)          # host work overlaps the kernels above
         prof["sampleinfo"] += tick() - t1
-        kmer_host = t["kmer"].cpu().numpy()
         if pending is not None:
             flush(pending)
         probs = outs[0][0] if len(outs) == 1 else torch.cat([o[0] for o in outs])
         labels = outs[0][1] if len(outs) == 1 else torch.cat([o[1] for o in outs])
-        pending = (_CallBatch(n, kmer_host, info_text, info_off, args.seq_len), probs, labels)
+        pending = (_CallBatch(n, t["kmer"], info_text, info_off, args.seq_len), probs, labels)
         sites_total += n
         chunks += 1
     if pending is not None:
@@ -383,8 +383,9 @@ def call_mods(args):
     if not os.path.exists(input_path):
         raise ValueError("--input_path does not exist!")
     if os.path.isdir(input_path):
-        raise ValueError("--input_path is a directory of fast5 files: feature extraction is outside this "
-                         "implementation; run `deepsignal_plant extract` first and pass its feature file")
+        raise ValueError("--input_path is a directory of fast5 files: reading fast5 (h5py) is outside this "
+                         "implementation; pass a feature file from `deepsignal_plant extract`, or decode the reads "
+                         "once into an archive with extract_features.save_reads and pass the .npz")
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
     if world > 1:
