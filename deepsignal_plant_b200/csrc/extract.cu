@@ -292,6 +292,76 @@ __device__ double pairwise_sum(Elem elem, int64_t n) {
     return ret;
 }
 
+// The same summation evaluated by one warp for whole-read sums (normalize_method 'zscore'): the stack walk
+// is uniform across the warp, lanes 0..7 own the eight accumulators of a leaf.
+template <typename Elem>
+__device__ double warp_pairwise_leaf(Elem elem, int64_t off, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    double res = 0.0;
+    if (n < 8) {
+        if (lane == 0) for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, elem(off + i));
+    } else {
+        const int64_t body = n - (n % 8);
+        double r = 0.0;
+        if (lane < 8) {
+            r = elem(off + lane);
+            for (int64_t i = 8; i < body; i += 8) r = __dadd_rn(r, elem(off + i + lane));
+        }
+        r = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 1));      // lanes 0,2,4,6: r0+r1, r2+r3, r4+r5, r6+r7
+        r = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 2));      // lanes 0,4
+        r = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 4));      // lane 0
+        res = r;
+        if (lane == 0) for (int64_t i = body; i < n; ++i) res = __dadd_rn(res, elem(off + i));
+    }
+    return __shfl_sync(0xffffffffu, res, 0);
+}
+
+template <typename Elem>
+__device__ double warp_pairwise_sum(Elem elem, int64_t n) {
+    if (n <= 128) return warp_pairwise_leaf(elem, 0, n);
+    constexpr int DEPTH = 64;
+    int64_t off_s[DEPTH], n_s[DEPTH];
+    double left_s[DEPTH];
+    int phase_s[DEPTH];
+    int sp = 0;
+    off_s[0] = 0; n_s[0] = n; phase_s[0] = 0; left_s[0] = 0.0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        const int64_t o = off_s[sp], c = n_s[sp];
+        if (phase_s[sp] == 0) {
+            if (c <= 128) { ret = warp_pairwise_leaf(elem, o, c); --sp; continue; }
+            int64_t n2 = c / 2; n2 -= n2 % 8;
+            phase_s[sp] = 1;
+            ++sp; off_s[sp] = o; n_s[sp] = n2; phase_s[sp] = 0;
+        } else if (phase_s[sp] == 1) {
+            int64_t n2 = c / 2; n2 -= n2 % 8;
+            left_s[sp] = ret; phase_s[sp] = 2;
+            ++sp; off_s[sp] = o + n2; n_s[sp] = c - n2; phase_s[sp] = 0;
+        } else {
+            ret = __dadd_rn(left_s[sp], ret); --sp;
+        }
+    }
+    return ret;
+}
+
+// _normalize_signals with 'zscore' (:180-181): shift = np.mean, scale = np.std of the rescaled read, both in
+// numpy's summation order.  One warp per read.
+__global__ void __launch_bounds__(128)
+read_zscore_kernel(const int16_t* __restrict__ raw, const int64_t* __restrict__ raw_off,
+                   const double* __restrict__ scaling, const double* __restrict__ offset, int64_t n_reads,
+                   double* __restrict__ shift_out, double* __restrict__ scale_out) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_reads) return;
+    const int16_t* x = raw + raw_off[r];
+    const int64_t n = raw_off[r + 1] - raw_off[r];
+    Rescale f;
+    f.scaling = scaling[r]; f.offset = offset[r]; f.on = !(f.scaling != f.scaling);
+    const double dn = (double)n;
+    const double mean = __ddiv_rn(warp_pairwise_sum([&](int64_t i) { return f(x[i]); }, n), dn);
+    const double var = __ddiv_rn(warp_pairwise_sum([&](int64_t i) { const double d = __dsub_rn(f(x[i]), mean); return __dmul_rn(d, d); }, n), dn);
+    if ((threadIdx.x & 31) == 0) { shift_out[r] = mean; scale_out[r] = __dsqrt_rn(var); }
+}
+
 // Philox4x32-10 (Salmon et al., SC'11): one 128-bit block per counter.
 __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -444,8 +514,7 @@ extern "C" int dsp_extract_features(int device,
     DSP_REQUIRE(seq_len > 0 && (seq_len & 1), DSP_ERR_INVALID, "kmer_len must be odd");
     DSP_REQUIRE(seq_len <= 31, DSP_ERR_INVALID, "dsp_extract_features: kmer_len must be at most 31 (one lane per base)");
     DSP_REQUIRE(signal_len > 0 && signal_len <= 128, DSP_ERR_INVALID, "dsp_extract_features: signal_len must be in 1..128");
-    DSP_REQUIRE(normalize_method == 0, DSP_ERR_INVALID,
-                "dsp_extract_features: only normalize_method 0 ('mad', the reference's default) runs on the device");
+    DSP_REQUIRE(normalize_method == 0 || normalize_method == 1, DSP_ERR_INVALID, "dsp_extract_features: normalize_method must be 0 (mad) or 1 (zscore)");
     DSP_REQUIRE(read_shift && read_scale, DSP_ERR_INVALID, "dsp_extract_features: read_shift / read_scale buffers are required");
     DSP_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -458,7 +527,10 @@ extern "C" int dsp_extract_features(int device,
         DSP_CUDA(cudaStreamSynchronize(st));
         table_device = device;
     }
-    if (n_reads > 0) {
+    if (n_reads > 0 && normalize_method == 1) {
+        read_zscore_kernel<<<(unsigned)((n_reads + 3) / 4), 128, 0, st>>>(raw, raw_off, scaling, offset, n_reads, read_shift, read_scale);
+        DSP_CUDA(cudaGetLastError());
+    } else if (n_reads > 0) {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         const int64_t grid = n_reads < (int64_t)n_sm * 3 ? n_reads : (int64_t)n_sm * 3;   // 3 CTAs of 72 KB per SM

@@ -13,8 +13,8 @@ what ``_get_alignment_info_from_fast5`` / ``_get_label_raw`` / ``_get_scaling_of
 wraps those three accessors around ``pack_reads``; INTEGRATION.md shows the stub.
 
 The arithmetic runs in libdsp_b200 only; there is no CPU fallback (``pack_reads`` / ``find_sites`` are
-host-side index bookkeeping, not arithmetic).  ``normalize_method="zscore"`` is not implemented on the
-device and raises.
+host-side index bookkeeping, not arithmetic).  Both ``normalize_method`` values of the reference run on
+the device (``mad``, the default, and ``zscore``).
 """
 from __future__ import annotations
 
@@ -309,9 +309,8 @@ def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method=
     ``read_scale`` (float64 per read: the median and MAD ``_normalize_signals`` used).
     ``drawn``: optional (n_sites, kmer_len, signals_len) int32 subsample offsets to replay (parity).
     ``out``: a dict returned by an earlier call with the same shapes, to be overwritten (no allocation)."""
-    if normalize_method != "mad":
-        raise NotImplementedError("normalize_method %r: only 'mad' (the reference's default) runs on the device"
-                                  % (normalize_method,))
+    if normalize_method not in ("mad", "zscore"):
+        raise ValueError("")                                            # _normalize_signals, :184-185
     if not torch.cuda.is_available():
         raise _native.DspError("dsp_extract_features needs a CUDA device; there is no CPU fallback")
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -341,7 +340,7 @@ def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method=
         rc = L.dsp_extract_features(
             device.index, ptr(d["raw"]), C.c_void_p(d["raw_off"].data_ptr()), ptr(d["scaling"]), ptr(d["offset"]),
             batch.n_reads, ptr(d["ev_start"]), ptr(d["ev_len"]), ptr(d["ev_base"]), ptr(site_read), ptr(site_ev), n,
-            T, S, 0, 1 if round_stats else 0, ptr(drawn_t), int(seed) & (2 ** 64 - 1),
+            T, S, 0 if normalize_method == "mad" else 1, 1 if round_stats else 0, ptr(drawn_t), int(seed) & (2 ** 64 - 1),
             C.c_void_p(out["read_shift"].data_ptr()), C.c_void_p(out["read_scale"].data_ptr()),
             ptr(out["kmer"]), ptr(out["base_means"]), ptr(out["base_stds"]), ptr(out["base_signal_lens"]),
             ptr(out["signals"]), C.c_void_p(st))

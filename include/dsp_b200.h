@@ -212,8 +212,8 @@ int dsp_format_sampleinfo(const char* chrom_text, const int64_t* chrom_off, cons
  *   concatenated table; the seq_len events centred on it must belong to the same read, which is the
  *   `num_bases <= loc < len - num_bases` rule of :341).
  * Per read: _rescale_signals (:276-277) and _normalize_signals (:179-190) with normalize_method 0 =
- * 'mad' (median / statsmodels.robust.mad, float64, then np.around(., 6)); their shift and scale are
- * left in read_shift / read_scale (n_reads doubles each).  Per site and base: len, np.mean, np.std
+ * 'mad' (median / statsmodels.robust.mad) or 1 = 'zscore' (np.mean / np.std), float64, then
+ * np.around(., 6); their shift and scale are left in read_shift / read_scale (n_reads doubles each).  Per site and base: len, np.mean, np.std
  * (float64, numpy's pairwise summation order) and the seq_len x signal_len rectangle of
  * _get_signals_rect (:232-251), written as float32 into the five tensors dsp_forward takes
  * (kmer = base2code_dna codes).  round_stats != 0 rounds means/stds to 6 decimals first, which is

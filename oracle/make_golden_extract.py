@@ -31,10 +31,12 @@ from oracle import extract_oracle as eo  # noqa: E402
 from deepsignal_plant_b200 import synthetic  # noqa: E402
 
 CASES = {
-    # name: (reads kwargs, motifs, mod_loc, kmer_len, signals_len, with chrom2len, random seed)
+    # name: (reads kwargs, motifs, mod_loc, kmer_len, signals_len, with chrom2len, random seed[, normalize_method])
     "cg_13_16": (dict(n_reads=10, seed=5, mean_bases=160, long_every=3), "CG", 0, 13, 16, True, 12345),
     "chgchh_17_20": (dict(n_reads=6, seed=6, mean_bases=120, long_every=2, no_scaling_every=3), "CHG,CHH", 0, 17, 20,
                      False, 777),
+    "cg_13_16_zscore": (dict(n_reads=8, seed=8, mean_bases=170, long_every=3, no_scaling_every=4), "CG", 0, 13, 16, True, 99,
+                        "zscore"),
 }
 
 
@@ -46,7 +48,9 @@ def main():
     manifest_path = os.path.join(GOLD, "manifest.json")
     manifest = json.load(open(manifest_path))
     manifest["extract"] = {}
-    for name, (rkw, motifs, mod_loc, K, S, with_len, rseed) in CASES.items():
+    for name, case in CASES.items():
+        rkw, motifs, mod_loc, K, S, with_len, rseed = case[:7]
+        method = case[7] if len(case) > 7 else "mad"
         reads = synthetic.make_reads(**rkw)
         table = {"/fake/%s.fast5" % r["readname"]: r for r in reads}
         ref_ex._get_alignment_info_from_fast5 = lambda fp, cg, bs: (
@@ -59,10 +63,10 @@ def main():
         motif_seqs = get_motif_seqs(motifs)
         assert sorted(motif_seqs) == sorted(eo.get_motif_seqs(motifs))
         random.seed(rseed)
-        feats, err = ref_ex._extract_features(list(table), "RawGenomeCorrected_000", "BaseCalled_template", "mad",
+        feats, err = ref_ex._extract_features(list(table), "RawGenomeCorrected_000", "BaseCalled_template", method,
                                               motif_seqs, mod_loc, chrom2len, K, S, 1, None, (None, None, None))
         assert err == 0 and len(feats) > 0
-        mine, drawn = eo.extract_features(reads, "mad", motif_seqs, mod_loc, chrom2len, K, S, 1,
+        mine, drawn = eo.extract_features(reads, method, motif_seqs, mod_loc, chrom2len, K, S, 1,
                                           rng=random.Random(rseed))
         assert len(mine) == len(feats)
         for a, b in zip(feats, mine):           # the oracle reproduces the reference bit for bit
@@ -78,11 +82,13 @@ def main():
             lens=np.array([f[9] for f in feats], np.int64), rect=np.array([f[10] for f in feats], np.float64),
             drawn=eo.drawn_to_array(drawn, K, S), lines=np.array(lines),
             motifs=np.array(motifs), mod_loc=np.int64(mod_loc), kmer_len=np.int64(K), signals_len=np.int64(S),
-            chrom_len=np.int64(200000 if with_len else -1), random_seed=np.int64(rseed))
+            chrom_len=np.int64(200000 if with_len else -1), random_seed=np.int64(rseed),
+            normalize_method=np.array(method))
         np.savez_compressed(os.path.join(GOLD, "extract_%s.npz" % name), **out)
         n_long = int((out["lens"] > S).sum())
         manifest["extract"][name] = dict(sites=len(feats), reads=len(reads), samples=int(out["raw"].shape[0]),
-                                         bases_longer_than_rect=n_long, max_dwell=int(out["lens"].max()))
+                                         bases_longer_than_rect=n_long, max_dwell=int(out["lens"].max()),
+                                         normalize_method=method)
         print(name, manifest["extract"][name])
     json.dump(manifest, open(manifest_path, "w"), indent=1, sort_keys=True)
 

@@ -23,11 +23,15 @@ def load(name):
     return z, reads, K, S, chrom2len, eo.get_motif_seqs(str(z["motifs"])), int(z["mod_loc"])
 
 
+def method_of(z):
+    return str(z["normalize_method"])
+
+
 # ---------------------------------------------------------------------------- CPU: oracle + host logic
 @pytest.mark.parametrize("name", EXTRACT_CASES)
 def test_oracle_reproduces_reference_fixture(name):
     z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
-    feats, drawn = eo.extract_features(reads, "mad", motif_seqs, mod_loc, chrom2len, K, S, 1,
+    feats, drawn = eo.extract_features(reads, method_of(z), motif_seqs, mod_loc, chrom2len, K, S, 1,
                                        rng=random.Random(int(z["random_seed"])))
     assert len(feats) == cases.MANIFEST["extract"][name]["sites"] == len(z["info"])
     assert ["\t".join([f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]]) for f in feats] == list(z["info"])
@@ -46,7 +50,7 @@ def test_feature_lines_of_the_fixture_round_trip(name):
     # the lines the reference's _features_to_str wrote carry the 6-decimal means/stds: features_to_arrays(round_stats=True)
     from oracle import features_oracle
     z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
-    feats, _ = eo.extract_features(reads, "mad", motif_seqs, mod_loc, chrom2len, K, S, 1,
+    feats, _ = eo.extract_features(reads, method_of(z), motif_seqs, mod_loc, chrom2len, K, S, 1,
                                    rng=random.Random(int(z["random_seed"])))
     arr = eo.features_to_arrays(feats, round_stats=True)
     info, kmers, means, stds, lens, sig, labels = features_oracle.read_features([str(x) for x in z["lines"]])
@@ -133,17 +137,18 @@ def test_host_argument_errors():
     with pytest.raises(ValueError, match="outside"):
         ef.pack_reads([bad])
     sites = ef.find_sites(batch, ["CG"], 0, None, 13)
-    with pytest.raises(NotImplementedError):
-        ef.extract_tensors(batch, sites, normalize_method="zscore")
+    with pytest.raises(ValueError):
+        ef.extract_tensors(batch, sites, normalize_method="median")
     if not torch.cuda.is_available():
         with pytest.raises(_native.DspError, match="no CPU fallback"):
             ef.extract_tensors(batch, sites)
 
 
 # ---------------------------------------------------------------------------- GPU: bit-exact parity
-def _check_against(feats, drawn, batch, sites, K, S, round_stats):
+def _check_against(feats, drawn, batch, sites, K, S, round_stats, method="mad"):
     want = eo.features_to_arrays(feats, round_stats=round_stats)
-    got = ef.extract_tensors(batch, sites, K, S, round_stats=round_stats, drawn=eo.drawn_to_array(drawn, K, S))
+    got = ef.extract_tensors(batch, sites, K, S, normalize_method=method, round_stats=round_stats,
+                             drawn=eo.drawn_to_array(drawn, K, S))
     for k in ("kmer", "base_signal_lens", "base_means", "base_stds", "signals"):
         g = got[k].cpu().numpy()
         assert g.dtype == np.float32 and g.shape == want[k].shape, k
@@ -158,7 +163,7 @@ def test_gpu_extract_matches_reference_fixture_bit_for_bit(name, round_stats):
     z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
     batch = ef.pack_reads(reads)
     sites = ef.find_sites(batch, motif_seqs, mod_loc, chrom2len, K)
-    got = ef.extract_tensors(batch, sites, K, S, round_stats=round_stats, drawn=z["drawn"])
+    got = ef.extract_tensors(batch, sites, K, S, normalize_method=method_of(z), round_stats=round_stats, drawn=z["drawn"])
     means, stds = (np.around(z["means"], 6), np.around(z["stds"], 6)) if round_stats else (z["means"], z["stds"])
     eq = lambda a, b: np.array_equal(a.cpu().numpy().view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
     assert eq(got["base_means"], means) and eq(got["base_stds"], stds)
@@ -167,7 +172,8 @@ def test_gpu_extract_matches_reference_fixture_bit_for_bit(name, round_stats):
     # the per-read shift / scale _normalize_signals used, float64 bit for bit
     for i, rd in enumerate(reads):
         x = rd["raw"] if rd["scaling"] is None else eo.rescale_signals(rd["raw"], rd["scaling"], rd["offset"])
-        assert got["read_shift"][i].item() == float(np.median(x)) and got["read_scale"][i].item() == float(eo.mad(x))
+        want = (np.median(x), eo.mad(x)) if method_of(z) == "mad" else (np.mean(x), np.std(x))
+        assert got["read_shift"][i].item() == float(want[0]) and got["read_scale"][i].item() == float(want[1])
 
 
 @pytest.mark.gpu
@@ -193,6 +199,9 @@ def test_gpu_extract_matches_oracle_on_fresh_reads(seed, K, S, motifs):
     batch = ef.pack_reads(reads)
     sites = ef.find_sites(batch, motif_seqs, 0, chrom2len, K)
     feats, drawn = eo.extract_features(reads, "mad", motif_seqs, 0, chrom2len, K, S, 1, rng=random.Random(seed))
+    fz, dz = eo.extract_features(reads[:30] + reads[-4:], "zscore", motif_seqs, 0, chrom2len, K, S, 1, rng=random.Random(seed))
+    bz = ef.pack_reads(reads[:30] + reads[-4:])
+    _check_against(fz, dz, bz, ef.find_sites(bz, motif_seqs, 0, chrom2len, K), K, S, False, "zscore")
     assert len(feats) == len(sites) > 300
     lens = np.array([f[9] for f in feats])
     assert (lens.sum(1) > 768).sum() >= 5 and (lens.sum(1) <= 768).sum() > 200     # windowed and recomputing sites
