@@ -332,7 +332,7 @@ def call_mods_from_reads(args, model, write, device=0):
         batch = allreads.slice(lo, hi)
         lo = hi
         t1 = tick()
-        sites = ef.find_sites(batch, motif_seqs, args.mod_loc, chrom2len, args.seq_len, positions, regioninfo)
+        sites = ef.find_sites_device(batch, motif_seqs, args.mod_loc, chrom2len, args.seq_len, positions, regioninfo, dev)
         prof["find_sites"] += tick() - t1
         n = len(sites)
         # --f5_batch_size only seeds the chunking: aim at one full model batch of sites per chunk

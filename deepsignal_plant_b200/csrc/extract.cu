@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include <cub/block/block_scan.cuh>
 #include <cub/block/block_reduce.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <math_constants.h>
 
 namespace dsp {
@@ -493,6 +495,58 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_features_kernel(SitePara
     }
 }
 
+// ---- site search: get_refloc_of_methysite_in_motif (utils/process_utils.py:97-112) + the site filters of
+// _extract_features (:341-352), evaluated per event of the concatenated event table
+constexpr int MAX_MOTIFS = 64, MAX_MOTIF_LEN = 8;
+
+struct SitePredicate {
+    const uint8_t* ev_base; const int64_t* ev_off; int64_t n_reads;
+    const int64_t* chrom_start; const uint8_t* minus; const int64_t* region_start; const int64_t* region_end;
+    int n_motifs, motif_len, methyloc, num_bases;
+    unsigned long long motif[MAX_MOTIFS];              // up to 8 letters, first letter in the low byte
+
+    __device__ __forceinline__ int64_t read_of(int64_t e) const {     // largest r with ev_off[r] <= e
+        int64_t lo = 0, hi = n_reads;
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (ev_off[mid] <= e) lo = mid; else hi = mid; }
+        return lo;
+    }
+    __device__ __forceinline__ int64_t pos_of(int64_t r, int64_t loc, int64_t rlen) const {
+        return minus[r] ? chrom_start[r] + rlen - 1 - loc : chrom_start[r] + loc;
+    }
+    __device__ bool operator()(int64_t e) const {
+        const int64_t r = read_of(e);
+        const int64_t r0 = ev_off[r], rlen = ev_off[r + 1] - r0, loc = e - r0;
+        const int64_t i = loc - methyloc;                              // where the motif would start
+        if (i < 0 || i + motif_len > rlen) return false;
+        if (loc < num_bases || loc >= rlen - num_bases) return false;  // :341
+        unsigned long long w = 0;
+        for (int k = 0; k < motif_len; ++k) w |= (unsigned long long)ev_base[r0 + i + k] << (8 * k);
+        bool hit = false;
+        for (int m = 0; m < n_motifs; ++m) hit |= (w == motif[m]);
+        if (!hit) return false;
+        if (region_start) {                                            // :350-351
+            const int64_t pos = pos_of(r, loc, rlen);
+            if (pos < region_start[r] || pos >= region_end[r]) return false;
+        }
+        return true;
+    }
+};
+
+__global__ void site_columns_kernel(SitePredicate q, const int64_t* __restrict__ chrom_len, const int64_t* __restrict__ site_ev,
+                                    const int64_t* __restrict__ n_sel, int64_t cap, int32_t* __restrict__ site_read,
+                                    int64_t* __restrict__ pos, int64_t* __restrict__ pos_in_strand) {
+    const int64_t n = *n_sel < cap ? *n_sel : cap;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = site_ev[s], r = q.read_of(e);
+        const int64_t rlen = q.ev_off[r + 1] - q.ev_off[r], loc = e - q.ev_off[r];
+        const int64_t p = q.pos_of(r, loc, rlen);
+        const int64_t cl = chrom_len ? chrom_len[r] : -1;
+        site_read[s] = (int32_t)r;
+        pos[s] = p;
+        pos_in_strand[s] = cl < 0 ? -1 : (q.minus[r] ? cl - 1 - p : p);   // :343-348
+    }
+}
+
 const uint8_t kBase2Code[16] = {'A', 'C', 'G', 'T', 'N', 'W', 'S', 'M', 'K', 'R', 'Y', 'B', 'V', 'D', 'H', 'Z'};
 
 }  // namespace
@@ -564,5 +618,56 @@ extern "C" int dsp_extract_features(int device,
         site_features_kernel<<<(unsigned)grid, SITE_WARPS * 32, smem, st>>>(p);
         DSP_CUDA(cudaGetLastError());
     }
+    return DSP_OK;
+}
+
+extern "C" int dsp_find_sites(int device, const uint8_t* ev_base, const int64_t* ev_off, int64_t n_reads, int64_t n_events,
+                              const char* motifs, int32_t n_motifs, int32_t motif_len, int32_t methyloc, int32_t seq_len,
+                              const int64_t* chrom_start, const uint8_t* minus_strand, const int64_t* chrom_len,
+                              const int64_t* region_start, const int64_t* region_end, int64_t max_sites,
+                              int32_t* site_read, int64_t* site_ev, int64_t* pos, int64_t* pos_in_strand,
+                              int64_t* n_sites_host, void* stream) {
+    DSP_REQUIRE(n_sites_host, DSP_ERR_INVALID, "dsp_find_sites: n_sites_host is required");
+    *n_sites_host = 0;
+    DSP_REQUIRE(seq_len > 0 && (seq_len & 1), DSP_ERR_INVALID, "kmer_len must be odd");
+    DSP_REQUIRE(n_motifs >= 1 && n_motifs <= MAX_MOTIFS && motif_len >= 1 && motif_len <= MAX_MOTIF_LEN && motifs, DSP_ERR_INVALID,
+                "dsp_find_sites: 1..%d motifs of 1..%d letters", MAX_MOTIFS, MAX_MOTIF_LEN);
+    DSP_REQUIRE(n_reads >= 0 && n_events >= 0 && max_sites >= 0 && n_events < (1ll << 31), DSP_ERR_INVALID, "dsp_find_sites: bad count");
+    DSP_REQUIRE((region_start == nullptr) == (region_end == nullptr), DSP_ERR_INVALID, "dsp_find_sites: region_start and region_end go together");
+    if (n_reads == 0 || n_events == 0) return DSP_OK;
+    DSP_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SitePredicate q;
+    q.ev_base = ev_base; q.ev_off = ev_off; q.n_reads = n_reads; q.chrom_start = chrom_start; q.minus = minus_strand;
+    q.region_start = region_start; q.region_end = region_end;
+    q.n_motifs = n_motifs; q.motif_len = motif_len; q.methyloc = methyloc; q.num_bases = (seq_len - 1) / 2;
+    for (int m = 0; m < MAX_MOTIFS; ++m) q.motif[m] = 0;
+    for (int m = 0; m < n_motifs; ++m)
+        for (int k = 0; k < motif_len; ++k) q.motif[m] |= (unsigned long long)(uint8_t)motifs[m * motif_len + k] << (8 * k);
+    // events in ascending order = reads in order, positions ascending within a read: the reference's site order
+    cub::CountingInputIterator<int64_t> events(0);
+    int64_t* d_count = nullptr;
+    int64_t* d_sel = nullptr;                           // all hits (n_events at most) before the max_sites cut
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    DSP_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, events, d_sel, d_count, (int)n_events, q, st));
+    DSP_CUDA(cudaMallocAsync((void**)&d_count, sizeof(int64_t), st));
+    DSP_CUDA(cudaMallocAsync((void**)&d_sel, sizeof(int64_t) * (size_t)n_events, st));
+    DSP_CUDA(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, st));
+    cudaError_t e = cub::DeviceSelect::If(d_tmp, tmp_bytes, events, d_sel, d_count, (int)n_events, q, st);
+    int64_t n = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && n > 0 && n <= max_sites) {
+        e = cudaMemcpyAsync(site_ev, d_sel, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) {
+            site_columns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, chrom_len, site_ev, d_count, max_sites, site_read, pos, pos_in_strand);
+            e = cudaGetLastError();
+        }
+    }
+    cudaFreeAsync(d_tmp, st); cudaFreeAsync(d_sel, st); cudaFreeAsync(d_count, st);
+    if (e != cudaSuccess) { set_error("dsp_find_sites: %s", cudaGetErrorString(e)); return DSP_ERR_CUDA; }
+    *n_sites_host = n;
+    DSP_REQUIRE(n <= max_sites, DSP_ERR_NOMEM, "dsp_find_sites: %lld sites found, buffers hold %lld", (long long)n, (long long)max_sites);
     return DSP_OK;
 }

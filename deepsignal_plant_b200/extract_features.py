@@ -116,7 +116,7 @@ class ReadBatch:
             up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
             self._dev = dict(device=device, raw=up(self.raw), raw_off=up(self.raw_off), scaling=up(self.scaling),
                              offset=up(self.offset), ev_start=up(self.ev_start), ev_len=up(self.ev_len),
-                             ev_base=up(self.ev_base))
+                             ev_base=up(self.ev_base), ev_off=up(self.ev_off))
         return self._dev
 
 
@@ -264,6 +264,63 @@ def find_sites(batch, motif_seqs, methyloc, chrom2len, kmer_len, positions=None,
                           for r, p in zip(rd, pos)], bool)
     rd, loc, pos, pis = rd[keep], loc[keep], pos[keep], pis[keep]
     return Sites(rd.astype(np.int32), (batch.ev_off[rd] + loc).astype(np.int64), pos.astype(np.int64), pis.astype(np.int64))
+
+
+def find_sites_device(batch, motif_seqs, methyloc, chrom2len, kmer_len, positions=None, regioninfo=(None, None, None),
+                      device=None):
+    """``find_sites`` evaluated by ``dsp_find_sites`` on the batch's device-resident event table: same sites,
+    same order; the result also keeps its device copies, so ``extract_tensors`` uploads nothing.  A
+    ``positions`` set (a host-side string-set lookup, ``:354``) falls back to ``find_sites``."""
+    if positions is not None:
+        return find_sites(batch, motif_seqs, methyloc, chrom2len, kmer_len, positions, regioninfo)
+    if kmer_len % 2 == 0:
+        raise ValueError("kmer_len must be odd")
+    if not torch.cuda.is_available():
+        raise _native.DspError("dsp_find_sites needs a CUDA device; there is no CPU fallback")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    motifs = sorted(set(motif_seqs))
+    mlen = len(motifs[0])
+    if any(len(m) != mlen for m in motifs):
+        raise ValueError("motifs must have one length")             # the reference takes len(list(motifset)[0]), :107
+    L = _native.lib()
+    d = batch.to_device(device)
+    n_reads, n_events = batch.n_reads, int(batch.ev_base.shape[0])
+    rg_chrom, rg_start, rg_end = regioninfo
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    cstart = up(batch.chrom_start)
+    minus = up(np.array([s == '-' for s in batch.alignstrand], np.uint8))
+    clen = up(np.array([chrom2len.get(c, -1) for c in batch.chrom], np.int64)) if chrom2len is not None else None
+    rs = re_ = None
+    if rg_chrom is not None:
+        rlen = np.diff(batch.ev_off)
+        same = np.array([c == rg_chrom for c in batch.chrom], bool)
+        lo = batch.chrom_start if rg_start is None else np.full(n_reads, rg_start, np.int64)
+        hi = batch.chrom_start + rlen if rg_end is None else np.full(n_reads, rg_end, np.int64)
+        dead = ~same | (lo >= batch.chrom_start + rlen) | (hi <= batch.chrom_start)           # :307-308, :326-327
+        rs, re_ = up(np.where(dead, 0, lo).astype(np.int64)), up(np.where(dead, 0, hi).astype(np.int64))
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+    cap = max(1024, n_events // 8)
+    text = "".join(motifs).encode("ascii")
+    while True:
+        i64 = dict(dtype=torch.int64, device=device)
+        out = (torch.empty(cap, dtype=torch.int32, device=device), torch.empty(cap, **i64), torch.empty(cap, **i64),
+               torch.empty(cap, **i64))
+        n = C.c_int64(0)
+        with torch.cuda.device(device):
+            rc = L.dsp_find_sites(device.index, ptr(d["ev_base"]), C.c_void_p(d["ev_off"].data_ptr()), n_reads, n_events,
+                                  text, len(motifs), mlen, int(methyloc), int(kmer_len), ptr(cstart), ptr(minus), ptr(clen),
+                                  ptr(rs), ptr(re_), cap, *[ptr(t) for t in out], C.byref(n),
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc == 4 and n.value > cap:                                # DSP_ERR_NOMEM: now the count is known
+            cap = int(n.value)
+            continue
+        _native.check(rc, "dsp_find_sites")
+        break
+    k = int(n.value)
+    site_read, site_ev, pos, pis = (t[:k] for t in out)
+    sites = Sites(site_read.cpu().numpy(), site_ev.cpu().numpy(), pos.cpu().numpy(), pis.cpu().numpy())
+    sites._dev = (device, site_read, site_ev)
+    return sites
 
 
 def sampleinfo(batch, sites):

@@ -234,6 +234,27 @@ int dsp_extract_features(int device,
                          float* kmer, float* base_means, float* base_stds, float* base_signal_lens,
                          float* signals, void* stream);
 
+/* dsp_find_sites: which bases of a batch of decoded reads are targets --
+ * get_refloc_of_methysite_in_motif (utils/process_utils.py:97-112) over every read, then the site filters
+ * of _extract_features in its order (extract_features.py:341-352): a margin of (seq_len-1)/2 bases at both
+ * read ends, the strand-aware genome position, the optional region.  DEVICE pointers except `motifs`
+ * (HOST: n_motifs x motif_len ASCII letters, the expanded list get_motif_seqs returns) and n_sites_host.
+ *   ev_base / ev_off: the concatenated event tables as in dsp_extract_features (n_events letters);
+ *   per read: chrom_start (mapped_start), minus_strand (1 when mapped_strand is '-'), chrom_len (contig
+ *   length, < 0 or NULL pointer = unknown -> pos_in_strand -1), and, when a region is given, the half-open
+ *   position range [region_start, region_end) the read may contribute (an empty range for reads on other
+ *   contigs; both NULL = no region).
+ * Outputs (capacity max_sites), in the reference's order (reads in order, positions ascending in the read):
+ *   site_read, site_ev (what dsp_extract_features takes), pos, pos_in_strand.  *n_sites_host receives the
+ *   number found (the call synchronises `stream`); DSP_ERR_NOMEM, with nothing written, if it exceeds max_sites.
+ * The --positions set filter of :354 is a host-side string-set lookup and stays with the caller. */
+int dsp_find_sites(int device, const uint8_t* ev_base, const int64_t* ev_off, int64_t n_reads, int64_t n_events,
+                   const char* motifs, int32_t n_motifs, int32_t motif_len, int32_t methyloc, int32_t seq_len,
+                   const int64_t* chrom_start, const uint8_t* minus_strand, const int64_t* chrom_len,
+                   const int64_t* region_start, const int64_t* region_end, int64_t max_sites,
+                   int32_t* site_read, int64_t* site_ev, int64_t* pos, int64_t* pos_in_strand,
+                   int64_t* n_sites_host, void* stream);
+
 /* Known-answer test of the tcgen05/TMEM/bulk-copy building blocks on `device`: a one-CTA
  * FP16 GEMM with FP32 accumulation checked against a double-precision host product.
  * which: 0,1 = both operands from shared memory; 2,3 = A operand staged in TMEM.

@@ -352,3 +352,35 @@ def test_gpu_call_mods_from_a_decoded_reads_archive(tmp_path):
     assert cli.main(argv[:6] + [out2] + argv[7:] + ["--positions", pos_file, "--region", some[0]]) == 0
     got = ["\t".join(l.split("\t")[:3]) for l in open(out2).read().splitlines()]
     assert got == ["\t".join([f[0], str(f[1]), f[2]]) for f in feats[::2] if f[0] == some[0]] and len(got) > 50
+
+
+@pytest.mark.gpu
+def test_gpu_find_sites_matches_host_search_and_reference():
+    for name in EXTRACT_CASES:
+        z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
+        batch = ef.pack_reads(reads)
+        dev = ef.find_sites_device(batch, motif_seqs, mod_loc, chrom2len, K)
+        assert ef.sampleinfo(batch, dev) == list(z["info"])
+    reads = synthetic.make_reads(40, seed=12, mean_bases=300)
+    chrom2len = {"chr1": 200000, "chr2": 200000}
+    batch = ef.pack_reads(reads)
+    full = ef.find_sites(batch, eo.get_motif_seqs("CHG"), 0, chrom2len, 13)
+    some = (batch.chrom[int(full.site_read[len(full) // 2])], int(full.pos[len(full) // 2]))
+    regions = [(None, None, None), ("chr2", None, None), (some[0], some[1] - 40, some[1] + 25), ("chrNone", None, None),
+               (some[0], some[1], None)]
+    for motifs, mod_loc, K in (("CHG", 0, 13), ("CHG", 2, 9), ("CG", 1, 5), ("N", 0, 3), ("CHH,CHG", 0, 17)):
+        ms = eo.get_motif_seqs(motifs)
+        for region in regions:
+            host = ef.find_sites(batch, ms, mod_loc, chrom2len, K, regioninfo=region)
+            dev = ef.find_sites_device(batch, ms, mod_loc, chrom2len, K, regioninfo=region)
+            for f in ("site_read", "site_ev", "pos", "pos_in_strand"):
+                assert np.array_equal(getattr(host, f), getattr(dev, f)), (motifs, region, f)
+            assert getattr(dev, f).dtype == getattr(host, f).dtype
+    assert len(ef.find_sites_device(batch, eo.get_motif_seqs("N"), 0, None, 3)) > batch.ev_base.shape[0] // 2   # capacity retry
+    positions = {"||".join([batch.chrom[r], str(int(p)), batch.alignstrand[r]]) for r, p in zip(full.site_read[::3], full.pos[::3])}
+    sub = ef.find_sites_device(batch, eo.get_motif_seqs("CHG"), 0, chrom2len, 13, positions=positions)
+    assert len(sub) == len(positions)
+    # the device-found sites feed the extraction without another upload, same tensors as from the host search
+    a = ef.extract_tensors(batch, full, 13, 16, seed=3)
+    b = ef.extract_tensors(batch, ef.find_sites_device(batch, eo.get_motif_seqs("CHG"), 0, chrom2len, 13), 13, 16, seed=3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
