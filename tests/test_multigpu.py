@@ -60,3 +60,30 @@ def test_call_mods_cli_two_ranks_keeps_file_order(tmp_path):
     lines = open(out).read().splitlines()
     assert len(lines) == n and ["\t".join(l.split("\t")[:6]) for l in lines] == info
     assert not [p for p in os.listdir(tmp_path) if ".part" in p]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_call_mods_archive_two_ranks_keeps_read_order(tmp_path):
+    # decoded-reads archive sharded by contiguous read ranges, one process per GPU, no collective on the data path
+    import random
+    from deepsignal_plant_b200 import extract_features as ef, synthetic
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    from oracle import extract_oracle as eo
+    reads = synthetic.make_reads(31, seed=44, mean_bases=300)
+    arch = str(tmp_path / "reads.npz")
+    ef.save_reads(arch, reads)
+    torch.manual_seed(1234)
+    ckpt = str(tmp_path / "m.ckpt")
+    torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
+    out = str(tmp_path / "calls.tsv")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29536", "-m", "deepsignal_plant_b200", "call_mods", "-i", arch, "-m", ckpt, "-o", out,
+           "--max_batch", "1024", "--f5_batch_size", "5", "--motifs", "CG"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    feats, _ = eo.extract_features(reads, "mad", eo.get_motif_seqs("CG"), 0, None, 13, 16, 1, rng=random.Random(0))
+    lines = open(out).read().splitlines()
+    assert len(lines) == len(feats) > 400
+    assert [l.split("\t")[:6] for l in lines] == [[f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]] for f in feats]
+    assert [l.split("\t")[9] for l in lines] == [f[6][4:9] for f in feats]
+    assert not [p for p in os.listdir(tmp_path) if ".part" in p]
