@@ -32,6 +32,8 @@ iupac_alphabets = {'A': ['A'], 'T': ['T'], 'C': ['C'], 'G': ['G'], 'R': ['A', 'G
                    'D': ['A', 'G', 'T'], 'H': ['A', 'C', 'T'], 'V': ['A', 'C', 'G'], 'N': ['A', 'C', 'G', 'T']}
 key_sep = "||"
 _ALPHABET = np.frombuffer(b"ACGTNWSMKRYBVDHZ", np.uint8)
+_ALPHABET_LUT = np.zeros(256, bool)
+_ALPHABET_LUT[_ALPHABET] = True
 
 
 def get_motif_seqs(motifs, is_dna=True):
@@ -79,13 +81,16 @@ class ReadBatch:
         n = self.n_reads
         if self.ev_base.shape[0] != self.ev_len.shape[0] or self.ev_start.shape[0] != self.ev_len.shape[0]:
             raise ValueError("event columns differ in length")         # the reference asserts (:87-88)
-        if not np.isin(self.ev_base, _ALPHABET).all():
-            bad = chr(int(self.ev_base[~np.isin(self.ev_base, _ALPHABET)][0]))
-            raise KeyError(bad)                                         # base2code_dna[x] in the reference
-        ev_read = np.repeat(np.arange(n), np.diff(self.ev_off))
-        if n and ((self.ev_start < 0).any() or (self.ev_len < 0).any()
-                  or (self.ev_start + self.ev_len > np.diff(self.raw_off)[ev_read]).any()):
-            raise ValueError("an event reaches outside its read's raw signal")
+        ok = _ALPHABET_LUT[self.ev_base]
+        if not ok.all():
+            raise KeyError(chr(int(self.ev_base[int(np.argmin(ok))])))  # base2code_dna[x] in the reference
+        if n and self.ev_len.shape[0]:
+            if int(self.ev_start.min()) < 0 or int(self.ev_len.min()) < 0:
+                raise ValueError("an event reaches outside its read's raw signal")
+            filled = np.diff(self.ev_off) > 0
+            last = np.maximum.reduceat(self.ev_start + self.ev_len, self.ev_off[:-1][filled])
+            if (last > np.diff(self.raw_off)[filled]).any():
+                raise ValueError("an event reaches outside its read's raw signal")
 
     # ---- the archive form: flat arrays in an .npz (what a fast5 decoder writes once; see save_reads)
     ARCHIVE_KEYS = ("raw", "raw_off", "ev_off", "scaling", "offset", "ev_start", "ev_len", "ev_base",
@@ -126,17 +131,54 @@ def save_reads(path, reads):
     np.savez(path, **pack_reads(reads).arrays())
 
 
+class _MappedArchive:
+    """The members of an uncompressed .npz (``np.savez`` stores them as plain .npy files inside the zip)
+    memory-mapped in place: loading a 600 MB archive costs page-table entries instead of a 600 MB copy,
+    and the chunks go from the page cache straight into the host->device copy."""
+
+    def __init__(self, path):
+        import zipfile
+        self.files, self._arr = [], {}
+        with zipfile.ZipFile(path) as zf, open(path, "rb") as f:
+            for info in zf.infolist():
+                name = info.filename[:-4] if info.filename.endswith(".npy") else info.filename
+                self.files.append(name)
+                if info.compress_type != zipfile.ZIP_STORED:
+                    self._arr[name] = None                           # compressed member: read it the ordinary way
+                    continue
+                f.seek(info.header_offset)
+                hdr = f.read(30)                                     # local file header: name and extra lengths at 26, 28
+                start = info.header_offset + 30 + int.from_bytes(hdr[26:28], "little") + int.from_bytes(hdr[28:30], "little")
+                f.seek(start)
+                version = np.lib.format.read_magic(f)
+                shape, fortran, dtype = (np.lib.format.read_array_header_1_0(f) if version == (1, 0)
+                                         else np.lib.format.read_array_header_2_0(f))
+                if dtype.hasobject or fortran:
+                    self._arr[name] = None
+                    continue
+                n = int(np.prod(shape))
+                self._arr[name] = (np.memmap(path, dtype=dtype, mode="r", offset=f.tell(), shape=shape) if n
+                                   else np.zeros(shape, dtype))
+        self._path = path
+
+    def __getitem__(self, k):
+        a = self._arr[k]
+        if a is None:
+            a = self._arr[k] = np.load(self._path)[k]
+        return a
+
+
 def load_reads(path):
-    """-> ReadBatch straight from the archive's flat arrays (no per-read objects)."""
-    z = np.load(path)
+    """-> ReadBatch straight from the archive's flat arrays (memory-mapped, no per-read objects)."""
+    z = _MappedArchive(path)
     missing = [k for k in ReadBatch.ARCHIVE_KEYS if k not in z.files]
     if missing:
         raise ValueError("%s is not a decoded-reads archive (missing %s)" % (path, ", ".join(missing)))
     b = object.__new__(ReadBatch)
     b.n_reads = int(z["readname"].shape[0])
     for k in ("readname", "strand", "alignstrand", "chrom"):
-        setattr(b, k, z[k].tolist())
-    b.chrom_start = z["chrom_start"].astype(np.int64, copy=False)
+        setattr(b, k, np.asarray(z[k]).tolist())
+    b.chrom_start = np.asarray(z["chrom_start"]).astype(np.int64, copy=False)
     b.raw_off, b.ev_off = z["raw_off"].astype(np.int64, copy=False), z["ev_off"].astype(np.int64, copy=False)
     b.raw = z["raw"].astype(np.int16, copy=False)
     b.ev_start, b.ev_len = z["ev_start"].astype(np.int64, copy=False), z["ev_len"].astype(np.int64, copy=False)

@@ -384,3 +384,43 @@ def test_gpu_find_sites_matches_host_search_and_reference():
     a = ef.extract_tensors(batch, full, 13, 16, seed=3)
     b = ef.extract_tensors(batch, ef.find_sites_device(batch, eo.get_motif_seqs("CHG"), 0, chrom2len, 13), 13, 16, seed=3)
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.gpu
+def test_gpu_extract_at_scale_is_batching_invariant_and_matches_oracle_sample():
+    # ~0.2 M sites: whole batch == two halves (bit for bit: nothing depends on what else is in the batch),
+    # zero padding is centred, lens are the event lengths, and a sample of reads equals the oracle
+    K, S = 13, 16
+    base = synthetic.make_reads(120, seed=55, mean_bases=3000, long_every=5, stall_every=40)
+    reads = [dict(base[i % len(base)], readname="r%05d" % i) for i in range(480)]
+    ms = eo.get_motif_seqs("CG")
+    whole = ef.pack_reads(reads)
+    sw = ef.find_sites_device(whole, ms, 0, None, K)
+    tw = ef.extract_tensors(whole, sw, K, S, seed=1)
+    assert len(sw) > 150000
+    parts = [ef.pack_reads(reads[:200]), ef.pack_reads(reads[200:])]
+    tp = [ef.extract_tensors(b, ef.find_sites_device(b, ms, 0, None, K), K, S, seed=1) for b in parts]
+    lens = tw["base_signal_lens"]
+    short = (lens <= S)
+    for k in ("kmer", "base_means", "base_stds", "base_signal_lens"):
+        assert torch.equal(tw[k], torch.cat([t[k] for t in tp])), k
+    sig_parts = torch.cat([t["signals"] for t in tp])
+    assert torch.equal(tw["signals"][short], sig_parts[short])
+    assert torch.equal(tw["read_shift"], torch.cat([t["read_shift"] for t in tp]))
+    assert torch.equal(tw["read_scale"], torch.cat([t["read_scale"] for t in tp]))
+    # structure of the rectangle: a short base occupies a centred run of n columns, zeros outside
+    ev = torch.from_numpy(sw.site_ev).cuda()[:, None] + torch.arange(-(K // 2), K // 2 + 1, device="cuda")[None, :]
+    assert torch.equal(lens.long(), torch.from_numpy(whole.ev_len).cuda()[ev])
+    col = torch.arange(S, device="cuda")[None, None, :]
+    left = ((S - lens.long()) // 2)[:, :, None]
+    outside = (col < left) | (col >= left + lens.long()[:, :, None])
+    assert (tw["signals"][short & True][outside[short]] == 0).all()
+    # a sample of reads against the oracle (same sites, stats bit for bit, short rows bit for bit)
+    feats, _ = eo.extract_features(reads[:6], "mad", ms, 0, None, K, S, 1, rng=random.Random(0))
+    want = eo.features_to_arrays(feats, round_stats=False)
+    n = len(feats)
+    assert np.array_equal(sw.site_read[:n], np.repeat(np.arange(6), np.bincount(sw.site_read[:n], minlength=6)))
+    for k in ("kmer", "base_means", "base_stds", "base_signal_lens"):
+        assert np.array_equal(tw[k][:n].cpu().numpy().view(np.uint32), want[k].view(np.uint32)), k
+    sh = short[:n].cpu().numpy()
+    assert np.array_equal(tw["signals"][:n].cpu().numpy()[sh], want["signals"][sh])
