@@ -244,20 +244,20 @@ struct NormSamples {
 // numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src, DOUBLE_pairwise_sum) of elem(0..n-1):
 // n < 8 a running sum from 0; n <= 128 eight interleaved accumulators combined as
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then the tail; larger n split at n/2 rounded down to a multiple of 8.
-template <typename Elem>
-__device__ double pairwise_leaf(Elem elem, int64_t off, int64_t n) {
+template <typename I, typename Elem>
+__device__ double pairwise_leaf(Elem elem, I off, I n) {
     if (n < 8) {
         double res = 0.0;
-        for (int64_t i = 0; i < n; ++i) res = __dadd_rn(res, elem(off + i));
+        for (I i = 0; i < n; ++i) res = __dadd_rn(res, elem(off + i));
         return res;
     }
     double r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = elem(off + j);
-    int64_t i = 8;
+    for (int j = 0; j < 8; ++j) r[j] = elem(off + (I)j);
+    I i = 8;
     for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], elem(off + i + j));
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], elem(off + i + (I)j));
     }
     double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                            __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
@@ -265,26 +265,26 @@ __device__ double pairwise_leaf(Elem elem, int64_t off, int64_t n) {
     return res;
 }
 
-template <typename Elem>
-__device__ double pairwise_sum(Elem elem, int64_t n) {
-    if (n <= 128) return pairwise_leaf(elem, 0, n);
+template <typename I, typename Elem>
+__device__ double pairwise_sum(Elem elem, I n) {
+    if (n <= 128) return pairwise_leaf<I>(elem, (I)0, n);
     // explicit stack instead of recursion: frames are (offset, count, phase, left value)
-    constexpr int DEPTH = 40;
-    int64_t off_s[DEPTH], n_s[DEPTH];
+    constexpr int DEPTH = sizeof(I) == 4 ? 26 : 40;
+    I off_s[DEPTH], n_s[DEPTH];
     double left_s[DEPTH];
     int phase_s[DEPTH];
     int sp = 0;
     off_s[0] = 0; n_s[0] = n; phase_s[0] = 0; left_s[0] = 0.0;
     double ret = 0.0;
     while (sp >= 0) {
-        const int64_t o = off_s[sp], c = n_s[sp];
+        const I o = off_s[sp], c = n_s[sp];
         if (phase_s[sp] == 0) {
-            if (c <= 128) { ret = pairwise_leaf(elem, o, c); --sp; continue; }
-            int64_t n2 = c / 2; n2 -= n2 % 8;
+            if (c <= 128) { ret = pairwise_leaf<I>(elem, o, c); --sp; continue; }
+            I n2 = c / 2; n2 -= n2 % 8;
             phase_s[sp] = 1;
             ++sp; off_s[sp] = o; n_s[sp] = n2; phase_s[sp] = 0;
         } else if (phase_s[sp] == 1) {
-            int64_t n2 = c / 2; n2 -= n2 % 8;
+            I n2 = c / 2; n2 -= n2 % 8;
             left_s[sp] = ret; phase_s[sp] = 2;
             ++sp; off_s[sp] = o + n2; n_s[sp] = c - n2; phase_s[sp] = 0;
         } else {
@@ -389,21 +389,38 @@ struct SiteParams {
 };
 
 constexpr int SITE_WARPS = 8;                      // sites per CTA (one warp each)
-constexpr int WIN_MAX = 768;                       // samples of a site's window held in shared memory (6 KB per warp)
+constexpr int WIN_MAX = 448;                       // samples of a site's window held in shared memory (3.5 KB per warp; 4 CTAs per SM)
+constexpr int RND_MAX = WIN_MAX + 4 * 32;          // uniforms for the subsample draws of a windowed site (one per sample)
 
 // ordered uniform S-subset of 0..n-1 by selection sampling (Knuth 3.4.2 S): offset i is taken with
 // probability (still needed) / (still available) -- the distribution of sorted(random.sample(range(n), S))
+// uniform i of row `row` = word (i & 3) of Philox block (i >> 2) of that row
+__device__ __forceinline__ uint4 subset_block(int64_t row, uint32_t block, uint64_t seed) {
+    return philox4x32((uint32_t)row, (uint32_t)(row >> 32), block, 0x65787472u, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
 template <typename Put>
 __device__ __forceinline__ void draw_ordered_subset(int64_t n, int S, int64_t row, uint64_t seed, Put put) {
     int need = S, s = 0;
     uint4 blk = make_uint4(0, 0, 0, 0);
     for (int64_t i = 0; i < n && need > 0; ++i) {
-        if ((i & 3) == 0) blk = philox4x32((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(i >> 2), 0x65787472u,
-                                           (uint32_t)seed, (uint32_t)(seed >> 32));
+        if ((i & 3) == 0) blk = subset_block(row, (uint32_t)(i >> 2), seed);
         const uint32_t u = (i & 3) == 0 ? blk.x : (i & 3) == 1 ? blk.y : (i & 3) == 2 ? blk.z : blk.w;
         // u / 2^32 < need / (n - i)   <=>   u * (n - i) < need * 2^32
         if ((uint64_t)u * (uint64_t)(n - i) < ((uint64_t)need << 32)) { put(s++, i); --need; }
     }
+}
+
+// the same draw with the uniforms already in shared memory (drawn by the whole warp)
+template <typename Put>
+__device__ __forceinline__ void draw_ordered_subset_from(const uint32_t* u, int n, int S, Put put) {
+    int need = S, s = 0;
+    for (int i = 0; i < n && need > 0; ++i)
+        if ((uint64_t)u[i] * (uint64_t)(n - i) < ((uint64_t)need << 32)) { put(s++, i); --need; }
+}
+
+__host__ __device__ inline size_t site_smem_per_warp(int T, int S) {
+    return (size_t)WIN_MAX * 8 + (size_t)T * 16 + (size_t)RND_MAX * 4 + 32 * 4 + (((size_t)T * S * 2 + 15) & ~(size_t)15);
 }
 
 // One warp per site.  The seq_len events of a site are neighbours in the raw signal, so the warp first
@@ -412,16 +429,19 @@ __device__ __forceinline__ void draw_ordered_subset(int64_t n, int S, int64_t ro
 // from shared memory) and, for a base longer than the rectangle, its subsample offsets; finally all lanes
 // emit the T x S rectangle with coalesced stores.  A site whose window does not fit (a stalled base)
 // takes the same steps with the samples recomputed from the raw signal instead of read from the window.
-__global__ void __launch_bounds__(SITE_WARPS * 32) site_features_kernel(SiteParams p) {
+__global__ void __launch_bounds__(SITE_WARPS * 32, 4) site_features_kernel(SiteParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = p.T, S = p.S;
-    const size_t per_warp = (size_t)WIN_MAX * 8 + (size_t)T * 16 + (((size_t)T * S * 2 + 15) & ~(size_t)15);
+    const size_t per_warp = site_smem_per_warp(T, S);
     unsigned char* base = smem_raw + warp * per_warp;
     double* win = reinterpret_cast<double*>(base);
     int64_t* b_off = reinterpret_cast<int64_t*>(base + (size_t)WIN_MAX * 8);       // [T] first sample of base j (read-relative)
     int64_t* b_len = b_off + T;                                                     // [T]
-    uint16_t* sel = reinterpret_cast<uint16_t*>(base + (size_t)WIN_MAX * 8 + (size_t)T * 16);   // [T][S] subsample offsets
+    uint32_t* rnd = reinterpret_cast<uint32_t*>(b_len + T);                         // [RND_MAX] uniforms of the long bases
+    int* b_blk = reinterpret_cast<int*>(rnd + RND_MAX);                             // [32] first Philox block of base j in rnd
+    uint16_t* sel = reinterpret_cast<uint16_t*>(b_blk + 32);                        // [T][S] subsample offsets
+    const int shift_S = (S & (S - 1)) == 0 ? __ffs(S) - 1 : -1;
 
     for (int64_t site = (int64_t)blockIdx.x * SITE_WARPS + warp; site < p.n_sites; site += (int64_t)gridDim.x * SITE_WARPS) {
         const int32_t rd = p.site_read[site];
@@ -452,31 +472,52 @@ __global__ void __launch_bounds__(SITE_WARPS * 32) site_features_kernel(SitePara
             const double* a = win + (off - st);
             double mean, sd;
             if (windowed) {
-                mean = __ddiv_rn(pairwise_sum([&](int64_t i) { return a[i]; }, n), dn);
+                mean = __ddiv_rn(pairwise_sum<int>([&](int i) { return a[i]; }, (int)n), dn);
                 const double m0 = mean;
-                sd = __dsqrt_rn(__ddiv_rn(pairwise_sum([&](int64_t i) { const double d = __dsub_rn(a[i], m0); return __dmul_rn(d, d); }, n), dn));
+                sd = __dsqrt_rn(__ddiv_rn(pairwise_sum<int>([&](int i) { const double d = __dsub_rn(a[i], m0); return __dmul_rn(d, d); }, (int)n), dn));
             } else {
-                mean = __ddiv_rn(pairwise_sum([&](int64_t i) { return v(off + i); }, n), dn);
+                mean = __ddiv_rn(pairwise_sum<int64_t>([&](int64_t i) { return v(off + i); }, n), dn);
                 const double m0 = mean;
-                sd = __dsqrt_rn(__ddiv_rn(pairwise_sum([&](int64_t i) { const double d = __dsub_rn(v(off + i), m0); return __dmul_rn(d, d); }, n), dn));
+                sd = __dsqrt_rn(__ddiv_rn(pairwise_sum<int64_t>([&](int64_t i) { const double d = __dsub_rn(v(off + i), m0); return __dmul_rn(d, d); }, n), dn));
             }
             if (p.round_stats) { mean = around6(mean); sd = around6(sd); }   // _features_to_str, :388-389
             p.kmer[row] = (float)c_base2code[p.ev_base[ev0 + lane]];
             p.means[row] = (float)mean;
             p.stds[row] = (float)sd;
             p.lens[row] = (float)n;
-            if (n > S) {
-                if (!p.drawn) {
-                    if (n <= 65536) draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { sel[lane * S + s] = (uint16_t)i; });
-                    else draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { p.signals[row * S + s] = (float)v(off + i); });
+        }
+        if (!p.drawn) {
+            // ordered subsamples of the bases longer than the rectangle.  Windowed site: the Philox blocks of
+            // all its long bases are drawn by the whole warp (base j's blocks at b_blk[j] in rnd), then each
+            // owner lane only compares; otherwise each owner lane draws its own.
+            const bool lng = lane < T && n > S;
+            const int nblk = (lng && windowed) ? (int)((n + 3) >> 2) : 0;
+            int incl = nblk;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const bool coop = windowed && total > 0 && total * 4 <= RND_MAX;
+            if (coop) {
+                b_blk[lane] = incl - nblk;
+                __syncwarp();
+                for (int b = lane; b < total; b += 32) {
+                    int j = 0;
+                    for (int t = 1; t < T; ++t) if (b_blk[t] <= b) j = t;
+                    const uint4 blk = subset_block(site * T + j, (uint32_t)(b - b_blk[j]), p.seed);
+                    *reinterpret_cast<uint4*>(rnd + 4 * b) = blk;
                 }
+                __syncwarp();
+                if (lng) draw_ordered_subset_from(rnd + 4 * (incl - nblk), (int)n, S, [&](int s, int i) { sel[lane * S + s] = (uint16_t)i; });
+            } else if (lng) {
+                if (n <= 65536) draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { sel[lane * S + s] = (uint16_t)i; });
+                else draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { p.signals[row * S + s] = (float)v(off + i); });
             }
         }
         __syncwarp();
         // _get_signals_rect (:232-251): centred zero pad, or the ordered subsample
         float* out = p.signals + site * T * S;
         for (int e = lane; e < T * S; e += 32) {
-            const int j = e / S, sidx = e - j * S;
+            const int j = shift_S >= 0 ? e >> shift_S : e / S, sidx = e - j * S;
             const int64_t nj = b_len[j];
             int64_t i;
             if (nj <= S) {
@@ -604,11 +645,11 @@ extern "C" int dsp_extract_features(int device,
         p.T = seq_len; p.S = signal_len; p.round_stats = round_stats;
         p.drawn = drawn; p.seed = seed; p.shift = read_shift; p.scale = read_scale;
         p.kmer = kmer; p.means = base_means; p.stds = base_stds; p.lens = base_signal_lens; p.signals = signals;
-        const size_t per_warp = (size_t)WIN_MAX * 8 + (size_t)seq_len * 16 + (((size_t)seq_len * signal_len * 2 + 15) & ~(size_t)15);
-        const size_t smem = per_warp * SITE_WARPS;
-        static size_t smem_allowed = 48 * 1024;
+        const size_t smem = site_smem_per_warp(seq_len, signal_len) * SITE_WARPS;
+        static size_t smem_allowed = 0;
         if (smem > smem_allowed) {
-            DSP_CUDA(cudaFuncSetAttribute(site_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DSP_CUDA(cudaFuncSetAttribute(site_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+            DSP_CUDA(cudaFuncSetAttribute(site_features_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             smem_allowed = smem;
         }
         int n_sm = 148;

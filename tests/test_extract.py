@@ -204,7 +204,7 @@ def test_gpu_extract_matches_oracle_on_fresh_reads(seed, K, S, motifs):
     _check_against(fz, dz, bz, ef.find_sites(bz, motif_seqs, 0, chrom2len, K), K, S, False, "zscore")
     assert len(feats) == len(sites) > 300
     lens = np.array([f[9] for f in feats])
-    assert (lens.sum(1) > 768).sum() >= 5 and (lens.sum(1) <= 768).sum() > 200     # windowed and recomputing sites
+    assert (lens.sum(1) > 448).sum() >= 5 and (lens.sum(1) <= 448).sum() > 200     # windowed and recomputing sites
     for round_stats in (False, True):
         got = _check_against(feats, drawn, batch, sites, K, S, round_stats)
     assert got["read_scale"][-3].item() == 0.0
@@ -388,7 +388,7 @@ def test_gpu_find_sites_matches_host_search_and_reference():
 
 @pytest.mark.gpu
 def test_gpu_extract_at_scale_is_batching_invariant_and_matches_oracle_sample():
-    # ~0.2 M sites: whole batch == two halves (bit for bit: nothing depends on what else is in the batch),
+    # ~90 k sites: whole batch == two halves (bit for bit: nothing depends on what else is in the batch),
     # zero padding is centred, lens are the event lengths, and a sample of reads equals the oracle
     K, S = 13, 16
     base = synthetic.make_reads(120, seed=55, mean_bases=3000, long_every=5, stall_every=40)
@@ -397,7 +397,7 @@ def test_gpu_extract_at_scale_is_batching_invariant_and_matches_oracle_sample():
     whole = ef.pack_reads(reads)
     sw = ef.find_sites_device(whole, ms, 0, None, K)
     tw = ef.extract_tensors(whole, sw, K, S, seed=1)
-    assert len(sw) > 150000
+    assert len(sw) > 80000
     parts = [ef.pack_reads(reads[:200]), ef.pack_reads(reads[200:])]
     tp = [ef.extract_tensors(b, ef.find_sites_device(b, ms, 0, None, K), K, S, seed=1) for b in parts]
     lens = tw["base_signal_lens"]
@@ -414,7 +414,7 @@ def test_gpu_extract_at_scale_is_batching_invariant_and_matches_oracle_sample():
     col = torch.arange(S, device="cuda")[None, None, :]
     left = ((S - lens.long()) // 2)[:, :, None]
     outside = (col < left) | (col >= left + lens.long()[:, :, None])
-    assert (tw["signals"][short & True][outside[short]] == 0).all()
+    assert (tw["signals"][short][outside[short]] == 0).all()
     # a sample of reads against the oracle (same sites, stats bit for bit, short rows bit for bit)
     feats, _ = eo.extract_features(reads[:6], "mad", ms, 0, None, K, S, 1, rng=random.Random(0))
     want = eo.features_to_arrays(feats, round_stats=False)
