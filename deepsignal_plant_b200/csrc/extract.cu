@@ -385,7 +385,7 @@ struct SiteParams {
     int T, S, round_stats;
     const int32_t* drawn; uint64_t seed;
     const double* shift; const double* scale;
-    float *kmer, *means, *stds, *lens, *signals;
+    void *kmer, *means, *stds, *lens, *signals;       // float (what the classifier reads) or double (what the feature file prints)
 };
 
 constexpr int SITE_WARPS = 8;                      // sites per CTA (one warp each)
@@ -429,6 +429,7 @@ __host__ __device__ inline size_t site_smem_per_warp(int T, int S) {
 // from shared memory) and, for a base longer than the rectangle, its subsample offsets; finally all lanes
 // emit the T x S rectangle with coalesced stores.  A site whose window does not fit (a stalled base)
 // takes the same steps with the samples recomputed from the raw signal instead of read from the window.
+template <typename OutT>
 __global__ void __launch_bounds__(SITE_WARPS * 32, 4) site_features_kernel(SiteParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -442,6 +443,11 @@ __global__ void __launch_bounds__(SITE_WARPS * 32, 4) site_features_kernel(SiteP
     int* b_blk = reinterpret_cast<int*>(rnd + RND_MAX);                             // [32] first Philox block of base j in rnd
     uint16_t* sel = reinterpret_cast<uint16_t*>(b_blk + 32);                        // [T][S] subsample offsets
     const int shift_S = (S & (S - 1)) == 0 ? __ffs(S) - 1 : -1;
+    OutT* const o_kmer = static_cast<OutT*>(p.kmer);
+    OutT* const o_means = static_cast<OutT*>(p.means);
+    OutT* const o_stds = static_cast<OutT*>(p.stds);
+    OutT* const o_lens = static_cast<OutT*>(p.lens);
+    OutT* const o_signals = static_cast<OutT*>(p.signals);
 
     for (int64_t site = (int64_t)blockIdx.x * SITE_WARPS + warp; site < p.n_sites; site += (int64_t)gridDim.x * SITE_WARPS) {
         const int32_t rd = p.site_read[site];
@@ -481,10 +487,10 @@ __global__ void __launch_bounds__(SITE_WARPS * 32, 4) site_features_kernel(SiteP
                 sd = __dsqrt_rn(__ddiv_rn(pairwise_sum<int64_t>([&](int64_t i) { const double d = __dsub_rn(v(off + i), m0); return __dmul_rn(d, d); }, n), dn));
             }
             if (p.round_stats) { mean = around6(mean); sd = around6(sd); }   // _features_to_str, :388-389
-            p.kmer[row] = (float)c_base2code[p.ev_base[ev0 + lane]];
-            p.means[row] = (float)mean;
-            p.stds[row] = (float)sd;
-            p.lens[row] = (float)n;
+            o_kmer[row] = (OutT)c_base2code[p.ev_base[ev0 + lane]];
+            o_means[row] = (OutT)mean;
+            o_stds[row] = (OutT)sd;
+            o_lens[row] = (OutT)n;
         }
         if (!p.drawn) {
             // ordered subsamples of the bases longer than the rectangle.  Windowed site: the Philox blocks of
@@ -510,19 +516,19 @@ __global__ void __launch_bounds__(SITE_WARPS * 32, 4) site_features_kernel(SiteP
                 if (lng) draw_ordered_subset_from(rnd + 4 * (incl - nblk), (int)n, S, [&](int s, int i) { sel[lane * S + s] = (uint16_t)i; });
             } else if (lng) {
                 if (n <= 65536) draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { sel[lane * S + s] = (uint16_t)i; });
-                else draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { p.signals[row * S + s] = (float)v(off + i); });
+                else draw_ordered_subset(n, S, row, p.seed, [&](int s, int64_t i) { o_signals[row * S + s] = (OutT)v(off + i); });
             }
         }
         __syncwarp();
         // _get_signals_rect (:232-251): centred zero pad, or the ordered subsample
-        float* out = p.signals + site * T * S;
+        OutT* out = o_signals + site * T * S;
         for (int e = lane; e < T * S; e += 32) {
             const int j = shift_S >= 0 ? e >> shift_S : e / S, sidx = e - j * S;
             const int64_t nj = b_len[j];
             int64_t i;
             if (nj <= S) {
                 i = sidx - (S - nj) / 2;
-                if (i < 0 || i >= nj) { out[e] = 0.0f; continue; }
+                if (i < 0 || i >= nj) { out[e] = (OutT)0; continue; }
             } else if (p.drawn) {
                 i = p.drawn[site * T * S + e];         // parity mode: replay the reference's random.sample offsets
             } else if (nj <= 65536) {
@@ -530,7 +536,7 @@ __global__ void __launch_bounds__(SITE_WARPS * 32, 4) site_features_kernel(SiteP
             } else {
                 continue;                              // written by the base's own lane above
             }
-            out[e] = (float)(windowed ? win[b_off[j] - st + i] : v(b_off[j] + i));
+            out[e] = (OutT)(windowed ? win[b_off[j] - st + i] : v(b_off[j] + i));
         }
         __syncwarp();
     }
@@ -595,16 +601,18 @@ const uint8_t kBase2Code[16] = {'A', 'C', 'G', 'T', 'N', 'W', 'S', 'M', 'K', 'R'
 
 using namespace dsp;
 
-extern "C" int dsp_extract_features(int device,
-                                    const int16_t* raw, const int64_t* raw_off, const double* scaling, const double* offset,
-                                    int64_t n_reads,
-                                    const int64_t* ev_start, const int64_t* ev_len, const uint8_t* ev_base,
-                                    const int32_t* site_read, const int64_t* site_ev, int64_t n_sites,
-                                    int32_t seq_len, int32_t signal_len, int32_t normalize_method, int32_t round_stats,
-                                    const int32_t* drawn, uint64_t seed,
-                                    double* read_shift, double* read_scale,
-                                    float* kmer, float* base_means, float* base_stds, float* base_signal_lens,
-                                    float* signals, void* stream) {
+namespace dsp {
+namespace {
+int extract_features_impl(int device, bool f64,
+                          const int16_t* raw, const int64_t* raw_off, const double* scaling, const double* offset,
+                          int64_t n_reads,
+                          const int64_t* ev_start, const int64_t* ev_len, const uint8_t* ev_base,
+                          const int32_t* site_read, const int64_t* site_ev, int64_t n_sites,
+                          int32_t seq_len, int32_t signal_len, int32_t normalize_method, int32_t round_stats,
+                          const int32_t* drawn, uint64_t seed,
+                          double* read_shift, double* read_scale,
+                          void* kmer, void* base_means, void* base_stds, void* base_signal_lens,
+                          void* signals, void* stream) {
     DSP_REQUIRE(n_reads >= 0 && n_sites >= 0, DSP_ERR_INVALID, "dsp_extract_features: negative count");
     DSP_REQUIRE(seq_len > 0 && (seq_len & 1), DSP_ERR_INVALID, "kmer_len must be odd");
     DSP_REQUIRE(seq_len <= 31, DSP_ERR_INVALID, "dsp_extract_features: kmer_len must be at most 31 (one lane per base)");
@@ -622,12 +630,12 @@ extern "C" int dsp_extract_features(int device,
         DSP_CUDA(cudaStreamSynchronize(st));
         table_device = device;
     }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     if (n_reads > 0 && normalize_method == 1) {
         read_zscore_kernel<<<(unsigned)((n_reads + 3) / 4), 128, 0, st>>>(raw, raw_off, scaling, offset, n_reads, read_shift, read_scale);
         DSP_CUDA(cudaGetLastError());
     } else if (n_reads > 0) {
-        int n_sm = 148;
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         const int64_t grid = n_reads < (int64_t)n_sm * 3 ? n_reads : (int64_t)n_sm * 3;   // 3 CTAs of 72 KB per SM
         static bool attr_set = false;
         if (!attr_set) {
@@ -646,20 +654,51 @@ extern "C" int dsp_extract_features(int device,
         p.drawn = drawn; p.seed = seed; p.shift = read_shift; p.scale = read_scale;
         p.kmer = kmer; p.means = base_means; p.stds = base_stds; p.lens = base_signal_lens; p.signals = signals;
         const size_t smem = site_smem_per_warp(seq_len, signal_len) * SITE_WARPS;
-        static size_t smem_allowed = 0;
-        if (smem > smem_allowed) {
-            DSP_CUDA(cudaFuncSetAttribute(site_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
-            DSP_CUDA(cudaFuncSetAttribute(site_features_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            smem_allowed = smem;
+        static size_t smem_allowed[2] = {0, 0};
+        auto kern = f64 ? site_features_kernel<double> : site_features_kernel<float>;
+        if (smem > smem_allowed[f64]) {
+            DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+            DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            smem_allowed[f64] = smem;
         }
-        int n_sm = 148;
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         int64_t grid = (n_sites + SITE_WARPS - 1) / SITE_WARPS;
         if (grid > (int64_t)n_sm * 64) grid = (int64_t)n_sm * 64;
-        site_features_kernel<<<(unsigned)grid, SITE_WARPS * 32, smem, st>>>(p);
+        kern<<<(unsigned)grid, SITE_WARPS * 32, smem, st>>>(p);
         DSP_CUDA(cudaGetLastError());
     }
     return DSP_OK;
+}
+}  // namespace
+}  // namespace dsp
+
+extern "C" int dsp_extract_features(int device,
+                                    const int16_t* raw, const int64_t* raw_off, const double* scaling, const double* offset,
+                                    int64_t n_reads,
+                                    const int64_t* ev_start, const int64_t* ev_len, const uint8_t* ev_base,
+                                    const int32_t* site_read, const int64_t* site_ev, int64_t n_sites,
+                                    int32_t seq_len, int32_t signal_len, int32_t normalize_method, int32_t round_stats,
+                                    const int32_t* drawn, uint64_t seed,
+                                    double* read_shift, double* read_scale,
+                                    float* kmer, float* base_means, float* base_stds, float* base_signal_lens,
+                                    float* signals, void* stream) {
+    return extract_features_impl(device, false, raw, raw_off, scaling, offset, n_reads, ev_start, ev_len, ev_base, site_read, site_ev,
+                                 n_sites, seq_len, signal_len, normalize_method, round_stats, drawn, seed, read_shift, read_scale,
+                                 kmer, base_means, base_stds, base_signal_lens, signals, stream);
+}
+
+extern "C" int dsp_extract_features_f64(int device,
+                                        const int16_t* raw, const int64_t* raw_off, const double* scaling, const double* offset,
+                                        int64_t n_reads,
+                                        const int64_t* ev_start, const int64_t* ev_len, const uint8_t* ev_base,
+                                        const int32_t* site_read, const int64_t* site_ev, int64_t n_sites,
+                                        int32_t seq_len, int32_t signal_len, int32_t normalize_method, int32_t round_stats,
+                                        const int32_t* drawn, uint64_t seed,
+                                        double* read_shift, double* read_scale,
+                                        double* kmer, double* base_means, double* base_stds, double* base_signal_lens,
+                                        double* signals, void* stream) {
+    return extract_features_impl(device, true, raw, raw_off, scaling, offset, n_reads, ev_start, ev_len, ev_base, site_read, site_ev,
+                                 n_sites, seq_len, signal_len, normalize_method, round_stats, drawn, seed, read_shift, read_scale,
+                                 kmer, base_means, base_stds, base_signal_lens, signals, stream);
 }
 
 extern "C" int dsp_find_sites(int device, const uint8_t* ev_base, const int64_t* ev_off, int64_t n_reads, int64_t n_events,
