@@ -16,10 +16,32 @@ import sys
 
 def build_parser():
     parser = argparse.ArgumentParser(prog="deepsignal_plant_b200",
-                                     description="deepsignal-plant call_mods / call_freq on B200 (sm_100a) kernels")
+                                     description="deepsignal-plant extract / call_mods / call_freq on B200 (sm_100a) kernels")
     sub = parser.add_subparsers(title="modules", dest="module")
     cm = sub.add_parser("call_mods", description="call modifications")
     cf = sub.add_parser("call_freq", description="call frequency of modifications at genome level")
+
+    ex = sub.add_parser("extract", description="extract features from decoded re-squiggled reads (an .npz archive written by "
+                                               "extract_features.save_reads) into the reference's feature file")
+    g = ex.add_argument_group("INPUT")
+    g.add_argument("--fast5_dir", "-i", action="store", type=str, required=True,
+                   help="the decoded-reads archive (.npz); the reference's flag name is kept")
+    g.add_argument("--is_dna", action="store", type=str, required=False, default="yes")
+    g.add_argument("--reference_path", action="store", type=str, required=False, default=None)
+    g = ex.add_argument_group("EXTRACTION")
+    g.add_argument("--normalize_method", action="store", type=str, choices=["mad", "zscore"], default="mad", required=False)
+    g.add_argument("--methy_label", action="store", type=int, choices=[1, 0], required=False, default=1)
+    g.add_argument("--seq_len", action="store", type=int, required=False, default=13)
+    g.add_argument("--signal_len", action="store", type=int, required=False, default=16)
+    g.add_argument("--motifs", action="store", type=str, required=False, default="CG")
+    g.add_argument("--mod_loc", action="store", type=int, required=False, default=0)
+    g.add_argument("--region", action="store", type=str, required=False, default=None)
+    g.add_argument("--positions", action="store", type=str, required=False, default=None)
+    g = ex.add_argument_group("OUTPUT")
+    g.add_argument("--write_path", "-o", action="store", type=str, required=True)
+    g.add_argument("--gzip", action="store_true", default=False, required=False)
+    ex.add_argument("--nproc", "-p", action="store", type=int, default=10, required=False, help="host threads for formatting")
+    ex.add_argument("--f5_batch_size", action="store", type=int, default=30, required=False, help="reads per extraction chunk")
 
     g = cm.add_argument_group("INPUT")
     g.add_argument("--input_path", "-i", action="store", type=str, required=True,
@@ -83,6 +105,9 @@ def main(argv=None):
     if args.module == "call_mods":
         from .call_modifications import call_mods
         call_mods(args)
+    elif args.module == "extract":
+        from .extract_features import extract_to_file
+        extract_to_file(args)
     elif args.module == "call_freq":
         from .call_mods_freq import call_mods_frequency_to_file
         call_mods_frequency_to_file(args)

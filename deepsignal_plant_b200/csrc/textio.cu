@@ -179,6 +179,41 @@ int format_f32(float x, char* out) {
     return (int)(o - out);
 }
 
+// str(numpy.float64(x)) == repr(float(x)): shortest digits that round-trip in float64, positional for
+// 1e-4 <= |x| < 1e16, scientific otherwise, at least one digit after a positional point, exponent with at
+// least two digits.  (What _features_to_str prints for means, stds and signals, extract_features.py:388-392.)
+int format_f64(double x, char* out) {
+    if (std::isnan(x)) { memcpy(out, "nan", 3); return 3; }
+    if (std::isinf(x)) { if (x < 0) { memcpy(out, "-inf", 4); return 4; } memcpy(out, "inf", 3); return 3; }
+    char* o = out;
+    if (std::signbit(x)) { *o++ = '-'; x = -x; }
+    if (x == 0.0) { memcpy(o, "0.0", 3); return (int)(o + 3 - out); }
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest
+    char digits[24]; int nd = 0; const char* p = buf;
+    for (; p < r.ptr && *p != 'e'; ++p) if (*p != '.') digits[nd++] = *p;
+    int ex = 0; { ++p; bool neg = (*p == '-'); ++p; for (; p < r.ptr; ++p) ex = ex * 10 + (*p - '0'); if (neg) ex = -ex; }
+    if (x >= 1e-4 && x < 1e16) {
+        if (ex < 0) {
+            *o++ = '0'; *o++ = '.';
+            for (int k = 0; k < -ex - 1; ++k) *o++ = '0';
+            memcpy(o, digits, nd); o += nd;
+        } else {
+            for (int k = 0; k <= ex; ++k) *o++ = k < nd ? digits[k] : '0';
+            *o++ = '.';
+            if (nd > ex + 1) { memcpy(o, digits + ex + 1, nd - ex - 1); o += nd - ex - 1; } else *o++ = '0';
+        }
+    } else {
+        *o++ = digits[0];
+        if (nd > 1) { *o++ = '.'; memcpy(o, digits + 1, nd - 1); o += nd - 1; }
+        *o++ = 'e'; *o++ = ex < 0 ? '-' : '+';
+        int a = ex < 0 ? -ex : ex;
+        if (a >= 100) { *o++ = (char)('0' + a / 100); a %= 100; }
+        *o++ = (char)('0' + a / 10); *o++ = (char)('0' + a % 10);
+    }
+    return (int)(o - out);
+}
+
 // numpy.round(x, 6) on float32: rint(x * 1e6f) / 1e6f in float32
 inline float round6(float x) { return rintf(x * 1e6f) / 1e6f; }
 
@@ -335,6 +370,57 @@ int dsp_format_sampleinfo(const char* chrom_text, const int64_t* chrom_off, cons
             *o++ = strand[r];
         }
     });
+    return DSP_OK;
+}
+
+// One feature-file line per site, as _features_to_str writes it (extract_features.py:381-395):
+//   sampleinfo \t k_mer \t means \t stds \t lens \t signals \t label \n
+// means / stds / signals are the float64 values dsp_extract_features_f64 produced with round_stats = 1,
+// printed like str(numpy.float64); lens as integers; values within a column joined by ',', the rows of the
+// signal rectangle by ';'.  kmer_letters is (n, seq_len) ASCII.  Two passes: format every site into a
+// thread-local arena to learn its length, then copy into place.
+int dsp_format_features(const char* info_text, const int64_t* info_off, const uint8_t* kmer_letters,
+                        const double* means, const double* stds, const double* lens, const double* signals,
+                        int32_t methy_label, int64_t n, int32_t seq_len, int32_t signal_len,
+                        char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads) {
+    DSP_REQUIRE(n >= 0 && out_bytes, DSP_ERR_INVALID, "dsp_format_features: bad argument");
+    *out_bytes = 0;
+    if (n == 0) return DSP_OK;
+    DSP_REQUIRE(info_text && info_off && kmer_letters && means && stds && lens && signals && out && seq_len > 0 && signal_len > 0,
+                DSP_ERR_INVALID, "dsp_format_features: null argument");
+    const int T = seq_len, S = signal_len;
+    const size_t worst = (size_t)T * (size_t)(2 * 26 + 22 + S * 26) + 64;   // per site, without the sample info
+    char lab[16];
+    const int lab_len = (int)(std::to_chars(lab, lab + 16, methy_label).ptr - lab);
+    auto one = [&](int64_t i, char* o) -> char* {
+        const int64_t il = info_off[i + 1] - info_off[i];
+        memcpy(o, info_text + info_off[i], (size_t)il); o += il; *o++ = '\t';
+        memcpy(o, kmer_letters + i * T, (size_t)T); o += T; *o++ = '\t';
+        for (int t = 0; t < T; ++t) { o += format_f64(means[i * T + t], o); *o++ = t + 1 < T ? ',' : '\t'; }
+        for (int t = 0; t < T; ++t) { o += format_f64(stds[i * T + t], o); *o++ = t + 1 < T ? ',' : '\t'; }
+        for (int t = 0; t < T; ++t) { o = std::to_chars(o, o + 24, (long long)lens[i * T + t]).ptr; *o++ = t + 1 < T ? ',' : '\t'; }
+        for (int t = 0; t < T; ++t) {
+            const double* row = signals + ((size_t)i * T + t) * S;
+            for (int k = 0; k < S; ++k) { o += format_f64(row[k], o); *o++ = k + 1 < S ? ',' : (t + 1 < T ? ';' : '\t'); }
+        }
+        memcpy(o, lab, (size_t)lab_len); o += lab_len;
+        *o++ = '\n';
+        return o;
+    };
+    std::vector<int64_t> off((size_t)n + 1);
+    off[0] = 0;
+    parallel_for(n, nthreads, [&](int64_t a, int64_t b) {
+        std::vector<char> scratch;
+        for (int64_t i = a; i < b; ++i) {
+            scratch.resize(worst + (size_t)(info_off[i + 1] - info_off[i]));
+            off[i + 1] = one(i, scratch.data()) - scratch.data();
+        }
+    });
+    for (int64_t i = 0; i < n; ++i) off[i + 1] += off[i];
+    *out_bytes = off[n];
+    DSP_REQUIRE(off[n] <= out_cap, DSP_ERR_NOMEM, "dsp_format_features: output needs %lld bytes, buffer has %lld",
+                (long long)off[n], (long long)out_cap);
+    parallel_for(n, nthreads, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) one(i, out + off[i]); });
     return DSP_OK;
 }
 

@@ -402,12 +402,14 @@ def sampleinfo_packed(batch, sites, nthreads=None):
 
 
 def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method="mad", round_stats=False,
-                    drawn=None, seed=0, device=None, out=None):
+                    drawn=None, seed=0, device=None, out=None, dtype=torch.float32):
     """Run ``dsp_extract_features``: -> dict of the five float32 CUDA tensors ``ModelBiLSTM.forward``
     takes (``kmer, base_means, base_stds, base_signal_lens, signals``) plus ``read_shift`` /
     ``read_scale`` (float64 per read: the median and MAD ``_normalize_signals`` used).
     ``drawn``: optional (n_sites, kmer_len, signals_len) int32 subsample offsets to replay (parity).
-    ``out``: a dict returned by an earlier call with the same shapes, to be overwritten (no allocation)."""
+    ``out``: a dict returned by an earlier call with the same shapes, to be overwritten (no allocation).
+    ``dtype=torch.float64`` (``dsp_extract_features_f64``) returns the values before the float32 narrowing,
+    which is what the feature file prints."""
     if normalize_method not in ("mad", "zscore"):
         raise ValueError("")                                            # _normalize_signals, :184-185
     if not torch.cuda.is_available():
@@ -423,7 +425,9 @@ def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method=
         drawn_t = torch.as_tensor(np.ascontiguousarray(drawn, np.int32)).to(device)
         if tuple(drawn_t.shape) != (n, T, S):
             raise ValueError("drawn must have shape (n_sites, kmer_len, signals_len)")
-    f32 = dict(dtype=torch.float32, device=device)
+    if dtype not in (torch.float32, torch.float64):
+        raise ValueError("dtype must be torch.float32 or torch.float64")
+    f32 = dict(dtype=dtype, device=device)
     if out is None:
         out = dict(kmer=torch.empty((n, T), **f32), base_means=torch.empty((n, T), **f32),
                    base_stds=torch.empty((n, T), **f32), base_signal_lens=torch.empty((n, T), **f32),
@@ -431,12 +435,13 @@ def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method=
                    read_shift=torch.empty(batch.n_reads, dtype=torch.float64, device=device),
                    read_scale=torch.empty(batch.n_reads, dtype=torch.float64, device=device))
     elif (tuple(out["signals"].shape) != (n, T, S) or out["read_shift"].shape[0] != batch.n_reads
-          or out["signals"].device != device):
+          or out["signals"].device != device or out["signals"].dtype != dtype):
         raise ValueError("out does not match this batch")
     ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
     with torch.cuda.device(device):
         st = torch.cuda.current_stream().cuda_stream
-        rc = L.dsp_extract_features(
+        entry = L.dsp_extract_features if dtype == torch.float32 else L.dsp_extract_features_f64
+        rc = entry(
             device.index, ptr(d["raw"]), C.c_void_p(d["raw_off"].data_ptr()), ptr(d["scaling"]), ptr(d["offset"]),
             batch.n_reads, ptr(d["ev_start"]), ptr(d["ev_len"]), ptr(d["ev_base"]), ptr(site_read), ptr(site_ev), n,
             T, S, 0 if normalize_method == "mad" else 1, 1 if round_stats else 0, ptr(drawn_t), int(seed) & (2 ** 64 - 1),
@@ -445,6 +450,75 @@ def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method=
             ptr(out["signals"]), C.c_void_p(st))
     _native.check(rc, "dsp_extract_features")
     return out
+
+
+def format_features(batch, sites, means, stds, lens, signals, methy_label, nthreads=None):
+    """bytes of the feature-file lines of the given sites (``_features_to_str``, ``:381-395``), written by
+    ``dsp_format_features``.  means/stds/lens (n, T) and signals (n, T, S): float64 host arrays as
+    ``extract_tensors(..., round_stats=True, dtype=torch.float64)`` returns them."""
+    import os
+    n = len(sites)
+    if n == 0:
+        return b""
+    L = _native.lib()
+    arr = [np.ascontiguousarray(a, np.float64) for a in (means, stds, lens, signals)]
+    T, S = arr[3].shape[1], arr[3].shape[2]
+    nb = (T - 1) // 2
+    letters = np.ascontiguousarray(batch.ev_base[sites.site_ev[:, None] + np.arange(-nb, nb + 1)[None, :]])
+    info_text, info_off = sampleinfo_packed(batch, sites, nthreads)
+    info_text = np.ascontiguousarray(info_text)
+    cap = int(info_off[n]) + n * (T * (2 * 26 + 22 + S * 26) + 64)
+    # sizes vary a lot (most values are short): ask first with a typical budget, grow on DSP_ERR_NOMEM
+    budget = int(info_off[n]) + n * (T * (2 * 10 + 4 + S * 10) + 32)
+    p = lambda a: a.ctypes.data
+    used = C.c_int64(0)
+    while True:
+        out = np.empty(min(budget, cap), np.uint8)
+        rc = L.dsp_format_features(p(info_text), p(info_off), p(letters), p(arr[0]), p(arr[1]), p(arr[2]), p(arr[3]),
+                                   int(methy_label), n, T, S, p(out), out.shape[0], C.byref(used),
+                                   int(nthreads or min(16, os.cpu_count() or 1)))
+        if rc == 4 and used.value > out.shape[0]:
+            budget = int(used.value)
+            continue
+        _native.check(rc, "dsp_format_features")
+        return out[:used.value].tobytes()
+
+
+def extract_to_file(args):
+    """``deepsignal_plant extract`` (``extract_features.py:563-633``) for a decoded-reads archive: the
+    feature file the reference writes (same lines, ``_features_to_str``), produced by the device kernels.
+    Returns the number of sites written."""
+    import gzip
+    import os
+    import time
+    start = time.time()
+    if not os.path.exists(args.fast5_dir):
+        raise ValueError("--fast5_dir not set right!")
+    if os.path.isdir(args.fast5_dir):
+        raise ValueError("--fast5_dir is a directory of fast5 files: reading fast5 (h5py) is outside this implementation; "
+                         "decode the reads once into an archive with extract_features.save_reads and pass the .npz")
+    allreads = load_reads(args.fast5_dir)
+    motif_seqs = get_motif_seqs(args.motifs, str(args.is_dna).lower() in ("yes", "true", "t", "1"))
+    chrom2len = get_contig2len(args.reference_path) if args.reference_path else None
+    positions = _read_position_file(args.positions) if args.positions else None
+    regioninfo = parse_region_str(args.region)
+    dev = torch.device("cuda", 0)
+    path = args.write_path + (".gz" if args.gzip and not args.write_path.endswith(".gz") else "")
+    step = max(1, int(args.f5_batch_size))
+    total = 0
+    with (gzip.open(path, "wb") if args.gzip else open(path, "wb")) as wf:
+        for lo in range(0, allreads.n_reads, step):
+            batch = allreads.slice(lo, min(lo + step, allreads.n_reads))
+            sites = find_sites_device(batch, motif_seqs, args.mod_loc, chrom2len, args.seq_len, positions, regioninfo, dev)
+            if len(sites) == 0:
+                continue
+            t = extract_tensors(batch, sites, args.seq_len, args.signal_len, args.normalize_method, True,
+                                seed=total, device=dev, dtype=torch.float64)
+            host = [t[k].cpu().numpy() for k in ("base_means", "base_stds", "base_signal_lens", "signals")]
+            wf.write(format_features(batch, sites, *host, args.methy_label, nthreads=max(1, args.nproc)))
+            total += len(sites)
+    print("[extract] {} sites from {} reads in {:.2f} seconds".format(total, allreads.n_reads, time.time() - start))
+    return total
 
 
 def _extract_features(reads, normalize_method, motif_seqs, methyloc, chrom2len, kmer_len, signals_len,

@@ -234,6 +234,32 @@ int dsp_extract_features(int device,
                          float* kmer, float* base_means, float* base_stds, float* base_signal_lens,
                          float* signals, void* stream);
 
+/* dsp_extract_features_f64: the same call with float64 outputs -- the values the reference holds before
+ * FloatTensor narrows them, needed where they are PRINTED (the feature file of `deepsignal_plant extract`):
+ * all five outputs are double (kmer codes and lens included). */
+int dsp_extract_features_f64(int device,
+                             const int16_t* raw, const int64_t* raw_off, const double* scaling, const double* offset,
+                             int64_t n_reads,
+                             const int64_t* ev_start, const int64_t* ev_len, const uint8_t* ev_base,
+                             const int32_t* site_read, const int64_t* site_ev, int64_t n_sites,
+                             int32_t seq_len, int32_t signal_len, int32_t normalize_method, int32_t round_stats,
+                             const int32_t* drawn, uint64_t seed,
+                             double* read_shift, double* read_scale,
+                             double* kmer, double* base_means, double* base_stds, double* base_signal_lens,
+                             double* signals, void* stream);
+
+/* dsp_format_features: _features_to_str (extract_features.py:381-395) for n sites, HOST pointers:
+ *   sampleinfo \t k_mer \t means \t stds \t lens \t signals \t methy_label \n
+ * info_text / info_off as dsp_format_sampleinfo writes them; kmer_letters (n, seq_len) ASCII; means, stds,
+ * lens (n, seq_len) and signals (n, seq_len, signal_len) as dsp_extract_features_f64 produced them with
+ * round_stats = 1.  Numbers are printed like str(numpy.float64) (shortest round-trip digits, positional in
+ * [1e-4, 1e16), scientific otherwise), lens as integers.  *out_bytes receives the size needed;
+ * DSP_ERR_NOMEM if out_cap is too small. */
+int dsp_format_features(const char* info_text, const int64_t* info_off, const uint8_t* kmer_letters,
+                        const double* means, const double* stds, const double* lens, const double* signals,
+                        int32_t methy_label, int64_t n, int32_t seq_len, int32_t signal_len,
+                        char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads);
+
 /* dsp_find_sites: which bases of a batch of decoded reads are targets --
  * get_refloc_of_methysite_in_motif (utils/process_utils.py:97-112) over every read, then the site filters
  * of _extract_features in its order (extract_features.py:341-352): a margin of (seq_len-1)/2 bases at both

@@ -125,6 +125,26 @@ def test_sampleinfo_native_formatter_and_archive_round_trip(tmp_path):
         ef.parse_region_str("chr1:a-b")
 
 
+@pytest.mark.parametrize("name", EXTRACT_CASES)
+def test_native_feature_line_formatter_reproduces_reference_lines(name):
+    # dsp_format_features on the reference's own float64 values == the lines its _features_to_str wrote
+    z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
+    batch = ef.pack_reads(reads)
+    sites = ef.find_sites(batch, motif_seqs, mod_loc, chrom2len, K)
+    text = ef.format_features(batch, sites, np.around(z["means"], 6), np.around(z["stds"], 6), z["lens"].astype(np.float64),
+                              z["rect"], 1, nthreads=3)
+    assert text.decode().splitlines() == [str(x) for x in z["lines"]]
+    # number spellings: str(numpy.float64) for the cases the fixtures do not contain
+    vals = np.array([0.0, -0.0, 1.0, -1.5, 1e-4, 9.9e-05, 1e-06, 2.5e-05, 123456.789012, 1e15, 1e16, 1.5e16, 12345678.9,
+                     0.1 + 0.2, 1 / 3, 5e-324, 1.7976931348623157e308, 100.0, 0.000123])
+    one = ef.Sites(sites.site_read[:1], sites.site_ev[:1], sites.pos[:1], sites.pos_in_strand[:1])
+    m = np.resize(vals, (1, K))
+    sig = np.resize(vals, (1, K, S))
+    line = ef.format_features(batch, one, m, m, np.full((1, K), 7.0), sig, 0).decode().rstrip("\n").split("\t")
+    assert line[7] == ",".join(str(np.float64(v)) for v in m[0]) and line[9] == ",".join(["7"] * K) and line[11] == "0"
+    assert line[10] == ";".join(",".join(str(np.float64(v)) for v in row) for row in sig[0])
+
+
 def test_host_argument_errors():
     reads = synthetic.make_reads(3, seed=2, mean_bases=60)
     batch = ef.pack_reads(reads)
@@ -424,3 +444,48 @@ def test_gpu_extract_at_scale_is_batching_invariant_and_matches_oracle_sample():
         assert np.array_equal(tw[k][:n].cpu().numpy().view(np.uint32), want[k].view(np.uint32)), k
     sh = short[:n].cpu().numpy()
     assert np.array_equal(tw["signals"][:n].cpu().numpy()[sh], want["signals"][sh])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", EXTRACT_CASES)
+def test_gpu_feature_file_lines_equal_the_reference_bytes(name):
+    # float64 outputs of the kernels + native formatter == what the reference's _features_to_str wrote
+    z, reads, K, S, chrom2len, motif_seqs, mod_loc = load(name)
+    batch = ef.pack_reads(reads)
+    sites = ef.find_sites_device(batch, motif_seqs, mod_loc, chrom2len, K)
+    t = ef.extract_tensors(batch, sites, K, S, normalize_method=method_of(z), round_stats=True, drawn=z["drawn"],
+                           dtype=torch.float64)
+    assert np.array_equal(t["base_means"].cpu().numpy(), np.around(z["means"], 6))      # float64, bit for bit
+    assert np.array_equal(t["base_stds"].cpu().numpy(), np.around(z["stds"], 6))
+    assert np.array_equal(t["signals"].cpu().numpy(), z["rect"])
+    host = [t[k].cpu().numpy() for k in ("base_means", "base_stds", "base_signal_lens", "signals")]
+    text = ef.format_features(batch, sites, *host, 1)
+    assert text.decode().splitlines() == [str(x) for x in z["lines"]]
+
+
+@pytest.mark.gpu
+def test_gpu_extract_cli_writes_the_reference_feature_file_format(tmp_path):
+    import gzip
+    from deepsignal_plant_b200 import cli, feature_io
+    from oracle import features_oracle
+    K, S = 13, 16
+    reads = synthetic.make_reads(40, seed=61, mean_bases=300, long_every=6)
+    arch = str(tmp_path / "reads.npz")
+    ef.save_reads(arch, reads)
+    out = str(tmp_path / "features.tsv")
+    assert cli.main(["extract", "-i", arch, "-o", out, "--motifs", "CG", "--f5_batch_size", "7", "--gzip", "--methy_label", "0"]) == 0
+    lines = gzip.open(out + ".gz", "rt").read().splitlines()
+    feats, _ = eo.extract_features(reads, "mad", eo.get_motif_seqs("CG"), 0, None, K, S, 0, rng=random.Random(0))
+    want = eo.features_to_arrays(feats, round_stats=True)
+    info, kmers, means, stds, lens, sig, labels = features_oracle.read_features(lines)
+    assert len(lines) == len(feats) > 500 and set(labels) == {0}
+    assert info == ["\t".join([f[0], str(f[1]), f[2], str(f[3]), f[4], f[5]]) for f in feats]
+    assert np.array_equal(np.asarray(kmers, np.float32), want["kmer"])
+    assert np.array_equal(np.asarray(means, np.float32), want["base_means"])
+    assert np.array_equal(np.asarray(stds, np.float32), want["base_stds"])
+    assert np.array_equal(np.asarray(lens, np.float32), want["base_signal_lens"])
+    short = want["base_signal_lens"] <= S
+    assert np.array_equal(np.asarray(sig, np.float32)[short], want["signals"][short])
+    # and the file is what this repository's own reader / call_mods take
+    rd = feature_io.FeatureFileReader(out + ".gz", K, S, batch_sites=4096, slots=3, nthreads=2)
+    assert sum(b.n for b in rd) == len(lines)
