@@ -157,7 +157,7 @@ class _MappedArchive:
                     self._arr[name] = None
                     continue
                 n = int(np.prod(shape))
-                self._arr[name] = (np.memmap(path, dtype=dtype, mode="r", offset=f.tell(), shape=shape) if n
+                self._arr[name] = (np.memmap(path, dtype=dtype, mode="c", offset=f.tell(), shape=shape) if n
                                    else np.zeros(shape, dtype))
         self._path = path
 
