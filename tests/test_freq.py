@@ -236,3 +236,36 @@ def test_contig_argument_forms(tmp_path):
     fa = tmp_path / "g.fasta"
     fa.write_text(">chr9 desc\nAC\n>chr2\nGT\n")
     assert cf.parse_contigs_arg(str(fa)) == ["chr9", "chr2"]
+
+
+@pytest.mark.gpu
+def test_gpu_freq_tables_combine_like_the_reference_script(tmp_path):
+    # scripts/combine_call_mods_freq_files.py:25-42 merges per-file tables keyed by (chrom, pos, strand): counts add,
+    # prob sums add (of %.3f-rounded values), rmet is recomputed.  Aggregating all files at once must agree with it:
+    # integer columns exactly, the sums within the rounding of the per-file text.
+    lines = synthetic.make_callmods_records(30000, n_chrom=4, n_pos=700, seed=9)
+    parts = [lines[:9000], lines[9000:21000], lines[21000:]]
+    files = []
+    for i, p in enumerate(parts):
+        f = tmp_path / ("calls%d.tsv" % i)
+        f.write_text("\n".join(p) + "\n")
+        files.append(str(f))
+    combined = {}
+    for f in files:
+        out = tmp_path / "part.freq.txt"
+        cf.write_sitekey2stats(cf.calculate_mods_frequency([f], 0.0), str(out), False, False, False)
+        for line in out.read_text().splitlines():
+            w = line.split("\t")
+            key = (w[0], int(w[1]), w[2])
+            c = combined.setdefault(key, [-1, 0.0, 0.0, 0, 0, 0, 0.0, "-"])
+            c[0] = int(w[3]); c[1] += float(w[4]); c[2] += float(w[5]); c[3] += int(w[6]); c[4] += int(w[7]); c[5] += int(w[8])
+            c[6] = c[3] / float(c[5]); c[7] = w[10]
+    whole = tmp_path / "whole.freq.txt"
+    cf.write_sitekey2stats(cf.calculate_mods_frequency(files, 0.0), str(whole), False, False, False)
+    rows = [l.split("\t") for l in whole.read_text().splitlines()]
+    assert len(rows) == len(combined) > 2000
+    for w in rows:
+        c = combined[(w[0], int(w[1]), w[2])]
+        assert (int(w[6]), int(w[7]), int(w[8])) == (c[3], c[4], c[5])
+        assert abs(float(w[4]) - c[1]) <= 0.0016 and abs(float(w[5]) - c[2]) <= 0.0016
+        assert w[9] == "%.4f" % c[6]
