@@ -61,10 +61,10 @@ def traffic_of_dominant_kernel(batch):
     None when no capture is recorded (profiles/roofline_traffic.json says which run it came from)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if not os.path.exists(p):
-        return None
+        return None, None
     d = json.load(open(p))
-    return {"bytes_per_launch": d["dram_bytes_per_site"] * batch, "unit": "B", "kernel": d["kernel"], "source": d["source"],
-            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_site"] * batch}
+    return d["dram_bytes_per_site"] * batch, {"unit": "B per launch", "kernel": d["kernel"], "source": d["source"],
+                                              "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_site"] * batch}
 
 
 class ClockSampler(threading.Thread):
@@ -288,6 +288,7 @@ def main():
 
     pk = peaks()
     achieved = (flop_rec * args.batch / (kern_ms * 1e-3) / 1e12) if kern_ms > 0 else None
+    traffic = traffic_of_dominant_kernel(args.batch) if headline else (None, None)
     line = {
         "metric": METRIC if headline else METRIC.replace("both_bilstm bn13_sn16", "%s bn%d_sn%d" % (args.module, T_, S_)), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -299,7 +300,7 @@ def main():
                    "l2": "%d distinct input batches cycled (%.0f MB > L2)" % (args.buffers, args.buffers * args.batch * in_bytes_site / 1e6),
                    "parallelism": "site-batch shards, one process per GPU, no collective"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": (achieved / pk["tflops"]) if achieved else None, "traffic": traffic_of_dominant_kernel(args.batch) if headline else None,
+                     "frac": (achieved / pk["tflops"]) if achieved else None, "traffic": traffic[0], "traffic_detail": traffic[1],
                      "kernel": "recurrent BiLSTM layer kernels (%d launches/step, %.3f ms/step)" % (kern_launches, kern_ms),
                      "peak_source": pk["source"], "last_step_kernel_ms": class_ms,
                      "whole_step_frac": value / world * flop_site / 1e12 / pk["tflops"], "flop_per_site": flop_site},
