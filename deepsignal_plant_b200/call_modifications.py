@@ -326,13 +326,18 @@ def call_mods_from_reads(args, model, write, device=0):
         write(feature_io.format_calls(b, probs.cpu().numpy(), labels.cpu().numpy()))
         prof["format"] += tick() - t1
 
+    # Upload, site search and extraction of chunk i+1 run on a side stream: the search has to tell the host how
+    # many sites it found, and on the classifier's stream that read-back would wait for chunk i's whole forward.
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
     lo = lo_r
     while lo < hi_r:
         hi = min(lo + step, hi_r)
         batch = allreads.slice(lo, hi)
         lo = hi
         t1 = tick()
-        sites = ef.find_sites_device(batch, motif_seqs, args.mod_loc, chrom2len, args.seq_len, positions, regioninfo, dev)
+        with torch.cuda.stream(side):
+            sites = ef.find_sites_device(batch, motif_seqs, args.mod_loc, chrom2len, args.seq_len, positions, regioninfo, dev)
         prof["find_sites"] += tick() - t1
         n = len(sites)
         # --f5_batch_size only seeds the chunking: aim at one full model batch of sites per chunk
@@ -340,8 +345,12 @@ def call_mods_from_reads(args, model, write, device=0):
         if n == 0:
             continue
         t1 = tick()
-        t = ef.extract_tensors(batch, sites, args.seq_len, args.signal_len, args.normalize_method, False,
-                               seed=sites_total, device=dev)
+        with torch.cuda.stream(side):
+            t = ef.extract_tensors(batch, sites, args.seq_len, args.signal_len, args.normalize_method, False,
+                                   seed=sites_total, device=dev)
+        main.wait_stream(side)
+        for v in t.values():
+            v.record_stream(main)
         outs = []
         for a in range(0, n, max_batch):                       # the model's workspace holds max_batch sites
             z = min(a + max_batch, n)
