@@ -49,6 +49,30 @@ def get_motif_seqs(motifs, is_dna=True):
     return out
 
 
+_STAGING = {}          # dtype -> [pinned tensor, event of the last copy out of it]
+
+
+def _upload(a, device):
+    """Host array -> device tensor.  Large arrays (views of a memory-mapped archive, typically) go through a
+    reusable page-locked staging buffer: a plain memcpy out of the page cache, then an asynchronous copy at
+    full PCIe rate -- a pageable cudaMemcpy straight from a file mapping runs at about 1 GB/s."""
+    a = np.ascontiguousarray(a)
+    if a.nbytes < (1 << 20):
+        return torch.from_numpy(np.array(a)).to(device)
+    tdtype = torch.from_numpy(np.zeros(0, a.dtype)).dtype
+    slot = _STAGING.get(a.dtype)
+    if slot is None or slot[0].numel() < a.size:
+        slot = _STAGING[a.dtype] = [torch.empty(int(a.size * 1.25), dtype=tdtype).pin_memory(), None]
+    if slot[1] is not None:
+        slot[1].synchronize()                                   # the previous copy out of this buffer has finished
+    np.copyto(slot[0][:a.size].numpy(), a.reshape(-1))
+    with torch.cuda.device(device):
+        out = slot[0][:a.size].to(device, non_blocking=True).reshape(a.shape)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream())
+    return out
+
+
 class ReadBatch:
     """Flat arrays of a batch of decoded reads (host numpy; ``to_device`` uploads them once)."""
 
@@ -118,7 +142,7 @@ class ReadBatch:
 
     def to_device(self, device):
         if self._dev is None or self._dev["device"] != device:
-            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
+            up = lambda a: _upload(a, device)
             self._dev = dict(device=device, raw=up(self.raw), raw_off=up(self.raw_off), scaling=up(self.scaling),
                              offset=up(self.offset), ev_start=up(self.ev_start), ev_len=up(self.ev_len),
                              ev_base=up(self.ev_base), ev_off=up(self.ev_off))
