@@ -1,14 +1,19 @@
 // Feature extraction from decoded re-squiggled reads:
 //   deepsignal_plant/extract_features.py  _rescale_signals (:276-277), _normalize_signals (:179-190),
 //   the per-site body of _extract_features (:343-372) and _get_signals_rect (:232-251).
-// HBM-bound integer/double work, bit-exact against numpy's float64 arithmetic:
-//   read_scale_kernel   one CTA per read: median and MAD of the rescaled samples by a block-wide radix
-//                       select over order-preserving 64-bit keys computed on the fly from the int16
-//                       samples (nothing is materialised; the read is walked 14 times out of L1/L2);
-//   site_features_kernel one thread per (site, base): normalise + round the base's samples on the fly,
-//                       numpy-order pairwise sums for mean/std, the 13 x 16 rectangle (centred zero pad, or
-//                       an ordered subsample -- caller-supplied offsets in parity mode, Philox selection
-//                       sampling otherwise), written straight into the five tensors dsp_forward takes.
+// Integer / float64 work, bit-exact against numpy's arithmetic:
+//   read_scale_kernel    one CTA per read: two passes over the int16 samples (min/max, then a shared-memory
+//                        histogram of the DAC levels); median and MAD are radix-selected over the histogram
+//                        bins, exact because equal DAC values give equal float64 values (reads spanning more
+//                        than 16 384 levels run the same select over the samples);
+//   read_zscore_kernel   normalize_method 'zscore': whole-read np.mean / np.std in numpy's pairwise order, one
+//                        warp per read;
+//   site_features_kernel one warp per site: the site's window of samples is normalised once into shared
+//                        memory, lane j owns base j (len, np.mean, np.std in numpy's pairwise order, ordered
+//                        subsample -- caller-supplied offsets in parity mode, Philox selection sampling
+//                        otherwise), all lanes emit the 13 x 16 rectangle; float32 outputs are the five tensors
+//                        dsp_forward takes, float64 outputs what the feature file prints;
+//   dsp_find_sites       motif search + the reference's site filters as one DeviceSelect over the event table.
 // Every double operation is an explicit round-to-nearest intrinsic so that nvcc cannot contract a
 // multiply and an add into an FMA (numpy does not).
 #include "common.cuh"
