@@ -5,8 +5,9 @@
     python tools/fast5_to_archive.py -i fast5_dir -o reads.npz [--corrected_group RawGenomeCorrected_000]
                                      [--basecall_subgroup BaseCalled_template] [--recursively yes]
 
-NEEDS h5py, which this build image does not have: the script is NOT exercised by the test-suite here.  It
-reads exactly the fields the reference's three accessors read (deepsignal_plant/extract_features.py):
+NEEDS h5py, which this build image does not have: tests/test_fast5_converter.py exercises it against a
+stand-in module (and, in the build container, runs the reference's own accessors on the same stand-in); it
+has not been run on real fast5 files here.  It reads exactly the fields the reference's three accessors read (deepsignal_plant/extract_features.py):
   * `_get_alignment_info_from_fast5` (:150-176) / `_get_alignment_attrs_of_each_strand` (:94-129):
     Analyses/<corrected_group>/<basecall_subgroup>/Alignment attrs mapped_strand, mapped_chrom, mapped_start;
     strand 't' for a template subgroup, 'c' otherwise; reads without an Alignment group are skipped (:166-173);
@@ -40,11 +41,10 @@ def decode_fast5(path, corrected_group, basecall_subgroup):
         read = f["Raw/Reads/" + first]
         events = f[strand_path + "/Events"]
         rel = events.attrs["read_start_rel_to_raw"]
-        try:
-            ch = f["UniqueGlobalKey/channel_id"].attrs
-            scaling, offset = np.float64(ch["range"]) / np.float64(ch["digitisation"]), np.float64(ch["offset"])
-        except (KeyError, IOError):
-            scaling, offset = None, None
+        # a file without channel info raises KeyError here, which makes it an unreadable file below -- what happens in
+        # the reference too (_get_scaling_of_a_read only catches IOError; _extract_features counts the read as an error)
+        ch = f["UniqueGlobalKey/channel_id"].attrs
+        scaling, offset = np.float64(ch["range"]) / np.float64(ch["digitisation"]), np.float64(ch["offset"])
         return dict(readname=_text(read.attrs["read_id"]), strand="t" if strand_path.endswith("template") else "c",
                     alignstrand=_text(attrs["mapped_strand"]), chrom=_text(attrs["mapped_chrom"]),
                     chrom_start=int(attrs["mapped_start"]), raw=np.asarray(read["Signal"][()]),
