@@ -11,6 +11,7 @@
 //                       float32 renormalise / round(6), str() of a numpy float32 (shortest
 //                       round-trip digits, scientific below 1e-4), argmax label, centre 5-mer.
 #include "common.cuh"
+#include <algorithm>
 #include <atomic>
 #include <charconv>
 #include <cmath>
@@ -131,8 +132,8 @@ int parse_line(const ParseJob& j, int64_t i) {
 }
 
 template <typename F>
-void parallel_for(int64_t n, int nthreads, F&& body) {
-    if (nthreads <= 1 || n < 256) { body(0, n); return; }
+void parallel_for(int64_t n, int nthreads, F&& body, int64_t serial_below = 256) {
+    if (nthreads <= 1 || n < serial_below) { body(0, n); return; }
     std::vector<std::thread> th;
     const int64_t per = (n + nthreads - 1) / nthreads;
     for (int t = 0; t < nthreads; ++t) {
@@ -183,6 +184,30 @@ int format_f32(float x, char* out) {
 // 1e-4 <= |x| < 1e16, scientific otherwise, at least one digit after a positional point, exponent with at
 // least two digits.  (What _features_to_str prints for means, stds and signals, extract_features.py:388-392.)
 int format_f64(double x, char* out) {
+    // fast path for what the feature file is made of: a value that IS k / 1e6 (np.around(., 6)) with
+    // 1e-4 <= |x| and at most 15 significant digits prints as that decimal, trailing zeros dropped
+    {
+        const double ax = std::fabs(x);
+        if (ax >= 1e-4 && ax < 1e9) {
+            const double kd = std::nearbyint(ax * 1e6);
+            if (kd / 1e6 == ax) {
+                char* o = out;
+                if (std::signbit(x)) *o++ = '-';
+                unsigned long long k = (unsigned long long)kd;
+                const unsigned long long ip = k / 1000000ull;
+                unsigned fp = (unsigned)(k % 1000000ull);
+                o = std::to_chars(o, o + 24, ip).ptr;
+                *o++ = '.';
+                if (fp == 0) { *o++ = '0'; return (int)(o - out); }
+                char d[6];
+                for (int i = 5; i >= 0; --i) { d[i] = (char)('0' + fp % 10); fp /= 10; }
+                int nd = 6;
+                while (d[nd - 1] == '0') --nd;
+                memcpy(o, d, (size_t)nd);
+                return (int)(o + nd - out);
+            }
+        }
+    }
     if (std::isnan(x)) { memcpy(out, "nan", 3); return 3; }
     if (std::isinf(x)) { if (x < 0) { memcpy(out, "-inf", 4); return 4; } memcpy(out, "inf", 3); return 3; }
     char* o = out;
@@ -407,20 +432,34 @@ int dsp_format_features(const char* info_text, const int64_t* info_off, const ui
         *o++ = '\n';
         return o;
     };
-    std::vector<int64_t> off((size_t)n + 1);
-    off[0] = 0;
-    parallel_for(n, nthreads, [&](int64_t a, int64_t b) {
-        std::vector<char> scratch;
-        for (int64_t i = a; i < b; ++i) {
-            scratch.resize(worst + (size_t)(info_off[i + 1] - info_off[i]));
-            off[i + 1] = one(i, scratch.data()) - scratch.data();
+    // one formatting pass: every worker appends the lines of its contiguous range to its own buffer, the
+    // buffers are then copied into place in range order
+    struct Part { int64_t a = 0, b = 0; std::vector<char> text; };
+    const int64_t nparts = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)std::max(1, nthreads) * 4));
+    std::vector<Part> parts((size_t)nparts);
+    for (int64_t q = 0; q < nparts; ++q) { parts[q].a = n * q / nparts; parts[q].b = n * (q + 1) / nparts; }
+    parallel_for(nparts, nthreads, [&](int64_t qa, int64_t qb) {
+        for (int64_t q = qa; q < qb; ++q) {
+            Part& pt = parts[q];
+            size_t used = 0;
+            pt.text.resize((size_t)(pt.b - pt.a) * (worst / 3) + worst + 4096);
+            for (int64_t i = pt.a; i < pt.b; ++i) {
+                const size_t need = worst + (size_t)(info_off[i + 1] - info_off[i]);
+                if (pt.text.size() - used < need) pt.text.resize(pt.text.size() * 2 + need);
+                used = (size_t)(one(i, pt.text.data() + used) - pt.text.data());
+            }
+            pt.text.resize(used);
         }
-    });
-    for (int64_t i = 0; i < n; ++i) off[i + 1] += off[i];
-    *out_bytes = off[n];
-    DSP_REQUIRE(off[n] <= out_cap, DSP_ERR_NOMEM, "dsp_format_features: output needs %lld bytes, buffer has %lld",
-                (long long)off[n], (long long)out_cap);
-    parallel_for(n, nthreads, [&](int64_t a, int64_t b) { for (int64_t i = a; i < b; ++i) one(i, out + off[i]); });
+    }, 2);
+    std::vector<int64_t> off((size_t)nparts + 1);
+    off[0] = 0;
+    for (int64_t q = 0; q < nparts; ++q) off[q + 1] = off[q] + (int64_t)parts[q].text.size();
+    *out_bytes = off[nparts];
+    DSP_REQUIRE(off[nparts] <= out_cap, DSP_ERR_NOMEM, "dsp_format_features: output needs %lld bytes, buffer has %lld",
+                (long long)off[nparts], (long long)out_cap);
+    parallel_for(nparts, nthreads, [&](int64_t qa, int64_t qb) {
+        for (int64_t q = qa; q < qb; ++q) memcpy(out + off[q], parts[q].text.data(), parts[q].text.size());
+    }, 2);
     return DSP_OK;
 }
 

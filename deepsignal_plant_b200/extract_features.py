@@ -476,14 +476,14 @@ def extract_tensors(batch, sites, kmer_len=13, signals_len=16, normalize_method=
     return out
 
 
-def format_features(batch, sites, means, stds, lens, signals, methy_label, nthreads=None):
+def format_features(batch, sites, means, stds, lens, signals, methy_label, nthreads=None, as_array=False):
     """bytes of the feature-file lines of the given sites (``_features_to_str``, ``:381-395``), written by
     ``dsp_format_features``.  means/stds/lens (n, T) and signals (n, T, S): float64 host arrays as
     ``extract_tensors(..., round_stats=True, dtype=torch.float64)`` returns them."""
     import os
     n = len(sites)
     if n == 0:
-        return b""
+        return np.zeros(0, np.uint8) if as_array else b""
     L = _native.lib()
     arr = [np.ascontiguousarray(a, np.float64) for a in (means, stds, lens, signals)]
     T, S = arr[3].shape[1], arr[3].shape[2]
@@ -505,7 +505,7 @@ def format_features(batch, sites, means, stds, lens, signals, methy_label, nthre
             budget = int(used.value)
             continue
         _native.check(rc, "dsp_format_features")
-        return out[:used.value].tobytes()
+        return out[:used.value] if as_array else out[:used.value].tobytes()
 
 
 def extract_to_file(args):
@@ -530,6 +530,7 @@ def extract_to_file(args):
     path = args.write_path + (".gz" if args.gzip and not args.write_path.endswith(".gz") else "")
     step = max(1, int(args.f5_batch_size))
     total = 0
+    pinned = {}
     with (gzip.open(path, "wb") if args.gzip else open(path, "wb")) as wf:
         for lo in range(0, allreads.n_reads, step):
             batch = allreads.slice(lo, min(lo + step, allreads.n_reads))
@@ -538,8 +539,18 @@ def extract_to_file(args):
                 continue
             t = extract_tensors(batch, sites, args.seq_len, args.signal_len, args.normalize_method, True,
                                 seed=total, device=dev, dtype=torch.float64)
-            host = [t[k].cpu().numpy() for k in ("base_means", "base_stds", "base_signal_lens", "signals")]
-            wf.write(format_features(batch, sites, *host, args.methy_label, nthreads=max(1, args.nproc)))
+            host = []
+            for k in ("base_means", "base_stds", "base_signal_lens", "signals"):     # page-locked landing buffers, reused
+                need = t[k].numel()
+                if k not in pinned or pinned[k].numel() < need:
+                    pinned[k] = torch.empty(int(need * 1.25), dtype=torch.float64).pin_memory()
+                dst = pinned[k][:need].view(t[k].shape)
+                dst.copy_(t[k], non_blocking=True)
+                host.append(dst)
+            torch.cuda.current_stream(dev).synchronize()
+            text = format_features(batch, sites, *[h.numpy() for h in host], args.methy_label, nthreads=max(1, args.nproc),
+                                   as_array=True)
+            wf.write(memoryview(text))
             total += len(sites)
     print("[extract] {} sites from {} reads in {:.2f} seconds".format(total, allreads.n_reads, time.time() - start))
     return total

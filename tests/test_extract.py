@@ -143,6 +143,20 @@ def test_native_feature_line_formatter_reproduces_reference_lines(name):
     line = ef.format_features(batch, one, m, m, np.full((1, K), 7.0), sig, 0).decode().rstrip("\n").split("\t")
     assert line[7] == ",".join(str(np.float64(v)) for v in m[0]) and line[9] == ",".join(["7"] * K) and line[11] == "0"
     assert line[10] == ";".join(",".join(str(np.float64(v)) for v in row) for row in sig[0])
+    # randomised: 6-decimal values of every magnitude (the fast path) and raw doubles (shortest round-trip digits)
+    rng = np.random.default_rng(3)
+    n = 400
+    many = ef.Sites(np.resize(sites.site_read, n), np.resize(sites.site_ev, n), np.resize(sites.pos, n), np.resize(sites.pos_in_strand, n))
+    mag = 10.0 ** rng.integers(-7, 9, (n, K, S))
+    sig = np.around(rng.normal(0, 1, (n, K, S)) * mag, 6)
+    raw = rng.normal(0, 1, (n, K)) * 10.0 ** rng.integers(-12, 18, (n, K))
+    lines = ef.format_features(batch, many, raw, np.around(raw, 6), np.full((n, K), 3.0), sig, 1, nthreads=4).decode().splitlines()
+    assert len(lines) == n
+    for i in (0, 1, 57, 199, 398, 399):
+        w = lines[i].split("\t")
+        assert w[7] == ",".join(str(v) for v in raw[i]) and w[8] == ",".join(str(v) for v in np.around(raw[i], 6))
+        assert w[10] == ";".join(",".join(str(v) for v in row) for row in sig[i])
+    assert "\n".join(lines) + "\n" == ef.format_features(batch, many, raw, np.around(raw, 6), np.full((n, K), 3.0), sig, 1, nthreads=1).decode()
 
 
 def test_host_argument_errors():

@@ -26,8 +26,9 @@ def main():
     ap.add_argument("--nproc", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--archive", action="store_true", help="input is a decoded-reads .npz (extract_features.save_reads)")
     ap.add_argument("--reads", type=int, default=2000)
+    ap.add_argument("--extract", action="store_true", help="time `extract` (archive -> the reference's feature file) instead")
     a = ap.parse_args()
-    if a.archive:
+    if a.archive or a.extract:
         return archive(a)
     base_n = 8192
     feats = synthetic.make_features(base_n, 13, 16, seed=1)
@@ -66,12 +67,16 @@ def archive(a):
         torch.manual_seed(1234)
         torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
         argv = ["call_mods", "-i", path, "-m", ckpt, "-o", out, "--motifs", "CG", "--f5_batch_size", "130"]
+        if a.extract:
+            argv = ["extract", "-i", path, "-o", out, "--motifs", "CG", "--f5_batch_size", "130", "--nproc", str(a.nproc)]
         cli.main(argv)
         t0 = time.perf_counter()
         cli.main(argv)
         dt = time.perf_counter() - t0
         nout = sum(1 for _ in open(out, "rb"))
-        print(json.dumps({"metric": "call_mods command line, decoded-reads archive -> calls file (sites/s, wall clock incl. archive and model load)",
+        what = ("extract command line, decoded-reads archive -> feature file (sites/s, wall clock)" if a.extract else
+                "call_mods command line, decoded-reads archive -> calls file (sites/s, wall clock incl. archive and model load)")
+        print(json.dumps({"metric": what,
                           "reads": a.reads, "sites": nout, "seconds": dt, "value": nout / dt, "unit": "sites/s",
                           "input_bytes": os.path.getsize(path), "output_bytes": os.path.getsize(out)}))
 
