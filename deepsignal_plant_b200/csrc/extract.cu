@@ -642,10 +642,10 @@ int extract_features_impl(int device, bool f64,
         DSP_CUDA(cudaGetLastError());
     } else if (n_reads > 0) {
         const int64_t grid = n_reads < (int64_t)n_sm * 3 ? n_reads : (int64_t)n_sm * 3;   // 3 CTAs of 72 KB per SM
-        static bool attr_set = false;
-        if (!attr_set) {
+        static int attr_device = -1;                   // function attributes are per device
+        if (attr_device != device) {
             DSP_CUDA(cudaFuncSetAttribute(read_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_BINS * (int)sizeof(int)));
-            attr_set = true;
+            attr_device = device;
         }
         read_scale_kernel<<<(unsigned)grid, SEL_THREADS, HIST_BINS * sizeof(int), st>>>(raw, raw_off, scaling, offset, n_reads, read_shift, read_scale);
         DSP_CUDA(cudaGetLastError());
@@ -660,6 +660,8 @@ int extract_features_impl(int device, bool f64,
         p.kmer = kmer; p.means = base_means; p.stds = base_stds; p.lens = base_signal_lens; p.signals = signals;
         const size_t smem = site_smem_per_warp(seq_len, signal_len) * SITE_WARPS;
         static size_t smem_allowed[2] = {0, 0};
+        static int smem_device = -1;
+        if (smem_device != device) { smem_allowed[0] = smem_allowed[1] = 0; smem_device = device; }
         auto kern = f64 ? site_features_kernel<double> : site_features_kernel<float>;
         if (smem > smem_allowed[f64]) {
             DSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
