@@ -8,8 +8,8 @@
 // STABLE radix sort on the key (equal keys keep file order) and each key's run is replayed
 // sequentially by one thread -- bit-identical sums to the reference's Python loop.
 //
-// HBM-bound integer/byte work: callable records are filtered and packed into aligned 32-byte structs in
-// one pass (file order kept), the sort key is the site key with its never-set bits squeezed out (order
+// HBM-bound integer/byte work: callable records are compacted (file order kept) and packed into aligned
+// 32-byte structs, the sort key is the site key with its never-set bits squeezed out (order
 // preserving; 32-bit keys when they fit), one stable radix sort of (key, position) pairs on exactly the bits
 // in use, run-length encode, replay (one 32-byte sector per record), optional re-order by first appearance.
 #include "common.cuh"
@@ -60,14 +60,11 @@ struct Scratch {
 // sorted position costs one sector per record instead of three scattered ones.
 struct __align__(32) Rec { uint64_t key; double p0, p1; uint32_t idx; int32_t label; };
 
-struct LoadRec {
-    const uint64_t* key; const double* p0; const double* p1; const int32_t* label;
-    __device__ __forceinline__ Rec operator()(uint32_t i) const { Rec r; r.key = key[i]; r.p0 = p0[i]; r.p1 = p1[i]; r.idx = i; r.label = label[i]; return r; }
-};
-struct Callable {
-    double prob_cf;
-    __device__ __forceinline__ bool operator()(const Rec& r) const { return !(fabs(r.p0 - r.p1) < prob_cf); }   // txt_formater.py:23-26
-};
+__global__ void callable_flags_kernel(const double* __restrict__ p0, const double* __restrict__ p1, int64_t n,
+                                      double prob_cf, uint8_t* __restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = !(fabs(p0[i] - p1[i]) < prob_cf);     // txt_formater.py:23-26
+}
 
 // Which key bits are ever set (bitwise OR of all keys): the sort key is the key with every never-set bit
 // squeezed out (an order-preserving "parallel bit extract"), which for chrom<<40|pos keys turns a 43-bit sort
@@ -98,10 +95,19 @@ __global__ void key_bits_kernel(const uint64_t* __restrict__ key, int64_t n, uns
     if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicOr(out, ((unsigned long long)hi << 32) | lo);
 }
 
+// Callable record c (c-th in file order, original index idx[c]) -> its packed Rec, its squeezed sort key and its
+// position.  idx is increasing, so the four input streams are read almost sequentially.
 template <typename K>
-__global__ void sort_keys_kernel(const Rec* __restrict__ rec, int64_t m, BitRuns runs, K* __restrict__ out, uint32_t* __restrict__ pos) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m) { out[i] = (K)runs.squeeze(rec[i].key); pos[i] = (uint32_t)i; }
+__global__ void pack_kernel(const uint32_t* __restrict__ idx, int64_t m, const uint64_t* __restrict__ key,
+                            const double* __restrict__ p0, const double* __restrict__ p1, const int32_t* __restrict__ label,
+                            BitRuns runs, Rec* __restrict__ rec, K* __restrict__ kc, uint32_t* __restrict__ pc) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const uint32_t i = idx[c];
+    Rec r; r.key = key[i]; r.p0 = p0[i]; r.p1 = p1[i]; r.idx = i; r.label = label[i];
+    rec[c] = r;
+    kc[c] = (K)runs.squeeze(r.key);
+    pc[c] = (uint32_t)c;
 }
 
 // one thread per site: sequential float64 replay of its records in file order
@@ -157,7 +163,8 @@ inline unsigned blocks(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 // Steps 2-5 on squeezed sort keys of type K (32-bit when the keys in use fit, else 64-bit).
 template <typename K>
-int aggregate_sorted(Scratch& sc, cudaStream_t st, const Rec* rec, int64_t m, const BitRuns& runs, int sort_by_key,
+int aggregate_sorted(Scratch& sc, cudaStream_t st, const uint32_t* idx, int64_t m, const uint64_t* key, const double* p0,
+                     const double* p1, const int32_t* label, const BitRuns& runs, int sort_by_key,
                      void* tmp, size_t tmp_cap,
                      uint64_t* out_key, int64_t* out_first, double* out_p0, double* out_p1,
                      int32_t* out_met, int32_t* out_unmet, int32_t* out_cov, int64_t* n_sites_host) {
@@ -169,9 +176,9 @@ int aggregate_sorted(Scratch& sc, cudaStream_t st, const Rec* rec, int64_t m, co
         return sc.alloc((uint8_t**)&tmp, tmp_cap);
     };
     // 2. stable sort of (squeezed key, position in rec) on the bits in use: equal keys keep file order
-    K *kc, *ks; uint32_t *pc, *ps;
-    if ((rc = sc.alloc(&kc, m)) || (rc = sc.alloc(&ks, m)) || (rc = sc.alloc(&pc, m)) || (rc = sc.alloc(&ps, m))) return rc;
-    sort_keys_kernel<K><<<blocks(m), 256, 0, st>>>(rec, m, runs, kc, pc);
+    K *kc, *ks; uint32_t *pc, *ps; Rec* rec;
+    if ((rc = sc.alloc(&rec, m)) || (rc = sc.alloc(&kc, m)) || (rc = sc.alloc(&ks, m)) || (rc = sc.alloc(&pc, m)) || (rc = sc.alloc(&ps, m))) return rc;
+    pack_kernel<K><<<blocks(m), 256, 0, st>>>(idx, m, key, p0, p1, label, runs, rec, kc, pc);
     DSP_CUDA(cudaGetLastError());
     DSP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kc, ks, pc, ps, (int)m, 0, runs.bits, st));
     if ((rc = ensure_tmp(tmp_bytes))) return rc;
@@ -255,16 +262,17 @@ extern "C" int dsp_freq_aggregate(int device, const uint64_t* key, const double*
     key_bits_kernel<<<148 * 8, 256, 0, st>>>(key, n, d_bits);
     DSP_CUDA(cudaGetLastError());
 
-    // 1. callable filter + pack: callable records, in file order, as 32-byte Rec
-    Rec* rec; int64_t* d_m;
-    if ((rc = sc.alloc(&rec, n)) || (rc = sc.alloc(&d_m, 2))) return rc;
-    cub::CountingInputIterator<uint32_t> counting(0);
-    cub::TransformInputIterator<Rec, LoadRec, cub::CountingInputIterator<uint32_t>> records(counting, LoadRec{key, p0, p1, label});
+    // 1. callable filter -> compacted record indices (file order preserved)
+    uint8_t* flag; uint32_t* idx; int64_t* d_m;
+    if ((rc = sc.alloc(&flag, n)) || (rc = sc.alloc(&idx, n)) || (rc = sc.alloc(&d_m, 2))) return rc;
+    callable_flags_kernel<<<blocks(n), 256, 0, st>>>(p0, p1, n, prob_cf, flag);
+    DSP_CUDA(cudaGetLastError());
     size_t tmp_bytes = 0;
-    DSP_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, records, rec, d_m, (int)n, Callable{prob_cf}, st));
+    cub::CountingInputIterator<uint32_t> counting(0);
+    DSP_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, counting, flag, idx, d_m, (int)n, st));
     void* tmp; size_t tmp_cap = tmp_bytes;
     if ((rc = sc.alloc((uint8_t**)&tmp, tmp_cap))) return rc;
-    DSP_CUDA(cub::DeviceSelect::If(tmp, tmp_bytes, records, rec, d_m, (int)n, Callable{prob_cf}, st));
+    DSP_CUDA(cub::DeviceSelect::Flagged(tmp, tmp_bytes, counting, flag, idx, d_m, (int)n, st));
     int64_t m = 0;
     unsigned long long bits_used = 0;
     DSP_CUDA(cudaMemcpyAsync(&m, d_m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -291,8 +299,8 @@ extern "C" int dsp_freq_aggregate(int device, const uint64_t* key, const double*
         runs.bits = out;
     }
     return runs.bits <= 32
-        ? aggregate_sorted<uint32_t>(sc, st, rec, m, runs, sort_by_key, tmp, tmp_cap, out_key, out_first, out_p0, out_p1, out_met, out_unmet, out_cov, n_sites_host)
-        : aggregate_sorted<uint64_t>(sc, st, rec, m, runs, sort_by_key, tmp, tmp_cap, out_key, out_first, out_p0, out_p1, out_met, out_unmet, out_cov, n_sites_host);
+        ? aggregate_sorted<uint32_t>(sc, st, idx, m, key, p0, p1, label, runs, sort_by_key, tmp, tmp_cap, out_key, out_first, out_p0, out_p1, out_met, out_unmet, out_cov, n_sites_host)
+        : aggregate_sorted<uint64_t>(sc, st, idx, m, key, p0, p1, label, runs, sort_by_key, tmp, tmp_cap, out_key, out_first, out_p0, out_p1, out_met, out_unmet, out_cov, n_sites_host);
 }
 
 extern "C" int dsp_freq_release_cache(void) {
