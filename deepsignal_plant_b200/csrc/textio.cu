@@ -92,6 +92,43 @@ bool split_exact(const char* b, const char* e, char sep, int count, F&& each) {
     return true;
 }
 
+// `count` floating-point values separated by `sep` filling [b, e) exactly, tokenised and converted in one
+// forward scan: the common spelling -- [-]digits[.digits], at most 15 significant digits, which is what
+// `extract` writes -- is an exact integer divided by an exact power of ten (one correctly rounded operation,
+// like parse_double's fast path); anything else in a field goes through parse_double on that field.
+template <typename Store>
+bool parse_float_list(const char* b, const char* e, char sep, int count, Store&& store) {
+    static const double P10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+    const char* p = b;
+    for (int i = 0; i < count; ++i) {
+        const char* q = p;
+        bool neg = false;
+        if (q < e && *q == '-') { neg = true; ++q; }
+        unsigned long long mant = 0;
+        int nd = 0, frac = -1;
+        for (; q < e; ++q) {
+            const unsigned c = (unsigned)(*q - '0');
+            if (c <= 9) { mant = mant * 10 + c; ++nd; if (frac >= 0) ++frac; }
+            else if (*q == '.' && frac < 0) frac = 0;
+            else break;
+        }
+        double v;
+        if ((q == e || *q == sep) && nd >= 1 && nd <= 15) {
+            v = (double)mant / P10[frac < 0 ? 0 : frac];
+            if (neg) v = -v;
+        } else {
+            const char* s = (const char*)memchr(p, sep, (size_t)(e - p));
+            if (s == nullptr) s = e;
+            if (!parse_double(p, s, &v)) return false;
+            q = s;
+        }
+        if (i + 1 < count) { if (q == e) return false; p = q + 1; }      // too few fields
+        else if (q != e) return false;                                   // too many fields
+        store(i, v);
+    }
+    return true;
+}
+
 struct ParseJob {
     const char* text; const int64_t* begin; const int64_t* end; int T, S;
     float *kmer, *means, *stds, *lens, *signals; int32_t* labels; int32_t* info_len;
@@ -104,7 +141,12 @@ int parse_line(const ParseJob& j, int64_t i) {
     const char* f[13];
     f[0] = b;
     int nf = 1;
-    for (const char* p = b; p < e && nf <= 12; ++p) if (*p == '\t') f[nf++] = p + 1;
+    for (const char* p = b; nf <= 12;) {                       // 12 columns = 11 tabs; a 12th tab is an error
+        const char* t = (const char*)memchr(p, '\t', (size_t)(e - p));
+        if (t == nullptr) break;
+        f[nf++] = t + 1;
+        p = t + 1;
+    }
     if (nf != 12) return 13;
     f[12] = e + 1;
     const int T = j.T, S = j.S;
@@ -115,17 +157,13 @@ int parse_line(const ParseJob& j, int64_t i) {
         if (code < 0) return 7;
         j.kmer[i * T + t] = (float)code;
     }
-    double d;
-    if (!split_exact(f[7], f[8] - 1, ',', T, [&](int t, const char* x, const char* y) {
-            if (!parse_double(x, y, &d)) return false; j.means[i * T + t] = (float)d; return true; })) return 8;
-    if (!split_exact(f[8], f[9] - 1, ',', T, [&](int t, const char* x, const char* y) {
-            if (!parse_double(x, y, &d)) return false; j.stds[i * T + t] = (float)d; return true; })) return 9;
+    if (!parse_float_list(f[7], f[8] - 1, ',', T, [&](int t, double d) { j.means[i * T + t] = (float)d; })) return 8;
+    if (!parse_float_list(f[8], f[9] - 1, ',', T, [&](int t, double d) { j.stds[i * T + t] = (float)d; })) return 9;
     long long v;
     if (!split_exact(f[9], f[10] - 1, ',', T, [&](int t, const char* x, const char* y) {
             if (!parse_int(x, y, &v)) return false; j.lens[i * T + t] = (float)v; return true; })) return 10;
     if (!split_exact(f[10], f[11] - 1, ';', T, [&](int t, const char* x, const char* y) {
-            return split_exact(x, y, ',', S, [&](int s, const char* p, const char* q) {
-                if (!parse_double(p, q, &d)) return false; j.signals[(i * T + t) * S + s] = (float)d; return true; }); })) return 11;
+            return parse_float_list(x, y, ',', S, [&](int s, double d) { j.signals[(i * T + t) * S + s] = (float)d; }); })) return 11;
     if (!parse_int(f[11], e, &v)) return 12;
     j.labels[i] = (int32_t)v;
     return 0;

@@ -125,8 +125,73 @@ class FeatureFileReader:
             self._slots[i] = _Slot(self.batch_sites, self.T, self.S, self.pinned)
         return self._slots[i]
 
+    def _parse(self, L, s, ptr, nbytes, is_final):
+        """One ``dsp_parse_features`` call into slot ``s`` -> (sites, bytes consumed)."""
+        n, used = C.c_int64(0), C.c_int64(0)
+        while True:
+            rc = L.dsp_parse_features(
+                ptr, nbytes, int(is_final), self.T, self.S, self.batch_sites,
+                s.kmer.data_ptr(), s.means.data_ptr(), s.stds.data_ptr(), s.lens.data_ptr(), s.signals.data_ptr(),
+                s.labels.data_ptr(), s.info_text.ctypes.data, s.info_text.size, s.info_off.ctypes.data,
+                C.byref(n), C.byref(used), self.nthreads)
+            if rc == 4 and s.info_text.size < nbytes:          # DSP_ERR_NOMEM: unusually long sample-info columns
+                s.info_text = np.empty(min(nbytes, s.info_text.size * 4), np.uint8)
+                continue
+            _native.check(rc, "dsp_parse_features(%s)" % self.path)
+            return int(n.value), int(used.value)
+
+    def _batch(self, s, n, k):
+        b = FeatureBatch()
+        b.n, b.seq_len, b.slot = n, self.T, k % self.nslots
+        b.kmer, b.base_means, b.base_stds, b.base_signal_lens = s.kmer[:n], s.means[:n], s.stds[:n], s.lens[:n]
+        b.signals, b.labels = s.signals[:n], s.labels[:n]
+        b.info_text, b.info_off = s.info_text, s.info_off
+        return b
+
+    def _iter_mapped(self, L):
+        """Plain files are parsed in place from a read-only mapping: no read() copy, and the page-cache
+        faults are taken by the parser's worker threads instead of one reading thread."""
+        import mmap
+        with open(self.path, "rb") as f:
+            size = os.fstat(f.fileno()).st_size
+            start, end = shard_bounds(f, *self.byte_range) if self.byte_range is not None else (0, size)
+            if end <= start:
+                return
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            view = np.frombuffer(mm, np.uint8)
+            base = view.ctypes.data
+            est_line = 4 * self.T * 10 + self.T * self.S * 10       # refined after the first block
+            pos, k = start, 0
+            while pos < end:
+                want = min(int(est_line * self.batch_sites * 1.05) + (1 << 16), end - pos)
+                final = pos + want == end
+                if final and bytes(view[pos:min(pos + 4096, end)]).isspace() and bytes(view[pos:end]).isspace():
+                    return
+                s = self._slot(k % self.nslots)
+                n, used = self._parse(L, s, base + pos, want, final)
+                if n == 0:
+                    if final:
+                        return
+                    est_line *= 2                        # a line longer than the whole block: look further
+                    continue
+                pos += used
+                est_line = max(64, used // n)
+                self.sites_read += n
+                k += 1
+                yield self._batch(s, n, k - 1)
+        finally:
+            del view
+            try:
+                mm.close()
+            except BufferError:                          # a caller still holds a view; the mapping goes with it
+                pass
+
     def __iter__(self):
         L = _native.lib()
+        if not self.path.endswith(".gz"):
+            yield from self._iter_mapped(L)
+            return
         f = gzip.open(self.path, "rb") if self.path.endswith(".gz") else open(self.path, "rb")
         remaining = None
         with f:
