@@ -96,14 +96,50 @@ bool split_exact(const char* b, const char* e, char sep, int count, F&& each) {
 // forward scan: the common spelling -- [-]digits[.digits], at most 15 significant digits, which is what
 // `extract` writes -- is an exact integer divided by an exact power of ten (one correctly rounded operation,
 // like parse_double's fast path); anything else in a field goes through parse_double on that field.
+// value of up to eight ASCII digits held in the TOP bytes of y (first digit in the lowest of them), '0' already
+// subtracted, lower bytes zero: the usual three multiply-and-shift steps (pairs, quads, all eight)
+inline uint32_t eight_digits(uint64_t y) {
+    y = (y * 10) + (y >> 8);
+    return (uint32_t)((((y & 0x000000FF000000FFull) * 0x000F424000000064ull) +
+                       (((y >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32);
+}
+
 template <typename Store>
 bool parse_float_list(const char* b, const char* e, char sep, int count, Store&& store) {
     static const double P10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+    static const unsigned long long P10I[8] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull};
     const char* p = b;
     for (int i = 0; i < count; ++i) {
         const char* q = p;
         bool neg = false;
         if (q < e && *q == '-') { neg = true; ++q; }
+        // the spelling `extract` writes, [-]d+.d{0,7} followed by the separator, with the fraction taken eight
+        // bytes at a time (needs eight readable bytes after the point, i.e. not the last values of the list)
+        {
+            const char* r = q;
+            unsigned long long ip = 0;
+            int ni = 0;
+            for (; r < e && (unsigned)(*r - '0') <= 9 && ni < 8; ++r, ++ni) ip = ip * 10 + (unsigned)(*r - '0');
+            if (ni >= 1 && ni <= 7 && r + 9 <= e && *r == '.') {
+                uint64_t x;
+                memcpy(&x, r + 1, 8);
+                const uint64_t ge0 = (x | 0x8080808080808080ull) - 0x3030303030303030ull;      // high bit: byte >= '0'
+                const uint64_t nondigit = (~ge0 | (x + 0x4646464646464646ull) | x) & 0x8080808080808080ull;
+                if (nondigit) {
+                    const int n = __builtin_ctzll(nondigit) >> 3;                             // fraction digits, 0..7
+                    if (r[1 + n] == sep) {
+                        const int sh = 8 * (8 - n);
+                        const unsigned long long frac = n ? eight_digits((x << sh) - (0x3030303030303030ull << sh)) : 0;
+                        double v = (double)(ip * P10I[n] + frac) / P10[n];
+                        if (neg) v = -v;
+                        if (i + 1 == count) return false;                                     // a separator follows: too many fields
+                        store(i, v);
+                        p = r + 2 + n;
+                        continue;
+                    }
+                }
+            }
+        }
         unsigned long long mant = 0;
         int nd = 0, frac = -1;
         for (; q < e; ++q) {
@@ -299,9 +335,35 @@ int dsp_parse_features(const char* text, int64_t nbytes, int32_t is_final, int32
     std::vector<int64_t> begins, ends;
     begins.reserve((size_t)(max_sites < (1 << 20) ? max_sites : (1 << 20)));
     ends.reserve(begins.capacity());
+    // the newline positions of the block, found by all workers (this is also where a mapped file's pages are
+    // first touched, so the page-cache faults are spread over the threads)
+    std::vector<int64_t> newlines;
+    {
+        const int P = nthreads > 1 && nbytes >= (1 << 20) ? nthreads : 1;
+        std::vector<std::vector<int64_t>> part((size_t)P);
+        parallel_for(P, P, [&](int64_t a, int64_t b) {
+            for (int64_t r = a; r < b; ++r) {
+                const int64_t lo = nbytes * r / P, hi = nbytes * (r + 1) / P;
+                std::vector<int64_t>& v = part[(size_t)r];
+                v.reserve((size_t)((hi - lo) / 1024 + 16));
+                for (int64_t q = lo; q < hi;) {
+                    const char* nl = (const char*)memchr(text + q, '\n', (size_t)(hi - q));
+                    if (!nl) break;
+                    v.push_back(nl - text);
+                    q = (nl - text) + 1;
+                }
+            }
+        }, 2);
+        size_t total = 0;
+        for (auto& v : part) total += v.size();
+        newlines.reserve(total);
+        for (auto& v : part) newlines.insert(newlines.end(), v.begin(), v.end());
+    }
     int64_t pos = 0, n = 0;
+    size_t next_nl = 0;
     while (pos < nbytes && n < max_sites) {
-        const char* nl = (const char*)memchr(text + pos, '\n', (size_t)(nbytes - pos));
+        const bool has_nl = next_nl < newlines.size();
+        const char* nl = has_nl ? text + newlines[next_nl++] : nullptr;
         int64_t stop;
         if (nl) stop = nl - text; else if (is_final) stop = nbytes; else break;
         int64_t b = pos, e = stop;

@@ -147,3 +147,46 @@ def test_writer_worker(tmp_path):
     out = tmp_path / "o.tsv"
     cm._write_predstr_to_file(str(out), q, True)
     assert gzip.open(str(out) + ".gz", "rt").read() == "a\t1\nb\t2\nc\t3\n"
+
+
+def test_parser_matches_python_float_on_random_spellings(tmp_path):
+    # every number goes float(text) -> float32 in the reference (call_modifications.py:90-95, FloatTensor); the
+    # parser's fast paths (exact integer / power of ten, eight fraction digits at a time) must agree bit for bit
+    rng = np.random.default_rng(11)
+    T, S, n = 13, 16, 300
+
+    def spell(v, how):
+        if how == 0:
+            return repr(round(float(v), int(rng.integers(0, 8))))
+        if how == 1:
+            return "%.*f" % (int(rng.integers(0, 8)), v)
+        if how == 2:
+            return "%d" % int(v * 100)
+        if how == 3:
+            return "%.*e" % (int(rng.integers(0, 12)), v)
+        if how == 4:
+            return "%.17g" % v
+        if how == 5:
+            return "+%s" % abs(round(float(v), 3))
+        if how == 6:
+            return "%07.3f" % abs(v)
+        return ["-0.0", "0.", ".5", "-.25", "1e-7", "12345678.9", "0.12345678", "1234567.1234567", "00.5", "9999999.9999999"][int(rng.integers(0, 10))]
+
+    lines, want_m, want_s = [], [], []
+    for i in range(n):
+        vals = rng.normal(0, 1, T * 2 + T * S) * 10.0 ** rng.integers(-3, 4, T * 2 + T * S)
+        toks = [spell(v, int(rng.integers(0, 8))) for v in vals]
+        means, stds, sig = toks[:T], toks[T:2 * T], toks[2 * T:]
+        lines.append("\t".join(["chr1", str(i), "+", str(i), "read%d" % (i // 7), "t", "ACGTACGTACGTA", ",".join(means), ",".join(stds),
+                                ",".join(["5"] * T), ";".join(",".join(sig[t * S:(t + 1) * S]) for t in range(T)), "1"]))
+        want_m.append([np.float32(float(x)) for x in means + stds])
+        want_s.append([np.float32(float(x)) for x in sig])
+    p = tmp_path / "rand.tsv"
+    p.write_text("\n".join(lines) + "\n")
+    got_m, got_s = [], []
+    for b in feature_io.FeatureFileReader(str(p), T, S, batch_sites=64, pinned=False, nthreads=3):
+        got_m.append(np.concatenate([b.base_means.numpy(), b.base_stds.numpy()], 1))
+        got_s.append(b.signals.numpy().reshape(b.n, -1).copy())          # the slot is recycled a few batches later
+    got_m, got_s = np.concatenate(got_m), np.concatenate(got_s)
+    assert np.array_equal(got_m.view(np.uint32), np.array(want_m, np.float32).view(np.uint32))
+    assert np.array_equal(got_s.view(np.uint32), np.array(want_s, np.float32).view(np.uint32))
