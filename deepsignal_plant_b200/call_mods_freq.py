@@ -54,28 +54,96 @@ class SiteStats:
 
 
 class Records:
-    """Column form of call_mods lines (``utils/txt_formater.py:8-21``), file order."""
+    """Column form of call_mods lines (``utils/txt_formater.py:8-21``), file order.
 
-    def __init__(self, chrom, pos, strand, pos_in_strand, p0, p1, label, kmer):
-        self.chrom = np.asarray(chrom, dtype=object)
+    ``chrom`` / ``strand`` / ``kmer`` read as object arrays of ``str`` like the reference's fields.  Records
+    that come from the native parser keep them compact instead -- chromosome codes + a name table, fixed-width
+    byte cells -- and only turn the rows somebody asks for into Python strings (``meta_at``)."""
+    FIELDS = ("chrom", "pos", "strand", "pos_in_strand", "p0", "p1", "label", "kmer")
+
+    def __init__(self, chrom, pos, strand, pos_in_strand, p0, p1, label, kmer, chrom_codes=None):
+        self._chrom = None if chrom is None else np.asarray(chrom, dtype=object)
+        self._codes = chrom_codes                       # (int32 codes, list of names) or None
         self.pos = np.asarray(pos, dtype=np.int64)
-        self.strand = np.asarray(strand, dtype=object)
+        self._strand = strand if _is_cells(strand) else np.asarray(strand, dtype=object)
         self.pos_in_strand = np.asarray(pos_in_strand, dtype=np.int64)
         self.p0 = np.asarray(p0, dtype=np.float64)
         self.p1 = np.asarray(p1, dtype=np.float64)
         self.label = np.asarray(label, dtype=np.int32)
-        self.kmer = np.asarray(kmer, dtype=object)
+        self._kmer = kmer if _is_cells(kmer) else np.asarray(kmer, dtype=object)
 
     def __len__(self):
         return int(self.pos.shape[0])
+
+    @property
+    def chrom(self):
+        if self._chrom is None:
+            codes, names = self._codes
+            self._chrom = np.asarray(names, dtype=object)[codes] if len(names) else np.empty(0, object)
+        return self._chrom
+
+    @property
+    def strand(self):
+        return _cells_to_str(self._strand)
+
+    @property
+    def kmer(self):
+        return _cells_to_str(self._kmer)
+
+    def meta_at(self, idx):
+        """(strand, pos_in_strand, kmer) of the given records only, strings as object arrays."""
+        return _cells_to_str(self._strand[idx]), self.pos_in_strand[idx], _cells_to_str(self._kmer[idx])
+
+    def chrom_ranks(self):
+        """(ids, names): chromosome ids by rank in Python string order, so that integer key order equals the
+        reference's ``(chrom, pos)`` tuple order (``call_mods_freq.py:88``)."""
+        if self._codes is None:
+            return _chrom_ids(self.chrom)
+        codes, names = self._codes
+        order = sorted(range(len(names)), key=lambda i: names[i])
+        rank = np.empty(len(names), np.int64)
+        rank[order] = np.arange(len(names))
+        return rank[codes], [names[i] for i in order]
+
+    def chrom_in(self, wanted):
+        """Boolean mask of the records whose chromosome is in the set ``wanted``."""
+        if self._codes is None:
+            return np.fromiter((c in wanted for c in self.chrom.tolist()), dtype=bool, count=len(self))
+        codes, names = self._codes
+        return np.array([nm in wanted for nm in names], bool)[codes] if len(names) else np.zeros(0, bool)
+
+    def select(self, keep):
+        codes = None if self._codes is None else (self._codes[0][keep], self._codes[1])
+        return Records(None if codes is not None else self.chrom[keep], self.pos[keep], self._strand[keep],
+                       self.pos_in_strand[keep], self.p0[keep], self.p1[keep], self.label[keep], self._kmer[keep], codes)
 
     @staticmethod
     def concat(parts):
         parts = [p for p in parts if len(p)]
         if not parts:
             return Records([], [], [], [], [], [], [], [])
-        return Records(*(np.concatenate([getattr(p, f) for p in parts]) for f in
-                         ("chrom", "pos", "strand", "pos_in_strand", "p0", "p1", "label", "kmer")))
+        if len(parts) == 1:
+            return parts[0]
+        cat = lambda f: np.concatenate([getattr(p, f) for p in parts])
+        compact = all(p._codes is not None and _is_cells(p._strand) and _is_cells(p._kmer) for p in parts)
+        if not compact:
+            return Records(cat("chrom"), cat("pos"), cat("strand"), cat("pos_in_strand"), cat("p0"), cat("p1"), cat("label"),
+                           cat("kmer"))
+        names, index, codes = [], {}, []
+        for p in parts:                                  # one name table for all parts
+            remap = np.array([index.setdefault(nm, len(index)) for nm in p._codes[1]], np.int32)
+            names = list(index)
+            codes.append(remap[p._codes[0]])
+        return Records(None, cat("pos"), cat("_strand"), cat("pos_in_strand"), cat("p0"), cat("p1"), cat("label"), cat("_kmer"),
+                       (np.concatenate(codes), names))
+
+
+def _is_cells(a):
+    return isinstance(a, np.ndarray) and a.dtype.kind == "S"
+
+
+def _cells_to_str(a):
+    return a.astype(str).astype(object) if _is_cells(a) else a
 
 
 def parse_lines(lines):
@@ -90,11 +158,61 @@ def parse_lines(lines):
     return Records(chrom, pos, strand, pis, p0, p1, label, kmer)
 
 
+def _read_mods_file_native(path, nthreads=None):
+    """``dsp_parse_calls`` over the whole file (mapped in place, or decompressed): compact ``Records``, or None
+    when a strand / k-mer column is wider than the parser's fixed cells."""
+    import mmap
+    L = _native.lib()
+    nthreads = int(nthreads or min(32, os.cpu_count() or 1))
+    if path.endswith(".gz"):
+        with gzip.open(path, "rb") as f:
+            buf = np.frombuffer(f.read(), np.uint8)
+        mm = None
+    else:
+        with open(path, "rb") as f:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        buf = np.frombuffer(mm, np.uint8)
+    try:
+        n = C.c_int64(0)
+        cap = int(np.count_nonzero(buf == 10)) + 1      # lines <= newlines + 1
+        code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
+        p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
+        strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
+        names = np.empty(1 << 16, np.uint8)
+        while True:
+            nb, nn = C.c_int64(0), C.c_int32(0)
+            p = lambda a: a.ctypes.data
+            rc = L.dsp_parse_calls(buf.ctypes.data, buf.size, cap, p(code), p(pos), p(strand), p(pis), p(p0), p(p1), p(label),
+                                   p(kmer), p(names), names.size, C.byref(nb), C.byref(nn), C.byref(n), nthreads)
+            if rc == 5:                                  # DSP_ERR_UNSUPPORTED: unusually wide strand / k-mer column
+                return None
+            if rc == 4 and nb.value > names.size:        # DSP_ERR_NOMEM: many long chromosome names
+                names = np.empty(int(nb.value), np.uint8)
+                continue
+            _native.check(rc, "dsp_parse_calls(%s)" % path)
+            break
+        m = int(n.value)
+        if m == 0:
+            return Records([], [], [], [], [], [], [], [])
+        table = names[:int(nb.value)].tobytes().decode().split("\n")[:int(nn.value)]
+        return Records(None, pos[:m], strand[:m], pis[:m], p0[:m], p1[:m], label[:m], kmer[:m], (code[:m], table))
+    finally:
+        del buf
+        if mm is not None:
+            try:
+                mm.close()
+            except BufferError:
+                pass
+
+
 def read_mods_file(path):
     """One call_mods file (plain or .gz, ``call_mods_freq.py:45-48``) -> ``Records``."""
-    import pandas as pd
     if os.path.getsize(path) == 0:
         return Records([], [], [], [], [], [], [], [])
+    rec = _read_mods_file_native(path)
+    if rec is not None:
+        return rec
+    import pandas as pd
     try:
         df = pd.read_csv(path, sep="\t", header=None, usecols=[0, 1, 2, 3, 6, 7, 8, 9],
                          names=list(range(10)), dtype={0: str, 2: str, 9: str, 1: np.int64, 3: np.int64,
@@ -218,21 +336,20 @@ def aggregate_records(rec, prob_cf, contig_name=None, sort_by_key=False, device=
     callable appearance, or by (chrom, pos) when ``sort_by_key``)."""
     n_total = len(rec)
     if contig_name is not None:                       # call_mods_freq.py:52
-        keep = np.fromiter((c == contig_name for c in rec.chrom.tolist()), dtype=bool, count=n_total)
-        rec = Records(*(getattr(rec, f)[keep] for f in ("chrom", "pos", "strand", "pos_in_strand", "p0", "p1", "label", "kmer")))
+        rec = rec.select(rec.chrom_in({contig_name}))
     if len(rec) == 0:
         e = np.empty(0)
         return FreqTable(np.empty(0, object), e.astype(np.int64), np.empty(0, object), e.astype(np.int64), np.empty(0, object),
                          e, e, e.astype(np.int32), e.astype(np.int32), e.astype(np.int32), e.astype(np.int64), n_total, 0)
-    ids, names = _chrom_ids(rec.chrom)
+    ids, names = rec.chrom_ranks()
     keys = make_keys(ids, rec.pos)
     k, first, s0, s1, met, unmet, cov = _aggregate_device(keys, rec.p0, rec.p1, rec.label, prob_cf, sort_by_key, device)
     k = k.view(np.uint64)
     names = np.asarray(names, dtype=object)
     chrom = names[(k >> np.uint64(POS_BITS)).astype(np.int64)]
     pos = (k & np.uint64((1 << POS_BITS) - 1)).astype(np.int64)
-    return FreqTable(chrom, pos, rec.strand[first], rec.pos_in_strand[first], rec.kmer[first], s0, s1, met, unmet, cov,
-                     first, n_total, int(cov.sum()))
+    strand, pis, kmer = rec.meta_at(first)
+    return FreqTable(chrom, pos, strand, pis, kmer, s0, s1, met, unmet, cov, first, n_total, int(cov.sum()))
 
 
 def calculate_mods_frequency(mods_files, prob_cf, contig_name=None, device=0):
@@ -463,9 +580,7 @@ def call_mods_frequency_to_file(args):
     else:
         print("start processing {} contigs..".format(len(contigs)))
         rec = Records.concat([read_mods_file(f) for f in mods_files])
-        wanted = set(contigs)
-        keep = np.fromiter((c in wanted for c in rec.chrom.tolist()), dtype=bool, count=len(rec))
-        rec = Records(*(getattr(rec, f)[keep] for f in ("chrom", "pos", "strand", "pos_in_strand", "p0", "p1", "label", "kmer")))
+        rec = rec.select(rec.chrom_in(set(contigs)))
         table = aggregate_records(rec, args.prob_cf)
         print("{} of {} calls used for {} contigs..".format(table.n_used, len(rec), len(contigs)))
         table = order_by_contig(table, contigs, args.sort)

@@ -16,7 +16,9 @@
 #include <charconv>
 #include <cmath>
 #include <cstring>
+#include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace dsp {
@@ -560,6 +562,137 @@ int dsp_format_features(const char* info_text, const int64_t* info_off, const ui
     parallel_for(nparts, nthreads, [&](int64_t qa, int64_t qb) {
         for (int64_t q = qa; q < qb; ++q) memcpy(out + off[q], parts[q].text.data(), parts[q].text.size());
     }, 2);
+    return DSP_OK;
+}
+
+// ---- call_mods lines -> columns (the input of call_freq) ----------------------------------------------------
+// ModRecord.__init__ (utils/txt_formater.py:8-21): words = line.strip().split("\t"); chromosome = words[0],
+// pos = int(words[1]), strand = words[2], pos_in_strand = int(words[3]), prob_0 = float(words[6]),
+// prob_1 = float(words[7]), called_label = int(words[8]), k_mer = words[9].  Columns beyond the tenth are ignored,
+// fewer than ten are an error (IndexError in the reference).  Chromosome names are interned: chrom_code[i]
+// indexes the '\n'-separated list written to `names` (order of first appearance per worker, then merged).
+// strand and k_mer are copied into fixed-width, zero-padded cells (STRAND_W / KMER_W bytes); a longer value
+// returns DSP_ERR_UNSUPPORTED so that the caller can take its general path.  With max_records == 0 the call only
+// counts the lines of the block (*n_records).
+int dsp_parse_calls(const char* text, int64_t nbytes, int64_t max_records,
+                    int32_t* chrom_code, int64_t* pos, char* strand, int64_t* pos_in_strand,
+                    double* p0, double* p1, int32_t* label, char* kmer,
+                    char* names, int64_t names_cap, int64_t* names_bytes, int32_t* n_names,
+                    int64_t* n_records, int32_t nthreads) {
+    constexpr int STRAND_W = 4, KMER_W = 24;
+    DSP_REQUIRE(text && n_records && nbytes >= 0 && max_records >= 0, DSP_ERR_INVALID, "dsp_parse_calls: bad argument");
+    *n_records = 0;
+    // lines = text.split('\n') with each line strip()-ed; blank lines die in the reference (IndexError) except a trailing one
+    std::vector<int64_t> newlines;
+    {
+        const int P = nthreads > 1 && nbytes >= (1 << 20) ? nthreads : 1;
+        std::vector<std::vector<int64_t>> part((size_t)P);
+        parallel_for(P, P, [&](int64_t a, int64_t b) {
+            for (int64_t r = a; r < b; ++r) {
+                const int64_t lo = nbytes * r / P, hi = nbytes * (r + 1) / P;
+                for (int64_t q = lo; q < hi;) {
+                    const char* nl = (const char*)memchr(text + q, '\n', (size_t)(hi - q));
+                    if (!nl) break;
+                    part[(size_t)r].push_back(nl - text);
+                    q = (nl - text) + 1;
+                }
+            }
+        }, 2);
+        for (auto& v : part) newlines.insert(newlines.end(), v.begin(), v.end());
+    }
+    // trailing white space is not a line; everything before it is split at the newlines
+    int64_t eff_end = nbytes;
+    while (eff_end > 0 && is_space(text[eff_end - 1])) --eff_end;
+    const int64_t n_nl = std::lower_bound(newlines.begin(), newlines.end(), eff_end) - newlines.begin();
+    const int64_t n = eff_end > 0 ? n_nl + 1 : 0;
+    *n_records = n;
+    if (max_records == 0) return DSP_OK;
+    DSP_REQUIRE(n <= max_records, DSP_ERR_NOMEM, "dsp_parse_calls: %lld records, buffers hold %lld", (long long)n, (long long)max_records);
+    DSP_REQUIRE(chrom_code && pos && strand && pos_in_strand && p0 && p1 && label && kmer && names && names_bytes && n_names,
+                DSP_ERR_INVALID, "dsp_parse_calls: null argument");
+    const int P = n >= 4096 && nthreads > 1 ? nthreads : 1;
+    struct Local { std::unordered_map<std::string_view, int32_t> ids; std::vector<std::string_view> names; int64_t a = 0, b = 0; };
+    std::vector<Local> locals((size_t)P);
+    std::atomic<int64_t> bad_line{-1};
+    std::atomic<int> bad_kind{0};                  // 1 malformed, 2 field too wide
+    parallel_for(P, P, [&](int64_t ra, int64_t rb) {
+        for (int64_t r = ra; r < rb; ++r) {
+            Local& L = locals[(size_t)r];
+            L.a = n * r / P; L.b = n * (r + 1) / P;
+            for (int64_t i = L.a; i < L.b; ++i) {
+                int64_t lb = i ? newlines[(size_t)i - 1] + 1 : 0, le = i < n_nl ? newlines[(size_t)i] : eff_end;
+                while (lb < le && is_space(text[lb])) ++lb;                  // line.strip()
+                while (le > lb && is_space(text[le - 1])) --le;
+                const char* b = text + lb;
+                const char* e = text + le;
+                const char* f[11];
+                f[0] = b;
+                int nf = 1;
+                for (const char* q = b; nf <= 10;) {
+                    const char* t = (const char*)memchr(q, '\t', (size_t)(e - q));
+                    if (t == nullptr) break;
+                    f[nf++] = t + 1;
+                    q = t + 1;
+                }
+                int kind = 0;
+                if (nf < 10) kind = 1;                                       // also an empty line inside the file
+                else {
+                    const char* fe[10];
+                    for (int c = 0; c < 10; ++c) fe[c] = (c + 1 < nf) ? f[c + 1] - 1 : e;
+                    long long v;
+                    if (!parse_int(f[1], fe[1], &v)) kind = 1; else pos[i] = v;
+                    if (!kind && !parse_int(f[3], fe[3], &v)) kind = 1; else if (!kind) pos_in_strand[i] = v;
+                    if (!kind && !parse_double(f[6], fe[6], &p0[i])) kind = 1;
+                    if (!kind && !parse_double(f[7], fe[7], &p1[i])) kind = 1;
+                    if (!kind && !parse_int(f[8], fe[8], &v)) kind = 1; else if (!kind) label[i] = (int32_t)v;
+                    const int64_t sl = fe[2] - f[2], kl = fe[9] - f[9];
+                    if (!kind && (sl > STRAND_W || kl > KMER_W)) kind = 2;
+                    if (!kind) {
+                        memset(strand + i * STRAND_W, 0, STRAND_W); memcpy(strand + i * STRAND_W, f[2], (size_t)sl);
+                        memset(kmer + i * KMER_W, 0, KMER_W); memcpy(kmer + i * KMER_W, f[9], (size_t)kl);
+                        const std::string_view name(f[0], (size_t)(fe[0] - f[0]));
+                        auto it = L.ids.find(name);
+                        if (it == L.ids.end()) { it = L.ids.emplace(name, (int32_t)L.names.size()).first; L.names.push_back(name); }
+                        chrom_code[i] = it->second;
+                    }
+                }
+                if (kind) {
+                    int64_t expect = -1;
+                    if (bad_line.compare_exchange_strong(expect, i)) bad_kind = kind;
+                    return;
+                }
+            }
+        }
+    }, 2);
+    if (bad_line >= 0) {
+        if (bad_kind == 2) { set_error("call_mods file: line %lld has a strand or k-mer column wider than the fixed cells", (long long)bad_line.load() + 1); return 5; }
+        set_error("call_mods file: line %lld is malformed (ten tab-separated columns: ints in 2, 4, 9, floats in 7, 8)", (long long)bad_line.load() + 1);
+        return DSP_ERR_INVALID;
+    }
+    // merge the workers' name tables (worker order, first appearance inside a worker) and renumber their codes
+    std::unordered_map<std::string_view, int32_t> global;
+    std::vector<std::string_view> gnames;
+    std::vector<std::vector<int32_t>> remap((size_t)P);
+    for (int r = 0; r < P; ++r) {
+        for (const std::string_view& nm : locals[(size_t)r].names) {
+            auto it = global.find(nm);
+            if (it == global.end()) { it = global.emplace(nm, (int32_t)gnames.size()).first; gnames.push_back(nm); }
+            remap[(size_t)r].push_back(it->second);
+        }
+    }
+    parallel_for(P, P, [&](int64_t ra, int64_t rb) {
+        for (int64_t r = ra; r < rb; ++r) {
+            const std::vector<int32_t>& m = remap[(size_t)r];
+            for (int64_t i = locals[(size_t)r].a; i < locals[(size_t)r].b; ++i) chrom_code[i] = m[(size_t)chrom_code[i]];
+        }
+    }, 2);
+    int64_t used = 0;
+    for (const std::string_view& nm : gnames) used += (int64_t)nm.size() + 1;
+    *names_bytes = used;
+    *n_names = (int32_t)gnames.size();
+    DSP_REQUIRE(used <= names_cap, DSP_ERR_NOMEM, "dsp_parse_calls: chromosome names need %lld bytes, buffer has %lld", (long long)used, (long long)names_cap);
+    char* o = names;
+    for (const std::string_view& nm : gnames) { memcpy(o, nm.data(), nm.size()); o += nm.size(); *o++ = '\n'; }
     return DSP_OK;
 }
 

@@ -36,7 +36,8 @@ typedef enum {
     DSP_ERR_INVALID = 1,     /* bad argument / unsupported shape */
     DSP_ERR_CUDA = 2,        /* a CUDA runtime or driver call failed */
     DSP_ERR_STATE = 3,       /* call order violated (e.g. forward before pack) */
-    DSP_ERR_NOMEM = 4
+    DSP_ERR_NOMEM = 4,
+    DSP_ERR_UNSUPPORTED = 5  /* valid input this entry point does not cover; the caller has a general path */
 } dsp_status;
 
 /* module = ModelBiLSTM's `module` argument (models.py:120-128) */
@@ -155,6 +156,20 @@ int dsp_freq_aggregate(int device, const uint64_t* key, const double* p0, const 
                        uint64_t* out_key, int64_t* out_first, double* out_p0, double* out_p1,
                        int32_t* out_met, int32_t* out_unmet, int32_t* out_cov,
                        int64_t* n_sites_host, void* stream);
+
+/* dsp_parse_calls: ModRecord.__init__ (utils/txt_formater.py:8-21) for a whole call_mods file held in memory
+ * (HOST pointers): every line is strip()-ed and split on tabs; columns 1, 3, 8 are parsed like int(), 6 and 7
+ * like float() (correctly rounded to float64), chromosome names (column 0) are interned -- chrom_code[i] indexes
+ * the '\n'-separated list written to `names` (*n_names entries, *names_bytes bytes; DSP_ERR_NOMEM if names_cap
+ * is too small) -- strand (column 2) and k_mer (column 9) are copied into zero-padded cells of 4 and 24 bytes
+ * (a longer value returns DSP_ERR_UNSUPPORTED).  Columns beyond the tenth are ignored; fewer than ten, an empty
+ * line inside the file or an unparsable number return DSP_ERR_INVALID (the reference raises).  With
+ * max_records == 0 only the lines are counted (*n_records) and no output pointer is touched. */
+int dsp_parse_calls(const char* text, int64_t nbytes, int64_t max_records,
+                    int32_t* chrom_code, int64_t* pos, char* strand, int64_t* pos_in_strand,
+                    double* p0, double* p1, int32_t* label, char* kmer,
+                    char* names, int64_t names_cap, int64_t* names_bytes, int32_t* n_names,
+                    int64_t* n_records, int32_t nthreads);
 
 /* dsp_freq_aggregate keeps its scratch device memory cached between calls; this frees it. */
 int dsp_freq_release_cache(void);

@@ -8,6 +8,7 @@ import torch
 
 import cases
 from deepsignal_plant_b200 import call_mods_freq as cf
+from deepsignal_plant_b200 import _native as _native_mod
 from deepsignal_plant_b200 import synthetic
 from oracle import freq_oracle
 
@@ -269,3 +270,53 @@ def test_gpu_freq_tables_combine_like_the_reference_script(tmp_path):
         assert (int(w[6]), int(w[7]), int(w[8])) == (c[3], c[4], c[5])
         assert abs(float(w[4]) - c[1]) <= 0.0016 and abs(float(w[5]) - c[2]) <= 0.0016
         assert w[9] == "%.4f" % c[6]
+
+
+def test_native_calls_parser_matches_python_field_rules(tmp_path):
+    # dsp_parse_calls == ModRecord's field rules (parse_lines) on synthetic records, the edge-case file, extra
+    # columns, CRLF / padded lines; compact Records behave like the object-array ones
+    lines = synthetic.make_callmods_records(60000, n_chrom=12, n_pos=900, seed=3) + inputs("edge")
+    lines[7] = lines[7] + "\textra\tcolumns"
+    lines[8] = "  " + lines[8] + " \r"
+    want = cf.parse_lines(lines)
+    p = tmp_path / "calls.tsv"
+    p.write_text("\n".join(lines) + "\n")
+    got = cf._read_mods_file_native(str(p), nthreads=4)
+    assert got is not None and got._codes is not None and len(got) == len(want)
+    for fld in cf.Records.FIELDS:
+        a, b = getattr(got, fld), getattr(want, fld)
+        assert a.dtype == b.dtype and (a == b).all(), fld
+    assert np.array_equal(got.p0.view(np.uint64), want.p0.view(np.uint64)) and np.array_equal(got.p1.view(np.uint64), want.p1.view(np.uint64))
+    ids_a, names_a = got.chrom_ranks()
+    ids_b, names_b = cf._chrom_ids(want.chrom)
+    assert names_a == names_b and np.array_equal(ids_a, ids_b)
+    wanted = {"chr10", "chr3", "nope"}
+    keep = got.chrom_in(wanted)
+    assert np.array_equal(keep, want.chrom_in(wanted)) and 0 < keep.sum() < len(got)
+    sub = got.select(keep)
+    assert (sub.chrom == want.chrom[keep]).all() and (sub.kmer == want.kmer[keep]).all() and sub._codes is not None
+    idx = np.array([5, 0, 59999, 7])
+    s_, q_, k_ = got.meta_at(idx)
+    assert (s_ == want.strand[idx]).all() and (q_ == want.pos_in_strand[idx]).all() and (k_ == want.kmer[idx]).all()
+    # two files with different chromosome tables concatenate into one table
+    a, b = tmp_path / "a.tsv", tmp_path / "b.tsv.gz"
+    a.write_text("\n".join(lines[:100]) + "\n")
+    with gzip.open(b, "wt") as f:
+        f.write("\n".join(lines[50000:50200]))                     # no trailing newline
+    both = cf.Records.concat([cf.read_mods_file(str(a)), cf.read_mods_file(str(b))])
+    ref = cf.parse_lines(lines[:100] + lines[50000:50200])
+    assert both._codes is not None and all((getattr(both, f) == getattr(ref, f)).all() for f in cf.Records.FIELDS)
+    # a k-mer column wider than the fixed cells takes the general path; malformed lines fail loudly
+    wide = tmp_path / "wide.tsv"
+    wide.write_text(lines[0].rsplit("\t", 1)[0] + "\t" + "ACGT" * 10 + "\n" + lines[1] + "\n")
+    assert cf._read_mods_file_native(str(wide)) is None
+    rec = cf.read_mods_file(str(wide))
+    assert rec.kmer[0] == "ACGT" * 10 and rec.pos[1] == want.pos[1]
+    for bad in ("chr1\t5\t+\n", lines[0].replace("\t0.", "\tx.", 1) + "\n", lines[0] + "\n\n" + lines[1] + "\n"):
+        q = tmp_path / "bad.tsv"
+        q.write_text(bad)
+        with pytest.raises(_native_mod.DspError):
+            cf._read_mods_file_native(str(q))
+    e = tmp_path / "empty.tsv"
+    e.write_text("")
+    assert len(cf.read_mods_file(str(e))) == 0
