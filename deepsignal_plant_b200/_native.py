@@ -18,7 +18,7 @@ SYMBOLS = (
     "dsp_forward_host_wait", "dsp_launch_count",
     "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate", "dsp_selftest",
     "dsp_parse_features", "dsp_format_calls", "dsp_freq_release_cache", "dsp_extract_features", "dsp_format_sampleinfo", "dsp_find_sites", "dsp_extract_features_f64",
-    "dsp_format_features", "dsp_parse_calls",
+    "dsp_format_features", "dsp_parse_calls", "dsp_format_freq",
 )
 
 MODULES = {"both_bilstm": 0, "seq_bilstm": 1, "signal_bilstm": 2}
@@ -85,6 +85,8 @@ def lib():
     L.dsp_extract_features_f64.argtypes = L.dsp_extract_features.argtypes
     L.dsp_format_features.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp, i64, C.POINTER(i64), i32]
     L.dsp_parse_calls.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i32),
+                                  C.POINTER(i64), i32]
+    L.dsp_format_freq.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, i64,
                                   C.POINTER(i64), i32]
     L.dsp_find_sites.argtypes = [C.c_int, vp, vp, i64, i64, C.c_char_p, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64,
                                  vp, vp, vp, vp, C.POINTER(i64), vp]

@@ -375,6 +375,9 @@ def render_table(table, is_sort=False, is_bed=False):
         table = _table_from_mapping(table)
     if is_sort:
         table = table.sorted()
+    text = _render_native(table, is_bed)
+    if text is not None:
+        return text
     out = io.StringIO()
     chrom, pos, strand = table.chrom.tolist(), table.pos.tolist(), table.strand.tolist()
     cov, met, unmet = table.coverage.tolist(), table.met.tolist(), table.unmet.tolist()
@@ -392,6 +395,37 @@ def render_table(table, is_sort=False, is_bed=False):
                 out.write("%s\t%d\t%s\t%d\t%.3f\t%.3f\t%d\t%d\t%d\t%.4f\t%s\n" % (c, p, s, q, a, b, mt, um, cv,
                                                                                  float(mt) / cv, k))
     return out.getvalue()
+
+
+def _render_native(table, is_bed):
+    """``dsp_format_freq`` (host threads); None when a text column holds a newline or NUL (the Python loop below
+    prints anything)."""
+    n = len(table)
+    if n == 0:
+        return ""
+    cols = []
+    for a in (table.chrom, table.strand, table.kmer):
+        t = "\n".join(a.tolist())
+        if t.count("\n") != n - 1 or "\0" in t:
+            return None
+        cols.append(t.encode())
+    L = _native.lib()
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    pos, pis = c(table.pos, np.int64), c(table.pos_in_strand, np.int64)
+    s0, s1 = c(table.prob_0, np.float64), c(table.prob_1, np.float64)
+    met, unmet, cov = c(table.met, np.int32), c(table.unmet, np.int32), c(table.coverage, np.int32)
+    cap = sum(len(x) for x in cols) + n * 160
+    p = lambda a: a.ctypes.data
+    used = C.c_int64(0)
+    while True:
+        out = np.empty(cap, np.uint8)
+        rc = L.dsp_format_freq(cols[0], cols[1], cols[2], p(pos), p(pis), p(s0), p(s1), p(met), p(unmet), p(cov), n,
+                               int(bool(is_bed)), p(out), cap, C.byref(used), min(16, os.cpu_count() or 1))
+        if rc == 4 and used.value > cap:
+            cap = int(used.value)
+            continue
+        _native.check(rc, "dsp_format_freq")
+        return out[:used.value].tobytes().decode()
 
 
 def _table_from_mapping(d):

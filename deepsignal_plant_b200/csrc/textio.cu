@@ -696,4 +696,88 @@ int dsp_parse_calls(const char* text, int64_t nbytes, int64_t max_records,
     return DSP_OK;
 }
 
+// write_sitekey2stats (call_mods_freq.py:87-120) for n sites in output order, HOST pointers.  chrom / strand / kmer:
+// the n strings of each column joined by '\n' (no trailing newline needed).  Rows with coverage 0 are skipped (:104).
+//   tsv: "%s\t%d\t%s\t%d\t%.3f\t%.3f\t%d\t%d\t%d\t%.4f\t%s\n"  (:112-118), rmet = float(met) / coverage
+//   bed: chrom, pos, pos+1, ".", cov, strand, pos, pos+1, "0,0,0", cov, int(round(rmet * 100 + 0.001, 0))  (:106-110)
+int dsp_format_freq(const char* chrom_text, const char* strand_text, const char* kmer_text,
+                    const int64_t* pos, const int64_t* pos_in_strand, const double* prob_0, const double* prob_1,
+                    const int32_t* met, const int32_t* unmet, const int32_t* coverage, int64_t n, int32_t is_bed,
+                    char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads) {
+    DSP_REQUIRE(n >= 0 && out_bytes, DSP_ERR_INVALID, "dsp_format_freq: bad argument");
+    *out_bytes = 0;
+    if (n == 0) return DSP_OK;
+    DSP_REQUIRE(chrom_text && strand_text && kmer_text && pos && pos_in_strand && prob_0 && prob_1 && met && unmet && coverage && out,
+                DSP_ERR_INVALID, "dsp_format_freq: null argument");
+    auto split = [n](const char* t, std::vector<const char*>& b, std::vector<int32_t>& l) -> bool {
+        b.resize((size_t)n); l.resize((size_t)n);
+        const char* p = t;
+        for (int64_t i = 0; i < n; ++i) {
+            const char* e = (i + 1 < n) ? strchr(p, '\n') : p + strlen(p);
+            if (e == nullptr) return false;
+            if (i + 1 == n && e > p && e[-1] == '\n') --e;
+            b[(size_t)i] = p; l[(size_t)i] = (int32_t)(e - p);
+            p = e + 1;
+        }
+        return true;
+    };
+    std::vector<const char*> cb, sb, kb;
+    std::vector<int32_t> cl, sl, kl;
+    DSP_REQUIRE(split(chrom_text, cb, cl) && split(strand_text, sb, sl) && split(kmer_text, kb, kl), DSP_ERR_INVALID,
+                "dsp_format_freq: a text column has fewer than n entries");
+    struct Part { int64_t a = 0, b = 0; std::vector<char> text; };
+    const int64_t nparts = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)std::max(1, nthreads) * 4));
+    std::vector<Part> parts((size_t)nparts);
+    for (int64_t q = 0; q < nparts; ++q) { parts[q].a = n * q / nparts; parts[q].b = n * (q + 1) / nparts; }
+    parallel_for(nparts, nthreads, [&](int64_t qa, int64_t qb) {
+        for (int64_t q = qa; q < qb; ++q) {
+            Part& pt = parts[q];
+            size_t used = 0;
+            for (int64_t i = pt.a; i < pt.b; ++i) {
+                if (coverage[i] <= 0) continue;
+                const size_t need = (size_t)cl[i] + sl[i] + kl[i] + 1024;       // %.3f of a double can be long
+                if (pt.text.size() - used < need) pt.text.resize(pt.text.size() * 2 + need + 4096);
+                char* o = pt.text.data() + used;
+                const double rmet = (double)met[i] / (double)coverage[i];
+                memcpy(o, cb[i], (size_t)cl[i]); o += cl[i]; *o++ = '\t';
+                if (is_bed) {
+                    o = std::to_chars(o, o + 24, (long long)pos[i]).ptr; *o++ = '\t';
+                    o = std::to_chars(o, o + 24, (long long)pos[i] + 1).ptr; *o++ = '\t';
+                    *o++ = '.'; *o++ = '\t';
+                    o = std::to_chars(o, o + 24, coverage[i]).ptr; *o++ = '\t';
+                    memcpy(o, sb[i], (size_t)sl[i]); o += sl[i]; *o++ = '\t';
+                    o = std::to_chars(o, o + 24, (long long)pos[i]).ptr; *o++ = '\t';
+                    o = std::to_chars(o, o + 24, (long long)pos[i] + 1).ptr; *o++ = '\t';
+                    memcpy(o, "0,0,0\t", 6); o += 6;
+                    o = std::to_chars(o, o + 24, coverage[i]).ptr; *o++ = '\t';
+                    o = std::to_chars(o, o + 24, (long long)std::nearbyint(rmet * 100 + 0.001)).ptr;
+                } else {
+                    o = std::to_chars(o, o + 24, (long long)pos[i]).ptr; *o++ = '\t';
+                    memcpy(o, sb[i], (size_t)sl[i]); o += sl[i]; *o++ = '\t';
+                    o = std::to_chars(o, o + 24, (long long)pos_in_strand[i]).ptr; *o++ = '\t';
+                    o += snprintf(o, 400, "%.3f\t%.3f\t", prob_0[i], prob_1[i]);
+                    o = std::to_chars(o, o + 24, met[i]).ptr; *o++ = '\t';
+                    o = std::to_chars(o, o + 24, unmet[i]).ptr; *o++ = '\t';
+                    o = std::to_chars(o, o + 24, coverage[i]).ptr; *o++ = '\t';
+                    o += snprintf(o, 400, "%.4f\t", rmet);
+                    memcpy(o, kb[i], (size_t)kl[i]); o += kl[i];
+                }
+                *o++ = '\n';
+                used = (size_t)(o - pt.text.data());
+            }
+            pt.text.resize(used);
+        }
+    }, 2);
+    std::vector<int64_t> off((size_t)nparts + 1);
+    off[0] = 0;
+    for (int64_t q = 0; q < nparts; ++q) off[q + 1] = off[q] + (int64_t)parts[q].text.size();
+    *out_bytes = off[nparts];
+    DSP_REQUIRE(off[nparts] <= out_cap, DSP_ERR_NOMEM, "dsp_format_freq: output needs %lld bytes, buffer has %lld",
+                (long long)off[nparts], (long long)out_cap);
+    parallel_for(nparts, nthreads, [&](int64_t qa, int64_t qb) {
+        for (int64_t q = qa; q < qb; ++q) memcpy(out + off[q], parts[q].text.data(), parts[q].text.size());
+    }, 2);
+    return DSP_OK;
+}
+
 }  // extern "C"

@@ -171,6 +171,17 @@ int dsp_parse_calls(const char* text, int64_t nbytes, int64_t max_records,
                     char* names, int64_t names_cap, int64_t* names_bytes, int32_t* n_names,
                     int64_t* n_records, int32_t nthreads);
 
+/* dsp_format_freq: the text of write_sitekey2stats (call_mods_freq.py:87-120) for n sites already in output order
+ * (HOST pointers).  chrom_text / strand_text / kmer_text hold the n strings of the column joined by '\n',
+ * NUL-terminated.  Sites with coverage 0 are skipped (:104).  is_bed == 0: the 11-column table
+ * "%s\t%d\t%s\t%d\t%.3f\t%.3f\t%d\t%d\t%d\t%.4f\t%s" (:112-118); else the bedMethyl line of :106-110
+ * with percent = int(round(met / coverage * 100 + 0.001, 0)).  *out_bytes receives the size needed;
+ * DSP_ERR_NOMEM if out_cap is too small. */
+int dsp_format_freq(const char* chrom_text, const char* strand_text, const char* kmer_text,
+                    const int64_t* pos, const int64_t* pos_in_strand, const double* prob_0, const double* prob_1,
+                    const int32_t* met, const int32_t* unmet, const int32_t* coverage, int64_t n, int32_t is_bed,
+                    char* out, int64_t out_cap, int64_t* out_bytes, int32_t nthreads);
+
 /* dsp_freq_aggregate keeps its scratch device memory cached between calls; this frees it. */
 int dsp_freq_release_cache(void);
 

@@ -320,3 +320,27 @@ def test_native_calls_parser_matches_python_field_rules(tmp_path):
     e = tmp_path / "empty.tsv"
     e.write_text("")
     assert len(cf.read_mods_file(str(e))) == 0
+
+
+def test_native_table_writer_equals_the_python_loop(monkeypatch):
+    # dsp_format_freq vs the per-site Python formatting of write_sitekey2stats, on random rows (ties of %.3f / %.4f,
+    # zero coverage, large sums) and both output formats; odd text columns take the Python loop
+    rng = np.random.default_rng(5)
+    n = 20000
+    obj = lambda xs: np.asarray(xs, dtype=object)
+    s0 = np.concatenate([rng.random(n - 6) * rng.choice([1, 50, 1e4], n - 6), [0.0005, 0.0015, 2.0005, 1e15, 0.00049999999999999994, 123456.7895]])
+    cov = rng.integers(0, 60, n).astype(np.int32)
+    met = (rng.random(n) * cov).astype(np.int32)
+    t = cf.FreqTable(obj(["chr%d" % (i % 7) for i in range(n)]), rng.integers(0, 10 ** 9, n), obj(["+-"[i % 2] for i in range(n)]),
+                     rng.integers(-1, 10 ** 9, n), obj(["ACGTN"[i % 5] * 5 for i in range(n)]), s0, s0[::-1].copy(), met,
+                     (cov - met).astype(np.int32), cov, np.arange(n))
+    for bed in (False, True):
+        native = cf._render_native(t, bed)
+        assert native is not None and native == cf.render_table(t, False, bed)
+        with monkeypatch.context() as m:
+            m.setattr(cf, "_render_native", lambda *a: None)
+            assert cf.render_table(t, False, bed) == native
+    assert cf._render_native(t.reorder(np.arange(0)), False) == ""
+    odd = cf.FreqTable(obj(["chr\n1"]), np.array([5]), obj(["+"]), np.array([5]), obj(["AACGT"]), np.array([1.0]), np.array([0.0]),
+                       np.array([1], np.int32), np.array([0], np.int32), np.array([1], np.int32), np.arange(1))
+    assert cf._render_native(odd, False) is None and cf.render_table(odd).startswith("chr\n1\t5\t+")
