@@ -174,7 +174,7 @@ def _read_mods_file_native(path, nthreads=None):
         buf = np.frombuffer(mm, np.uint8)
     try:
         n = C.c_int64(0)
-        cap = int(np.count_nonzero(buf == 10)) + 1      # lines <= newlines + 1
+        cap = buf.size // 20 + 2                        # a well-formed line has at least 20 bytes; untouched pages cost nothing
         code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
         p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
         strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
@@ -188,6 +188,12 @@ def _read_mods_file_native(path, nthreads=None):
                 return None
             if rc == 4 and nb.value > names.size:        # DSP_ERR_NOMEM: many long chromosome names
                 names = np.empty(int(nb.value), np.uint8)
+                continue
+            if rc == 4 and n.value > cap:                # more (shorter, hence malformed) lines than the bound: let it say so
+                cap = int(n.value)
+                code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
+                p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
+                strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
                 continue
             _native.check(rc, "dsp_parse_calls(%s)" % path)
             break
