@@ -26,6 +26,12 @@ def build_parser():
     g = ex.add_argument_group("INPUT")
     g.add_argument("--fast5_dir", "-i", action="store", type=str, required=True,
                    help="the decoded-reads archive (.npz); the reference's flag name is kept")
+    g.add_argument("--recursively", "-r", action="store", type=str, required=False, default="yes",
+                   help="accepted for compatibility (fast5 directories are decoded by tools/fast5_to_archive.py)")
+    g.add_argument("--corrected_group", action="store", type=str, required=False, default="RawGenomeCorrected_000",
+                   help="accepted for compatibility (used when the archive is made)")
+    g.add_argument("--basecall_subgroup", action="store", type=str, required=False, default="BaseCalled_template",
+                   help="accepted for compatibility (used when the archive is made)")
     g.add_argument("--is_dna", action="store", type=str, required=False, default="yes")
     g.add_argument("--reference_path", action="store", type=str, required=False, default=None)
     g = ex.add_argument_group("EXTRACTION")
@@ -39,6 +45,9 @@ def build_parser():
     g.add_argument("--positions", action="store", type=str, required=False, default=None)
     g = ex.add_argument_group("OUTPUT")
     g.add_argument("--write_path", "-o", action="store", type=str, required=True)
+    g.add_argument("--w_is_dir", action="store", type=str, required=False, default="no",
+                   help="only 'no' (one output file) is supported")
+    g.add_argument("--w_batch_num", action="store", type=int, required=False, default=200, help="accepted for compatibility")
     g.add_argument("--gzip", action="store_true", default=False, required=False)
     ex.add_argument("--nproc", "-p", action="store", type=int, default=10, required=False, help="host threads for formatting")
     ex.add_argument("--f5_batch_size", action="store", type=int, default=30, required=False, help="reads per extraction chunk")
@@ -58,6 +67,13 @@ def build_parser():
                    help="genome FASTA: contig lengths give the pos_in_strand column")
     g.add_argument("--positions", action="store", type=str, required=False, default=None)
     g.add_argument("--region", action="store", type=str, required=False, default=None)
+    g.add_argument("--methy_label", action="store", type=int, choices=[1, 0], required=False, default=1,
+                   help="accepted for compatibility (the label column is not part of the calls)")
+    g.add_argument("--recursively", "-r", action="store", type=str, required=False, default="yes", help="accepted for compatibility")
+    g.add_argument("--corrected_group", action="store", type=str, required=False, default="RawGenomeCorrected_000",
+                   help="accepted for compatibility (used when the archive is made)")
+    g.add_argument("--basecall_subgroup", action="store", type=str, required=False, default="BaseCalled_template",
+                   help="accepted for compatibility (used when the archive is made)")
     g = cm.add_argument_group("CALL")
     g.add_argument("--model_path", "-m", action="store", type=str, required=True, help="file path of the trained model (.ckpt)")
     g.add_argument("--model_type", type=str, default="both_bilstm", choices=["both_bilstm", "seq_bilstm", "signal_bilstm"])

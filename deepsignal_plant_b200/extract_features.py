@@ -521,6 +521,8 @@ def extract_to_file(args):
     if os.path.isdir(args.fast5_dir):
         raise ValueError("--fast5_dir is a directory of fast5 files: reading fast5 (h5py) is outside this implementation; "
                          "decode the reads once into an archive with extract_features.save_reads and pass the .npz")
+    if str(getattr(args, "w_is_dir", "no")).lower() in ("yes", "true", "t", "1"):
+        raise ValueError("--w_is_dir yes (one file per batch) is not supported; the features go to one file")
     allreads = load_reads(args.fast5_dir)
     motif_seqs = get_motif_seqs(args.motifs, str(args.is_dna).lower() in ("yes", "true", "t", "1"))
     chrom2len = get_contig2len(args.reference_path) if args.reference_path else None

@@ -101,3 +101,33 @@ def test_synthetic_rectangle_rule():
     assert (f["kmer"][:, 6] == 1).all()
     g = synthetic.make_features(64, 13, 16, seed=3)
     assert all(np.array_equal(f[k], g[k]) for k in f)
+
+
+def test_command_line_accepts_the_reference_flags():
+    # every --flag of the reference's extract / call_mods / call_freq parsers (deepsignal_plant.py:120-316, 438-475,
+    # listed here so that the test runs without /root/reference) parses here too, with the reference's defaults
+    from deepsignal_plant_b200 import cli
+    ref = {
+        "extract": ["--fast5_dir", "--recursively", "--corrected_group", "--basecall_subgroup", "--is_dna", "--reference_path",
+                    "--normalize_method", "--methy_label", "--seq_len", "--signal_len", "--motifs", "--mod_loc", "--region",
+                    "--positions", "--write_path", "--w_is_dir", "--w_batch_num", "--gzip", "--nproc", "--f5_batch_size"],
+        "call_mods": ["--input_path", "--f5_batch_size", "--model_path", "--model_type", "--seq_len", "--signal_len", "--layernum1",
+                      "--layernum2", "--class_num", "--dropout_rate", "--n_vocab", "--n_embed", "--is_base", "--is_signallen",
+                      "--batch_size", "--hid_rnn", "--result_file", "--gzip", "--recursively", "--corrected_group",
+                      "--basecall_subgroup", "--reference_path", "--is_dna", "--normalize_method", "--methy_label", "--motifs",
+                      "--mod_loc", "--region", "--positions", "--nproc", "--nproc_gpu"],
+        "call_freq": ["--input_path", "--file_uid", "--result_file", "--bed", "--sort", "--gzip", "--prob_cf", "--contigs", "--nproc"],
+    }
+    parser = cli.build_parser()
+    sub = [a for a in parser._actions if a.__class__.__name__ == "_SubParsersAction"][0]
+    for name, flags in ref.items():
+        have = {o for a in sub.choices[name]._actions for o in a.option_strings}
+        assert not [f for f in flags if f not in have], name
+    a = parser.parse_args(["extract", "-i", "reads.npz", "-o", "f.tsv"])
+    assert (a.normalize_method, a.methy_label, a.seq_len, a.signal_len, a.motifs, a.mod_loc, a.f5_batch_size, a.nproc, a.w_is_dir) == \
+        ("mad", 1, 13, 16, "CG", 0, 30, 10, "no")
+    c = parser.parse_args(["call_mods", "-i", "x", "-m", "m.ckpt", "-o", "o.tsv"])
+    assert (c.model_type, c.seq_len, c.signal_len, c.layernum1, c.layernum2, c.class_num, c.hid_rnn, c.n_vocab, c.n_embed,
+            c.batch_size, c.motifs, c.mod_loc) == ("both_bilstm", 13, 16, 3, 1, 2, 256, 16, 4, 512, "CG", 0)
+    f = parser.parse_args(["call_freq", "-i", "a", "-i", "b", "-o", "o"])
+    assert f.input_path == ["a", "b"] and f.prob_cf == 0.5 and not f.bed and not f.sort
