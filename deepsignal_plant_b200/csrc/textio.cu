@@ -755,11 +755,14 @@ int dsp_format_freq(const char* chrom_text, const char* strand_text, const char*
                     o = std::to_chars(o, o + 24, (long long)pos[i]).ptr; *o++ = '\t';
                     memcpy(o, sb[i], (size_t)sl[i]); o += sl[i]; *o++ = '\t';
                     o = std::to_chars(o, o + 24, (long long)pos_in_strand[i]).ptr; *o++ = '\t';
-                    o += snprintf(o, 400, "%.3f\t%.3f\t", prob_0[i], prob_1[i]);
+                    // "%.3f" / "%.4f": std::to_chars with a precision prints what printf does in the C locale
+                    // (correctly rounded), without depending on the process locale
+                    o = std::to_chars(o, o + 400, prob_0[i], std::chars_format::fixed, 3).ptr; *o++ = '\t';
+                    o = std::to_chars(o, o + 400, prob_1[i], std::chars_format::fixed, 3).ptr; *o++ = '\t';
                     o = std::to_chars(o, o + 24, met[i]).ptr; *o++ = '\t';
                     o = std::to_chars(o, o + 24, unmet[i]).ptr; *o++ = '\t';
                     o = std::to_chars(o, o + 24, coverage[i]).ptr; *o++ = '\t';
-                    o += snprintf(o, 400, "%.4f\t", rmet);
+                    o = std::to_chars(o, o + 400, rmet, std::chars_format::fixed, 4).ptr; *o++ = '\t';
                     memcpy(o, kb[i], (size_t)kl[i]); o += kl[i];
                 }
                 *o++ = '\n';
