@@ -222,7 +222,10 @@ def main():
     L = _native.lib()
 
     if args.meas_skip_y:
-        os.environ["DSP_B200_MEAS_SKIP_Y"] = "1"
+        # only the measurement build (DSP_B200_VARIANT=skipy DSP_B200_DEFINES=-DDSP_MEAS_SKIP_Y, loaded through
+        # DSP_B200_LIB) reads this; the shipped library has no result-changing switch
+        assert "skipy" in os.path.basename(_native.LIB_PATH), "--meas-skip-y needs the skipy variant build (see tools/gpu_variants.sh)"
+        os.environ["DSP_B200_SKIP_Y_NOW"] = "1"
     # ---- timed region: inputs resident in HBM ------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:                       # one sampler per job: rank 0's GPU stands for the box

@@ -97,8 +97,12 @@ int pack_lstm_stack(Model* m, const char* prefix, int num_layers, int in0, int H
             if (rc) return rc;
         }
         if (m->cfg.precision == DSP_PRECISION_FP16) {
+            // lstm_seq layer 0: columns [E, E + 2|3) are mean, std(, len) (models.py:188-195)
+            const bool split = l == 0 && strcmp(prefix, "lstm_seq") == 0 && tc_seq_split(m);
+            const int e = m->cfg.is_base ? m->cfg.embedding_size : 0, nsc = m->cfg.is_signallen ? 3 : 2;
             int rc = tc_pack_lstm_layer(m, L, raw[0][0]->data(), raw[0][1]->data(), raw[0][2]->data(), raw[0][3]->data(),
-                                        raw[1][0]->data(), raw[1][1]->data(), raw[1][2]->data(), raw[1][3]->data());
+                                        raw[1][0]->data(), raw[1][1]->data(), raw[1][2]->data(), raw[1][3]->data(),
+                                        split ? e : 0, split ? nsc : 0, (split && m->cfg.is_signallen) ? e + 2 : -1);
             if (rc) return rc;
         }
         out.push_back(L);
@@ -350,9 +354,6 @@ int dsp_pack_weights(dsp_handle h) {
     if ((rc = pack_lstm_stack(m, "lstm_comb", c.num_layers1, H, H, m->lstm_comb))) return rc;
     if ((rc = pack_dense(m, "fc1", 2 * H, H, m->fc1, 2))) return rc;
     if ((rc = pack_dense(m, "fc2", H, c.num_classes, m->fc2, 0))) return rc;
-    if (c.precision == DSP_PRECISION_FP16) {
-        if ((rc = tc_finalize_pack(m))) return rc;
-    }
     DSP_CUDA(cudaDeviceSynchronize());
     m->packed = true;
     return DSP_OK;

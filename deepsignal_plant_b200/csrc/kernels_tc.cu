@@ -984,11 +984,20 @@ branch_kernel(const LayerParams p) {
 
 // ---------------------------------------------------------------------------------------------
 // Feature assembly into slab images (models.py:182-195): per (site, t) one row of
-// [embed(kmer) | mean | std | len | 0...] (seq) and of the signal rectangle (signal), FP16.
+// [embed(kmer) | mean | std | len/32 | mean_lo | std_lo | len_lo | 0...] (seq) and of the signal
+// rectangle (signal), FP16.  The three scalar features arrive as float32 of any magnitude (lens are
+// raw sample counts, call_modifications.py:161): each is carried as an FP16 value plus the FP16
+// residual of that rounding in a spare K column of the 16-wide image (`split`; the matching W_ih
+// column is duplicated at pack time), i.e. to ~22 bits at no extra MMA; lens are pre-scaled by 2^-5
+// (the weight column by 2^5) so that counts up to 2^21 stay inside the FP16 range.
+constexpr float SEQ_LEN_SCALE = 1.f / 32.f;
+__device__ __forceinline__ float clamp_half(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ float half_residual(float v) { return v - __half2float(__float2half_rn(v)); }
+
 __global__ void prep_images_kernel(const float* __restrict__ kmer, const float* __restrict__ means,
                                    const float* __restrict__ stds, const float* __restrict__ lens,
                                    const float* __restrict__ signals, const float* __restrict__ embed,
-                                   int E, int vocab, int use_len, int S, int T, int64_t n, int64_t n_pad,
+                                   int E, int vocab, int use_len, int split, int S, int T, int64_t n, int64_t n_pad,
                                    uint8_t* __restrict__ xseq_img, uint8_t* __restrict__ xsig_img) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (site, t)
     if (idx >= n_pad * T) return;
@@ -1009,9 +1018,15 @@ __global__ void prep_images_kernel(const float* __restrict__ kmer, const float* 
                 code = code < 0 ? 0 : (code >= vocab ? vocab - 1 : code);
                 for (int e = 0; e < E && c < 16; ++e) f[c++] = embed[code * E + e];
             }
-            if (c < 16) f[c++] = means[site * T + t];
-            if (c < 16) f[c++] = stds[site * T + t];
-            if (use_len && c < 16) f[c++] = lens[site * T + t];
+            const int nsc = use_len ? 3 : 2;
+            float sc[3];
+            sc[0] = clamp_half(means[site * T + t]);
+            sc[1] = clamp_half(stds[site * T + t]);
+            sc[2] = use_len ? clamp_half(lens[site * T + t] * (split ? SEQ_LEN_SCALE : 1.f)) : 0.f;
+            for (int i = 0; i < nsc && c + i < 16; ++i) {
+                f[c + i] = sc[i];
+                if (split) f[c + nsc + i] = half_residual(sc[i]);
+            }
         }
         uint8_t* dst = xseq_img + slab + row * SLAB_ROW_BYTES;
 #pragma unroll
@@ -1041,6 +1056,8 @@ __global__ void prep_images_kernel(const float* __restrict__ kmer, const float* 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { const int k = chunk * 8 + i; f[i] = (valid && k < S) ? src[k] : 0.f; }
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = clamp_half(f[i]);          // an FP16 inf would turn into NaN probabilities
             uint4 o;
             o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]); o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
             *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = o;
@@ -1073,6 +1090,9 @@ struct TcState {
     uint8_t* hfin_img = nullptr;   // [tiles][hi,lo][2H/64] slabs: [h_fwd(T-1) | h_bwd(0)] as FP16 hi + FP16 residual
     TcDensePack* head_pack = nullptr;
     bool tc_head = false;
+    bool seq_split = false;        // scalar sequence features as FP16 value + residual columns
+    bool pdl = true;               // programmatic dependent launch between the kernels of a forward
+    int force_dual = -1;           // hidden-128 layers: -1 pick by wave cost, 0 layer_kernel, 1 branch_kernel
     int64_t tiles = 0;
     std::vector<TcLstmPack*> lstm_packs;
     std::vector<TcDensePack*> dense_packs;
@@ -1090,9 +1110,6 @@ int tc_alloc(Model* m, void** p, size_t bytes) {
     m->device_allocs.push_back(*p);
     return DSP_OK;
 }
-
-// programmatic dependent launch between the layer kernels of a forward (DSP_B200_PDL=0 turns it off)
-bool g_pdl = true;
 
 template <int KSX, int H, int MODE, int NOUT>
 int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st) {
@@ -1117,7 +1134,7 @@ int launch_layer(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st)
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl ? 2 : 1;
+    cfg.numAttrs = ((TcState*)m->tc_state)->pdl ? 2 : 1;
     DSP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     m->launches++;
     return DSP_OK;
@@ -1139,7 +1156,7 @@ int launch_branch(Model* m, const LayerParams& p, int64_t tiles, cudaStream_t st
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl ? 2 : 1;
+    cfg.numAttrs = ((TcState*)m->tc_state)->pdl ? 2 : 1;
     DSP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     m->launches++;
     return DSP_OK;
@@ -1176,7 +1193,15 @@ int tc_create(Model* m) {
                 "DSP_PRECISION_FP16 supports signal_len <= 64 and <= 16 sequence features per base");
     TcState* s = new TcState();
     m->tc_state = s;
-    if (const char* e = getenv("DSP_B200_PDL")) g_pdl = atoi(e) != 0;
+    // Launch-strategy switches (neither changes a result) are read ONCE here, at handle creation:
+    // DSP_B200_PDL=0 turns programmatic dependent launch off, DSP_B200_BRANCH_DUAL=0|1 forces which kernel
+    // runs the hidden-128 layers.
+    if (const char* e = getenv("DSP_B200_PDL")) s->pdl = atoi(e) != 0;
+    if (const char* e = getenv("DSP_B200_BRANCH_DUAL")) s->force_dual = atoi(e) != 0;
+    {
+        const int e = c.is_base ? c.embedding_size : 0, nsc = c.is_signallen ? 3 : 2;
+        s->seq_split = c.module != DSP_SIGNAL_BILSTM && e + 2 * nsc <= 16;
+    }
     s->tiles = ((m->cap + TILE - 1) / TILE + 1) / 2 * 2;     // whole CTA pairs
     const size_t per_tile_t = (size_t)s->tiles * c.seq_len * SLAB_BYTES;
     int rc;
@@ -1195,6 +1220,11 @@ int tc_create(Model* m) {
     DSP_CUDA(cudaMemset(s->hfin_img, 0, (size_t)s->tiles * 2 * (2 * c.hidden_size / 64) * SLAB_BYTES));
     s->tc_head = c.num_classes <= HEAD_MAX_CLASSES;
     return DSP_OK;
+}
+
+bool tc_seq_split(const Model* m) {
+    const TcState* s = (const TcState*)m->tc_state;
+    return s && s->seq_split;
 }
 
 void tc_destroy(Model* m) {
@@ -1218,10 +1248,30 @@ void tc_drop_packs(Model* m) {
 
 int tc_pack_lstm_layer(Model* m, LstmLayer& L,
                        const float* wih0, const float* whh0, const float* bih0, const float* bhh0,
-                       const float* wih1, const float* whh1, const float* bih1, const float* bhh1) {
+                       const float* wih1, const float* whh1, const float* bih1, const float* bhh1,
+                       int split_first, int split_n, int len_col) {
     TcState* s = (TcState*)m->tc_state;
-    const int H = L.H, K = L.K;
+    const int H = L.H;
+    int K = L.K;
     DSP_REQUIRE(H == 128 || H == 256, DSP_ERR_INVALID, "tcgen05 path: LSTM hidden size %d unsupported", H);
+    // First layer of lstm_seq: the scalar features [split_first, split_first + split_n) arrive as FP16 value +
+    // FP16 residual (prep_images_kernel), so their W_ih columns appear twice; the len column (and its twin) is
+    // scaled by 1 / SEQ_LEN_SCALE.  Powers of two: the FP16 rounding of the weights is unchanged.
+    std::vector<float> wext[2];
+    if (split_n > 0) {
+        const int K2 = K + split_n;
+        const float* src[2] = {wih0, wih1};
+        for (int d = 0; d < 2; ++d) {
+            wext[d].assign((size_t)4 * H * K2, 0.f);
+            for (int r = 0; r < 4 * H; ++r)
+                for (int k = 0; k < K2; ++k) {
+                    const int k0 = k < K ? k : split_first + (k - K);
+                    wext[d][(size_t)r * K2 + k] = src[d][(size_t)r * K + k0] * (k0 == len_col ? 1.f / SEQ_LEN_SCALE : 1.f);
+                }
+        }
+        wih0 = wext[0].data(); wih1 = wext[1].data();
+        K = K2;
+    }
     const int KSX = (K + 63) / 64, KSH = H / 64, KS = KSX + KSH, NCH = H / 32;
     DSP_REQUIRE(KSX == 1 || KSX == 4 || KSX == 8, DSP_ERR_INVALID, "tcgen05 path: LSTM input width %d unsupported", K);
     TcLstmPack* pk = new TcLstmPack();
@@ -1347,8 +1397,6 @@ int tc_pack_head(Model* m, DenseF32& D, const float* w, const float* b) {
     return DSP_OK;
 }
 
-int tc_finalize_pack(Model*) { return DSP_OK; }
-
 int tc_forward_chunk(Model* m, const float* kmer, const float* means, const float* stds, const float* lens,
                      const float* signals, const float* const* h0, const float* const* c0,
                      const int64_t* sstride, uint64_t seed, uint64_t chunk_id, int64_t n,
@@ -1363,7 +1411,7 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
         const int64_t total = tiles * TILE * T;
         prep_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
             kmer, means, stds, lens, signals, m->embed, c.is_base ? c.embedding_size : 0, c.vocab_size, c.is_signallen,
-            c.signal_len, T, n, tiles * TILE, seq ? s->xseq_img : nullptr, sig ? s->xsig_img : nullptr);
+            s->seq_split ? 1 : 0, c.signal_len, T, n, tiles * TILE, seq ? s->xseq_img : nullptr, sig ? s->xsig_img : nullptr);
         m->launches++;
         DSP_CUDA(cudaGetLastError());
     }
@@ -1384,9 +1432,12 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
             p.y_img = head_tc ? s->hfin_img : s->ybuf[l & 1]; p.hfinal = (final_layer && !head_tc) ? s->hfinal : nullptr;
             p.n = n; p.T = T; p.xk16 = pk->xk16; p.y_slabs = 2 * hid / 64; p.y_col_off = 0;
             p.write_y = final_layer ? (head_tc ? 2 : 0) : 1;
-            // measurement hook (bench.py --meas-skip-y): skip the inter-layer activation stores of the hidden-256
-            // layers once the images hold realistic data from earlier passes, to price those stores
-            if (p.write_y == 1 && hid == 256) { const char* e = getenv("DSP_B200_MEAS_SKIP_Y"); if (e && atoi(e)) p.write_y = 0; }
+#ifdef DSP_MEAS_SKIP_Y
+            // measurement BUILD only (DSP_B200_VARIANT=skipy DSP_B200_DEFINES=-DDSP_MEAS_SKIP_Y, bench.py --meas-skip-y):
+            // skip the inter-layer activation stores of the hidden-256 layers once the images hold realistic data
+            // from earlier passes, to price those stores.  Results are wrong; the shipped library has no such switch.
+            if (p.write_y == 1 && hid == 256) { const char* e = getenv("DSP_B200_SKIP_Y_NOW"); if (e && atoi(e)) p.write_y = 0; }
+#endif
             Span sp(m, is_comb ? 1 : 4, st);
             // Two ways to run a hidden-128 layer: one CTA pair per (tile pair, direction), or both directions
             // as two chains of one CTA pair (branch_kernel: ~1.8x the time per CTA for 2x the work).  Pick
@@ -1397,7 +1448,7 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
                 const double single_cost = (double)((2 * tiles + sms - 1) / sms);
                 const double dual_cost = 1.8 * (double)((tiles + sms - 1) / sms);
                 dual = dual_cost < single_cost;
-                if (const char* e = getenv("DSP_B200_BRANCH_DUAL")) dual = atoi(e) != 0;
+                if (s->force_dual >= 0) dual = s->force_dual != 0;
             }
             if (dual) { p.w_img = pk->w_img_dual; p.bias = pk->bias_dual; }
             int rc = dual ? launch_branch<1>(m, p, tiles, st) : launch_lstm(m, pk->KSX, hid, p, tiles, st);

@@ -1,0 +1,189 @@
+// Stable multi-way partition of fixed-size items into up to 16 destination buffers, as three
+// kernels (count per block -> scan -> scatter).  Used with ONE destination as the stream compaction
+// of callable records on a single GPU (freq.cu) and with `world` destinations -- peer memory windows
+// mapped over NVLink -- as the fused partition + all-to-all of the multi-GPU call_freq (comm.cu):
+// the scatter kernel stores every item straight into the receiving GPU's window at its final
+// position, so the exchange overlaps the partition store by store and no send buffer exists.
+//
+// Stability is the point: items bound for the same destination keep their order (file order of the
+// per-read calls), because the float64 sums of call_mods_freq.py:60-61 are order sensitive.
+// HBM/NVLink-bound byte work: every item is read twice (count, scatter) and written once.
+#pragma once
+#include "freq.cuh"
+
+namespace dsp {
+namespace route {
+
+constexpr int MAXW = 16;
+constexpr int RT = 256;                       // threads per block
+constexpr int RWARPS = RT / 32;
+
+struct Plan {
+    int64_t n = 0;
+    int64_t per_block = 0;                    // items per block (multiple of RT)
+    int blocks = 0;
+};
+inline Plan make_plan(int64_t n, int n_sm) {
+    Plan p;
+    p.n = n;
+    const int64_t want = (int64_t)(n_sm > 0 ? n_sm : 148) * 8;
+    int64_t per = (n + want - 1) / want;
+    if (per < 4096) per = 4096;
+    per = (per + RT - 1) / RT * RT;
+    p.per_block = per;
+    p.blocks = (int)((n + per - 1) / per);
+    if (p.blocks < 1) p.blocks = 1;
+    return p;
+}
+
+__host__ __device__ __forceinline__ int owner_of_key(uint64_t key, int world) {
+    // multiplicative hash of the 64-bit site key, 31 bits, mod world (same as call_mods_freq.owner_of_key)
+    return (int)(((key * 0x9E3779B97F4A7C15ull) >> 33) % (uint64_t)world);
+}
+
+// ---- sources --------------------------------------------------------------------------------------
+// A source turns item index i into (keep?, destination, payload).
+struct RecFromColumns {                       // call_mods columns -> packed Rec, by key hash
+    typedef Rec Item;
+    const uint64_t* key; const double* p0; const double* p1; const int32_t* label;
+    uint64_t gidx_base; double prob_cf; int world;
+    __device__ __forceinline__ bool dest_of(int64_t i, int& d, uint64_t& k) const {
+        if (fabs(p0[i] - p1[i]) < prob_cf) return false;               // txt_formater.py:23-26
+        k = key[i];
+        d = world == 1 ? 0 : owner_of_key(k, world);
+        return true;
+    }
+    __device__ __forceinline__ void load(int64_t i, Item& it) const {
+        it.key = key[i]; it.p0 = p0[i]; it.p1 = p1[i];
+        it.gl = (gidx_base + (uint64_t)i) | (label[i] == 1 ? REC_LABEL_BIT : 0ull);
+    }
+};
+
+template <int UNITS>                           // rows of UNITS x 16 bytes, by range of a 64-bit field
+struct RowsByRange {
+    struct __align__(16) Item { uint4 u[UNITS]; };
+    const Item* rows; int field_word;           // index of the 64-bit field inside the row
+    uint64_t bounds[MAXW + 1]; int world;
+    __device__ __forceinline__ bool dest_of(int64_t i, int& d, uint64_t& k) const {
+        k = reinterpret_cast<const uint64_t*>(rows + i)[field_word];
+        int lo = 0;
+        for (int w = 1; w < world; ++w) lo += (k >= bounds[w]) ? 1 : 0;     // bounds ascending
+        d = lo;
+        return true;
+    }
+    __device__ __forceinline__ void load(int64_t i, Item& it) const { it = rows[i]; }
+};
+
+// ---- kernels ----------------------------------------------------------------------------------------
+template <typename Src>
+__global__ void __launch_bounds__(RT) count_kernel(Src src, Plan plan, int world, int32_t* __restrict__ blk_counts,
+                                                  unsigned long long* __restrict__ key_bits) {
+    __shared__ int s_cnt[MAXW];
+    if (threadIdx.x < MAXW) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t lo = (int64_t)blockIdx.x * plan.per_block;
+    const int64_t hi = min(plan.n, lo + plan.per_block);
+    int mine[MAXW];
+#pragma unroll
+    for (int d = 0; d < MAXW; ++d) mine[d] = 0;
+    uint64_t bits = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += RT) {
+        int d; uint64_t k;
+        if (src.dest_of(i, d, k)) {
+            bits |= k;
+#pragma unroll
+            for (int e = 0; e < MAXW; ++e) mine[e] += (e == d) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < MAXW; ++d) {
+        if (d < world) {
+            const int w = __reduce_add_sync(0xffffffffu, mine[d]);
+            if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[d], w);
+        }
+    }
+    const unsigned blo = __reduce_or_sync(0xffffffffu, (unsigned)bits), bhi = __reduce_or_sync(0xffffffffu, (unsigned)(bits >> 32));
+    if ((threadIdx.x & 31) == 0 && (blo | bhi)) atomicOr(key_bits, ((unsigned long long)bhi << 32) | blo);
+    __syncthreads();
+    if (threadIdx.x < world) blk_counts[(size_t)blockIdx.x * MAXW + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// one warp per destination: exclusive scan of the per-block counts; totals[d] = items bound for d
+__global__ void __launch_bounds__(MAXW * 32) scan_kernel(const int32_t* __restrict__ blk_counts, int blocks, int world,
+                                                        int64_t* __restrict__ blk_off, int64_t* __restrict__ totals) {
+    const int d = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (d >= world) return;
+    int64_t carry = 0;
+    for (int b0 = 0; b0 < blocks; b0 += 32) {
+        const int b = b0 + lane;
+        const int64_t v = b < blocks ? blk_counts[(size_t)b * MAXW + d] : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (b < blocks) blk_off[(size_t)b * MAXW + d] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) totals[d] = carry;
+}
+
+struct Targets {
+    void* dst[MAXW];                          // destination buffers (this GPU's or a peer's window)
+    int64_t base[MAXW];                       // first position of THIS source's segment in dst[d]
+};
+
+// Items of block b bound for d land at dst[d][base[d] + blk_off[b][d] + rank inside the block], in order.
+// `tg` is read from device memory: on the multi-GPU path the bases are computed on the device from the
+// count matrix the ranks publish to each other (no host round trip between count and scatter).
+template <typename Src>
+__global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int world, const int64_t* __restrict__ blk_off,
+                                                    const Targets* __restrict__ tg, const int* __restrict__ abort_flag) {
+    typedef typename Src::Item Item;
+    __shared__ int s_warp[RWARPS][MAXW];
+    __shared__ int64_t s_run[MAXW];
+    __shared__ Item* s_dst[MAXW];
+    if (abort_flag && *abort_flag) return;                               // a window would overflow: nobody writes
+    if (threadIdx.x < MAXW) {
+        const int d = threadIdx.x;
+        s_run[d] = d < world ? tg->base[d] + blk_off[(size_t)blockIdx.x * MAXW + d] : 0;
+        s_dst[d] = d < world ? reinterpret_cast<Item*>(tg->dst[d]) : nullptr;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t lo = (int64_t)blockIdx.x * plan.per_block;
+    const int64_t hi = min(plan.n, lo + plan.per_block);
+    for (int64_t t0 = lo; t0 < hi; t0 += RT) {
+        const int64_t i = t0 + threadIdx.x;
+        int d = -1; uint64_t k;
+        bool keep = false;
+        if (i < hi) { int dd; keep = src.dest_of(i, dd, k); if (keep) d = dd; }
+        int rank = 0;
+        for (int e = 0; e < world; ++e) {
+            const unsigned m = __ballot_sync(0xffffffffu, d == e);
+            if (d == e) rank = __popc(m & lt);
+            if (lane == 0) s_warp[warp][e] = __popc(m);
+        }
+        __syncthreads();
+        if (keep) {
+            int before = 0;
+            for (int w = 0; w < warp; ++w) before += s_warp[w][d];
+            Item it;
+            src.load(i, it);
+            s_dst[d][s_run[d] + before + rank] = it;
+        }
+        __syncthreads();
+        if (threadIdx.x < world) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < RWARPS; ++w) tot += s_warp[w][threadIdx.x];
+            s_run[threadIdx.x] += tot;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace route
+}  // namespace dsp

@@ -10,10 +10,12 @@ void tc_destroy(Model* m);
 // weight_hh (4H,H), bias_ih (4H), bias_hh (4H)); d0 = forward, d1 = reverse
 int tc_pack_lstm_layer(Model* m, LstmLayer& L,
                        const float* wih0, const float* whh0, const float* bih0, const float* bhh0,
-                       const float* wih1, const float* whh1, const float* bih1, const float* bhh1);
+                       const float* wih1, const float* whh1, const float* bih1, const float* bhh1,
+                       int split_first = 0, int split_n = 0, int len_col = -1);
+// true when the first lstm_seq layer takes its scalar features as FP16 value + residual columns
+bool tc_seq_split(const Model* m);
 int tc_pack_dense(Model* m, DenseF32& D, const float* w, const float* b);
 int tc_pack_head(Model* m, DenseF32& fc1, const float* w, const float* b);
-int tc_finalize_pack(Model* m);
 void tc_drop_packs(Model* m);      // forget the packed layers before a re-pack (their device memory is freed by the caller)
 int tc_forward_chunk(Model* m, const float* kmer, const float* means, const float* stds, const float* lens,
                      const float* signals, const float* const* h0, const float* const* c0,

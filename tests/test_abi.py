@@ -38,6 +38,14 @@ def test_sass_is_sm100a_only():
     assert archs == {"100a"}, archs
 
 
+def test_shipped_library_has_no_result_changing_switch():
+    # measurement hooks that change results (skipping activation stores) exist only in variant builds
+    # (-DDSP_MEAS_SKIP_Y); the shipped .so must not even contain the switch's name
+    blob = open(_native.LIB_PATH, "rb").read()
+    for needle in (b"MEAS_SKIP", b"SKIP_Y_NOW"):
+        assert needle not in blob, needle
+
+
 @pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
 def test_create_fails_loudly_without_gpu():
     L = _native.lib()
