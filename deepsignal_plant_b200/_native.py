@@ -19,6 +19,8 @@ SYMBOLS = (
     "dsp_set_timing", "dsp_get_timing", "dsp_freq_aggregate", "dsp_selftest",
     "dsp_parse_features", "dsp_format_calls", "dsp_freq_release_cache", "dsp_extract_features", "dsp_format_sampleinfo", "dsp_find_sites", "dsp_extract_features_f64",
     "dsp_format_features", "dsp_parse_calls", "dsp_format_freq",
+    "dsp_comm_create", "dsp_comm_export", "dsp_comm_connect", "dsp_comm_destroy", "dsp_freq_aggregate_distributed",
+    "dsp_comm_route_rows", "dsp_comm_last_timing",
 )
 
 MODULES = {"both_bilstm": 0, "seq_bilstm": 1, "signal_bilstm": 2}
@@ -90,6 +92,14 @@ def lib():
                                   C.POINTER(i64), i32]
     L.dsp_find_sites.argtypes = [C.c_int, vp, vp, i64, i64, C.c_char_p, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64,
                                  vp, vp, vp, vp, C.POINTER(i64), vp]
+    L.dsp_comm_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, i64]
+    L.dsp_comm_export.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    L.dsp_comm_connect.argtypes = [vp, vp, i64]
+    L.dsp_comm_destroy.argtypes = [vp]
+    L.dsp_freq_aggregate_distributed.argtypes = [vp, vp, vp, vp, vp, i64, u64, C.c_double, vp, i32, vp, i64,
+                                                 C.POINTER(i64), C.POINTER(i64), vp]
+    L.dsp_comm_route_rows.argtypes = [vp, vp, i64, i32, i32, vp, vp, i64, C.POINTER(i64), vp]
+    L.dsp_comm_last_timing.argtypes = [vp, vp]
     for name in SYMBOLS:
         getattr(L, name)  # AttributeError here means header and library disagree
     _lib = L

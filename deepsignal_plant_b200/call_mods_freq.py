@@ -11,10 +11,10 @@ and ``utils/txt_formater.py`` (``ModRecord`` parsing rules, ``SiteStats`` attrib
 ``split_key``).  The text is parsed into columns on the host, the segmented reduction --
 callable filter, grouping by (chrom, pos), ordered float64 replay, integer counts, output
 ordering -- runs in ``dsp_freq_aggregate`` (csrc/freq.cu), and the bytes written are
-identical to the reference's.  With ``torch.distributed`` initialised,
-``aggregate_records_distributed`` shards records by site key across ranks with one
-variable-size all-to-all (NCCL over NVLink) and no partial-sum merging, because float64
-addition is order sensitive.
+identical to the reference's.  Under ``torchrun`` (one process per GPU) ``call_mods_frequency_to_file`` hands
+over to ``freq_dist.call_freq_distributed``: ranks parse contiguous byte shards, records are routed by site key
+over NVLink peer memory (csrc/comm.cu) with no partial-sum merging, because float64 addition is order
+sensitive, and every rank writes its own slice of the table.
 """
 from __future__ import annotations
 
@@ -94,6 +94,28 @@ class Records:
         """(strand, pos_in_strand, kmer) of the given records only, strings as object arrays."""
         return _cells_to_str(self._strand[idx]), self.pos_in_strand[idx], _cells_to_str(self._kmer[idx])
 
+    def chrom_codes(self):
+        """(int32 codes, list of names): the chromosome column as codes into a name table (any order)."""
+        if self._codes is not None:
+            return self._codes
+        names, index = [], {}
+        codes = np.fromiter((index.setdefault(c, len(index)) for c in self.chrom.tolist()), dtype=np.int32, count=len(self))
+        return codes, list(index)
+
+    def meta_cells(self, idx):
+        """(strand, pos_in_strand, kmer) of the given records as fixed-width byte cells (S8 / int64 / S24) -- the form
+        in which site rows carry their text columns between ranks."""
+        def cells(a, width):
+            a = a[idx]
+            if _is_cells(a):
+                return a.astype("S%d" % width)
+            b = np.asarray([x.encode() for x in a.tolist()], dtype=object)
+            if len(b) and max(len(x) for x in b) > width:
+                raise ValueError("a strand / k-mer column wider than %d bytes cannot travel between ranks; "
+                                 "run call_freq in one process for this input" % width)
+            return b.astype("S%d" % width) if len(b) else np.empty(0, "S%d" % width)
+        return cells(self._strand, 8), self.pos_in_strand[idx], cells(self._kmer, 24)
+
     def chrom_ranks(self):
         """(ids, names): chromosome ids by rank in Python string order, so that integer key order equals the
         reference's ``(chrom, pos)`` tuple order (``call_mods_freq.py:88``)."""
@@ -158,13 +180,38 @@ def parse_lines(lines):
     return Records(chrom, pos, strand, pis, p0, p1, label, kmer)
 
 
-def _read_mods_file_native(path, nthreads=None):
-    """``dsp_parse_calls`` over the whole file (mapped in place, or decompressed): compact ``Records``, or None
-    when a strand / k-mer column is wider than the parser's fixed cells."""
+def _shard_view(buf, byte_range):
+    """The lines of ``buf`` whose first byte lies in [lo, hi): a line belongs to the shard it starts in."""
+    lo, hi = byte_range
+    n = buf.size
+
+    def line_start_at_or_after(p):
+        if p <= 0:
+            return 0
+        if p >= n:
+            return n
+        if buf[p - 1] == 10:
+            return p
+        blk = 1 << 16
+        q = p
+        while q < n:
+            hit = np.flatnonzero(buf[q:q + blk] == 10)
+            if hit.size:
+                return q + int(hit[0]) + 1
+            q += blk
+        return n
+    return buf[line_start_at_or_after(lo):line_start_at_or_after(hi)]
+
+
+def _read_mods_file_native(path, nthreads=None, byte_range=None):
+    """``dsp_parse_calls`` over the whole file (mapped in place, or decompressed) or over the lines that start inside
+    ``byte_range``: compact ``Records``, or None when a strand / k-mer column is wider than the parser's fixed cells."""
     import mmap
     L = _native.lib()
     nthreads = int(nthreads or min(32, os.cpu_count() or 1))
     if path.endswith(".gz"):
+        if byte_range is not None:
+            raise ValueError("byte_range needs an uncompressed call_mods file")
         with gzip.open(path, "rb") as f:
             buf = np.frombuffer(f.read(), np.uint8)
         mm = None
@@ -172,7 +219,12 @@ def _read_mods_file_native(path, nthreads=None):
         with open(path, "rb") as f:
             mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
         buf = np.frombuffer(mm, np.uint8)
+    whole = buf
+    if byte_range is not None:
+        buf = _shard_view(buf, byte_range)
     try:
+        if buf.size == 0:
+            return Records([], [], [], [], [], [], [], [])
         n = C.c_int64(0)
         cap = buf.size // 20 + 2                        # a well-formed line has at least 20 bytes; untouched pages cost nothing
         code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
@@ -203,7 +255,7 @@ def _read_mods_file_native(path, nthreads=None):
         table = names[:int(nb.value)].tobytes().decode().split("\n")[:int(nn.value)]
         return Records(None, pos[:m], strand[:m], pis[:m], p0[:m], p1[:m], label[:m], kmer[:m], (code[:m], table))
     finally:
-        del buf
+        del buf, whole
         if mm is not None:
             try:
                 mm.close()
@@ -211,13 +263,18 @@ def _read_mods_file_native(path, nthreads=None):
                 pass
 
 
-def read_mods_file(path):
-    """One call_mods file (plain or .gz, ``call_mods_freq.py:45-48``) -> ``Records``."""
+def read_mods_file(path, byte_range=None):
+    """One call_mods file (plain or .gz, ``call_mods_freq.py:45-48``) -> ``Records``; ``byte_range=(lo, hi)`` keeps
+    only the lines that start inside it (one rank's shard of an uncompressed file)."""
     if os.path.getsize(path) == 0:
         return Records([], [], [], [], [], [], [], [])
-    rec = _read_mods_file_native(path)
+    rec = _read_mods_file_native(path, byte_range=byte_range)
     if rec is not None:
         return rec
+    if byte_range is not None:
+        with open(path, "rb") as f:
+            data = np.frombuffer(f.read(), np.uint8)
+        return parse_lines(_shard_view(data, byte_range).tobytes().decode().splitlines())
     import pandas as pd
     try:
         df = pd.read_csv(path, sep="\t", header=None, usecols=[0, 1, 2, 3, 6, 7, 8, 9],
@@ -276,6 +333,18 @@ class FreqTable:
                          f(self.prob_0), f(self.prob_1), f(self.met), f(self.unmet), f(self.coverage),
                          f(self.first_index), self.n_records, self.n_used)
 
+    @staticmethod
+    def concat(tables):
+        tables = [t for t in tables if len(t)]
+        if not tables:
+            e = np.empty(0)
+            return FreqTable(np.empty(0, object), e.astype(np.int64), np.empty(0, object), e.astype(np.int64), np.empty(0, object),
+                             e, e, e.astype(np.int32), e.astype(np.int32), e.astype(np.int32), e.astype(np.int64))
+        cat = lambda f: np.concatenate([getattr(t, f) for t in tables])
+        return FreqTable(cat("chrom"), cat("pos"), cat("strand"), cat("pos_in_strand"), cat("kmer"), cat("prob_0"), cat("prob_1"),
+                         cat("met"), cat("unmet"), cat("coverage"), cat("first_index"),
+                         sum(t.n_records for t in tables), sum(t.n_used for t in tables))
+
     def sorted(self):
         """``sorted(keys, key=split_key)`` (``call_mods_freq.py:88``): (chrom str, pos int)."""
         uniq, inv = np.unique(self.chrom.astype(str), return_inverse=True)   # code-point order, like Python str
@@ -297,21 +366,47 @@ def make_keys(chrom_ids, pos):
     return (chrom_ids.astype(np.uint64) << np.uint64(POS_BITS)) | pos.astype(np.uint64)
 
 
-def _aggregate_device(keys, p0, p1, label, prob_cf, sort_by_key, device):
-    """numpy columns -> (key, first, s0, s1, met, unmet, cov) numpy arrays via the GPU."""
+MAX_RECORDS_PER_PASS = 1 << 30       # dsp_freq_aggregate takes < 2^31 records; its scratch is ~100 B per record
+
+
+def _aggregate_device(keys, p0, p1, label, prob_cf, sort_by_key, device, max_records=None):
+    """numpy columns -> (key, first, s0, s1, met, unmet, cov) numpy arrays via the GPU.  More than ``max_records``
+    records are aggregated in several passes over key-hash shards: a site's records never span two shards and keep
+    their order inside one, so every sum is the same as in one pass; the rows are then put back in the one-pass
+    order (a genome-scale run of > 2^31 calls, which the reference streams through a dict)."""
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("call_freq aggregation needs a CUDA device; there is no CPU path")
-    L = _native.lib()
     n = int(keys.shape[0])
+    limit = int(max_records or MAX_RECORDS_PER_PASS)
     dev = torch.device("cuda", device)
-    with torch.cuda.device(dev):
-        t_key = torch.from_numpy(keys.view(np.int64)).to(dev)
-        t_p0 = torch.from_numpy(np.ascontiguousarray(p0)).to(dev)
-        t_p1 = torch.from_numpy(np.ascontiguousarray(p1)).to(dev)
-        t_lab = torch.from_numpy(np.ascontiguousarray(label, dtype=np.int32)).to(dev)
-        out = _aggregate_tensors(t_key, t_p0, t_p1, t_lab, prob_cf, sort_by_key, dev)
-        return tuple(t.cpu().numpy() for t in out)
+
+    def one_pass(k, a, b, lab, by_key):
+        with torch.cuda.device(dev):
+            t_key = torch.from_numpy(np.ascontiguousarray(k).view(np.int64)).to(dev)
+            t_p0 = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            t_p1 = torch.from_numpy(np.ascontiguousarray(b)).to(dev)
+            t_lab = torch.from_numpy(np.ascontiguousarray(lab, dtype=np.int32)).to(dev)
+            out = _aggregate_tensors(t_key, t_p0, t_p1, t_lab, prob_cf, by_key, dev)
+            return tuple(t.cpu().numpy() for t in out)
+    if n <= limit:
+        return one_pass(keys, p0, p1, label, sort_by_key)
+    shards = -(-n // limit) * 2                        # hashing balances sites, not records: leave room
+    owner = owner_of_key(keys, shards)
+    parts = []
+    for s in range(shards):
+        idx = np.flatnonzero(owner == s)
+        if idx.size == 0:
+            continue
+        if idx.size > limit:
+            raise RuntimeError("one key-hash shard holds %d records (> %d): a single site dominates the input" % (idx.size, limit))
+        k, first, s0, s1, met, unmet, cov = one_pass(keys[idx], p0[idx], p1[idx], label[idx], True)
+        parts.append((k, idx[first], s0, s1, met, unmet, cov))
+    if not parts:
+        return one_pass(keys[:0], p0[:0], p1[:0], label[:0], sort_by_key)
+    cols = [np.concatenate([p[i] for p in parts]) for i in range(7)]
+    order = np.argsort(cols[0].view(np.uint64), kind="stable") if sort_by_key else np.argsort(cols[1], kind="stable")
+    return tuple(c[order] for c in cols)
 
 
 def _aggregate_tensors(t_key, t_p0, t_p1, t_lab, prob_cf, sort_by_key, dev):
@@ -460,104 +555,13 @@ def write_sitekey2stats(sitekey2stats, result_file, is_sort, is_bed, is_gzip):
     wf.close()
 
 
-# ---- multi-GPU: shard by site key, one all-to-all, no partial sums -------------------------
+# ---- key-hash shards (multi-pass on one GPU here; the multi-GPU exchange lives in freq_dist.py / csrc/comm.cu) ----
 
 def owner_of_key(keys, world):
-    """Rank that owns a site key: multiplicative hash of the 64-bit key, mod world."""
+    """Shard that owns a site key: multiplicative hash of the 64-bit key, mod world (``route::owner_of_key`` in
+    csrc/route.cuh is the same function on the device)."""
     h = (keys.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(33)
     return (h % np.uint64(world)).astype(np.int64)
-
-
-def owner_of_key_t(keys, world):
-    """``owner_of_key`` on an int64 torch tensor (any device): the same 31-bit hash, computed with
-    wrapping int64 arithmetic (arithmetic shift + mask = logical shift)."""
-    h = (keys * (-7046029254386353131)) >> 33            # 0x9E3779B97F4A7C15 as a signed 64-bit constant
-    return (h & 0x7FFFFFFF) % world
-
-
-def exchange_rows(rows, dest, world, group=None):
-    """Variable-size all-to-all of int64 rows that stay on their device: row i of ``rows`` (m, w) goes
-    to rank ``dest[i]``; rows bound for the same rank keep their order; the result concatenates what
-    source ranks 0..world-1 sent, in rank order.  One ``all_to_all_single`` with split sizes = NCCL
-    send/recv over NVLink on GPUs (gloo in the CPU tests)."""
-    import torch
-    import torch.distributed as dist
-    order = torch.sort(dest, stable=True).indices
-    counts = torch.bincount(dest, minlength=world)
-    send = rows[order].contiguous()
-    recv_counts = torch.empty_like(counts)
-    dist.all_to_all_single(recv_counts, counts, group=group)
-    in_splits, out_splits = counts.tolist(), recv_counts.tolist()
-    recv = rows.new_empty((int(sum(out_splits)), rows.shape[1]))
-    dist.all_to_all_single(recv, send, out_splits, in_splits, group=group)
-    return recv
-
-
-def _gpu_local_aggregate(got, prob_cf, dev):
-    """(m,5) int64 device rows [key, p0 bits, p1 bits, label, gidx] -> (s,7) int64 device rows
-    [key, first_gidx, s0 bits, s1 bits, met, unmet, cov] via dsp_freq_aggregate."""
-    import torch
-    if got.shape[0] == 0:
-        return torch.empty((0, 7), dtype=torch.int64, device=dev)
-    key = got[:, 0].contiguous()
-    p0 = got[:, 1].contiguous().view(torch.float64)
-    p1 = got[:, 2].contiguous().view(torch.float64)
-    lab = got[:, 3].to(torch.int32).contiguous()
-    k, first, s0, s1, met, unmet, cov = _aggregate_tensors(key, p0, p1, lab, prob_cf, True, dev)
-    return torch.stack([k, got[:, 4][first], s0.view(torch.int64), s1.view(torch.int64),
-                        met.to(torch.int64), unmet.to(torch.int64), cov.to(torch.int64)], dim=1)
-
-
-def aggregate_tensors_distributed(key, p0, p1, label, gidx, prob_cf, sort_by_key=False, group=None, local_aggregate=None):
-    """Multi-GPU ``calculate_mods_frequency`` on tensors that are already on this rank's device
-    (int64 keys, float64 probabilities, int32 labels, int64 global record indices of THIS rank's
-    contiguous shard, file order).  Callable records are routed to ``owner_of_key_t`` with one
-    variable-size all-to-all, so all records of a site reach one rank in ascending global order and
-    the float64 sums are the reference's bit for bit (no partial-sum merge: float64 addition is
-    order sensitive).  Each rank aggregates its keys with ``dsp_freq_aggregate``; the per-site rows
-    are collected on rank 0 and ordered by first callable appearance (dict insertion order) or by
-    key.  Nothing but split sizes visits the host.  Returns on rank 0 an (s, 7) int64 tensor
-    [key, first_gidx, s0 bits, s1 bits, met, unmet, cov]; ``None`` elsewhere."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    dev = key.device
-    keep = ~((p0 - p1).abs() < prob_cf)                   # txt_formater.py:23-26, before the exchange
-    rows = torch.stack([key, p0.view(torch.int64), p1.view(torch.int64), label.to(torch.int64), gidx], dim=1)[keep]
-    got = exchange_rows(rows, owner_of_key_t(rows[:, 0], world), world, group)
-    if local_aggregate is None:
-        if dev.type != "cuda":
-            raise RuntimeError("call_freq aggregation needs a CUDA device; there is no CPU path")
-        with torch.cuda.device(dev):
-            mine = _gpu_local_aggregate(got, prob_cf, dev)
-    else:
-        mine = torch.from_numpy(np.ascontiguousarray(local_aggregate(got.cpu().numpy(), prob_cf))).to(dev)
-    merged = exchange_rows(mine, torch.zeros(mine.shape[0], dtype=torch.int64, device=dev), world, group)
-    if rank != 0:
-        return None
-    order = torch.sort(merged[:, 0] if sort_by_key else merged[:, 1], stable=True).indices
-    return merged[order]
-
-
-def aggregate_records_distributed(keys, p0, p1, label, gidx, prob_cf, sort_by_key=False, device=None,
-                                  group=None, local_aggregate=None):
-    """numpy front end of ``aggregate_tensors_distributed``: every rank passes ITS contiguous shard
-    of the records in file order (``gidx`` = global record index, ascending across ranks).  Returns
-    on rank 0 a tuple of numpy arrays (key uint64, first_gidx, s0, s1, met, unmet, cov); ``None``
-    elsewhere.  ``local_aggregate(rows, prob_cf) -> rows7`` replaces the GPU step in the CPU (gloo) tests."""
-    import torch
-    if device is None and local_aggregate is None:
-        raise RuntimeError("call_freq aggregation needs a CUDA device; there is no CPU path")
-    dev = torch.device("cuda", device) if device is not None else torch.device("cpu")
-    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt, copy=False)).to(dev)
-    m = aggregate_tensors_distributed(t(keys.view(np.int64), np.int64), t(p0, np.float64), t(p1, np.float64),
-                                      t(label, np.int32), t(gidx, np.int64), prob_cf, sort_by_key, group, local_aggregate)
-    if m is None:
-        return None
-    m = m.cpu().numpy()
-    return (m[:, 0].copy().view(np.uint64), m[:, 1].copy(), m[:, 2].copy().view(np.float64), m[:, 3].copy().view(np.float64),
-            m[:, 4].astype(np.int32), m[:, 5].astype(np.int32), m[:, 6].astype(np.int32))
 
 
 def parse_contigs_arg(contigs):
@@ -596,7 +600,9 @@ def order_by_contig(table, contigs, is_sort):
 def call_mods_frequency_to_file(args):
     """``call_mods_freq.py:218-296``: collect files, aggregate, write.  With ``--contigs`` only the
     listed contigs are used and the rows come out contig by contig like the reference's per-contig
-    mode (its temp files and ``--nproc`` worker processes are replaced by one GPU pass)."""
+    mode (its temp files and ``--nproc`` worker processes are replaced by GPU passes, one contig at a time so
+    that memory stays bounded by the largest contig).  Under ``torchrun`` (WORLD_SIZE > 1) the work is spread
+    over the ranks' GPUs (``freq_dist.py``)."""
     print("[main]call_freq starts..")
     start = time.time()
     mods_files = []
@@ -612,17 +618,61 @@ def call_mods_frequency_to_file(args):
             raise ValueError("--input_path is not a file or a directory!")
     print("get {} input file(s)..".format(len(mods_files)))
     contigs = parse_contigs_arg(getattr(args, "contigs", None))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        from . import freq_dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        ndev = torch.cuda.device_count()
+        if ndev == 0:
+            raise RuntimeError("call_freq aggregation needs a CUDA device; there is no CPU path")
+        if not dist.is_initialized():
+            # one GPU per rank: NCCL carries the (tiny) control plane; ranks sharing a GPU fall back to gloo for it --
+            # the records travel through CUDA IPC windows either way
+            if ndev >= world:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            else:
+                dist.init_process_group("gloo")
+        device = local % ndev
+        torch.cuda.set_device(device)
+        print("read the input files..")
+        table, considered, path = freq_dist.call_freq_distributed(sorted(mods_files) if getattr(args, "sort_files", False) else mods_files,
+                                                                  args.prob_cf, args.result_file, args.sort, args.bed, args.gzip,
+                                                                  contigs=contigs, device=device)
+        if dist.get_rank() == 0 and table.n_records > 0:
+            print("{:.2f}% ({} of {}) calls used..".format(table.n_used / float(table.n_records) * 100, table.n_used, table.n_records))
+            print("[main]call_freq costs %.1f seconds.." % (time.time() - start))
+        return
     if contigs is None:
         print("read the input files..")
         sites_stats = calculate_mods_frequency(mods_files, args.prob_cf)
         print("write the result..")
         write_sitekey2stats(sites_stats, args.result_file, args.sort, args.bed, args.gzip)
     else:
+        # The reference splits the input by contig into temp files and aggregates one contig per worker
+        # (call_mods_freq.py:154-200), so its memory is bounded by the largest contig.  Same bound here: the
+        # records are parsed once file by file, kept only for the listed contigs, and aggregated one contig per
+        # GPU pass in the reference's concatenation order.
         print("start processing {} contigs..".format(len(contigs)))
-        rec = Records.concat([read_mods_file(f) for f in mods_files])
-        rec = rec.select(rec.chrom_in(set(contigs)))
-        table = aggregate_records(rec, args.prob_cf)
-        print("{} of {} calls used for {} contigs..".format(table.n_used, len(rec), len(contigs)))
-        table = order_by_contig(table, contigs, args.sort)
+        wanted = set(contigs)
+        parts, n_all = [], 0
+        for f in mods_files:
+            r = read_mods_file(f)
+            n_all += len(r)
+            parts.append(r.select(r.chrom_in(wanted)))
+        rec = Records.concat(parts)
+        del parts
+        codes, names = rec.chrom_codes()
+        tables, used = [], 0
+        for contig in sorted(set(contigs), key=lambda c: c + "."):
+            if contig not in names:
+                continue
+            sub = rec.select(codes == names.index(contig))
+            t = aggregate_records(sub, args.prob_cf)
+            used += t.n_used
+            tables.append(t.sorted() if args.sort else t)
+        print("{} of {} calls used for {} contigs..".format(used, len(rec), len(contigs)))
+        table = FreqTable.concat(tables)
         write_sitekey2stats(table, args.result_file, False, args.bed, args.gzip)
     print("[main]call_freq costs %.1f seconds.." % (time.time() - start))

@@ -26,6 +26,7 @@
 #include <cub/cub.cuh>
 #include <mutex>
 #include <list>
+#include <cstdlib>
 
 namespace dsp {
 
@@ -143,13 +144,10 @@ __global__ void __launch_bounds__(RS) replay_kernel(const uint32_t* __restrict__
     }
 }
 
-__global__ void row_first_kernel(const SiteRow* __restrict__ rows, int64_t n, uint64_t* __restrict__ first, uint32_t* __restrict__ id) {
+template <typename F>
+__global__ void row_field_kernel(const SiteRow* __restrict__ rows, int64_t n, int by_key, F* __restrict__ f, uint32_t* __restrict__ id) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { first[i] = rows[i].first; id[i] = (uint32_t)i; }
-}
-__global__ void row_key_kernel(const SiteRow* __restrict__ rows, int64_t n, uint64_t* __restrict__ key, uint32_t* __restrict__ id) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { key[i] = rows[i].key; id[i] = (uint32_t)i; }
+    if (i < n) { f[i] = (F)(by_key ? rows[i].key : rows[i].first); id[i] = (uint32_t)i; }
 }
 __global__ void gather_rows_kernel(const SiteRow* __restrict__ rows, const uint32_t* __restrict__ perm, int64_t n, SiteRow* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,6 +207,16 @@ int sites_from_records(Scratch& sc, cudaStream_t st, const Rec* rec, int64_t m, 
                        SiteRow* rows, int64_t* nseg_host) {
     *nseg_host = 0;
     if (m == 0) return DSP_OK;
+    {
+        // the replay gathers one aligned 32-byte record per sorted position: ask L2 not to fetch the neighbouring
+        // sectors of the 128-byte line (measured: 125 B of DRAM reads per record without this)
+        static bool hinted[64] = {};
+        if (sc.device >= 0 && sc.device < 64 && !hinted[sc.device]) {
+            hinted[sc.device] = true;
+            if (!getenv("DSP_B200_KEEP_L2_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+            cudaGetLastError();
+        }
+    }
     DSP_REQUIRE(m < (int64_t)0x7fffffff, DSP_ERR_INVALID, "call_freq: %lld records in one aggregation pass (< 2^31; shard by key)", (long long)m);
     const BitRuns runs = make_bit_runs(bits_used);
     return runs.bits <= 32 ? sites_typed<uint32_t>(sc, st, rec, m, runs, rows, nseg_host)
@@ -231,9 +239,9 @@ int pack_callable(Scratch& sc, cudaStream_t st, const uint64_t* key, const doubl
     tg.dst[0] = rec; tg.base[0] = 0;
     DSP_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned long long), st));
     DSP_CUDA(cudaMemcpyAsync(d_tg, &tg, sizeof(tg), cudaMemcpyHostToDevice, st));
-    count_kernel<RecFromColumns><<<plan.blocks, RT, 0, st>>>(src, plan, 1, blk_counts, d_bits);
+    count_kernel<RecFromColumns><<<plan.blocks, RT, 0, st>>>(src, plan, 1, blk_counts);
     scan_kernel<<<1, MAXW * 32, 0, st>>>(blk_counts, plan.blocks, 1, blk_off, totals);
-    scatter_kernel<RecFromColumns><<<plan.blocks, RT, 0, st>>>(src, plan, 1, blk_off, d_tg, nullptr);
+    scatter_kernel<RecFromColumns><<<plan.blocks, RT, 0, st>>>(src, plan, 1, blk_off, d_tg, nullptr, d_bits);
     DSP_CUDA(cudaGetLastError());
     int64_t m = 0;
     DSP_CUDA(cudaMemcpyAsync(&m, totals, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -243,27 +251,32 @@ int pack_callable(Scratch& sc, cudaStream_t st, const uint64_t* key, const doubl
     return DSP_OK;
 }
 
-// rows (n) -> permutation that orders them by `first` (by_key == 0) or by key; bits = significant bits of the field
-int order_rows(Scratch& sc, cudaStream_t st, const SiteRow* rows, int64_t n, int by_key, uint32_t** perm_out) {
-    uint64_t *f, *fs; uint32_t *id, *perm;
+template <typename F>
+int order_rows_typed(Scratch& sc, cudaStream_t st, const SiteRow* rows, int64_t n, int by_key, uint32_t** perm_out, int end_bit) {
+    F *f, *fs; uint32_t *id, *perm;
     int rc;
     if ((rc = sc.alloc(&f, n)) || (rc = sc.alloc(&fs, n)) || (rc = sc.alloc(&id, n)) || (rc = sc.alloc(&perm, n))) return rc;
-    if (by_key) row_key_kernel<<<blocks(n), 256, 0, st>>>(rows, n, f, id);
-    else row_first_kernel<<<blocks(n), 256, 0, st>>>(rows, n, f, id);
+    row_field_kernel<F><<<blocks(n), 256, 0, st>>>(rows, n, by_key, f, id);
     DSP_CUDA(cudaGetLastError());
     size_t tmp_bytes = 0;
     void* tmp;
-    DSP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, f, fs, id, perm, (int)n, 0, 64, st));
+    DSP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, f, fs, id, perm, (int)n, 0, end_bit, st));
     if ((rc = sc.alloc((uint8_t**)&tmp, tmp_bytes))) return rc;
-    DSP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, f, fs, id, perm, (int)n, 0, 64, st));
+    DSP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, f, fs, id, perm, (int)n, 0, end_bit, st));
     *perm_out = perm;
     return DSP_OK;
 }
 
-int sort_rows(Scratch& sc, cudaStream_t st, const SiteRow* rows, int64_t n, int by_key, SiteRow* out) {
+// rows (n) -> permutation that orders them by `first` (by_key == 0) or by key; end_bit = significant bits of the field
+int order_rows(Scratch& sc, cudaStream_t st, const SiteRow* rows, int64_t n, int by_key, uint32_t** perm_out, int end_bit = 64) {
+    return end_bit <= 32 ? order_rows_typed<uint32_t>(sc, st, rows, n, by_key, perm_out, end_bit)
+                         : order_rows_typed<uint64_t>(sc, st, rows, n, by_key, perm_out, end_bit);
+}
+
+int sort_rows(Scratch& sc, cudaStream_t st, const SiteRow* rows, int64_t n, int by_key, SiteRow* out, int end_bit) {
     if (n == 0) return DSP_OK;
     uint32_t* perm;
-    int rc = order_rows(sc, st, rows, n, by_key, &perm);
+    int rc = order_rows(sc, st, rows, n, by_key, &perm, end_bit);
     if (rc) return rc;
     gather_rows_kernel<<<blocks(n), 256, 0, st>>>(rows, perm, n, out);
     DSP_CUDA(cudaGetLastError());
@@ -311,7 +324,9 @@ extern "C" int dsp_freq_aggregate(int device, const uint64_t* key, const double*
     int64_t nseg = 0;
     if ((rc = sites_from_records(sc, st, rec, m, bits, rows, &nseg))) return rc;
     uint32_t* perm = nullptr;                         // rows are in key order; dict insertion order = by first appearance
-    if (!sort_by_key && (rc = order_rows(sc, st, rows, nseg, 0, &perm))) return rc;
+    int first_bits = 1;
+    while (first_bits < 63 && (1ll << first_bits) < n) ++first_bits;              // `first` is a record index < n
+    if (!sort_by_key && (rc = order_rows(sc, st, rows, nseg, 0, &perm, first_bits))) return rc;
     emit_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(rows, perm, nseg, out_key, out_first, out_p0, out_p1, out_met, out_unmet, out_cov);
     DSP_CUDA(cudaGetLastError());
     DSP_CUDA(cudaStreamSynchronize(st));

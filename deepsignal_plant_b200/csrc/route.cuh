@@ -49,8 +49,9 @@ struct RecFromColumns {                       // call_mods columns -> packed Rec
     uint64_t gidx_base; double prob_cf; int world;
     __device__ __forceinline__ bool dest_of(int64_t i, int& d, uint64_t& k) const {
         if (fabs(p0[i] - p1[i]) < prob_cf) return false;               // txt_formater.py:23-26
+        if (world == 1) { d = 0; k = 0; return true; }                // one destination: the key is not needed to count
         k = key[i];
-        d = world == 1 ? 0 : owner_of_key(k, world);
+        d = owner_of_key(k, world);
         return true;
     }
     __device__ __forceinline__ void load(int64_t i, Item& it) const {
@@ -76,8 +77,7 @@ struct RowsByRange {
 
 // ---- kernels ----------------------------------------------------------------------------------------
 template <typename Src>
-__global__ void __launch_bounds__(RT) count_kernel(Src src, Plan plan, int world, int32_t* __restrict__ blk_counts,
-                                                  unsigned long long* __restrict__ key_bits) {
+__global__ void __launch_bounds__(RT) count_kernel(Src src, Plan plan, int world, int32_t* __restrict__ blk_counts) {
     __shared__ int s_cnt[MAXW];
     if (threadIdx.x < MAXW) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -86,11 +86,9 @@ __global__ void __launch_bounds__(RT) count_kernel(Src src, Plan plan, int world
     int mine[MAXW];
 #pragma unroll
     for (int d = 0; d < MAXW; ++d) mine[d] = 0;
-    uint64_t bits = 0;
     for (int64_t i = lo + threadIdx.x; i < hi; i += RT) {
         int d; uint64_t k;
         if (src.dest_of(i, d, k)) {
-            bits |= k;
 #pragma unroll
             for (int e = 0; e < MAXW; ++e) mine[e] += (e == d) ? 1 : 0;
         }
@@ -102,14 +100,12 @@ __global__ void __launch_bounds__(RT) count_kernel(Src src, Plan plan, int world
             if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[d], w);
         }
     }
-    const unsigned blo = __reduce_or_sync(0xffffffffu, (unsigned)bits), bhi = __reduce_or_sync(0xffffffffu, (unsigned)(bits >> 32));
-    if ((threadIdx.x & 31) == 0 && (blo | bhi)) atomicOr(key_bits, ((unsigned long long)bhi << 32) | blo);
     __syncthreads();
     if (threadIdx.x < world) blk_counts[(size_t)blockIdx.x * MAXW + threadIdx.x] = s_cnt[threadIdx.x];
 }
 
 // one warp per destination: exclusive scan of the per-block counts; totals[d] = items bound for d
-__global__ void __launch_bounds__(MAXW * 32) scan_kernel(const int32_t* __restrict__ blk_counts, int blocks, int world,
+static __global__ void __launch_bounds__(MAXW * 32) scan_kernel(const int32_t* __restrict__ blk_counts, int blocks, int world,
                                                         int64_t* __restrict__ blk_off, int64_t* __restrict__ totals) {
     const int d = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (d >= world) return;
@@ -139,7 +135,8 @@ struct Targets {
 // count matrix the ranks publish to each other (no host round trip between count and scatter).
 template <typename Src>
 __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int world, const int64_t* __restrict__ blk_off,
-                                                    const Targets* __restrict__ tg, const int* __restrict__ abort_flag) {
+                                                    const Targets* __restrict__ tg, const int* __restrict__ abort_flag,
+                                                    unsigned long long* __restrict__ key_bits_out) {
     typedef typename Src::Item Item;
     __shared__ int s_warp[RWARPS][MAXW];
     __shared__ int64_t s_run[MAXW];
@@ -155,6 +152,7 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
     const unsigned lt = (1u << lane) - 1u;
     const int64_t lo = (int64_t)blockIdx.x * plan.per_block;
     const int64_t hi = min(plan.n, lo + plan.per_block);
+    uint64_t bits = 0;
     for (int64_t t0 = lo; t0 < hi; t0 += RT) {
         const int64_t i = t0 + threadIdx.x;
         int d = -1; uint64_t k;
@@ -172,6 +170,7 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
             for (int w = 0; w < warp; ++w) before += s_warp[w][d];
             Item it;
             src.load(i, it);
+            bits |= *reinterpret_cast<const uint64_t*>(&it);            // first word of every item is its key
             s_dst[d][s_run[d] + before + rank] = it;
         }
         __syncthreads();
@@ -182,6 +181,10 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
             s_run[threadIdx.x] += tot;
         }
         __syncthreads();
+    }
+    if (key_bits_out) {
+        const unsigned blo = __reduce_or_sync(0xffffffffu, (unsigned)bits), bhi = __reduce_or_sync(0xffffffffu, (unsigned)(bits >> 32));
+        if (lane == 0 && (blo | bhi)) atomicOr(key_bits_out, ((unsigned long long)bhi << 32) | blo);
     }
 }
 

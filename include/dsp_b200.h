@@ -157,6 +157,53 @@ int dsp_freq_aggregate(int device, const uint64_t* key, const double* p0, const 
                        int32_t* out_met, int32_t* out_unmet, int32_t* out_cov,
                        int64_t* n_sites_host, void* stream);
 
+/* ---- multi-GPU call_freq: one process per GPU, records exchanged over NVLink peer memory -----------------
+ * The reference's only parallel form of the aggregation is per-contig worker processes over temp files
+ * (call_mods_freq.py:154-215, 262-295).  Here every rank parses a contiguous shard of the records (file order,
+ * global record index = gidx_base + i) and the per-site reduction is sharded by site key: callable records go
+ * to rank hash(key) % world, where they arrive grouped by source rank in file order and are summed in that
+ * order -- the float64 sums are the reference's bit for bit, there is no partial-sum merge.
+ *
+ * A communicator owns two receive windows (window_bytes each) and a control block in device memory; the other
+ * ranks of the box map them with CUDA IPC: export a blob on every rank, gather the blobs in rank order by any
+ * means (torch.distributed.all_gather_object in the Python mirror), connect.  All ranks must then make the same
+ * sequence of exchange calls (collective semantics).  A window that would overflow fails on every rank alike
+ * with DSP_ERR_NOMEM and nothing is written; a peer that never arrives fails after 30 s with DSP_ERR_CUDA. */
+typedef struct dsp_comm_s* dsp_comm;
+int dsp_comm_create(dsp_comm* out, int device, int rank, int world, int64_t window_bytes);
+int dsp_comm_export(dsp_comm c, void* blob, int64_t blob_cap, int64_t* blob_bytes);
+int dsp_comm_connect(dsp_comm c, const void* blobs_in_rank_order, int64_t blob_bytes);
+int dsp_comm_destroy(dsp_comm c);
+
+/* calculate_mods_frequency (call_mods_freq.py:29-74) across the ranks of `c`.  DEVICE pointers: this rank's
+ * n records in file order (columns as for dsp_freq_aggregate).  gidx_bounds_host (HOST, world + 1 ascending
+ * values): rank r holds the global records [bounds[r], bounds[r+1]); gidx_base = bounds[rank].
+ * Result: the sites whose FIRST callable record lies in this rank's shard -- that record supplies strand /
+ * pos_in_strand / k-mer (:55-59) and this rank is the one that parsed it -- as rows of 48 bytes
+ *   { uint64 key; uint64 first (global record index); double prob_0 sum, prob_1 sum; int32 met, unmet, coverage, 0 }
+ * in rows_out (DEVICE, capacity rows_cap), ordered by `first` (order_by_key == 0: concatenating the ranks'
+ * rows in rank order gives the reference's dict insertion order) or by key.  *n_rows_host = rows written,
+ * *n_callable_host (may be NULL) = callable records this rank RECEIVED.  Synchronises `stream`. */
+int dsp_freq_aggregate_distributed(dsp_comm c, const uint64_t* key, const double* p0, const double* p1,
+                                   const int32_t* label, int64_t n, uint64_t gidx_base, double prob_cf,
+                                   const uint64_t* gidx_bounds_host, int32_t order_by_key,
+                                   void* rows_out, int64_t rows_cap, int64_t* n_rows_host,
+                                   int64_t* n_callable_host, void* stream);
+
+/* The exchange primitive on its own: n rows of row_bytes (48 or 96) in DEVICE memory; the row's uint64 at
+ * field_offset selects the destination rank d with bounds[d] <= field < bounds[d+1] (bounds_host: world + 1
+ * ascending values, HOST; bounds[0] and bounds[world] are not compared).  Rows keep their order per
+ * (source, destination) and arrive concatenated in source-rank order in `out` (DEVICE, capacity out_cap_rows).
+ * Used to bring finished site rows with their text columns to key-range owners for a --sort table
+ * (call_mods_freq.py:87-90).  Synchronises `stream`. */
+int dsp_comm_route_rows(dsp_comm c, const void* rows, int64_t n, int32_t row_bytes, int32_t field_offset,
+                        const uint64_t* bounds_host, void* out, int64_t out_cap_rows, int64_t* n_out_host,
+                        void* stream);
+
+/* Milliseconds (CUDA events on the stream) of the four stages of the last dsp_freq_aggregate_distributed call:
+ * record exchange, local sort + replay, row exchange, ordering. */
+int dsp_comm_last_timing(dsp_comm c, float* ms4);
+
 /* dsp_parse_calls: ModRecord.__init__ (utils/txt_formater.py:8-21) for a whole call_mods file held in memory
  * (HOST pointers): every line is strip()-ed and split on tabs; columns 1, 3, 8 are parsed like int(), 6 and 7
  * like float() (correctly rounded to float64), chromosome names (column 0) are interned -- chrom_code[i] indexes

@@ -1,4 +1,4 @@
-"""call_freq: host logic + 2-rank gloo exchange on CPU; bit-exact GPU aggregation (-m gpu)."""
+"""call_freq: host logic on CPU; bit-exact GPU aggregation (-m gpu).  The multi-rank path is in test_freq_dist.py."""
 import gzip
 import os
 
@@ -57,82 +57,6 @@ def test_key_order_equals_python_tuple_order():
     assert np.argsort(keys, kind="stable").tolist() == want
     with pytest.raises(ValueError):
         cf.make_keys(ids, np.array([-1, 0, 0, 0, 0]))
-
-
-def _numpy_local_aggregate(rows, prob_cf):
-    """Test-side stand-in for the GPU step: ordered float64 replay per key (oracle semantics)."""
-    out = {}
-    for k, b0, b1, lab, g in rows.tolist():
-        p0 = np.int64(b0).view(np.float64).item()
-        p1 = np.int64(b1).view(np.float64).item()
-        r = out.get(k)
-        if r is None:
-            r = out[k] = [k, g, 0.0, 0.0, 0, 0, 0]
-        r[2] += p0
-        r[3] += p1
-        r[4 if lab == 1 else 5] += 1
-        r[6] += 1
-    res = np.zeros((len(out), 7), np.int64)
-    for i, r in enumerate(sorted(out.values())):
-        res[i] = [r[0], r[1], np.float64(r[2]).view(np.int64), np.float64(r[3]).view(np.int64), r[4], r[5], r[6]]
-    return res
-
-
-def _worker(rank, world, port, prob_cf, sort_by_key, q):
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    lines = synthetic.make_callmods_records(20000, n_chrom=6, n_pos=300, seed=9)
-    rec = cf.parse_lines(lines)
-    ids, names = cf._chrom_ids(rec.chrom)
-    keys = cf.make_keys(ids, rec.pos)
-    n = len(rec)
-    lo, hi = rank * n // world, (rank + 1) * n // world          # contiguous shards, file order
-    res = cf.aggregate_records_distributed(keys[lo:hi], rec.p0[lo:hi], rec.p1[lo:hi], rec.label[lo:hi],
-                                           np.arange(lo, hi, dtype=np.int64), prob_cf, sort_by_key,
-                                           device=None, local_aggregate=_numpy_local_aggregate)
-    if rank == 0:
-        q.put(tuple(a.tolist() for a in res))
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-@pytest.mark.parametrize("world,prob_cf,sort_by_key", [(2, 0.0, False), (2, 0.5, True), (3, 0.1, False)])
-def test_distributed_exchange_gloo(world, prob_cf, sort_by_key):
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, prob_cf, sort_by_key, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    got = q.get(timeout=180)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    key, first, s0, s1, met, unmet, cov = got
-    lines = synthetic.make_callmods_records(20000, n_chrom=6, n_pos=300, seed=9)
-    table = freq_oracle.aggregate(lines, prob_cf)
-    rec = cf.parse_lines(lines)
-    ids, names = cf._chrom_ids(rec.chrom)
-    items = list(table.items())
-    if sort_by_key:
-        items.sort(key=lambda kv: kv[0])
-    assert len(items) == len(key)
-    for i, ((chrom, pos), row) in enumerate(items):
-        assert key[i] == (names.index(chrom) << cf.POS_BITS) | pos
-        assert s0[i] == row[3] and s1[i] == row[4]                # float64, bit-exact
-        assert (met[i], unmet[i], cov[i]) == (row[5], row[6], row[7])
-        assert rec.chrom[first[i]] == chrom and rec.pos[first[i]] == pos
-
-
-def test_owner_hash_on_tensors_equals_numpy():
-    rng = np.random.default_rng(2)
-    keys = cf.make_keys(rng.integers(0, 200, 5000), rng.integers(0, 1 << 39, 5000))
-    for world in (1, 2, 3, 8):
-        got = cf.owner_of_key_t(torch.from_numpy(keys.view(np.int64)), world).numpy()
-        assert (got == cf.owner_of_key(keys, world)).all()
 
 
 def test_owner_of_key_is_balanced_and_deterministic():

@@ -1,5 +1,5 @@
 """Multi-GPU paths on a box with >= 2 B200s (skipped otherwise): the forward shards by site
-batch with no collective (bench.py under torchrun), call_freq adds one NCCL exchange and must
+batch with no collective (bench.py under torchrun), call_freq adds one exchange over NVLink peer memory (csrc/comm.cu) and must
 stay bit-exact."""
 import json
 import os
@@ -24,9 +24,9 @@ def _torchrun(n, script, *args, port=29533):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_freq_exchange_over_nccl_is_bit_exact():
-    out = _torchrun(2, "tools/freq_multigpu_check.py", "--records", "2000000")
-    assert out["ok"] and out["world"] == 2
+def test_freq_exchange_over_nvlink_is_bit_exact():
+    out = _torchrun(2, "tools/bench_freq_dist.py", "--records_per_rank", "2000000", "--iters", "2")
+    assert out["bit_exact"] is True and out["world"] == 2 and out["coverage_sum_equals_callable"] and out["slices_ordered"]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
