@@ -57,12 +57,20 @@ def peaks():
 
 def traffic_of_dominant_kernel(batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (lstm_comb layer 1,
-    layer_kernel<8,256,LSTM>) from the committed `ncu --set full` capture, scaled to this batch;
-    None when no capture is recorded (profiles/roofline_traffic.json says which run it came from)."""
+    layer_kernel<8,256,LSTM>) from the committed `ncu --set full` capture, scaled to this batch.  The capture
+    (profiles/roofline_traffic.json) carries the sha256 of the kernel source it was taken from: when
+    csrc/kernels_tc.cu has changed since, the number is stale and this returns (None, {"reason": ...})."""
+    import hashlib
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if not os.path.exists(p):
-        return None, None
+        return None, {"reason": "no ncu --set full capture recorded (profiles/roofline_traffic.json)"}
     d = json.load(open(p))
+    src = os.path.join(ROOT, "deepsignal_plant_b200", "csrc", "kernels_tc.cu")
+    sha = hashlib.sha256(open(src, "rb").read()).hexdigest()
+    if d.get("kernels_tc_sha256") != sha:
+        return None, {"reason": "profiles/roofline_traffic.json was captured from another version of csrc/kernels_tc.cu "
+                                "(%s..., now %s...): re-capture with tools/gpu_traffic.sh" % (str(d.get("kernels_tc_sha256"))[:12], sha[:12]),
+                      "stale_dram_bytes_per_site": d["dram_bytes_per_site"], "algorithmic_bytes_per_site": d["algorithmic_bytes_per_site"]}
     return d["dram_bytes_per_site"] * batch, {"unit": "B per launch", "kernel": d["kernel"], "source": d["source"],
                                               "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_site"] * batch}
 
@@ -112,11 +120,11 @@ def make_pool(n_buffers, batch, seed=0, T=13, S=16):
     return [tuple(np.ascontiguousarray(np.roll(base[k], 977 * b, axis=0)) for k in keys) for b in range(n_buffers)]
 
 
-def cpu_baseline_run(sites, threads):
-    """The reference's CPU path on the host cores: its forward restated on torch's own CPU operators
-    (oracle/torch_oracle.py: nn.LSTM -> oneDNN, nn.Linear, softmax), driven like `_call_mods` drives
-    it -- batches of 512 (the reference's default --batch_size), fresh torch.randn states per batch,
-    argmax.  oracle/ is used here as the baseline only.  Returns (sites/s, seconds)."""
+def port_baseline_run(sites, threads):
+    """The reference's forward restated on torch's own CPU operators (oracle/torch_oracle.py: nn.LSTM -> oneDNN,
+    nn.Linear, softmax), driven like `_call_mods` drives it -- batches of 512, fresh torch.randn states per batch,
+    argmax -- WITHOUT the reference's list -> tensor conversion and per-site text loop, i.e. an upper bound on the
+    reference's CPU speed.  oracle/ is used here as the baseline only.  Returns (sites/s, seconds)."""
     import torch
     from deepsignal_plant_b200 import synthetic
     from deepsignal_plant_b200.models import ModelBiLSTM
@@ -132,29 +140,63 @@ def cpu_baseline_run(sites, threads):
     return sites / dt, dt
 
 
+def reference_available():
+    from oracle import ref_import
+    return ref_import.available()
+
+
+def reference_callmods_run(sites, threads, repeat=1, timeout=1500):
+    """The UNMODIFIED reference (oracle/_ref, installed by oracle/build_ref.py) on the host cores: its own
+    ModelBiLSTM + `_call_mods` (call_modifications.py:130-192: nested lists -> FloatTensor, forward with fresh
+    torch.randn states, .numpy(), sklearn accuracy, per-site renormalise / round / str-join loop), batch 512, in a
+    subprocess with CUDA hidden (the reference picks CPU vs CUDA at import).  Returns the list of wall-clock
+    seconds of `repeat` calls over `sites` sites."""
+    from oracle import ref_import
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_ref_callmods.py"), "--n", str(sites), "--batch", "512",
+           "--threads", str(threads), "--repeat", str(repeat), "--time"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=ref_import.cpu_env(), cwd=ROOT)
+    if r.returncode != 0:
+        raise RuntimeError("reference _call_mods run failed: " + r.stderr[-800:])
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])["all_seconds"]
+
+
+def reference_callfreq_run(records, timeout=900):
+    """The unmodified reference's calculate_mods_frequency (call_mods_freq.py:29-74) on `records` synthetic
+    per-read calls, one Python process (its default mode).  Returns records/s."""
+    from oracle import ref_import
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_ref_callfreq.py"), "--records", str(records)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=ref_import.cpu_env(), cwd=ROOT)
+    if r.returncode != 0:
+        raise RuntimeError("reference calculate_mods_frequency run failed: " + r.stderr[-800:])
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])["records_per_s"]
+
+
 def reference_arm(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # bounded sample per step: the whole run (K steps) stays around a minute at ~2 k sites/s
+    # bounded sample per step: the whole run (K steps) stays within a few minutes at ~2 k sites/s
     sample = int(min(8192, max(512, (120000 // max(args.steps, 1)) // 512 * 512)))
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline_run(512, cores)
-    vals = []
-    t_all = 0.0
-    for _ in range(args.steps):
-        v, dt = cpu_baseline_run(sample, cores)
-        vals.append(v)
-        t_all += dt
+    if reference_available():
+        secs = reference_callmods_run(sample, cores, repeat=args.steps + max(0, min(args.warmup, 1)))[-args.steps:]
+        kind = "reference"
+        what = ("the UNMODIFIED reference (oracle/_ref): its ModelBiLSTM + _call_mods (list -> tensor, forward, per-site text loop), "
+                "torch CPU fp32, %d threads" % cores)
+    else:
+        for _ in range(max(0, min(args.warmup, 1))):
+            port_baseline_run(512, cores)
+        secs = [port_baseline_run(sample, cores)[1] for _ in range(args.steps)]
+        kind = "port"
+        what = "oracle/torch_oracle.py (the reference forward on the same torch CPU operators; oracle/_ref is not built), %d threads" % cores
+    t_all = sum(secs)
     value = sample * args.steps / t_all
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "both_bilstm bn13_sn16 h256 inference, batch 65536 (config 2)",
-                       "note": "reference CPU path: its forward restated on the same torch CPU operators (oracle/torch_oracle.py; "
-                               "/root/reference itself does not travel); each step = %d-site sample in batches of 512" % sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d sites per step, batch 512, torch CPU fp32 (oneDNN LSTM), %d threads" % (sample, cores)},
+                       "note": "reference CPU path: %s; each step = %d-site sample in batches of 512" % (what, sample)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d sites per step, batch 512, %s" % (sample, what)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -170,6 +212,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--buffers", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-freq", dest="no_freq", action="store_true", help="skip the call_freq measurement (the `freq` object)")
+    ap.add_argument("--freq-records", dest="freq_records", type=int, default=50_000_000, help="call_freq records per GPU")
     ap.add_argument("--meas-skip-y", action="store_true",
                     help="measurement only (INVALID as a result): after warm-up, skip the inter-layer activation stores")
     # BASELINE.json configs[3]: the other model variants (not the headline line)
@@ -291,7 +335,7 @@ def main():
 
     pk = peaks()
     achieved = (flop_rec * args.batch / (kern_ms * 1e-3) / 1e12) if kern_ms > 0 else None
-    traffic = traffic_of_dominant_kernel(args.batch) if headline else (None, None)
+    traffic = traffic_of_dominant_kernel(args.batch) if headline else (None, {"reason": "captured for the headline configuration only"})
     line = {
         "metric": METRIC if headline else METRIC.replace("both_bilstm bn13_sn16", "%s bn%d_sn%d" % (args.module, T_, S_)), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -313,15 +357,49 @@ def main():
     }
     if args.meas_skip_y:
         line["INVALID"] = "measurement run: activation stores skipped inside the timed region"
+    # ---- call_freq (BASELINE.json configs[4]): the per-site aggregation with its NVLink exchange, every N ----
+    freq = None
+    if headline and not args.no_freq:
+        from deepsignal_plant_b200 import freq_dist
+        del model, dev_pool, pin_pool, outs
+        torch.cuda.empty_cache()
+        grp = freq_dist.TorchGroup() if world > 1 else freq_dist.SoloGroup()
+        fm = freq_dist.measure(grp, local, args.freq_records, coverage=20, prob_cf=0.5, iters=5, check=True)
+        gbs = 28 * fm["records"] / fm["seconds"] / 1e9 / world
+        freq = {"metric": "call_freq records/s (per-site aggregation of per-read calls, records resident in HBM)",
+                "value": fm["records_per_s"], "unit": "records/s", "records": fm["records"], "sites": fm["sites"],
+                "callable_records": fm["callable"], "prob_cf": fm["prob_cf"], "ms": fm["seconds"] * 1e3, "n_gpus": world,
+                "bit_exact": fm["bit_exact"], "bit_exact_against": "dsp_freq_aggregate of the whole stream on rank 0 (itself byte-identical "
+                "to the reference's tables, tests/test_freq.py), row for row incl. float64 sum bits",
+                "coverage_sum_equals_callable": fm["coverage_sum_equals_callable"], "slices_ordered": fm["slices_ordered"],
+                "stage_ms_max_over_ranks": fm["stage_ms_max_over_ranks"],
+                "exchange": "fused stable partition + all-to-all: scatter kernel stores into peers' CUDA-IPC windows over NVLink (csrc/comm.cu); no NCCL on the data path",
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s per GPU", "frac": gbs / pk["hbm"],
+                             "algorithmic_bytes_per_record": 28}}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            sample = 65536                  # one BASELINE batch: ~10-30 s of host work at 2-8 k sites/s
-            v, dt = cpu_baseline_run(sample, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d sites, batch 512, torch CPU fp32 restatement of the reference forward, %d threads, %.1f s" % (sample, cores, dt)}
+            sample = 16384                  # ~10-20 s of host work at 1-2 k sites/s
+            v_port, dt_port = port_baseline_run(sample, cores)
+            if reference_available():
+                dt = reference_callmods_run(sample, cores, repeat=1)[0]
+                line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": "%d sites through the UNMODIFIED reference (oracle/_ref): its ModelBiLSTM + _call_mods "
+                                                  "(list -> tensor, forward, per-site text loop), batch 512, torch CPU fp32, %d threads, %.1f s"
+                                                  % (sample, cores, dt),
+                                        "port": {"value": v_port, "unit": UNIT, "kind": "port",
+                                                 "sample": "forward only on the same torch CPU operators (oracle/torch_oracle.py), %d sites, %.1f s" % (sample, dt_port)}}
+            else:
+                line["cpu_baseline"] = {"value": v_port, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": "%d sites, batch 512, torch CPU fp32 restatement of the reference forward, %d threads, %.1f s (oracle/_ref not built)" % (sample, cores, dt_port)}
+            if freq is not None and reference_available():
+                fr = reference_callfreq_run(1000000)
+                freq["cpu_baseline"] = {"value": fr, "unit": "records/s", "cores": 1, "kind": "reference",
+                                        "sample": "1 000 000 records through the unmodified reference's calculate_mods_frequency (one Python process, incl. line parsing)"}
         else:
             line["cpu_baseline"] = None
+        if freq is not None:
+            line["freq"] = freq
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

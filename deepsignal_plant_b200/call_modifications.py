@@ -402,8 +402,12 @@ def call_mods(args):
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     args.model_path = model_path
-    model = load_model(args, device)
     from_reads = input_path.endswith(".npz")                  # decoded reads instead of a feature file
+    gz_single = world > 1 and not from_reads and input_path.endswith(".gz")
+    if gz_single and rank == 0:
+        print("call_mods: a gzip feature file cannot be cut into byte shards; rank 0 processes it alone "
+              "(decompress it to use all %d GPUs)" % world)
+    model = load_model(args, device)
     args.input_path = input_path
 
     result_file = args.result_file
@@ -413,33 +417,56 @@ def call_mods(args):
     opener = (lambda p: gzip.open(p, "wb")) if args.gzip else (lambda p: open(p, "wb"))
     wq = queue.Queue(maxsize=8)
 
+    werr = []
+
     def writer():                                              # _write_predstr_to_file (:262-282)
-        with opener(my_file) as wf:
-            while True:
-                item = wq.get()
-                if item is None:
-                    return
-                wf.write(item)
+        # a failing write (disk full, bad path) must not leave the producers blocked on a full queue: remember the
+        # error, keep draining until the sentinel, re-raise in the main thread after the join
+        wf = None
+        try:
+            wf = opener(my_file)
+        except BaseException as e:
+            werr.append(e)
+        while True:
+            item = wq.get()
+            if item is None:
+                break
+            if wf is not None and not werr:
+                try:
+                    wf.write(item)
+                except BaseException as e:
+                    werr.append(e)
+        if wf is not None:
+            try:
+                wf.close()
+            except BaseException as e:
+                werr.append(e)
 
     wt = threading.Thread(target=writer, daemon=True)
     wt.start()
-    if from_reads:
-        sites, nb = call_mods_from_reads(args, model, wq.put, device)
+
+    def finish_writer():
         wq.put(None)
         wt.join()
+        if werr:
+            raise werr[0]
+    if from_reads:
+        sites, nb = call_mods_from_reads(args, model, wq.put, device)
+        finish_writer()
         print("call_mods rank {}: {} sites in {} read-batches".format(rank, sites, nb))
         _merge_parts(result_file, rank, world)
         print("[main] call_mods costs %.2f seconds.." % (time.time() - start))
         return sites
     rq = queue.Queue(maxsize=2)
-    reader = feature_io.FeatureFileReader(input_path, args.seq_len, args.signal_len,
-                                          batch_sites=getattr(args, "max_batch", 65536), slots=6,
-                                          nthreads=max(1, args.nproc), byte_range=_shard_of_file(input_path, rank, world))
+    idle = gz_single and rank > 0                              # nothing to read on this rank
+    reader = None if idle else feature_io.FeatureFileReader(
+        input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536), slots=6,
+        nthreads=max(1, args.nproc), byte_range=None if gz_single else _shard_of_file(input_path, rank, world))
     err = []
 
     def read():                                                # _read_features_file (:55-127)
         try:
-            for b in reader:
+            for b in (reader or ()):
                 rq.put(b)
         except BaseException as e:                             # surfaced in the main thread
             err.append(e)
@@ -456,9 +483,8 @@ def call_mods(args):
             yield b
 
     sites, accuracy, nb = call_mods_stream(model, batches(), wq.put)
-    wq.put(None)
-    wt.join()
     rt.join()
+    finish_writer()
     if err:
         raise err[0]
     print("call_mods rank {}: {} sites in {} feature-batches".format(rank, sites, nb))

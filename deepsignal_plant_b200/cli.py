@@ -5,9 +5,13 @@ reference's flag names and defaults.
     python -m deepsignal_plant_b200 call_mods -i features.tsv -m model.ckpt -o calls.tsv
     python -m deepsignal_plant_b200 call_freq -i calls.tsv -o freq.tsv [--bed] [--sort]
 
-Multi-GPU: launch ``call_mods`` under torchrun, one process per GPU; the feature file is cut into
-contiguous shards and the output is concatenated in file order.  ``extract``, ``train`` and
-``denoise`` stay with the reference (they are not on the accelerated path)."""
+    python -m deepsignal_plant_b200 extract   -i reads.npz -o features.tsv      # decoded reads -> the reference's feature file
+
+Multi-GPU: launch ``call_mods`` or ``call_freq`` under torchrun, one process per GPU.  ``call_mods`` cuts the feature
+file (or the reads archive) into contiguous shards and concatenates the output in file order, no collective on the
+data path; ``call_freq`` parses contiguous byte shards, exchanges the records by site key over NVLink peer memory and
+every rank writes its slice of the table (freq_dist.py).  ``extract`` here takes reads that are already decoded
+(reading fast5 needs h5py: outside this implementation); ``train`` and ``denoise`` stay with the reference."""
 from __future__ import annotations
 
 import argparse
@@ -27,7 +31,7 @@ def build_parser():
     g.add_argument("--fast5_dir", "-i", action="store", type=str, required=True,
                    help="the decoded-reads archive (.npz); the reference's flag name is kept")
     g.add_argument("--recursively", "-r", action="store", type=str, required=False, default="yes",
-                   help="accepted for compatibility (fast5 directories are decoded by tools/fast5_to_archive.py)")
+                   help="accepted for compatibility (the input is one archive of decoded reads, not a directory tree)")
     g.add_argument("--corrected_group", action="store", type=str, required=False, default="RawGenomeCorrected_000",
                    help="accepted for compatibility (used when the archive is made)")
     g.add_argument("--basecall_subgroup", action="store", type=str, required=False, default="BaseCalled_template",
@@ -110,8 +114,11 @@ def build_parser():
     g.add_argument("--prob_cf", type=float, action="store", required=False, default=0.5)
     g = cf.add_argument_group("PARALLEL")
     g.add_argument("--contigs", action="store", type=str, required=False, default=None,
-                   help="accepted for compatibility; all contigs are aggregated in one GPU pass")
-    g.add_argument("--nproc", action="store", type=int, required=False, default=1)
+                   help="a genome FASTA, a file with one contig name per line, or a comma-separated list: only these contigs are "
+                        "aggregated, one GPU pass per contig, and the rows come out contig by contig in the order of the reference's "
+                        "per-contig mode (call_mods_freq.py:203-215)")
+    g.add_argument("--nproc", action="store", type=int, required=False, default=1,
+                   help="accepted for compatibility (the reference's per-contig worker processes; here: torchrun ranks)")
     return parser
 
 

@@ -101,20 +101,58 @@ class ReadBatch:
         self._dev = None
         self._validate()
 
-    def _validate(self):
+    def bad_reads(self):
+        """Boolean mask of the reads the reference's per-read ``try/except`` would count as errors and skip
+        (``_extract_features``: ``error += 1``, extract_features.py:373-375): a base outside the alphabet
+        (``base2code_dna[x]`` raises KeyError) or an event that reaches outside the read's raw signal."""
         n = self.n_reads
-        if self.ev_base.shape[0] != self.ev_len.shape[0] or self.ev_start.shape[0] != self.ev_len.shape[0]:
-            raise ValueError("event columns differ in length")         # the reference asserts (:87-88)
+        bad = np.zeros(n, bool)
+        if n == 0 or self.ev_len.shape[0] == 0:
+            return bad
+        read_of_ev = np.repeat(np.arange(n), np.diff(self.ev_off))
         ok = _ALPHABET_LUT[self.ev_base]
         if not ok.all():
-            raise KeyError(chr(int(self.ev_base[int(np.argmin(ok))])))  # base2code_dna[x] in the reference
-        if n and self.ev_len.shape[0]:
-            if int(self.ev_start.min()) < 0 or int(self.ev_len.min()) < 0:
-                raise ValueError("an event reaches outside its read's raw signal")
-            filled = np.diff(self.ev_off) > 0
-            last = np.maximum.reduceat(self.ev_start + self.ev_len, self.ev_off[:-1][filled])
-            if (last > np.diff(self.raw_off)[filled]).any():
-                raise ValueError("an event reaches outside its read's raw signal")
+            bad[np.unique(read_of_ev[~ok])] = True
+        neg = (self.ev_start < 0) | (self.ev_len < 0)
+        if neg.any():
+            bad[np.unique(read_of_ev[neg])] = True
+        over = (self.ev_start + self.ev_len) > np.diff(self.raw_off)[read_of_ev]
+        if over.any():
+            bad[np.unique(read_of_ev[over])] = True
+        return bad
+
+    def drop_bad_reads(self):
+        """-> (batch without the offending reads, number dropped); one bad read no longer aborts the whole batch."""
+        bad = self.bad_reads()
+        nbad = int(bad.sum())
+        if nbad == 0:
+            return self, 0
+        keep = np.flatnonzero(~bad)
+        parts = [self.slice(int(i), int(i) + 1) for i in keep]
+        b = object.__new__(ReadBatch)
+        b.n_reads = len(keep)
+        for k in ("readname", "strand", "alignstrand", "chrom"):
+            src = getattr(self, k)
+            setattr(b, k, [src[int(i)] for i in keep] if isinstance(src, list) else src[keep])
+        b.chrom_start, b.scaling, b.offset = self.chrom_start[keep], self.scaling[keep], self.offset[keep]
+        b.raw_off = np.concatenate([[0], np.cumsum([p.raw.shape[0] for p in parts])]).astype(np.int64)
+        b.ev_off = np.concatenate([[0], np.cumsum([p.ev_len.shape[0] for p in parts])]).astype(np.int64)
+        cat = lambda f, dt: np.concatenate([getattr(p, f) for p in parts]).astype(dt, copy=False) if parts else np.zeros(0, dt)
+        b.raw, b.ev_start, b.ev_len, b.ev_base = cat("raw", np.int16), cat("ev_start", np.int64), cat("ev_len", np.int64), cat("ev_base", np.uint8)
+        b._dev = None
+        return b, nbad
+
+    def _validate(self):
+        if self.ev_base.shape[0] != self.ev_len.shape[0] or self.ev_start.shape[0] != self.ev_len.shape[0]:
+            raise ValueError("event columns differ in length")         # the reference asserts (:87-88)
+        bad = self.bad_reads()
+        if bad.any():
+            i = int(np.argmax(bad))
+            lo, hi = int(self.ev_off[i]), int(self.ev_off[i + 1])
+            ok = _ALPHABET_LUT[self.ev_base[lo:hi]]
+            if not ok.all():
+                raise KeyError(chr(int(self.ev_base[lo + int(np.argmin(ok))])))  # base2code_dna[x] in the reference
+            raise ValueError("an event reaches outside its read's raw signal")
 
     # ---- the archive form: flat arrays in an .npz (what a fast5 decoder writes once; see save_reads)
     ARCHIVE_KEYS = ("raw", "raw_off", "ev_off", "scaling", "offset", "ev_start", "ev_len", "ev_base",
@@ -193,7 +231,8 @@ class _MappedArchive:
 
 
 def load_reads(path):
-    """-> ReadBatch straight from the archive's flat arrays (memory-mapped, no per-read objects)."""
+    """-> ReadBatch straight from the archive's flat arrays (memory-mapped, no per-read objects); reads the
+    reference would count as errors are dropped (``n_errors``)."""
     z = _MappedArchive(path)
     missing = [k for k in ReadBatch.ARCHIVE_KEYS if k not in z.files]
     if missing:
@@ -209,7 +248,14 @@ def load_reads(path):
     b.ev_base = z["ev_base"].astype(np.uint8, copy=False)
     b.scaling, b.offset = z["scaling"].astype(np.float64, copy=False), z["offset"].astype(np.float64, copy=False)
     b._dev = None
-    b._validate()
+    if b.ev_base.shape[0] != b.ev_len.shape[0] or b.ev_start.shape[0] != b.ev_len.shape[0]:
+        raise ValueError("event columns differ in length")
+    # the reference wraps every read in try/except and only counts the failures (extract_features.py:373-375):
+    # a read with a base outside the alphabet or an event outside its raw signal is skipped, not fatal
+    b, nbad = b.drop_bad_reads()
+    if nbad:
+        print("extract_features: %d of %d reads skipped (error)" % (nbad, b.n_reads + nbad))
+    b.n_errors = nbad
     return b
 
 

@@ -56,19 +56,20 @@ def main():
     model = ref_models.ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True, module="both_bilstm")
     model.eval()
     batch = features_batch(a.n, 13, 16, a.feature_seed)
-    best = None
+    best, times = None, []
     for _ in range(a.repeat):
         torch.manual_seed(a.rng_seed)
         t0 = time.perf_counter()
         lines, acc, nb = ref_cm._call_mods(batch, model, a.batch, 0)
         dt = time.perf_counter() - t0
+        times.append(dt)
         best = dt if best is None else min(best, dt)
     if a.out:
         with open(a.out, "w") as f:
             f.write("\n".join(lines) + "\n")
     if a.time:
         print(json.dumps({"sites": a.n, "seconds": best, "sites_per_s": a.n / best, "threads": torch.get_num_threads(),
-                          "batch": a.batch, "batches": nb, "reference": ref_import.ref_root()}))
+                          "batch": a.batch, "batches": nb, "all_seconds": times, "reference": ref_import.ref_root()}))
 
 
 if __name__ == "__main__":

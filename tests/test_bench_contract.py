@@ -17,7 +17,11 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "sites/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["metric"].startswith("classified sites/sec") and d["steps"] == 1 and d["scaling"] == "weak"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the unmodified reference from oracle/_ref when it is built (kind "reference"), else the torch-operator port
+    sys.path.insert(0, ROOT)
+    from oracle import ref_import
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_import.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
@@ -35,3 +39,17 @@ def test_bench_refuses_to_run_without_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                        timeout=300, cwd=ROOT, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert r.returncode != 0 and "needs a GPU" in (r.stderr + r.stdout)
+
+
+def test_traffic_capture_is_tied_to_the_kernel_source():
+    # roofline.traffic comes from an ncu capture; bench.py must refuse to quote it for another version of the kernels
+    sys.path.insert(0, ROOT)
+    import hashlib
+    import bench
+    t, detail = bench.traffic_of_dominant_kernel(65536)
+    d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    sha = hashlib.sha256(open(os.path.join(ROOT, "deepsignal_plant_b200", "csrc", "kernels_tc.cu"), "rb").read()).hexdigest()
+    if d.get("kernels_tc_sha256") == sha:
+        assert t == d["dram_bytes_per_site"] * 65536
+    else:
+        assert t is None and "re-capture" in detail["reason"]

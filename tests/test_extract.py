@@ -503,3 +503,26 @@ def test_gpu_extract_cli_writes_the_reference_feature_file_format(tmp_path):
     # and the file is what this repository's own reader / call_mods take
     rd = feature_io.FeatureFileReader(out + ".gz", K, S, batch_sites=4096, slots=3, nthreads=2)
     assert sum(b.n for b in rd) == len(lines)
+
+
+def test_one_bad_read_is_skipped_not_fatal(tmp_path):
+    # the reference counts a failing read and goes on (extract_features.py:373-375)
+    from deepsignal_plant_b200 import extract_features as ef
+    from deepsignal_plant_b200 import synthetic
+    reads = synthetic.make_reads(6, seed=3, mean_bases=60)
+    good = ef.pack_reads(reads)
+    arrays = good.arrays()
+    lo, hi = int(good.ev_off[2]), int(good.ev_off[3])
+    arrays["ev_base"] = arrays["ev_base"].copy()
+    arrays["ev_base"][lo + 5] = ord("x")                                  # a letter outside base2code_dna
+    arrays["ev_len"] = arrays["ev_len"].copy()
+    arrays["ev_len"][int(good.ev_off[5]) - 1] += 10 ** 6                   # last event of read 4 runs off its raw signal
+    path = str(tmp_path / "reads.npz")
+    np.savez(path, **arrays)
+    got = ef.load_reads(path)
+    assert got.n_errors == 2 and got.n_reads == 4
+    assert list(got.readname) == [good.readname[i] for i in (0, 1, 3, 5)]
+    assert not got.bad_reads().any()
+    want = ef.pack_reads([reads[i] for i in (0, 1, 3, 5)])
+    for f in ("raw", "raw_off", "ev_off", "ev_start", "ev_len", "ev_base", "chrom_start"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f

@@ -63,15 +63,20 @@ def test_fp16_tensor_core_path_matches_reference(name):
     print("%s fp16: max|dprob|=%.2e agreement=%.5f" % (name, err, agree))
 
 
-@pytest.mark.parametrize("dual", ["0", "1"])
+@pytest.mark.parametrize("dual", ["0", "1", "fused"])
 def test_fp16_both_branch_kernels_match_reference(dual, monkeypatch):
-    # hidden-128 layers: one CTA pair per direction (layer_kernel) or both directions as two chains
-    # (branch_kernel); the library picks by wave cost, DSP_B200_BRANCH_DUAL forces either
-    monkeypatch.setenv("DSP_B200_BRANCH_DUAL", dual)
+    # hidden-128 layers: by default both branches + their fc layers run as ONE launch (branch_fused_kernel);
+    # DSP_B200_BRANCH_DUAL (read at handle creation) keeps the separate launches: 0 = one CTA pair per direction
+    # (layer_kernel), 1 = both directions as two chains (branch_kernel), each followed by the fc launches
+    if dual == "fused":
+        monkeypatch.delenv("DSP_B200_BRANCH_DUAL", raising=False)
+    else:
+        monkeypatch.setenv("DSP_B200_BRANCH_DUAL", dual)
     for name in ("both_13_16_s2", "both_17_20_s1234"):
         case = cases.slice_case(cases.load_case(name), 3000)
-        logits, probs, labels, _ = run_case(case, "fp16")
+        logits, probs, labels, model = run_case(case, "fp16")
         check(case, logits, probs, labels, PROB_TOL, 0.9995)
+        assert model.launch_count() == {"0": 9, "1": 9, "fused": 6}[dual]      # prep, branches(+fc), 3 x lstm_comb, head
 
 
 def test_fp16_full_batch_is_batching_and_order_invariant():
