@@ -318,13 +318,9 @@ def call_freq_distributed(mods_files, prob_cf, result_file, is_sort, is_bed, is_
 
 
 # ---- synthetic workload + measurement (BASELINE.json configs[4]; bench.py `freq` object, tools/bench_freq_dist.py) ----
-def synth_records(lo, hi, n_sites, dev, seed=1):
-    """Records [lo, hi) of the synthetic call_mods stream of BASELINE.json configs[4] as device tensors: a pure
-    function of the global record index (so any rank can produce any range and rank 0 can rebuild the whole stream
-    for the bit-exactness check): 5 chromosomes, ``n_sites`` positions in all, uniformly hit; prob_1 = m / 1e6 with m
-    uniform in [0, 1e6], prob_0 = (1e6 - m) / 1e6 -- the 6-decimal values call_mods prints -- label = prob_1 > prob_0."""
+def _synth_hash(lo, hi, dev, seed=1):
+    """Two wrapping-int64 hashes of the global record indices [lo, hi): (site hash, probability hash)."""
     import torch
-    M63 = 0x7FFFFFFFFFFFFFFF
 
     def lsr(x, s):
         return (x >> s) & ((1 << (64 - s)) - 1)
@@ -335,9 +331,27 @@ def synth_records(lo, hi, n_sites, dev, seed=1):
         return x ^ lsr(x, 31)
     g = torch.arange(lo, hi, device=dev, dtype=torch.int64)
     h = mix(g * (-7046029254386353131) + seed)                   # 0x9E3779B97F4A7C15
-    site = (h & M63) % n_sites
+    return h, mix(h)
+
+
+def synth_keys(lo, hi, n_sites, dev, seed=1):
+    """Site keys ((chrom << 40) | pos, int64) of the records [lo, hi) of the synthetic stream: 5 chromosomes,
+    ``n_sites`` positions in all, uniformly hit."""
+    h, _ = _synth_hash(lo, hi, dev, seed)
+    site = (h & 0x7FFFFFFFFFFFFFFF) % n_sites
+    return ((site % 5) << cf.POS_BITS) | (site // 5)
+
+
+def synth_records(lo, hi, n_sites, dev, seed=1):
+    """Records [lo, hi) of the synthetic call_mods stream of BASELINE.json configs[4] as device tensors: a pure
+    function of the global record index (so any rank can produce any range and rank 0 can rebuild the whole stream
+    for the bit-exactness check): keys from ``synth_keys``; prob_1 = m / 1e6 with m uniform in [0, 1e6],
+    prob_0 = (1e6 - m) / 1e6 -- the 6-decimal values call_mods prints -- label = prob_1 > prob_0."""
+    import torch
+    h, h2 = _synth_hash(lo, hi, dev, seed)
+    site = (h & 0x7FFFFFFFFFFFFFFF) % n_sites
     key = ((site % 5) << cf.POS_BITS) | (site // 5)
-    m = (mix(h) & M63) % 1000001
+    m = (h2 & 0x7FFFFFFFFFFFFFFF) % 1000001
     p1 = m.to(torch.float64) / 1e6
     p0 = (1000000 - m).to(torch.float64) / 1e6
     return key, p0, p1, (p1 > p0).to(torch.int32)

@@ -91,7 +91,7 @@ def test_reference_worker_loop_builds_and_drives_the_dropin(tmp_path):
     # torch.load(map_location=cpu) -> model_dict.update -> load_state_dict -> .cuda(device) -> .eval(), queue loop
     # until "kill".  Only the class behind the name ModelBiLSTM is substituted; a fresh CPU run of the reference
     # itself (other seeds than the fixture) is the expectation.
-    import deepsignal_plant_b200
+    from deepsignal_plant_b200.models import ModelBiLSTM as DropIn
     from run_ref_callmods import features_batch
     ref_cm, ref_models = ref_import.import_reference("call_modifications", "models")
     n, bs, wseed, fseed, rseed = 1536, 512, 5, 31, 99
@@ -104,7 +104,7 @@ def test_reference_worker_loop_builds_and_drives_the_dropin(tmp_path):
                    check=True, env=ref_import.cpu_env(), timeout=600)
     gold = open(out).read().splitlines()
 
-    class InitHiddenModel(deepsignal_plant_b200.ModelBiLSTM):
+    class InitHiddenModel(DropIn):
         def __init__(self, *a, **kw):
             super().__init__(*a, state_mode="init_hidden", **kw)
     args = types.SimpleNamespace(seq_len=13, signal_len=16, layernum1=3, layernum2=1, class_num=2, dropout_rate=0, hid_rnn=256,
