@@ -97,7 +97,7 @@ def lib():
     L.dsp_comm_connect.argtypes = [vp, vp, i64]
     L.dsp_comm_destroy.argtypes = [vp]
     L.dsp_freq_aggregate_distributed.argtypes = [vp, vp, vp, vp, vp, i64, u64, C.c_double, vp, i32, vp, i64,
-                                                 C.POINTER(i64), C.POINTER(i64), vp]
+                                                 C.POINTER(i64), C.POINTER(i64), vp, vp]
     L.dsp_comm_route_rows.argtypes = [vp, vp, i64, i32, i32, vp, vp, i64, C.POINTER(i64), vp]
     L.dsp_comm_last_timing.argtypes = [vp, vp]
     for name in SYMBOLS:

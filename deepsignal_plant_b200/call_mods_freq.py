@@ -558,10 +558,10 @@ def write_sitekey2stats(sitekey2stats, result_file, is_sort, is_bed, is_gzip):
 # ---- key-hash shards (multi-pass on one GPU here; the multi-GPU exchange lives in freq_dist.py / csrc/comm.cu) ----
 
 def owner_of_key(keys, world):
-    """Shard that owns a site key: multiplicative hash of the 64-bit key, mod world (``route::owner_of_key`` in
-    csrc/route.cuh is the same function on the device)."""
+    """Shard that owns a site key: multiplicative hash of the 64-bit key, its top 31 bits mapped onto [0, world) by
+    multiply-shift (``route::owner_of_key`` in csrc/route.cuh is the same function on the device)."""
     h = (keys.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(33)
-    return (h % np.uint64(world)).astype(np.int64)
+    return ((h * np.uint64(world)) >> np.uint64(31)).astype(np.int64)
 
 
 def parse_contigs_arg(contigs):

@@ -37,7 +37,11 @@ struct Ctrl {                                   // device memory; peers write, t
     unsigned long long bits[2][MAXW];           // OR of the keys a source routes
     unsigned long long flag_cnt[MAXW];          // epoch of source's last count publication
     unsigned long long flag_data[MAXW];         // epoch of source's last "stores landed" signal
+    uint64_t samples[2][MAXW][256];             // splitter selection: every rank's sample of its rows' sort field
+    int32_t nsamples[2][MAXW];
+    unsigned long long flag_smp[MAXW];
 };
+constexpr int NSAMP = 256;
 
 struct Result { int64_t n_recv; unsigned long long bits; int32_t err; int32_t pad; };   // err: 1 window overflow, 2 peer timeout
 
@@ -122,6 +126,63 @@ __global__ void signal_wait_kernel(Ctrl* local, Peers peers, int me, int world, 
     if (!ok) atomicOr(&res->err, 2);
 }
 
+// ---- balanced row placement: splitters of the `first` field chosen from every rank's sample ---------------------
+// Sites are spread over the ranks by key hash, but their FIRST callable records are not: with reads in random order
+// nearly every site is first seen in rank 0's shard, so sending rows to the rank that parsed that record would funnel
+// the whole table through one GPU.  Instead every rank publishes NSAMP evenly spaced `first` values of its rows to
+// all peers, everybody sorts the same world x NSAMP values and cuts them into `world` equal parts: the rows then go to
+// the rank whose [bounds[r], bounds[r+1]) holds their `first`, sorted there -- the slices of ranks 0..world-1 still
+// concatenate to dict insertion order, and every rank holds about 1/world of the table.
+__global__ void publish_samples_kernel(const SiteRow* __restrict__ rows, int64_t n, Peers peers, int me, int world, int parity,
+                                       unsigned long long epoch) {
+    const int t = threadIdx.x;                                 // NSAMP threads
+    const int ns = (int)(n < NSAMP ? n : NSAMP);
+    if (t < ns) {
+        const uint64_t v = rows[(int64_t)(((double)t + 0.5) * (double)n / (double)ns)].first;
+        for (int p = 0; p < world; ++p) peers.ctrl[p]->samples[parity][me][t] = v;
+    }
+    if (t < world) peers.ctrl[t]->nsamples[parity][me] = ns;
+    __threadfence_system();
+    __syncthreads();
+    if (t < world) *reinterpret_cast<volatile unsigned long long*>(&peers.ctrl[t]->flag_smp[me]) = epoch;
+}
+
+__global__ void __launch_bounds__(1024) splitters_kernel(const Ctrl* local, int world, int parity, unsigned long long epoch,
+                                                         uint64_t* __restrict__ bounds, Result* __restrict__ res) {
+    __shared__ uint64_t s[MAXW * NSAMP];
+    __shared__ int s_n, s_bad;
+    const int t = threadIdx.x;
+    if (t == 0) { s_n = 0; s_bad = 0; }
+    __syncthreads();
+    if (t < world && !wait_flag(&local->flag_smp[t], epoch)) atomicOr(&s_bad, 2);
+    __threadfence_system();
+    __syncthreads();
+    for (int i = t; i < MAXW * NSAMP; i += 1024) {
+        const int r = i / NSAMP, j = i % NSAMP;
+        const bool ok = r < world && j < *reinterpret_cast<const volatile int32_t*>(&local->nsamples[parity][r]);
+        s[i] = ok ? *reinterpret_cast<const volatile uint64_t*>(&local->samples[parity][r][j]) : ~0ull;
+        if (ok) atomicAdd(&s_n, 1);
+    }
+    __syncthreads();
+    for (int k = 2; k <= MAXW * NSAMP; k <<= 1)                 // bitonic sort, ascending; the padding sorts last
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < MAXW * NSAMP; i += 1024) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint64_t a = s[i], b = s[l];
+                    if (((i & k) == 0) ? (a > b) : (a < b)) { s[i] = b; s[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (t <= world) {
+        uint64_t v = t == 0 ? 0ull : ~0ull;
+        if (t > 0 && t < world && s_n > 0) v = s[(int)(((int64_t)s_n * t) / world)];
+        bounds[t] = v;
+    }
+    if (t == 0 && s_bad) res->err = s_bad;
+}
+
 }  // namespace
 }  // namespace dsp
 
@@ -139,9 +200,15 @@ struct dsp_comm_s {
     int* d_abort = nullptr;
     dsp::Result* d_res = nullptr;
     dsp::Result* h_res = nullptr;                // pinned
+    uint64_t* d_bounds = nullptr;                // world + 1 range bounds of the current row exchange
+    uint64_t* h_bounds = nullptr;                // pinned
     int n_sm = 148;
     float last_ms[4] = {0, 0, 0, 0};             // route records, aggregate, route rows, order (CUDA events of the last call)
     cudaEvent_t ev[5] = {};
+    // inside an exchange (window 0 = records, 1 = rows): count+scan+publish | wait for every rank's counts | scatter |
+    // signal + wait for every rank's stores
+    float detail_ms[2][4] = {};
+    cudaEvent_t dev[2][5] = {};
 };
 
 using namespace dsp;
@@ -170,17 +237,24 @@ int exchange(dsp_comm_s* c, Scratch& sc, cudaStream_t st, const Src& src, int64_
     const int parity = (int)(epoch & 1);
     Peers peers{}; Windows wins{};
     for (int r = 0; r < c->world; ++r) { peers.ctrl[r] = c->peer_ctrl[r]; wins.win[r] = c->peer_win[which][r]; }
+    cudaEvent_t* ev = c->dev[which];
     DSP_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned long long), st));
+    cudaEventRecord(ev[0], st);
     count_kernel<Src><<<plan.blocks, RT, 0, st>>>(src, plan, c->world, blk_counts);
     scan_kernel<<<1, MAXW * 32, 0, st>>>(blk_counts, plan.blocks, c->world, blk_off, totals);
     publish_kernel<<<1, 256, 0, st>>>(totals, peers, c->rank, c->world, parity, epoch);
+    cudaEventRecord(ev[1], st);
     prepare_kernel<<<1, 32, 0, st>>>(c->ctrl, wins, c->rank, c->world, parity, epoch, (int64_t)(c->window_bytes / item_bytes),
                                      c->d_tg, c->d_abort, c->d_res);
+    cudaEventRecord(ev[2], st);
     scatter_kernel<Src><<<plan.blocks, RT, 0, st>>>(src, plan, c->world, blk_off, c->d_tg, c->d_abort, d_bits);
+    cudaEventRecord(ev[3], st);
     signal_wait_kernel<<<1, 32, 0, st>>>(c->ctrl, peers, c->rank, c->world, parity, epoch, d_bits, c->d_res);
+    cudaEventRecord(ev[4], st);
     DSP_CUDA(cudaGetLastError());
     DSP_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, sizeof(Result), cudaMemcpyDeviceToHost, st));
     DSP_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->detail_ms[which][i], ev[i], ev[i + 1]);
     DSP_REQUIRE(!(c->h_res->err & 2), DSP_ERR_CUDA, "dsp_comm: rank %d timed out waiting for a peer (exchange %llu)", c->rank, epoch);
     DSP_REQUIRE(!(c->h_res->err & 1), DSP_ERR_NOMEM,
                 "dsp_comm: a receive window (%lld items of %zu bytes) would overflow; create the communicator with larger windows",
@@ -190,16 +264,33 @@ int exchange(dsp_comm_s* c, Scratch& sc, cudaStream_t st, const Src& src, int64_
     return DSP_OK;
 }
 
+// bounds_host != nullptr: upload them; nullptr: c->d_bounds already holds the bounds (splitters_kernel)
 template <int UNITS>
 int route_rows_units(dsp_comm_s* c, Scratch& sc, cudaStream_t st, const void* rows, int64_t n, int field_word,
-                     const uint64_t* bounds, int64_t* n_recv) {
+                     const uint64_t* bounds_host, int64_t* n_recv) {
     typedef route::RowsByRange<UNITS> Src;
+    if (bounds_host) {
+        for (int w = 0; w <= c->world; ++w) c->h_bounds[w] = bounds_host[w];
+        DSP_CUDA(cudaMemcpyAsync(c->d_bounds, c->h_bounds, sizeof(uint64_t) * (c->world + 1), cudaMemcpyHostToDevice, st));
+    }
     Src src{};
     src.rows = reinterpret_cast<const typename Src::Item*>(rows);
     src.field_word = field_word;
     src.world = c->world;
-    for (int w = 0; w <= c->world; ++w) src.bounds[w] = bounds[w];
+    src.bounds = c->d_bounds;
     return exchange<Src>(c, sc, st, src, n, 1, (size_t)UNITS * 16, n_recv, nullptr);
+}
+
+// choose c->d_bounds so that the `first` fields of all ranks' rows fall into `world` equal parts
+int choose_row_splitters(dsp_comm_s* c, cudaStream_t st, const SiteRow* rows, int64_t n) {
+    const unsigned long long epoch = ++c->epoch;
+    const int parity = (int)(epoch & 1);
+    Peers peers{};
+    for (int r = 0; r < c->world; ++r) peers.ctrl[r] = c->peer_ctrl[r];
+    publish_samples_kernel<<<1, NSAMP, 0, st>>>(rows, n, peers, c->rank, c->world, parity, epoch);
+    splitters_kernel<<<1, 1024, 0, st>>>(c->ctrl, c->world, parity, epoch, c->d_bounds, c->d_res);
+    DSP_CUDA(cudaGetLastError());
+    return DSP_OK;
 }
 
 }  // namespace
@@ -233,7 +324,10 @@ int dsp_comm_create(dsp_comm* out, int device, int rank, int world, int64_t wind
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_res, sizeof(Result));
     if (e == cudaSuccess) e = cudaMemset(c->d_res, 0, sizeof(Result));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_res, sizeof(Result));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_bounds, sizeof(uint64_t) * (route::MAXW + 1));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_bounds, sizeof(uint64_t) * (route::MAXW + 1));
     for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 10 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->dev[i / 5][i % 5]);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         set_error("dsp_comm_create: %s (two windows of %lld bytes)", cudaGetErrorString(e), (long long)c->window_bytes);
@@ -316,7 +410,10 @@ int dsp_comm_destroy(dsp_comm c) {
     if (c->d_abort) cudaFree(c->d_abort);
     if (c->d_res) cudaFree(c->d_res);
     if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->d_bounds) cudaFree(c->d_bounds);
+    if (c->h_bounds) cudaFreeHost(c->h_bounds);
     for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 10; ++i) if (c->dev[i / 5][i % 5]) cudaEventDestroy(c->dev[i / 5][i % 5]);
     cudaGetLastError();
     delete c;
     return DSP_OK;
@@ -345,8 +442,8 @@ int dsp_comm_route_rows(dsp_comm c, const void* rows, int64_t n, int32_t row_byt
 
 int dsp_freq_aggregate_distributed(dsp_comm c, const uint64_t* key, const double* p0, const double* p1, const int32_t* label,
                                    int64_t n, uint64_t gidx_base, double prob_cf, const uint64_t* gidx_bounds_host,
-                                   int32_t order_by_key, void* rows_out, int64_t rows_cap, int64_t* n_rows_host,
-                                   int64_t* n_callable_host, void* stream) {
+                                   int32_t row_placement, void* rows_out, int64_t rows_cap, int64_t* n_rows_host,
+                                   int64_t* n_callable_host, uint64_t* row_bounds_host, void* stream) {
     DSP_REQUIRE(c && n_rows_host && gidx_bounds_host, DSP_ERR_INVALID, "dsp_freq_aggregate_distributed: null argument");
     *n_rows_host = 0;
     if (n_callable_host) *n_callable_host = 0;
@@ -370,28 +467,34 @@ int dsp_freq_aggregate_distributed(dsp_comm c, const uint64_t* key, const double
     if ((rc = sc.alloc(&rows, m))) return rc;
     if ((rc = sites_from_records(sc, st, reinterpret_cast<const Rec*>(c->win[0]), m, bits, rows, &nseg))) return rc;
     DSP_CUDA(cudaEventRecord(c->ev[2], st));
-    // 3. rows -> the rank whose shard holds the site's first callable record
+    // 3. rows -> the rank that owns the range of `first` (global index of the site's first callable record) they fall
+    //    into: ranges of equal row count chosen from samples (row_placement 0), or the ranks' own record shards
+    //    (row_placement 1: a row ends up where its first callable record was parsed)
     int64_t home = 0;
-    if ((rc = route_rows_units<3>(c, sc, st, rows, nseg, 1, gidx_bounds_host, &home))) return rc;
+    if (row_placement == 0 && (rc = choose_row_splitters(c, st, rows, nseg))) return rc;
+    if ((rc = route_rows_units<3>(c, sc, st, rows, nseg, 1, row_placement == 0 ? nullptr : gidx_bounds_host, &home))) return rc;
+    if (row_bounds_host) {
+        DSP_CUDA(cudaMemcpyAsync(c->h_bounds, c->d_bounds, sizeof(uint64_t) * (c->world + 1), cudaMemcpyDeviceToHost, st));
+        DSP_CUDA(cudaStreamSynchronize(st));
+        for (int w = 0; w <= c->world; ++w) row_bounds_host[w] = c->h_bounds[w];
+    }
     DSP_CUDA(cudaEventRecord(c->ev[3], st));
     *n_rows_host = home;
     DSP_REQUIRE(home <= rows_cap, DSP_ERR_NOMEM, "dsp_freq_aggregate_distributed: %lld site rows, capacity %lld", (long long)home, (long long)rows_cap);
-    // 4. dict insertion order on this rank = ascending first record (or key order for a sorted table)
-    int end_bit = 64;
-    if (!order_by_key) {                              // `first` is a global record index < bounds[world]
-        end_bit = 1;
-        while (end_bit < 63 && (1ull << end_bit) < gidx_bounds_host[c->world]) ++end_bit;
-    }
-    if ((rc = sort_rows(sc, st, reinterpret_cast<const SiteRow*>(c->win[1]), home, order_by_key, reinterpret_cast<SiteRow*>(rows_out), end_bit))) return rc;
+    // 4. dict insertion order on this rank = ascending first record
+    int end_bit = 1;                                  // `first` is a global record index < bounds[world]
+    while (end_bit < 63 && (1ull << end_bit) < gidx_bounds_host[c->world]) ++end_bit;
+    if ((rc = sort_rows(sc, st, reinterpret_cast<const SiteRow*>(c->win[1]), home, 0, reinterpret_cast<SiteRow*>(rows_out), end_bit))) return rc;
     DSP_CUDA(cudaEventRecord(c->ev[4], st));
     DSP_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&c->last_ms[i], c->ev[i], c->ev[i + 1]);
     return DSP_OK;
 }
 
-int dsp_comm_last_timing(dsp_comm c, float* ms4) {
-    DSP_REQUIRE(c && ms4, DSP_ERR_INVALID, "dsp_comm_last_timing: null argument");
-    for (int i = 0; i < 4; ++i) ms4[i] = c->last_ms[i];
+int dsp_comm_last_timing(dsp_comm c, float* ms12) {
+    DSP_REQUIRE(c && ms12, DSP_ERR_INVALID, "dsp_comm_last_timing: null argument");
+    for (int i = 0; i < 4; ++i) ms12[i] = c->last_ms[i];
+    for (int i = 0; i < 8; ++i) ms12[4 + i] = c->detail_ms[i / 4][i % 4];
     return DSP_OK;
 }
 

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(RS) replay_kernel(const uint32_t* __restrict__
     for (int64_t base = lo; base < hi; base += RC) {
         const int len = (int)min((int64_t)RC, hi - base);
         for (int i = threadIdx.x; i < len; i += RS) {
-            const Rec r = rec[sorted_pos[base + i]];
+            const Rec r = load_rec(rec + sorted_pos[base + i]);
             s_p0[i] = r.p0; s_p1[i] = r.p1; s_gl[i] = r.gl;
         }
         __syncthreads();

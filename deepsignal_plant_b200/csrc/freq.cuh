@@ -11,6 +11,19 @@ namespace dsp {
 struct __align__(32) Rec { uint64_t key; double p0, p1; uint64_t gl; };
 constexpr uint64_t REC_LABEL_BIT = 1ull << 63;
 
+// One 256-bit access per record (LDG/STG.E.256 on sm_100): a record is one aligned 32-byte sector, and one store
+// instruction per record is also one NVLink write instead of two half-sector ones when the destination is a peer.
+__device__ __forceinline__ void store_rec(Rec* dst, const Rec& r) {
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(r.key), "l"((uint64_t)__double_as_longlong(r.p0)),
+                 "l"((uint64_t)__double_as_longlong(r.p1)), "l"(r.gl) : "memory");
+}
+__device__ __forceinline__ Rec load_rec(const Rec* src) {
+    uint64_t a, b, c, d;
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(src));
+    Rec r; r.key = a; r.p0 = __longlong_as_double((long long)b); r.p1 = __longlong_as_double((long long)c); r.gl = d;
+    return r;
+}
+
 // One site of the frequency table (call_mods_freq.py:55-66): 48 bytes.
 struct __align__(16) SiteRow { uint64_t key; uint64_t first; double s0, s1; int32_t met, unmet, cov, pad; };
 

@@ -37,8 +37,9 @@ inline Plan make_plan(int64_t n, int n_sm) {
 }
 
 __host__ __device__ __forceinline__ int owner_of_key(uint64_t key, int world) {
-    // multiplicative hash of the 64-bit site key, 31 bits, mod world (same as call_mods_freq.owner_of_key)
-    return (int)(((key * 0x9E3779B97F4A7C15ull) >> 33) % (uint64_t)world);
+    // multiplicative hash of the 64-bit site key, top 31 bits, mapped onto [0, world) by multiply-shift (no division);
+    // call_mods_freq.owner_of_key is the same function on the host
+    return (int)((((key * 0x9E3779B97F4A7C15ull) >> 33) * (uint64_t)world) >> 31);
 }
 
 // ---- sources --------------------------------------------------------------------------------------
@@ -58,13 +59,14 @@ struct RecFromColumns {                       // call_mods columns -> packed Rec
         it.key = key[i]; it.p0 = p0[i]; it.p1 = p1[i];
         it.gl = (gidx_base + (uint64_t)i) | (label[i] == 1 ? REC_LABEL_BIT : 0ull);
     }
+    static __device__ __forceinline__ void store(Item* dst, const Item& it) { store_rec(dst, it); }
 };
 
 template <int UNITS>                           // rows of UNITS x 16 bytes, by range of a 64-bit field
 struct RowsByRange {
     struct __align__(16) Item { uint4 u[UNITS]; };
     const Item* rows; int field_word;           // index of the 64-bit field inside the row
-    uint64_t bounds[MAXW + 1]; int world;
+    const uint64_t* bounds; int world;          // world + 1 ascending values in DEVICE memory
     __device__ __forceinline__ bool dest_of(int64_t i, int& d, uint64_t& k) const {
         k = reinterpret_cast<const uint64_t*>(rows + i)[field_word];
         int lo = 0;
@@ -73,6 +75,7 @@ struct RowsByRange {
         return true;
     }
     __device__ __forceinline__ void load(int64_t i, Item& it) const { it = rows[i]; }
+    static __device__ __forceinline__ void store(Item* dst, const Item& it) { *dst = it; }
 };
 
 // ---- kernels ----------------------------------------------------------------------------------------
@@ -83,23 +86,18 @@ __global__ void __launch_bounds__(RT) count_kernel(Src src, Plan plan, int world
     __syncthreads();
     const int64_t lo = (int64_t)blockIdx.x * plan.per_block;
     const int64_t hi = min(plan.n, lo + plan.per_block);
-    int mine[MAXW];
-#pragma unroll
-    for (int d = 0; d < MAXW; ++d) mine[d] = 0;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += RT) {
-        int d; uint64_t k;
-        if (src.dest_of(i, d, k)) {
-#pragma unroll
-            for (int e = 0; e < MAXW; ++e) mine[e] += (e == d) ? 1 : 0;
+    const int lane = threadIdx.x & 31;
+    int mine = 0;                                   // lane d of every warp counts destination d
+    for (int64_t i0 = lo; i0 < hi; i0 += RT) {
+        const int64_t i = i0 + threadIdx.x;
+        int d = -1; uint64_t k;
+        if (i < hi) { int dd; if (src.dest_of(i, dd, k)) d = dd; }
+        for (int e = 0; e < world; ++e) {
+            const int c = __popc(__ballot_sync(0xffffffffu, d == e));
+            if (lane == e) mine += c;
         }
     }
-#pragma unroll
-    for (int d = 0; d < MAXW; ++d) {
-        if (d < world) {
-            const int w = __reduce_add_sync(0xffffffffu, mine[d]);
-            if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[d], w);
-        }
-    }
+    if (lane < world && mine) atomicAdd(&s_cnt[lane], mine);
     __syncthreads();
     if (threadIdx.x < world) blk_counts[(size_t)blockIdx.x * MAXW + threadIdx.x] = s_cnt[threadIdx.x];
 }
@@ -171,7 +169,7 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
             Item it;
             src.load(i, it);
             bits |= *reinterpret_cast<const uint64_t*>(&it);            // first word of every item is its key
-            s_dst[d][s_run[d] + before + rank] = it;
+            Src::store(s_dst[d] + (s_run[d] + before + rank), it);
         }
         __syncthreads();
         if (threadIdx.x < world) {

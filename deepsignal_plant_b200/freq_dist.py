@@ -12,9 +12,12 @@ temp files (``call_mods_freq.py:154-215,262-295``).  Here (``torchrun``, RANK/WO
    by the single-GPU sort + ordered float64 replay (bit-identical sums, no partial-sum merging), and the
    finished site rows travel to the rank that parsed their first callable record -- the one that holds
    strand / pos_in_strand / k-mer (``call_mods_freq.py:55-59``);
-4. rows never funnel through one rank: in the default order (dict insertion = first callable appearance) rank r's
-   rows, sorted by first record, ARE the r-th slice of the table; for ``--sort`` / ``--contigs`` they make one
-   more hop (``dsp_comm_route_rows``) to key-range owners and are sorted there;
+4. rows never funnel through one rank: in the default order (dict insertion = first callable appearance) the table
+   is cut into ``world`` ranges of the first-record index holding about equal numbers of rows (splitters from an
+   all-gathered sample; with reads in random order almost every site is FIRST seen in rank 0's shard, so "home"
+   placement would put the whole table on rank 0); a rank's rows, sorted by first record, ARE its slice.  The text
+   columns of a site are then fetched from the rank that parsed that record (two small ``dsp_comm_route_rows``
+   exchanges).  For ``--sort`` / ``--contigs`` the rows make one more hop to key-range owners and are sorted there;
 5. every rank renders its slice (``dsp_format_freq``) and writes it at its byte offset of the result file.
 
 The device steps sit behind a small backend interface so that the host logic above (sharding, tables, order,
@@ -35,7 +38,10 @@ from . import call_mods_freq as cf
 SITE_ROW = np.dtype([("key", "<u8"), ("first", "<u8"), ("s0", "<f8"), ("s1", "<f8"),
                      ("met", "<i4"), ("unmet", "<i4"), ("cov", "<i4"), ("pad", "<i4")])
 FAT_ROW = np.dtype(SITE_ROW.descr + [("pis", "<i8"), ("strand", "S8"), ("kmer", "S24"), ("order", "<u8")])
-assert SITE_ROW.itemsize == 48 and FAT_ROW.itemsize == 96
+# the text columns of a site live with the rank that parsed its first callable record: request / reply rows
+META_REQ = np.dtype([("first", "<u8"), ("rank", "<u8"), ("idx", "<u8"), ("pad", "V24")])
+META_REPLY = np.dtype([("rank", "<u8"), ("idx", "<u8"), ("pis", "<i8"), ("strand", "S8"), ("kmer", "S24"), ("pad", "V40")])
+assert SITE_ROW.itemsize == 48 and FAT_ROW.itemsize == 96 and META_REQ.itemsize == 48 and META_REPLY.itemsize == 96
 U64_MAX = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
@@ -110,31 +116,34 @@ class DeviceBackend:
         except Exception:
             pass
 
-    def aggregate_tensors(self, t_key, t_p0, t_p1, t_lab, gidx_base, bounds, prob_cf, order_by_key=False, rows_cap=None):
-        """Device tensors in (this rank's records, file order) -> (rows tensor (m, 48) uint8 on the device,
-        callable records received)."""
+    def aggregate_tensors(self, t_key, t_p0, t_p1, t_lab, gidx_base, bounds, prob_cf, balanced=True, rows_cap=None):
+        """Device tensors in (this rank's records, file order) -> (rows tensor (m, 48) uint8 on the device: this rank's
+        slice of the table, ordered by first callable record; callable records received; the world + 1 ``first``
+        ranges of the slices).  ``balanced``: slices of about equal row count (sampled splitters); else rank r gets
+        the rows whose first callable record lies in its own shard."""
         torch = self.torch
         n = int(t_key.shape[0])
         cap = int(rows_cap if rows_cap is not None else self.window_bytes // SITE_ROW.itemsize)
         out = torch.empty((max(cap, 1), SITE_ROW.itemsize), dtype=torch.uint8, device=self.dev)
         b = np.ascontiguousarray(bounds, dtype=np.uint64)
         assert b.shape[0] == self.world + 1
+        used = np.zeros(self.world + 1, np.uint64)
         n_rows, n_call = C.c_int64(0), C.c_int64(0)
         with torch.cuda.device(self.dev):
             stream = torch.cuda.current_stream(self.dev).cuda_stream
             _native.check(self.L.dsp_freq_aggregate_distributed(
                 self.h, t_key.data_ptr() if n else None, t_p0.data_ptr() if n else None, t_p1.data_ptr() if n else None,
-                t_lab.data_ptr() if n else None, n, int(gidx_base), float(prob_cf), b.ctypes.data, int(bool(order_by_key)),
-                out.data_ptr(), cap, C.byref(n_rows), C.byref(n_call), stream), "dsp_freq_aggregate_distributed")
+                t_lab.data_ptr() if n else None, n, int(gidx_base), float(prob_cf), b.ctypes.data, 0 if balanced else 1,
+                out.data_ptr(), cap, C.byref(n_rows), C.byref(n_call), used.ctypes.data, stream), "dsp_freq_aggregate_distributed")
+        self.last_row_bounds = used
         return out[:n_rows.value], int(n_call.value)
 
-    def aggregate(self, keys, p0, p1, label, gidx_base, bounds, prob_cf):
-        """numpy columns in -> ``SITE_ROW`` array: the sites whose first callable record is in this rank's shard,
-        ordered by that record."""
+    def aggregate(self, keys, p0, p1, label, gidx_base, bounds, prob_cf, balanced=True):
+        """numpy columns in -> ``SITE_ROW`` array: this rank's slice of the table, ordered by first callable record."""
         torch = self.torch
         up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a).astype(dt, copy=False)).to(self.dev)
         rows, _ = self.aggregate_tensors(up(keys.view(np.int64), np.int64), up(p0, np.float64), up(p1, np.float64),
-                                         up(label, np.int32), gidx_base, bounds, prob_cf)
+                                         up(label, np.int32), gidx_base, bounds, prob_cf, balanced)
         return rows.cpu().numpy().reshape(-1).view(SITE_ROW)
 
     def route_rows(self, rows, field, bounds):
@@ -155,9 +164,12 @@ class DeviceBackend:
         return out[:n_out.value].cpu().numpy().reshape(-1).view(dt)
 
     def timing(self):
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 12)()
         _native.check(self.L.dsp_comm_last_timing(self.h, ms), "dsp_comm_last_timing")
-        return dict(zip(("route_records_ms", "sort_replay_ms", "route_rows_ms", "order_ms"), [float(x) for x in ms]))
+        names = ("route_records_ms", "sort_replay_ms", "route_rows_ms", "order_ms",
+                 "records_count_ms", "records_wait_counts_ms", "records_scatter_ms", "records_wait_stores_ms",
+                 "rows_count_ms", "rows_wait_counts_ms", "rows_scatter_ms", "rows_wait_stores_ms")
+        return dict(zip(names, [float(x) for x in ms]))
 
 
 # ---- control plane ------------------------------------------------------------------------------------
@@ -241,14 +253,29 @@ def distributed_table(rec, prob_cf, grp, backend, is_sort=False, contigs=None):
     keys = cf.make_keys(ids, rec.pos) if len(rec) else np.zeros(0, np.uint64)
     rows = backend.aggregate(keys, rec.p0, rec.p1, rec.label, base, bounds, prob_cf)
     used = int(np.sum(grp.all_gather_object(int(rows["cov"].sum()))))
-    # text columns of every site come from its first callable record, which this rank parsed
-    local = (rows["first"] - np.uint64(base)).astype(np.int64)
-    assert len(local) == 0 or (local.min() >= 0 and local.max() < len(rec))
-    strand, pis, kmer = rec.meta_cells(local)
+    # Text columns (strand, pos_in_strand, k-mer) of a site come from its first callable record (call_mods_freq.py:55-59),
+    # which lives with the rank that parsed it: ask that rank (one exchange of 48-byte requests routed by `first` over
+    # the ranks' record shards, one of 96-byte replies routed back by requesting rank).
     fat = np.zeros(len(rows), FAT_ROW)
     for f in SITE_ROW.names:
         fat[f] = rows[f]
-    fat["pis"], fat["strand"], fat["kmer"] = pis, strand, kmer
+    if grp.world > 1:
+        req = np.zeros(len(rows), META_REQ)
+        req["first"], req["rank"], req["idx"] = rows["first"], grp.rank, np.arange(len(rows), dtype=np.uint64)
+        asked = backend.route_rows(req, "first", bounds)
+        local = (asked["first"] - np.uint64(base)).astype(np.int64)
+        assert len(local) == 0 or (local.min() >= 0 and local.max() < len(rec))
+        strand, pis, kmer = rec.meta_cells(local)
+        reply = np.zeros(len(asked), META_REPLY)
+        reply["rank"], reply["idx"], reply["pis"], reply["strand"], reply["kmer"] = asked["rank"], asked["idx"], pis, strand, kmer
+        back = backend.route_rows(reply, "rank", np.arange(grp.world + 1, dtype=np.uint64))
+        assert len(back) == len(rows) and (back["rank"] == grp.rank).all()
+        at = back["idx"].astype(np.int64)
+        fat["pis"][at], fat["strand"][at], fat["kmer"][at] = back["pis"], back["strand"], back["kmer"]
+    else:
+        local = (rows["first"] - np.uint64(base)).astype(np.int64)
+        strand, pis, kmer = rec.meta_cells(local)
+        fat["pis"], fat["strand"], fat["kmer"] = pis, strand, kmer
     if is_sort or contigs is not None:
         if is_sort:
             b = _splitters_by_key(fat, grp)
@@ -401,15 +428,18 @@ def measure(grp, device, records_per_rank, coverage=20, prob_cf=0.5, iters=5, ch
                 stages = be.timing()
         mine = rows.cpu().numpy().reshape(-1).view(SITE_ROW)
         sums = grp.all_gather_object((rows_checksum(mine), int(mine["cov"].sum()), n_call,
-                                      bool(len(mine) == 0 or (np.diff(mine["first"].astype(np.int64)) > 0).all())))
-        stage_max = {k: max(d[k] for d in grp.all_gather_object(stages)) for k in stages}
+                                      bool(len(mine) == 0 or (np.diff(mine["first"].astype(np.int64)) > 0).all()), len(mine)))
+        every = grp.all_gather_object(stages)
+        stage_max = {k: max(d[k] for d in every) for k in stages}
+        stage_min = {k: min(d[k] for d in every) for k in stages}
     finally:
         be.close()
     del key, p0, p1, lab
     t = min(times)
     out = {"records": total, "world": world, "seconds": t, "records_per_s": total / t, "sites": sum(s[0][1] for s in sums),
            "callable": sum(s[2] for s in sums), "coverage_sum_equals_callable": sum(s[1] for s in sums) == sum(s[2] for s in sums),
-           "slices_ordered": all(s[3] for s in sums), "stage_ms_max_over_ranks": stage_max, "prob_cf": prob_cf,
+           "slices_ordered": all(s[3] for s in sums), "rows_per_rank": [s[4] for s in sums], "stage_ms_max_over_ranks": stage_max, "stage_ms_min_over_ranks": stage_min,
+           "prob_cf": prob_cf,
            "bit_exact": None}
     if check:
         ok = None

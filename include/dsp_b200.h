@@ -178,17 +178,22 @@ int dsp_comm_destroy(dsp_comm c);
 /* calculate_mods_frequency (call_mods_freq.py:29-74) across the ranks of `c`.  DEVICE pointers: this rank's
  * n records in file order (columns as for dsp_freq_aggregate).  gidx_bounds_host (HOST, world + 1 ascending
  * values): rank r holds the global records [bounds[r], bounds[r+1]); gidx_base = bounds[rank].
- * Result: the sites whose FIRST callable record lies in this rank's shard -- that record supplies strand /
- * pos_in_strand / k-mer (:55-59) and this rank is the one that parsed it -- as rows of 48 bytes
- *   { uint64 key; uint64 first (global record index); double prob_0 sum, prob_1 sum; int32 met, unmet, coverage, 0 }
- * in rows_out (DEVICE, capacity rows_cap), ordered by `first` (order_by_key == 0: concatenating the ranks'
- * rows in rank order gives the reference's dict insertion order) or by key.  *n_rows_host = rows written,
- * *n_callable_host (may be NULL) = callable records this rank RECEIVED.  Synchronises `stream`. */
+ * Result: this rank's slice of the table as rows of 48 bytes
+ *   { uint64 key; uint64 first (global index of the site's first callable record, which supplies strand /
+ *     pos_in_strand / k-mer, :55-59); double prob_0 sum, prob_1 sum; int32 met, unmet, coverage, 0 }
+ * in rows_out (DEVICE, capacity rows_cap), ordered by `first`: concatenating the ranks' slices in rank order gives
+ * the reference's dict insertion order.  row_placement 0: the slices are ranges of `first` holding about the same
+ * number of rows each, cut at splitters every rank derives from the same all-gathered sample (with reads in
+ * random order nearly every site is first seen in rank 0's shard, so "send the row to the rank that parsed its
+ * first record" would funnel the table through one GPU); row_placement 1: exactly that -- rank r receives the
+ * rows whose `first` lies in its own shard [bounds[r], bounds[r+1]).  row_bounds_host (HOST, world + 1 values, may
+ * be NULL) receives the ranges used.  *n_rows_host = rows written, *n_callable_host (may be NULL) = callable
+ * records this rank RECEIVED.  Synchronises `stream`. */
 int dsp_freq_aggregate_distributed(dsp_comm c, const uint64_t* key, const double* p0, const double* p1,
                                    const int32_t* label, int64_t n, uint64_t gidx_base, double prob_cf,
-                                   const uint64_t* gidx_bounds_host, int32_t order_by_key,
+                                   const uint64_t* gidx_bounds_host, int32_t row_placement,
                                    void* rows_out, int64_t rows_cap, int64_t* n_rows_host,
-                                   int64_t* n_callable_host, void* stream);
+                                   int64_t* n_callable_host, uint64_t* row_bounds_host, void* stream);
 
 /* The exchange primitive on its own: n rows of row_bytes (48 or 96) in DEVICE memory; the row's uint64 at
  * field_offset selects the destination rank d with bounds[d] <= field < bounds[d+1] (bounds_host: world + 1
@@ -200,9 +205,11 @@ int dsp_comm_route_rows(dsp_comm c, const void* rows, int64_t n, int32_t row_byt
                         const uint64_t* bounds_host, void* out, int64_t out_cap_rows, int64_t* n_out_host,
                         void* stream);
 
-/* Milliseconds (CUDA events on the stream) of the four stages of the last dsp_freq_aggregate_distributed call:
- * record exchange, local sort + replay, row exchange, ordering. */
-int dsp_comm_last_timing(dsp_comm c, float* ms4);
+/* Milliseconds (CUDA events on the stream) of the last dsp_freq_aggregate_distributed call, 12 values: the four
+ * stages (record exchange, local sort + replay, row exchange, ordering), then inside the record exchange and inside
+ * the row exchange: count + scan + publish | waiting for every rank's counts | scatter over NVLink | signal +
+ * waiting for every rank's stores. */
+int dsp_comm_last_timing(dsp_comm c, float* ms12);
 
 /* dsp_parse_calls: ModRecord.__init__ (utils/txt_formater.py:8-21) for a whole call_mods file held in memory
  * (HOST pointers): every line is strip()-ed and split on tabs; columns 1, 3, 8 are parsed like int(), 6 and 7

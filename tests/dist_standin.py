@@ -12,7 +12,7 @@ class StandInBackend:
     def __init__(self, grp):
         self.grp = grp
 
-    def aggregate(self, keys, p0, p1, label, gidx_base, bounds, prob_cf):
+    def aggregate(self, keys, p0, p1, label, gidx_base, bounds, prob_cf, balanced=True):
         parts = self.grp.all_gather_object((np.asarray(keys), np.asarray(p0), np.asarray(p1), np.asarray(label)))
         k = np.concatenate([x[0] for x in parts]); a = np.concatenate([x[1] for x in parts])
         b = np.concatenate([x[2] for x in parts]); lab = np.concatenate([x[3] for x in parts])
@@ -25,8 +25,13 @@ class StandInBackend:
                 r = table[int(k[i])] = [i, 0.0, 0.0, 0, 0]
             r[1] += float(a[i]); r[2] += float(b[i])
             r[3 if lab[i] == 1 else 4] += 1
-        lo, hi = int(bounds[self.grp.rank]), int(bounds[self.grp.rank + 1])
-        mine = sorted((r[0], key, r) for key, r in table.items() if lo <= r[0] < hi)
+        every = sorted((r[0], key, r) for key, r in table.items())           # dict insertion order = by first record
+        if balanced:                                                          # equal slices of that order
+            w, me = self.grp.world, self.grp.rank
+            mine = every[len(every) * me // w: len(every) * (me + 1) // w]
+        else:                                                                 # rows whose first record is in my shard
+            lo, hi = int(bounds[self.grp.rank]), int(bounds[self.grp.rank + 1])
+            mine = [e for e in every if lo <= e[0] < hi]
         rows = np.zeros(len(mine), fd.SITE_ROW)
         for j, (first, key, r) in enumerate(mine):
             rows[j] = (key, first, r[1], r[2], r[3], r[4], r[3] + r[4], 0)

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--records", type=int, default=1000000)
     ap.add_argument("--window_records", type=int, default=0)
     ap.add_argument("--expect_overflow", action="store_true")
+    ap.add_argument("--home_rows", action="store_true", help="row_placement 1: rows go to the rank that parsed their first record")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo")
@@ -61,7 +62,8 @@ def main():
         win = (a.window_records or int(n / world * 1.3) + 65536) * 32
         be = fd.DeviceBackend(rank, world, device, win, grp.all_gather_object)
         try:
-            rows, n_call = be.aggregate_tensors(key[lo:hi], p0[lo:hi], p1[lo:hi], lab[lo:hi], lo, bounds, a.prob_cf)
+            rows, n_call = be.aggregate_tensors(key[lo:hi], p0[lo:hi], p1[lo:hi], lab[lo:hi], lo, bounds, a.prob_cf,
+                                                balanced=not a.home_rows)
             overflow = 0
         except Exception as e:
             if not (a.expect_overflow and "overflow" in str(e)):
@@ -76,6 +78,9 @@ def main():
             return
         mine = rows.cpu().numpy().reshape(-1).view(fd.SITE_ROW)
         every = grp.all_gather_object(mine)
+        rb = be.last_row_bounds
+        in_range = bool(len(mine) == 0 or (mine["first"].min() >= rb[rank] and (rank == world - 1 or mine["first"].max() < rb[rank + 1])))
+        in_range = all(grp.all_gather_object(in_range))
         if rank == 0:
             got = np.concatenate(every)                          # rank order = first-appearance order
             k, first, s0, s1, met, unmet, cov = cf._aggregate_tensors(key, p0, p1, lab, a.prob_cf, False, dev)
@@ -85,7 +90,9 @@ def main():
                   and (got["s1"].view(np.int64) == s1.cpu().numpy().view(np.int64)).all()
                   and (got["met"] == met.cpu().numpy()).all() and (got["unmet"] == unmet.cpu().numpy()).all()
                   and (got["cov"] == cov.cpu().numpy()).all())
-            print(json.dumps({"ok": bool(ok), "world": world, "records": n, "sites": int(len(got)), "timing": be.timing()}), flush=True)
+            sizes = [len(e) for e in every]
+            print(json.dumps({"ok": bool(ok) and in_range, "world": world, "records": n, "sites": int(len(got)), "rows_per_rank": sizes,
+                              "row_bounds": [int(x) for x in rb[:-1]], "timing": be.timing()}), flush=True)
         be.close()
         dist.barrier()
         dist.destroy_process_group()

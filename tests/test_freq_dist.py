@@ -144,11 +144,16 @@ def test_reference_fixture_bytes_through_the_exchange(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4])
-def test_tensor_entry_equals_single_gpu_table_bit_for_bit(world):
-    out = _run_ranks(world, ["--tensor_check", "--records", 3000000, "--prob_cf", 0.3])
+@pytest.mark.parametrize("world,home", [(2, False), (4, False), (3, True)])
+def test_tensor_entry_equals_single_gpu_table_bit_for_bit(world, home):
+    out = _run_ranks(world, ["--tensor_check", "--records", 3000000, "--prob_cf", 0.3] + (["--home_rows"] if home else []))
     line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
     assert line["ok"] and line["world"] == world and line["sites"] > 10000, line
+    sizes = line["rows_per_rank"]
+    if home:      # records in random order: nearly every site is first seen in rank 0's shard
+        assert sizes[0] > 0.9 * sum(sizes), sizes
+    else:         # sampled splitters: every rank holds about 1/world of the table
+        assert max(sizes) < 1.25 * sum(sizes) / world and min(sizes) > 0.75 * sum(sizes) / world, sizes
 
 
 @pytest.mark.gpu
