@@ -247,7 +247,7 @@ int exchange(dsp_comm_s* c, Scratch& sc, cudaStream_t st, const Src& src, int64_
     prepare_kernel<<<1, 32, 0, st>>>(c->ctrl, wins, c->rank, c->world, parity, epoch, (int64_t)(c->window_bytes / item_bytes),
                                      c->d_tg, c->d_abort, c->d_res);
     cudaEventRecord(ev[2], st);
-    scatter_kernel<Src><<<plan.blocks, RT, 0, st>>>(src, plan, c->world, blk_off, c->d_tg, c->d_abort, d_bits);
+    ScatterLaunch<Src>::run(src, plan, c->world, blk_off, c->d_tg, c->d_abort, d_bits, st);
     cudaEventRecord(ev[3], st);
     signal_wait_kernel<<<1, 32, 0, st>>>(c->ctrl, peers, c->rank, c->world, parity, epoch, d_bits, c->d_res);
     cudaEventRecord(ev[4], st);

@@ -186,5 +186,114 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
     }
 }
 
+// The same scatter for 32-byte records bound for PEER windows: a tile of ST x RT items is ranked, staged in shared
+// memory grouped by destination, and copied out with consecutive threads writing consecutive records -- every warp
+// store covers 1 KB of one destination window instead of ~4 records for each of `world` windows, which is what NVLink
+// wants (few large writes instead of many 32-byte ones).  Same positions, same order as scatter_kernel.
+constexpr int ST = 4;                          // sub-tiles of RT items per staged tile
+template <typename Src>
+__global__ void __launch_bounds__(RT) scatter_staged_kernel(Src src, Plan plan, int world, const int64_t* __restrict__ blk_off,
+                                                           const Targets* __restrict__ tg, const int* __restrict__ abort_flag,
+                                                           unsigned long long* __restrict__ key_bits_out) {
+    typedef typename Src::Item Item;
+    static_assert(sizeof(Item) == 32, "staged scatter is written for 32-byte records");
+    __shared__ __align__(32) Item s_stage[ST * RT];
+    __shared__ int s_warp[ST][RWARPS][MAXW];
+    __shared__ int s_sub[ST][MAXW];            // items of sub-tile j bound for d
+    __shared__ int s_seg[MAXW + 1];            // first stage slot of destination d in this tile
+    __shared__ int64_t s_run[MAXW];
+    __shared__ Item* s_dst[MAXW];
+    if (abort_flag && *abort_flag) return;
+    if (threadIdx.x < MAXW) {
+        const int d = threadIdx.x;
+        s_run[d] = d < world ? tg->base[d] + blk_off[(size_t)blockIdx.x * MAXW + d] : 0;
+        s_dst[d] = d < world ? reinterpret_cast<Item*>(tg->dst[d]) : nullptr;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t lo = (int64_t)blockIdx.x * plan.per_block;
+    const int64_t hi = min(plan.n, lo + plan.per_block);
+    uint64_t bits = 0;
+    for (int64_t t0 = lo; t0 < hi; t0 += (int64_t)ST * RT) {
+        int dest[ST], rank[ST];
+#pragma unroll
+        for (int j = 0; j < ST; ++j) {
+            const int64_t i = t0 + (int64_t)j * RT + threadIdx.x;
+            int d = -1; uint64_t k;
+            if (i < hi) { int dd; if (src.dest_of(i, dd, k)) d = dd; }
+            dest[j] = d; rank[j] = 0;
+            for (int e = 0; e < world; ++e) {
+                const unsigned m = __ballot_sync(0xffffffffu, d == e);
+                if (d == e) rank[j] = __popc(m & lt);
+                if (lane == 0) s_warp[j][warp][e] = __popc(m);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < ST * MAXW) {
+            const int j = threadIdx.x / MAXW, d = threadIdx.x % MAXW;
+            int tot = 0;
+            if (d < world)
+#pragma unroll
+                for (int w = 0; w < RWARPS; ++w) tot += s_warp[j][w][d];
+            s_sub[j][d] = tot;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int d = 0; d < world; ++d) {
+                s_seg[d] = acc;
+#pragma unroll
+                for (int j = 0; j < ST; ++j) acc += s_sub[j][d];
+            }
+            for (int d = world; d <= MAXW; ++d) s_seg[d] = acc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ST; ++j) {
+            const int d = dest[j];
+            if (d >= 0) {
+                int slot = s_seg[d] + rank[j];
+                for (int jj = 0; jj < j; ++jj) slot += s_sub[jj][d];
+                for (int w = 0; w < warp; ++w) slot += s_warp[j][w][d];
+                Item it;
+                src.load(t0 + (int64_t)j * RT + threadIdx.x, it);
+                bits |= *reinterpret_cast<const uint64_t*>(&it);
+                s_stage[slot] = it;
+            }
+        }
+        __syncthreads();
+        const int total = s_seg[MAXW];
+        for (int sl = threadIdx.x; sl < total; sl += RT) {
+            int d = 0;
+            while (sl >= s_seg[d + 1]) ++d;                   // <= world steps
+            Src::store(s_dst[d] + (s_run[d] + (sl - s_seg[d])), s_stage[sl]);
+        }
+        __syncthreads();
+        if (threadIdx.x < world) s_run[threadIdx.x] += s_seg[threadIdx.x + 1] - s_seg[threadIdx.x];
+        __syncthreads();
+    }
+    if (key_bits_out) {
+        const unsigned blo = __reduce_or_sync(0xffffffffu, (unsigned)bits), bhi = __reduce_or_sync(0xffffffffu, (unsigned)(bits >> 32));
+        if (lane == 0 && (blo | bhi)) atomicOr(key_bits_out, ((unsigned long long)bhi << 32) | blo);
+    }
+}
+
+template <typename Src, bool STAGED = (sizeof(typename Src::Item) == 32)>
+struct ScatterLaunch {
+    static void run(const Src& src, const Plan& plan, int world, const int64_t* blk_off, const Targets* tg, const int* abort_flag,
+                    unsigned long long* bits, cudaStream_t st) {
+        scatter_kernel<Src><<<plan.blocks, RT, 0, st>>>(src, plan, world, blk_off, tg, abort_flag, bits);
+    }
+};
+template <typename Src>
+struct ScatterLaunch<Src, true> {
+    static void run(const Src& src, const Plan& plan, int world, const int64_t* blk_off, const Targets* tg, const int* abort_flag,
+                    unsigned long long* bits, cudaStream_t st) {
+        if (world > 1) scatter_staged_kernel<Src><<<plan.blocks, RT, 0, st>>>(src, plan, world, blk_off, tg, abort_flag, bits);
+        else scatter_kernel<Src><<<plan.blocks, RT, 0, st>>>(src, plan, world, blk_off, tg, abort_flag, bits);
+    }
+};
+
 }  // namespace route
 }  // namespace dsp
