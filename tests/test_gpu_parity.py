@@ -376,3 +376,27 @@ def test_fp16_label_bar_on_100k_sites_per_seed(seed):
           % (seed, n, err, flips, 100.0 * (1 - flips / n), margin.max() if flips else 0.0))
     assert err <= PROB_TOL
     assert flips <= n // 10000, "label agreement %.5f below 99.99 %%" % (1 - flips / n)
+
+
+def test_exact_epilogue_variant_build_still_matches_reference():
+    # the shipped library evaluates the gate non-linearities with tanh.approx (DSP_TANH_APPROX=2); the 2^x + reciprocal
+    # epilogue (-DDSP_TANH_APPROX=0, ~1e-7 relative error) stays buildable as libdsp_b200_exact.so:
+    #   DSP_B200_VARIANT=exact DSP_B200_DEFINES=-DDSP_TANH_APPROX=0 python -m deepsignal_plant_b200.build
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "deepsignal_plant_b200", "libdsp_b200_exact.so")
+    if not os.path.exists(lib):
+        pytest.skip("variant build libdsp_b200_exact.so is not present")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, torch, cases\n"
+            "case = cases.slice_case(cases.load_case('both_13_16_s2'), 4096)\n"
+            "m = cases.build_model(case['entry'], precision='fp16').cuda(0)\n"
+            "cases.inject_states(m, case['states'], torch.device('cuda:0'))\n"
+            "p = m(*(torch.from_numpy(case['feats'][k]).cuda(0) for k in cases.FEATURE_KEYS))[1].cpu().numpy()\n"
+            "print('ERR %%.3e AGREE %%.5f' %% (np.abs(p - case['probs']).max(), (p.argmax(1) == case['probs'].argmax(1)).mean()))\n"
+            % (root, os.path.join(root, "tests")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, DSP_B200_LIB=lib))
+    assert r.returncode == 0, r.stderr[-2000:]
+    err, agree = [l for l in r.stdout.splitlines() if l.startswith("ERR")][-1].split()[1::2]
+    assert float(err) <= PROB_TOL and float(agree) >= LABEL_AGREEMENT
