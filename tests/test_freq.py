@@ -268,3 +268,19 @@ def test_native_table_writer_equals_the_python_loop(monkeypatch):
     odd = cf.FreqTable(obj(["chr\n1"]), np.array([5]), obj(["+"]), np.array([5]), obj(["AACGT"]), np.array([1.0]), np.array([0.0]),
                        np.array([1], np.int32), np.array([0], np.int32), np.array([1], np.int32), np.arange(1))
     assert cf._render_native(odd, False) is None and cf.render_table(odd).startswith("chr\n1\t5\t+")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sort_by_key", [False, True])
+def test_gpu_freq_key_hash_passes_equal_one_pass(sort_by_key):
+    # more records than one dsp_freq_aggregate call takes (< 2^31) are aggregated in several passes over key-hash
+    # shards (call_mods_freq._aggregate_device): same rows, same order, same float64 bits as one pass
+    lines = synthetic.make_callmods_records(60000, n_chrom=7, n_pos=400, seed=21)
+    rec = cf.parse_lines(lines)
+    ids, names = cf._chrom_ids(rec.chrom)
+    keys = cf.make_keys(ids, rec.pos)
+    one = cf._aggregate_device(keys, rec.p0, rec.p1, rec.label, 0.2, sort_by_key, 0)
+    many = cf._aggregate_device(keys, rec.p0, rec.p1, rec.label, 0.2, sort_by_key, 0, max_records=7000)
+    assert len(one[0]) == len(many[0]) > 2000
+    for a, b in zip(one, many):
+        assert a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8))
