@@ -107,8 +107,9 @@ class ClockSampler(threading.Thread):
         sm = sorted(float(r[0]) for r in loaded)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        watts = [float(r[2]) for r in loaded]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "samples": len(self.rows), "samples_under_load": len(loaded),
-                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+                "power_w_max": max(float(r[2]) for r in self.rows), "power_w_mean_under_load": sum(watts) / len(watts), "reasons": reasons}
 
 
 def make_pool(n_buffers, batch, seed=0, T=13, S=16):
@@ -355,6 +356,13 @@ def main():
                 "d2h_bytes_per_step": args.batch * OUT_BYTES_PER_SITE, "api": "ModelBiLSTM.submit_host/wait_host (dsp_forward_host_submit), pinned host buffers in and out, 2 batches in flight"},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if clocks and clocks.get("power_w_mean_under_load"):
+        # at the power cap throughput follows energy per site: board power (nvidia-smi, mean of the samples under load,
+        # rank 0's GPU) x time per site at this rank's rate
+        w = clocks["power_w_mean_under_load"]
+        line["energy"] = {"microjoules_per_site": 1e6 * w / (value / world), "watts_mean_under_load": w,
+                          "picojoules_per_algorithmic_flop": 1e12 * w / (value / world * flop_site),
+                          "note": "board power of rank 0's GPU over both timed regions / device-resident sites/s per GPU"}
     if args.meas_skip_y:
         line["INVALID"] = "measurement run: activation stores skipped inside the timed region"
     # ---- call_freq (BASELINE.json configs[4]): the per-site aggregation with its NVLink exchange, every N ----

@@ -307,8 +307,10 @@ int dsp_destroy(dsp_handle h) {
         if (m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
     }
     for (int i = 0; i < Model::NTICKET; ++i) if (m->ev_ticket[i]) cudaEventDestroy(m->ev_ticket[i]);
+    for (int i = 0; i < Model::NBUF; ++i) if (m->ev_computed[i]) cudaEventDestroy(m->ev_computed[i]);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->compute_stream) cudaStreamDestroy(m->compute_stream);
+    if (m->d2h_stream) cudaStreamDestroy(m->d2h_stream);
     for (cudaEvent_t e : m->event_pool) cudaEventDestroy(e);
     cudaGetLastError();
     delete m;
@@ -419,11 +421,13 @@ static int host_setup(Model* m) {
     const size_t out_bytes = m->host_chunk * (sizeof(float) * 2 * C + sizeof(int32_t));
     DSP_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     DSP_CUDA(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
+    DSP_CUDA(cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking));
     for (int i = 0; i < Model::NBUF; ++i) {
         DSP_CUDA(cudaMalloc(&m->dev_in[i], in_bytes));
         DSP_CUDA(cudaMalloc(&m->dev_out[i], out_bytes));
         DSP_CUDA(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
         DSP_CUDA(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+        DSP_CUDA(cudaEventCreateWithFlags(&m->ev_computed[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < Model::NTICKET; ++i) DSP_CUDA(cudaEventCreateWithFlags(&m->ev_ticket[i], cudaEventDisableTiming));
     return DSP_OK;
@@ -500,16 +504,20 @@ static int host_enqueue(Model* m, const float* kmer, const float* base_means, co
         int rc = forward_chunk(m, d_kmer, d_means, d_stds, d_lens, d_sig, nullptr, nullptr, seed, (uint64_t)ci, cn,
                                d_logits, d_probs, d_labels, m->compute_stream);
         if (rc) return rc;
+        // results leave on their own stream: the device->host copies of chunk i run under chunk i+1's kernels instead
+        // of in front of them
+        DSP_CUDA(cudaEventRecord(m->ev_computed[b], m->compute_stream));
+        DSP_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ev_computed[b], 0));
         if (direct_out) {
-            DSP_CUDA(cudaMemcpyAsync(logits + s * C, d_logits, sizeof(float) * cn * C, cudaMemcpyDeviceToHost, m->compute_stream));
-            DSP_CUDA(cudaMemcpyAsync(probs + s * C, d_probs, sizeof(float) * cn * C, cudaMemcpyDeviceToHost, m->compute_stream));
-            if (labels) DSP_CUDA(cudaMemcpyAsync(labels + s, d_labels, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, m->compute_stream));
+            DSP_CUDA(cudaMemcpyAsync(logits + s * C, d_logits, sizeof(float) * cn * C, cudaMemcpyDeviceToHost, m->d2h_stream));
+            DSP_CUDA(cudaMemcpyAsync(probs + s * C, d_probs, sizeof(float) * cn * C, cudaMemcpyDeviceToHost, m->d2h_stream));
+            if (labels) DSP_CUDA(cudaMemcpyAsync(labels + s, d_labels, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, m->d2h_stream));
         } else {
             if (!m->pinned_out[b]) DSP_CUDA(cudaMallocHost(&m->pinned_out[b], out_bytes));
-            DSP_CUDA(cudaMemcpyAsync(m->pinned_out[b], dout, out_bytes, cudaMemcpyDeviceToHost, m->compute_stream));
+            DSP_CUDA(cudaMemcpyAsync(m->pinned_out[b], dout, out_bytes, cudaMemcpyDeviceToHost, m->d2h_stream));
             pend[b] = {s, cn, b, true};
         }
-        DSP_CUDA(cudaEventRecord(m->ev_done[b], m->compute_stream));
+        DSP_CUDA(cudaEventRecord(m->ev_done[b], m->d2h_stream));
     }
     if (!direct_out) for (int b = 0; b < Model::NBUF; ++b) { int rc = drain(pend[b]); if (rc) return rc; }
     return DSP_OK;
@@ -531,7 +539,7 @@ int dsp_forward_host(dsp_handle h, const float* kmer, const float* base_means, c
                             (!labels || is_device_accessible_host(labels));
     if ((rc = host_enqueue(m, kmer, base_means, base_stds, base_signal_lens, signals, seed, n, logits, probs, labels,
                            direct_in, direct_out))) return rc;
-    DSP_CUDA(cudaStreamSynchronize(m->compute_stream));
+    DSP_CUDA(cudaStreamSynchronize(m->d2h_stream));      // every chunk's results were copied out (in order) on this stream
     return DSP_OK;
 }
 
@@ -555,7 +563,7 @@ int dsp_forward_host_submit(dsp_handle h, const float* kmer, const float* base_m
     if (n > 0 && (rc = host_enqueue(m, kmer, base_means, base_stds, base_signal_lens, signals, seed, n, logits, probs, labels,
                                     true, true))) return rc;
     const uint64_t t = m->tickets_issued++;
-    DSP_CUDA(cudaEventRecord(m->ev_ticket[t % Model::NTICKET], m->compute_stream));
+    DSP_CUDA(cudaEventRecord(m->ev_ticket[t % Model::NTICKET], m->d2h_stream));   // after the last chunk's copies (n == 0: after all earlier work)
     *ticket = (int64_t)t;
     return DSP_OK;
 }

@@ -84,14 +84,14 @@ struct Model {
     size_t n_workspace_allocs = 0;          // device_allocs[0 .. n_workspace_allocs) survive a re-pack
 
     // host staging for dsp_forward_host
-    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr, d2h_stream = nullptr;
     static constexpr int NBUF = 3;          // chunks in flight: copy in / compute / copy out
     static constexpr int NTICKET = 8;
     void* pinned_in[NBUF] = {};             // staging for pageable caller memory (lazily allocated)
     void* pinned_out[NBUF] = {};
     void* dev_in[NBUF] = {};
     void* dev_out[NBUF] = {};
-    cudaEvent_t ev_h2d[NBUF] = {}, ev_done[NBUF] = {};
+    cudaEvent_t ev_h2d[NBUF] = {}, ev_done[NBUF] = {}, ev_computed[NBUF] = {};
     cudaEvent_t ev_ticket[NTICKET] = {};
     int64_t host_chunk = 0;                 // sites per staged chunk (two full waves of CTA pairs)
     uint64_t host_chunks_enqueued = 0;      // buffer ring position, carried across calls

@@ -118,6 +118,11 @@ class ModelBiLSTM(nn.Module):
         return h0, c0
 
     # ---- native handle ----------------------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):
+        # .cuda() / .to() / .float(): parameters may be swapped for new objects -- forget the cached list
+        self.__dict__.pop("_plist", None)
+        return super()._apply(fn, *args, **kwargs)
+
     def _param_device(self):
         return next(self.parameters()).device
 
@@ -154,7 +159,12 @@ class ModelBiLSTM(nn.Module):
             self._handle = h
             self._handle_device = dev.index
             self._packed_key = None
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # the Parameter objects persist across .cuda() / load_state_dict (their data pointer / version change): keep the
+        # list instead of walking the module tree on every forward
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in plist)
         if key != self._packed_key:
             self.pack_weights()
             self._packed_key = key

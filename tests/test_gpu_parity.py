@@ -75,7 +75,7 @@ def test_fp16_both_branch_kernels_match_reference(dual, monkeypatch):
     for name in ("both_13_16_s2", "both_17_20_s1234"):
         case = cases.slice_case(cases.load_case(name), 3000)
         logits, probs, labels, model = run_case(case, "fp16")
-        check(case, logits, probs, labels, PROB_TOL, 0.9995)
+        check(case, logits, probs, labels, PROB_TOL, 1.0 - 1.5 / 3000)          # at most one flip in 3 000 sites
         assert model.launch_count() == {"0": 9, "1": 9, "fused": 6}[dual]      # prep, branches(+fc), 3 x lstm_comb, head
 
 
@@ -111,7 +111,7 @@ def test_fp16_full_batch_is_batching_and_order_invariant():
     want = model_oracle.forward(params, cfg, *(feats[k][sample] for k in cases.FEATURE_KEYS),
                                 {g: tuple(x[:, sample] for x in hc) for g, hc in states.items()})[1]
     assert np.abs(full[sample] - want).max() <= PROB_TOL
-    assert (full[sample].argmax(1) == want.argmax(1)).mean() >= 0.999
+    assert int((full[sample].argmax(1) != want.argmax(1)).sum()) <= 1            # 2 048 sites: at most one flip
 
 
 def test_repacking_after_load_state_dict_replaces_the_weights():
@@ -139,7 +139,7 @@ def test_fp16_ragged_batches_and_chunking():
     for n, mb in ((1, 4096), (127, 4096), (129, 4096), (1000, 256)):
         sub = cases.slice_case(case, n)
         logits, probs, labels, _ = run_case(sub, "fp16", max_batch=mb)
-        check(sub, logits, probs, labels, PROB_TOL, 0.999 if n >= 1000 else 1.0 - 1.5 / n)
+        check(sub, logits, probs, labels, PROB_TOL, 1.0 - 1.5 / n)              # at most one flip at any of these sizes
 
 
 def test_ragged_and_tiny_batches_fp32():
@@ -290,7 +290,7 @@ def test_fp16_unusual_configurations_against_oracle(kw):
     cases.inject_states(model, states, torch.device("cuda:0"))
     probs = model(*(torch.from_numpy(feats[k]).cuda(0) for k in cases.FEATURE_KEYS))[1].cpu().numpy()
     assert probs.shape == want.shape and np.abs(probs - want).max() <= PROB_TOL
-    assert (probs.argmax(1) == want.argmax(1)).mean() >= 0.998
+    assert int((probs.argmax(1) != want.argmax(1)).sum()) <= 1                   # 1 111 sites: at most one flip
     assert (model.last_labels.cpu().numpy() == probs.argmax(1)).all()
 
 
@@ -343,7 +343,7 @@ def test_fp16_scalar_features_outside_the_fp16_range():
     err = np.abs(probs - want)[~touched].max()
     agree = (probs.argmax(1) == want.argmax(1))[~touched].mean()
     print("out-of-range scalars: max|dprob|=%.2e agreement=%.5f" % (err, agree))
-    assert err <= PROB_TOL and agree >= 0.999
+    assert err <= PROB_TOL and int((probs.argmax(1) != want.argmax(1))[~touched].sum()) <= 1
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13])
