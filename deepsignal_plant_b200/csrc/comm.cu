@@ -195,7 +195,8 @@ struct dsp_comm_s {
     dsp::Ctrl* peer_ctrl[dsp::route::MAXW] = {};
     bool opened[3][dsp::route::MAXW] = {};
     bool connected = false;
-    unsigned long long epoch = 0;
+    unsigned long long epoch = 0;                // one per collective operation; the flags carry it
+    unsigned long long n_exchanges = 0, n_samplings = 0;   // their parities pick the half of the count matrix / sample table
     dsp::route::Targets* d_tg = nullptr;
     int* d_abort = nullptr;
     dsp::Result* d_res = nullptr;
@@ -233,8 +234,10 @@ int exchange(dsp_comm_s* c, Scratch& sc, cudaStream_t st, const Src& src, int64_
     int rc;
     if ((rc = sc.alloc(&blk_counts, (size_t)plan.blocks * MAXW)) || (rc = sc.alloc(&blk_off, (size_t)plan.blocks * MAXW)) ||
         (rc = sc.alloc(&totals, MAXW)) || (rc = sc.alloc(&d_bits, 1))) return rc;
+    // consecutive exchanges alternate between the two halves of the count matrix: a rank that runs ahead publishes the
+    // next exchange's counts while a slower peer may still be reading this one's
     const unsigned long long epoch = ++c->epoch;
-    const int parity = (int)(epoch & 1);
+    const int parity = (int)(++c->n_exchanges & 1);
     Peers peers{}; Windows wins{};
     for (int r = 0; r < c->world; ++r) { peers.ctrl[r] = c->peer_ctrl[r]; wins.win[r] = c->peer_win[which][r]; }
     cudaEvent_t* ev = c->dev[which];
@@ -284,7 +287,7 @@ int route_rows_units(dsp_comm_s* c, Scratch& sc, cudaStream_t st, const void* ro
 // choose c->d_bounds so that the `first` fields of all ranks' rows fall into `world` equal parts
 int choose_row_splitters(dsp_comm_s* c, cudaStream_t st, const SiteRow* rows, int64_t n) {
     const unsigned long long epoch = ++c->epoch;
-    const int parity = (int)(epoch & 1);
+    const int parity = (int)(++c->n_samplings & 1);
     Peers peers{};
     for (int r = 0; r < c->world; ++r) peers.ctrl[r] = c->peer_ctrl[r];
     publish_samples_kernel<<<1, NSAMP, 0, st>>>(rows, n, peers, c->rank, c->world, parity, epoch);

@@ -186,17 +186,17 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
     }
 }
 
-// The same scatter for 32-byte records bound for PEER windows: a tile of ST x RT items is ranked, staged in shared
+// The same scatter for 32-byte records / 48-byte rows bound for PEER windows: a tile of ST x RT items is ranked, staged in shared
 // memory grouped by destination, and copied out with consecutive threads writing consecutive records -- every warp
 // store covers 1 KB of one destination window instead of ~4 records for each of `world` windows, which is what NVLink
 // wants (few large writes instead of many 32-byte ones).  Same positions, same order as scatter_kernel.
-constexpr int ST = 4;                          // sub-tiles of RT items per staged tile
 template <typename Src>
 __global__ void __launch_bounds__(RT) scatter_staged_kernel(Src src, Plan plan, int world, const int64_t* __restrict__ blk_off,
                                                            const Targets* __restrict__ tg, const int* __restrict__ abort_flag,
                                                            unsigned long long* __restrict__ key_bits_out) {
     typedef typename Src::Item Item;
-    static_assert(sizeof(Item) == 32, "staged scatter is written for 32-byte records");
+    constexpr int ST = sizeof(Item) <= 32 ? 4 : 3;          // sub-tiles of RT items per staged tile (stage <= 36 KB)
+    static_assert(sizeof(Item) <= 48, "the stage of ST x RT items must fit the static shared memory");
     __shared__ __align__(32) Item s_stage[ST * RT];
     __shared__ int s_warp[ST][RWARPS][MAXW];
     __shared__ int s_sub[ST][MAXW];            // items of sub-tile j bound for d
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(RT) scatter_staged_kernel(Src src, Plan plan, 
     }
 }
 
-template <typename Src, bool STAGED = (sizeof(typename Src::Item) == 32)>
+template <typename Src, bool STAGED = (sizeof(typename Src::Item) <= 48)>
 struct ScatterLaunch {
     static void run(const Src& src, const Plan& plan, int world, const int64_t* blk_off, const Targets* tg, const int* abort_flag,
                     unsigned long long* bits, cudaStream_t st) {
