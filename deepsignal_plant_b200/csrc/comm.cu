@@ -232,8 +232,8 @@ int exchange(dsp_comm_s* c, Scratch& sc, cudaStream_t st, const Src& src, int64_
     const Plan plan = make_plan(n, c->n_sm);
     int32_t* blk_counts; int64_t* blk_off; int64_t* totals; unsigned long long* d_bits;
     int rc;
-    if ((rc = sc.alloc(&blk_counts, (size_t)plan.blocks * MAXW)) || (rc = sc.alloc(&blk_off, (size_t)plan.blocks * MAXW)) ||
-        (rc = sc.alloc(&totals, MAXW)) || (rc = sc.alloc(&d_bits, 1))) return rc;
+    if ((rc = sc.alloc(&blk_counts, (size_t)plan.blocks * MAXD)) || (rc = sc.alloc(&blk_off, (size_t)plan.blocks * MAXD)) ||
+        (rc = sc.alloc(&totals, MAXD)) || (rc = sc.alloc(&d_bits, 1))) return rc;
     // consecutive exchanges alternate between the two halves of the count matrix: a rank that runs ahead publishes the
     // next exchange's counts while a slower peer may still be reading this one's
     const unsigned long long epoch = ++c->epoch;
@@ -244,7 +244,7 @@ int exchange(dsp_comm_s* c, Scratch& sc, cudaStream_t st, const Src& src, int64_
     DSP_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned long long), st));
     cudaEventRecord(ev[0], st);
     count_kernel<Src><<<plan.blocks, RT, 0, st>>>(src, plan, c->world, blk_counts);
-    scan_kernel<<<1, MAXW * 32, 0, st>>>(blk_counts, plan.blocks, c->world, blk_off, totals);
+    scan_kernel<<<1, MAXD * 32, 0, st>>>(blk_counts, plan.blocks, c->world, blk_off, totals);
     publish_kernel<<<1, 256, 0, st>>>(totals, peers, c->rank, c->world, parity, epoch);
     cudaEventRecord(ev[1], st);
     prepare_kernel<<<1, 32, 0, st>>>(c->ctrl, wins, c->rank, c->world, parity, epoch, (int64_t)(c->window_bytes / item_bytes),

@@ -232,15 +232,15 @@ int pack_callable(Scratch& sc, cudaStream_t st, const uint64_t* key, const doubl
     const Plan plan = make_plan(n, n_sm);
     int32_t* blk_counts; int64_t* blk_off; int64_t* totals; unsigned long long* d_bits; Targets* d_tg;
     int rc;
-    if ((rc = sc.alloc(&blk_counts, (size_t)plan.blocks * MAXW)) || (rc = sc.alloc(&blk_off, (size_t)plan.blocks * MAXW)) ||
-        (rc = sc.alloc(&totals, MAXW)) || (rc = sc.alloc(&d_bits, 1)) || (rc = sc.alloc(&d_tg, 1))) return rc;
+    if ((rc = sc.alloc(&blk_counts, (size_t)plan.blocks * MAXD)) || (rc = sc.alloc(&blk_off, (size_t)plan.blocks * MAXD)) ||
+        (rc = sc.alloc(&totals, MAXD)) || (rc = sc.alloc(&d_bits, 1)) || (rc = sc.alloc(&d_tg, 1))) return rc;
     RecFromColumns src{key, p0, p1, label, gidx_base, prob_cf, 1};
     Targets tg{};
     tg.dst[0] = rec; tg.base[0] = 0;
     DSP_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(unsigned long long), st));
     DSP_CUDA(cudaMemcpyAsync(d_tg, &tg, sizeof(tg), cudaMemcpyHostToDevice, st));
     count_kernel<RecFromColumns><<<plan.blocks, RT, 0, st>>>(src, plan, 1, blk_counts);
-    scan_kernel<<<1, MAXW * 32, 0, st>>>(blk_counts, plan.blocks, 1, blk_off, totals);
+    scan_kernel<<<1, MAXD * 32, 0, st>>>(blk_counts, plan.blocks, 1, blk_off, totals);
     scatter_kernel<RecFromColumns><<<plan.blocks, RT, 0, st>>>(src, plan, 1, blk_off, d_tg, nullptr, d_bits);
     DSP_CUDA(cudaGetLastError());
     int64_t m = 0;

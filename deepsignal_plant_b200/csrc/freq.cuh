@@ -58,10 +58,6 @@ struct BitRuns {
 };
 BitRuns make_bit_runs(unsigned long long bits_used);
 
-// Stable compaction / partition of callable records (the single-GPU front end uses world = 1):
-// see comm.cu.  Columns in file order -> packed Rec in dst[dest] at consecutive positions.
-struct RouteTargets { void* dst[16]; int64_t cap[16]; };
-
 // m packed records (file order within equal keys is their order in `rec`) -> one SiteRow per
 // distinct key, in ascending key order.  rows has capacity m.  Synchronises `st` once.
 int sites_from_records(Scratch& sc, cudaStream_t st, const Rec* rec, int64_t m, unsigned long long bits_used,

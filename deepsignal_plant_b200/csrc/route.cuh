@@ -14,7 +14,8 @@
 namespace dsp {
 namespace route {
 
-constexpr int MAXW = 16;
+constexpr int MAXW = 16;                      // ranks of a communicator (comm.cu)
+constexpr int MAXD = 32;                      // destinations of one partition; = warp size (one lane scans one destination)
 constexpr int RT = 256;                       // threads per block
 constexpr int RWARPS = RT / 32;
 
@@ -59,7 +60,14 @@ struct RecFromColumns {                       // call_mods columns -> packed Rec
         it.key = key[i]; it.p0 = p0[i]; it.p1 = p1[i];
         it.gl = (gidx_base + (uint64_t)i) | (label[i] == 1 ? REC_LABEL_BIT : 0ull);
     }
-    static __device__ __forceinline__ void store(Item* dst, const Item& it) { store_rec(dst, it); }
+    __device__ __forceinline__ void store(Item* dst, int64_t pos, const Item& it) const { store_rec(dst + pos, it); }
+    // everything of item i in one go (one round of loads): keep?, destination, payload
+    __device__ __forceinline__ bool load_all(int64_t i, Item& it, int& d) const {
+        it.key = key[i]; it.p0 = p0[i]; it.p1 = p1[i];
+        it.gl = (gidx_base + (uint64_t)i) | (label[i] == 1 ? REC_LABEL_BIT : 0ull);
+        d = world == 1 ? 0 : owner_of_key(it.key, world);
+        return !(fabs(it.p0 - it.p1) < prob_cf);
+    }
 };
 
 template <int UNITS>                           // rows of UNITS x 16 bytes, by range of a 64-bit field
@@ -75,57 +83,62 @@ struct RowsByRange {
         return true;
     }
     __device__ __forceinline__ void load(int64_t i, Item& it) const { it = rows[i]; }
-    static __device__ __forceinline__ void store(Item* dst, const Item& it) { *dst = it; }
+    __device__ __forceinline__ void store(Item* dst, int64_t pos, const Item& it) const { dst[pos] = it; }
+    __device__ __forceinline__ bool load_all(int64_t i, Item& it, int& d) const {
+        it = rows[i];
+        const uint64_t k = reinterpret_cast<const uint64_t*>(&it)[field_word];
+        int lo = 0;
+        for (int w = 1; w < world; ++w) lo += (k >= bounds[w]) ? 1 : 0;
+        d = lo;
+        return true;
+    }
 };
 
 // ---- kernels ----------------------------------------------------------------------------------------
 template <typename Src>
 __global__ void __launch_bounds__(RT) count_kernel(Src src, Plan plan, int world, int32_t* __restrict__ blk_counts) {
-    __shared__ int s_cnt[MAXW];
-    if (threadIdx.x < MAXW) s_cnt[threadIdx.x] = 0;
+    __shared__ int s_cnt[MAXD];
+    if (threadIdx.x < MAXD) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int64_t lo = (int64_t)blockIdx.x * plan.per_block;
     const int64_t hi = min(plan.n, lo + plan.per_block);
     const int lane = threadIdx.x & 31;
-    int mine = 0;                                   // lane d of every warp counts destination d
     for (int64_t i0 = lo; i0 < hi; i0 += RT) {
         const int64_t i = i0 + threadIdx.x;
         int d = -1; uint64_t k;
         if (i < hi) { int dd; if (src.dest_of(i, dd, k)) d = dd; }
-        for (int e = 0; e < world; ++e) {
-            const int c = __popc(__ballot_sync(0xffffffffu, d == e));
-            if (lane == e) mine += c;
-        }
+        // one vote per warp: the lanes bound for the same destination find each other, their leader adds the group
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        if (d >= 0 && lane == __ffs(m) - 1) atomicAdd(&s_cnt[d], __popc(m));
     }
-    if (lane < world && mine) atomicAdd(&s_cnt[lane], mine);
     __syncthreads();
-    if (threadIdx.x < world) blk_counts[(size_t)blockIdx.x * MAXW + threadIdx.x] = s_cnt[threadIdx.x];
+    if (threadIdx.x < world) blk_counts[(size_t)blockIdx.x * MAXD + threadIdx.x] = s_cnt[threadIdx.x];
 }
 
 // one warp per destination: exclusive scan of the per-block counts; totals[d] = items bound for d
-static __global__ void __launch_bounds__(MAXW * 32) scan_kernel(const int32_t* __restrict__ blk_counts, int blocks, int world,
+static __global__ void __launch_bounds__(MAXD * 32) scan_kernel(const int32_t* __restrict__ blk_counts, int blocks, int world,
                                                         int64_t* __restrict__ blk_off, int64_t* __restrict__ totals) {
     const int d = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (d >= world) return;
     int64_t carry = 0;
     for (int b0 = 0; b0 < blocks; b0 += 32) {
         const int b = b0 + lane;
-        const int64_t v = b < blocks ? blk_counts[(size_t)b * MAXW + d] : 0;
+        const int64_t v = b < blocks ? blk_counts[(size_t)b * MAXD + d] : 0;
         int64_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += y;
         }
-        if (b < blocks) blk_off[(size_t)b * MAXW + d] = carry + x - v;
+        if (b < blocks) blk_off[(size_t)b * MAXD + d] = carry + x - v;
         carry += __shfl_sync(0xffffffffu, x, 31);
     }
     if (lane == 0) totals[d] = carry;
 }
 
 struct Targets {
-    void* dst[MAXW];                          // destination buffers (this GPU's or a peer's window)
-    int64_t base[MAXW];                       // first position of THIS source's segment in dst[d]
+    void* dst[MAXD];                          // destination buffers (this GPU's or a peer's window)
+    int64_t base[MAXD];                       // first position of THIS source's segment in dst[d]
 };
 
 // Items of block b bound for d land at dst[d][base[d] + blk_off[b][d] + rank inside the block], in order.
@@ -136,13 +149,13 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
                                                     const Targets* __restrict__ tg, const int* __restrict__ abort_flag,
                                                     unsigned long long* __restrict__ key_bits_out) {
     typedef typename Src::Item Item;
-    __shared__ int s_warp[RWARPS][MAXW];
-    __shared__ int64_t s_run[MAXW];
-    __shared__ Item* s_dst[MAXW];
+    __shared__ int s_warp[RWARPS][MAXD];
+    __shared__ int64_t s_run[MAXD];
+    __shared__ Item* s_dst[MAXD];
     if (abort_flag && *abort_flag) return;                               // a window would overflow: nobody writes
-    if (threadIdx.x < MAXW) {
+    if (threadIdx.x < MAXD) {
         const int d = threadIdx.x;
-        s_run[d] = d < world ? tg->base[d] + blk_off[(size_t)blockIdx.x * MAXW + d] : 0;
+        s_run[d] = d < world ? tg->base[d] + blk_off[(size_t)blockIdx.x * MAXD + d] : 0;
         s_dst[d] = d < world ? reinterpret_cast<Item*>(tg->dst[d]) : nullptr;
     }
     __syncthreads();
@@ -156,12 +169,11 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
         int d = -1; uint64_t k;
         bool keep = false;
         if (i < hi) { int dd; keep = src.dest_of(i, dd, k); if (keep) d = dd; }
-        int rank = 0;
-        for (int e = 0; e < world; ++e) {
-            const unsigned m = __ballot_sync(0xffffffffu, d == e);
-            if (d == e) rank = __popc(m & lt);
-            if (lane == 0) s_warp[warp][e] = __popc(m);
-        }
+        for (int e = lane; e < world; e += 32) s_warp[warp][e] = 0;
+        __syncwarp();
+        const unsigned m = __match_any_sync(0xffffffffu, d);       // the lanes of this warp bound for the same destination
+        const int rank = __popc(m & lt);
+        if (d >= 0 && rank == 0) s_warp[warp][d] = __popc(m);
         __syncthreads();
         if (keep) {
             int before = 0;
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
             Item it;
             src.load(i, it);
             bits |= *reinterpret_cast<const uint64_t*>(&it);            // first word of every item is its key
-            Src::store(s_dst[d] + (s_run[d] + before + rank), it);
+            src.store(s_dst[d], s_run[d] + before + rank, it);
         }
         __syncthreads();
         if (threadIdx.x < world) {
@@ -191,22 +203,23 @@ __global__ void __launch_bounds__(RT) scatter_kernel(Src src, Plan plan, int wor
 // store covers 1 KB of one destination window instead of ~4 records for each of `world` windows, which is what NVLink
 // wants (few large writes instead of many 32-byte ones).  Same positions, same order as scatter_kernel.
 template <typename Src>
-__global__ void __launch_bounds__(RT) scatter_staged_kernel(Src src, Plan plan, int world, const int64_t* __restrict__ blk_off,
+__global__ void __launch_bounds__(RT, 4) scatter_staged_kernel(Src src, Plan plan, int world, const int64_t* __restrict__ blk_off,
                                                            const Targets* __restrict__ tg, const int* __restrict__ abort_flag,
                                                            unsigned long long* __restrict__ key_bits_out) {
     typedef typename Src::Item Item;
     constexpr int ST = sizeof(Item) <= 32 ? 4 : 3;          // sub-tiles of RT items per staged tile (stage <= 36 KB)
     static_assert(sizeof(Item) <= 48, "the stage of ST x RT items must fit the static shared memory");
     __shared__ __align__(32) Item s_stage[ST * RT];
-    __shared__ int s_warp[ST][RWARPS][MAXW];
-    __shared__ int s_sub[ST][MAXW];            // items of sub-tile j bound for d
-    __shared__ int s_seg[MAXW + 1];            // first stage slot of destination d in this tile
-    __shared__ int64_t s_run[MAXW];
-    __shared__ Item* s_dst[MAXW];
+    __shared__ int s_warp[ST][RWARPS][MAXD];
+    __shared__ int s_sub[ST][MAXD];            // items of sub-tile j bound for d
+    __shared__ int s_seg[MAXD + 1];            // first stage slot of destination d in this tile
+    __shared__ uint8_t s_sd[ST * RT];          // destination of every stage slot
+    __shared__ int64_t s_run[MAXD];
+    __shared__ Item* s_dst[MAXD];
     if (abort_flag && *abort_flag) return;
-    if (threadIdx.x < MAXW) {
+    if (threadIdx.x < MAXD) {
         const int d = threadIdx.x;
-        s_run[d] = d < world ? tg->base[d] + blk_off[(size_t)blockIdx.x * MAXW + d] : 0;
+        s_run[d] = d < world ? tg->base[d] + blk_off[(size_t)blockIdx.x * MAXD + d] : 0;
         s_dst[d] = d < world ? reinterpret_cast<Item*>(tg->dst[d]) : nullptr;
     }
     __syncthreads();
@@ -216,22 +229,28 @@ __global__ void __launch_bounds__(RT) scatter_staged_kernel(Src src, Plan plan, 
     const int64_t hi = min(plan.n, lo + plan.per_block);
     uint64_t bits = 0;
     for (int64_t t0 = lo; t0 < hi; t0 += (int64_t)ST * RT) {
+        // phase 1: all loads of the tile in flight together (no synchronisation between them)
+        Item item[ST];
         int dest[ST], rank[ST];
 #pragma unroll
         for (int j = 0; j < ST; ++j) {
             const int64_t i = t0 + (int64_t)j * RT + threadIdx.x;
-            int d = -1; uint64_t k;
-            if (i < hi) { int dd; if (src.dest_of(i, dd, k)) d = dd; }
-            dest[j] = d; rank[j] = 0;
-            for (int e = 0; e < world; ++e) {
-                const unsigned m = __ballot_sync(0xffffffffu, d == e);
-                if (d == e) rank[j] = __popc(m & lt);
-                if (lane == 0) s_warp[j][warp][e] = __popc(m);
-            }
+            int d = -1;
+            if (i < hi) { int dd; if (src.load_all(i, item[j], dd)) d = dd; }
+            dest[j] = d;
+        }
+        for (int e = threadIdx.x; e < ST * RWARPS * MAXD; e += RT) (&s_warp[0][0][0])[e] = 0;
+        __syncthreads();
+        // phase 2: stable ranks -- lanes bound for the same destination find each other, their first lane counts the group
+#pragma unroll
+        for (int j = 0; j < ST; ++j) {
+            const unsigned m = __match_any_sync(0xffffffffu, dest[j]);
+            rank[j] = __popc(m & lt);
+            if (dest[j] >= 0 && rank[j] == 0) s_warp[j][warp][dest[j]] = __popc(m);
         }
         __syncthreads();
-        if (threadIdx.x < ST * MAXW) {
-            const int j = threadIdx.x / MAXW, d = threadIdx.x % MAXW;
+        if (threadIdx.x < ST * MAXD) {
+            const int j = threadIdx.x / MAXD, d = threadIdx.x % MAXD;
             int tot = 0;
             if (d < world)
 #pragma unroll
@@ -239,14 +258,19 @@ __global__ void __launch_bounds__(RT) scatter_staged_kernel(Src src, Plan plan, 
             s_sub[j][d] = tot;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int acc = 0;
-            for (int d = 0; d < world; ++d) {
-                s_seg[d] = acc;
+        if (warp == 0) {                                       // exclusive scan over the destinations, one lane each
+            int tot = 0;
+            if (lane < world)
 #pragma unroll
-                for (int j = 0; j < ST; ++j) acc += s_sub[j][d];
+                for (int j = 0; j < ST; ++j) tot += s_sub[j][lane];
+            int x = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
             }
-            for (int d = world; d <= MAXW; ++d) s_seg[d] = acc;
+            s_seg[lane] = x - tot;
+            if (lane == 31) s_seg[MAXD] = x;
         }
         __syncthreads();
 #pragma unroll
@@ -256,18 +280,16 @@ __global__ void __launch_bounds__(RT) scatter_staged_kernel(Src src, Plan plan, 
                 int slot = s_seg[d] + rank[j];
                 for (int jj = 0; jj < j; ++jj) slot += s_sub[jj][d];
                 for (int w = 0; w < warp; ++w) slot += s_warp[j][w][d];
-                Item it;
-                src.load(t0 + (int64_t)j * RT + threadIdx.x, it);
-                bits |= *reinterpret_cast<const uint64_t*>(&it);
-                s_stage[slot] = it;
+                bits |= *reinterpret_cast<const uint64_t*>(&item[j]);
+                s_stage[slot] = item[j];
+                s_sd[slot] = (uint8_t)d;
             }
         }
         __syncthreads();
-        const int total = s_seg[MAXW];
+        const int total = s_seg[MAXD];
         for (int sl = threadIdx.x; sl < total; sl += RT) {
-            int d = 0;
-            while (sl >= s_seg[d + 1]) ++d;                   // <= world steps
-            Src::store(s_dst[d] + (s_run[d] + (sl - s_seg[d])), s_stage[sl]);
+            const int d = s_sd[sl];
+            src.store(s_dst[d], s_run[d] + (sl - s_seg[d]), s_stage[sl]);
         }
         __syncthreads();
         if (threadIdx.x < world) s_run[threadIdx.x] += s_seg[threadIdx.x + 1] - s_seg[threadIdx.x];
