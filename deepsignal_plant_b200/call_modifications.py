@@ -396,11 +396,17 @@ def call_mods(args):
                          "implementation; pass a feature file from `deepsignal_plant extract`, or decode the reads "
                          "once into an archive with extract_features.save_reads and pass the .npz")
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
+    device = 0
     if world > 1:
         import torch.distributed as dist
+        ndev = max(torch.cuda.device_count(), 1)
+        device = int(os.environ.get("LOCAL_RANK", "0")) % ndev        # one GPU per rank; ranks may share one (tests)
         if not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+            if ndev >= world:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+            else:
+                dist.init_process_group("gloo")
+        torch.cuda.set_device(device)
     args.model_path = model_path
     from_reads = input_path.endswith(".npz")                  # decoded reads instead of a feature file
     gz_single = world > 1 and not from_reads and input_path.endswith(".gz")
@@ -445,16 +451,47 @@ def call_mods(args):
     wt = threading.Thread(target=writer, daemon=True)
     wt.start()
 
+    # --freq_out: the calls of this run also feed call_freq directly -- every batch's lines are parsed back into record
+    # columns while they are still in memory (dsp_parse_calls, the parser call_freq uses on files), the table is
+    # aggregated at the end; under torchrun the ranks' shards meet through the NVLink exchange (freq_dist.py)
+    freq_out = getattr(args, "freq_out", None)
+    freq_parts = []
+
+    def sink(data):
+        wq.put(data)
+        if freq_out:
+            from . import call_mods_freq as cf
+            r = cf.parse_calls_buffer(data, nthreads=max(1, args.nproc))
+            if r is None:
+                r = cf.parse_lines(bytes(data).decode().splitlines())
+            freq_parts.append(r)
+
     def finish_writer():
         wq.put(None)
         wt.join()
         if werr:
             raise werr[0]
+
+    def finish_freq():
+        if not freq_out:
+            return
+        from . import call_mods_freq as cf
+        rec = cf.Records.concat(freq_parts)
+        prob_cf, is_sort, is_bed = getattr(args, "freq_prob_cf", 0.5), getattr(args, "freq_sort", False), getattr(args, "freq_bed", False)
+        if world > 1:
+            from . import freq_dist
+            table, _, _ = freq_dist.call_freq_distributed(None, prob_cf, freq_out, is_sort, is_bed, False, device=device, records=rec)
+        else:
+            table = cf.aggregate_records(rec, prob_cf, device=device)
+            cf.write_sitekey2stats(table, freq_out, is_sort, is_bed, False)
+        if rank == 0:
+            print("call_freq of this run: {} of {} calls used -> {}".format(table.n_used, table.n_records, freq_out))
     if from_reads:
-        sites, nb = call_mods_from_reads(args, model, wq.put, device)
+        sites, nb = call_mods_from_reads(args, model, sink, device)
         finish_writer()
         print("call_mods rank {}: {} sites in {} read-batches".format(rank, sites, nb))
         _merge_parts(result_file, rank, world)
+        finish_freq()
         print("[main] call_mods costs %.2f seconds.." % (time.time() - start))
         return sites
     rq = queue.Queue(maxsize=2)
@@ -482,13 +519,14 @@ def call_mods(args):
                 return
             yield b
 
-    sites, accuracy, nb = call_mods_stream(model, batches(), wq.put)
+    sites, accuracy, nb = call_mods_stream(model, batches(), sink)
     rt.join()
     finish_writer()
     if err:
         raise err[0]
     print("call_mods rank {}: {} sites in {} feature-batches".format(rank, sites, nb))
     _merge_parts(result_file, rank, world)
+    finish_freq()
     print("[main] call_mods costs %.2f seconds.." % (time.time() - start))
     return sites
 

@@ -223,37 +223,7 @@ def _read_mods_file_native(path, nthreads=None, byte_range=None):
     if byte_range is not None:
         buf = _shard_view(buf, byte_range)
     try:
-        if buf.size == 0:
-            return Records([], [], [], [], [], [], [], [])
-        n = C.c_int64(0)
-        cap = buf.size // 20 + 2                        # a well-formed line has at least 20 bytes; untouched pages cost nothing
-        code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
-        p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
-        strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
-        names = np.empty(1 << 16, np.uint8)
-        while True:
-            nb, nn = C.c_int64(0), C.c_int32(0)
-            p = lambda a: a.ctypes.data
-            rc = L.dsp_parse_calls(buf.ctypes.data, buf.size, cap, p(code), p(pos), p(strand), p(pis), p(p0), p(p1), p(label),
-                                   p(kmer), p(names), names.size, C.byref(nb), C.byref(nn), C.byref(n), nthreads)
-            if rc == 5:                                  # DSP_ERR_UNSUPPORTED: unusually wide strand / k-mer column
-                return None
-            if rc == 4 and nb.value > names.size:        # DSP_ERR_NOMEM: many long chromosome names
-                names = np.empty(int(nb.value), np.uint8)
-                continue
-            if rc == 4 and n.value > cap:                # more (shorter, hence malformed) lines than the bound: let it say so
-                cap = int(n.value)
-                code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
-                p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
-                strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
-                continue
-            _native.check(rc, "dsp_parse_calls(%s)" % path)
-            break
-        m = int(n.value)
-        if m == 0:
-            return Records([], [], [], [], [], [], [], [])
-        table = names[:int(nb.value)].tobytes().decode().split("\n")[:int(nn.value)]
-        return Records(None, pos[:m], strand[:m], pis[:m], p0[:m], p1[:m], label[:m], kmer[:m], (code[:m], table))
+        return parse_calls_buffer(buf, nthreads, what=path)
     finally:
         del buf, whole
         if mm is not None:
@@ -261,6 +231,48 @@ def _read_mods_file_native(path, nthreads=None, byte_range=None):
                 mm.close()
             except BufferError:
                 pass
+
+
+def parse_calls_buffer(buf, nthreads=None, what="<memory>"):
+    """``dsp_parse_calls`` over call_mods lines held in memory (a uint8 array or bytes): compact ``Records``, or None
+    when a strand / k-mer column is wider than the parser's fixed cells."""
+    L = _native.lib()
+    nthreads = int(nthreads or min(32, os.cpu_count() or 1))
+    if not isinstance(buf, np.ndarray):
+        buf = np.frombuffer(buf, np.uint8)
+    if buf.size == 0:
+        return Records([], [], [], [], [], [], [], [])
+    n = C.c_int64(0)
+    cap = buf.size // 20 + 2                        # a well-formed line has at least 20 bytes; untouched pages cost nothing
+    code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
+    p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
+    strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
+    names = np.empty(1 << 16, np.uint8)
+    while True:
+        nb, nn = C.c_int64(0), C.c_int32(0)
+        p = lambda a: a.ctypes.data
+        rc = L.dsp_parse_calls(buf.ctypes.data, buf.size, cap, p(code), p(pos), p(strand), p(pis), p(p0), p(p1), p(label),
+                               p(kmer), p(names), names.size, C.byref(nb), C.byref(nn), C.byref(n), nthreads)
+        if rc == 5:                                  # DSP_ERR_UNSUPPORTED: unusually wide strand / k-mer column
+            return None
+        if rc == 4 and nb.value > names.size:        # DSP_ERR_NOMEM: many long chromosome names
+            names = np.empty(int(nb.value), np.uint8)
+            continue
+        if rc == 4 and n.value > cap:                # more (shorter, hence malformed) lines than the bound: let it say so
+            cap = int(n.value)
+            code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
+            p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
+            strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
+            continue
+        _native.check(rc, "dsp_parse_calls(%s)" % what)
+        break
+    m = int(n.value)
+    if m == 0:
+        return Records([], [], [], [], [], [], [], [])
+    table = names[:int(nb.value)].tobytes().decode().split("\n")[:int(nn.value)]
+    # copies: the arrays above are sized for the worst case
+    return Records(None, pos[:m].copy(), strand[:m].copy(), pis[:m].copy(), p0[:m].copy(), p1[:m].copy(), label[:m].copy(),
+                   kmer[:m].copy(), (code[:m].copy(), table))
 
 
 def read_mods_file(path, byte_range=None):

@@ -98,6 +98,12 @@ def build_parser():
     g = cm.add_argument_group("OUTPUT")
     g.add_argument("--result_file", "-o", action="store", type=str, required=True)
     g.add_argument("--gzip", action="store_true", default=False)
+    g = cm.add_argument_group("CALL_FREQ IN THE SAME RUN (the per-site table without re-reading the calls file; under torchrun the "
+                              "ranks exchange their calls over NVLink, see call_freq)")
+    g.add_argument("--freq_out", type=str, default=None, help="also write the call_freq table of this run's calls here")
+    g.add_argument("--freq_prob_cf", type=float, default=0.5, help="call_freq --prob_cf")
+    g.add_argument("--freq_bed", action="store_true", default=False, help="call_freq --bed")
+    g.add_argument("--freq_sort", action="store_true", default=False, help="call_freq --sort")
     cm.add_argument("--nproc", "-p", action="store", type=int, default=10, help="host threads for parsing / formatting")
     cm.add_argument("--nproc_gpu", action="store", type=int, default=2,
                     help="accepted for compatibility; use torchrun for one process per GPU")

@@ -326,11 +326,12 @@ def default_window_bytes(n_local, grp):
 
 
 def call_freq_distributed(mods_files, prob_cf, result_file, is_sort, is_bed, is_gzip, contigs=None, grp=None,
-                          backend=None, device=0):
-    """``call_mods_frequency_to_file`` across the ranks of ``grp`` (default: the initialised process group)."""
+                          backend=None, device=0, records=None):
+    """``call_mods_frequency_to_file`` across the ranks of ``grp`` (default: the initialised process group).
+    ``records``: this rank's calls as ``cf.Records`` already in memory (contiguous shards in rank order, e.g. what
+    ``call_mods --freq_out`` has just produced) instead of files to parse."""
     grp = grp or TorchGroup()
-    units = plan_units(mods_files, grp.world)[grp.rank]
-    rec = read_units(units)
+    rec = records if records is not None else read_units(plan_units(mods_files, grp.world)[grp.rank])
     own_backend = backend is None
     if own_backend:
         backend = DeviceBackend(grp.rank, grp.world, device, default_window_bytes(len(rec), grp), grp.all_gather_object)

@@ -82,3 +82,39 @@ def test_reference_worker_protocol(tmp_path):
     lines = open(tmp_path / "o.tsv").read().splitlines()
     assert len(lines) == n and ["\t".join(l.split("\t")[:6]) for l in lines] == info
     assert fq.get() == "kill"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+def test_call_mods_freq_out_equals_call_freq_on_the_written_file(tmp_path, world):
+    # call_mods --freq_out: the per-site table of the run's own calls, without re-reading the calls file; with 2 ranks
+    # (sharing the GPU here) the ranks' calls meet through the NVLink-style exchange.  Must equal call_freq on the file.
+    import subprocess
+    import sys
+    from deepsignal_plant_b200 import feature_io, synthetic
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    from oracle import freq_oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 6000
+    feats = synthetic.make_features(n, 13, 16, seed=51)
+    info = synthetic.make_sampleinfo(n, seed=51, n_chrom=3, n_pos=300)
+    path = str(tmp_path / "features.tsv")
+    with open(path, "w") as f:
+        for i in range(n):
+            f.write(feature_io.features_to_str(info[i], feats["kmer"][i], feats["base_means"][i], feats["base_stds"][i],
+                                               feats["base_signal_lens"][i], feats["signals"][i], 0) + "\n")
+    torch.manual_seed(1234)
+    ckpt = str(tmp_path / "m.ckpt")
+    torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
+    out, freq = str(tmp_path / "calls.tsv"), str(tmp_path / "freq.tsv")
+    tail = ["-m", "deepsignal_plant_b200", "call_mods", "-i", path, "-m", ckpt, "-o", out, "--max_batch", "1024",
+            "--freq_out", freq, "--freq_prob_cf", "0.002", "--freq_sort"]
+    cmd = [sys.executable] + tail if world == 1 else \
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+         "--master-port", "29737"] + tail
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    lines = open(out).read().splitlines()
+    assert len(lines) == n
+    want = freq_oracle.render(freq_oracle.aggregate(lines, 0.002), True, False)
+    assert len(want) > 1000 and open(freq).read() == want
