@@ -437,7 +437,8 @@ def measure(grp, device, records_per_rank, coverage=20, prob_cf=0.5, iters=5, ch
         be.close()
     del key, p0, p1, lab
     t = min(times)
-    out = {"records": total, "world": world, "seconds": t, "records_per_s": total / t, "sites": sum(s[0][1] for s in sums),
+    out = {"records": total, "world": world, "seconds": t, "seconds_mean": sum(times) / len(times), "iterations": len(times),
+           "records_per_s": total / t, "sites": sum(s[0][1] for s in sums),
            "callable": sum(s[2] for s in sums), "coverage_sum_equals_callable": sum(s[1] for s in sums) == sum(s[2] for s in sums),
            "slices_ordered": all(s[3] for s in sums), "rows_per_rank": [s[4] for s in sums], "stage_ms_max_over_ranks": stage_max, "stage_ms_min_over_ranks": stage_min,
            "prob_cf": prob_cf,
