@@ -1902,11 +1902,23 @@ int tc_forward_chunk(Model* m, const float* kmer, const float* means, const floa
     {
         Span sp(m, 0, st);
         const int64_t total = tiles * TILE * T;
-        prep_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            kmer, means, stds, lens, signals, m->embed, c.is_base ? c.embedding_size : 0, c.vocab_size, c.is_signallen,
-            s->seq_split ? 1 : 0, c.signal_len, T, n, tiles * TILE, seq ? s->xseq_img : nullptr, sig ? s->xsig_img : nullptr);
+        // Programmatic dependent launch here too: the images this kernel writes were last read by the first-layer
+        // kernels of the PREVIOUS pass, which completed before that pass's head kernel could start its last wave, so
+        // the feature assembly may fill the SMs the head kernel leaves idle while it drains.
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)((total + 255) / 256));
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = s->pdl ? 1 : 0;
+        DSP_CUDA(cudaLaunchKernelEx(&cfg, prep_images_kernel, kmer, means, stds, lens, signals, (const float*)m->embed,
+                                    c.is_base ? c.embedding_size : 0, c.vocab_size, c.is_signallen, s->seq_split ? 1 : 0,
+                                    c.signal_len, T, n, tiles * TILE, seq ? s->xseq_img : (uint8_t*)nullptr,
+                                    sig ? s->xsig_img : (uint8_t*)nullptr));
         m->launches++;
-        DSP_CUDA(cudaGetLastError());
     }
     auto run_stack = [&](std::vector<LstmLayer>& layers, const uint8_t* x0, int grp, int hid, bool is_comb) -> int {
         const uint8_t* x = x0;
