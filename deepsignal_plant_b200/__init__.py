@@ -6,6 +6,8 @@ Public surface (mirrors ``deepsignal_plant``):
 * ``models.ModelBiLSTM``              -- drop-in for ``deepsignal_plant.models.ModelBiLSTM``
 * ``call_modifications._call_mods``   -- drop-in for the batch step that drives it
 * ``call_mods_freq``                  -- per-site frequency aggregation (call_freq)
+* ``freq_dist``                       -- the same across the GPUs of one box (torchrun; records exchanged over NVLink)
+* ``chain``                           -- call_mods -> call_freq without text in between (record columns on the device)
 
 All arithmetic runs in hand-written CUDA kernels inside ``libdsp_b200.so`` (C ABI in
 ``include/dsp_b200.h``); there is no CPU or PyTorch fallback.
