@@ -243,14 +243,17 @@ def parse_calls_buffer(buf, nthreads=None, what="<memory>"):
     if buf.size == 0:
         return Records([], [], [], [], [], [], [], [])
     n = C.c_int64(0)
-    cap = buf.size // 20 + 2                        # a well-formed line has at least 20 bytes; untouched pages cost nothing
+    nb, nn = C.c_int64(0), C.c_int32(0)
+    # first a counting pass (max_records = 0: newline scan only), then exactly sized columns: no oversized buffers, no copies
+    _native.check(L.dsp_parse_calls(buf.ctypes.data, buf.size, 0, None, None, None, None, None, None, None, None, None, 0,
+                                    C.byref(nb), C.byref(nn), C.byref(n), nthreads), "dsp_parse_calls(%s)" % what)
+    cap = max(int(n.value), 1)
     code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
     p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
     strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
     names = np.empty(1 << 16, np.uint8)
+    p = lambda a: a.ctypes.data
     while True:
-        nb, nn = C.c_int64(0), C.c_int32(0)
-        p = lambda a: a.ctypes.data
         rc = L.dsp_parse_calls(buf.ctypes.data, buf.size, cap, p(code), p(pos), p(strand), p(pis), p(p0), p(p1), p(label),
                                p(kmer), p(names), names.size, C.byref(nb), C.byref(nn), C.byref(n), nthreads)
         if rc == 5:                                  # DSP_ERR_UNSUPPORTED: unusually wide strand / k-mer column
@@ -258,21 +261,13 @@ def parse_calls_buffer(buf, nthreads=None, what="<memory>"):
         if rc == 4 and nb.value > names.size:        # DSP_ERR_NOMEM: many long chromosome names
             names = np.empty(int(nb.value), np.uint8)
             continue
-        if rc == 4 and n.value > cap:                # more (shorter, hence malformed) lines than the bound: let it say so
-            cap = int(n.value)
-            code, pos, pis = np.empty(cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int64)
-            p0, p1, label = np.empty(cap, np.float64), np.empty(cap, np.float64), np.empty(cap, np.int32)
-            strand, kmer = np.empty(cap, "S4"), np.empty(cap, "S24")
-            continue
         _native.check(rc, "dsp_parse_calls(%s)" % what)
         break
     m = int(n.value)
     if m == 0:
         return Records([], [], [], [], [], [], [], [])
     table = names[:int(nb.value)].tobytes().decode().split("\n")[:int(nn.value)]
-    # copies: the arrays above are sized for the worst case
-    return Records(None, pos[:m].copy(), strand[:m].copy(), pis[:m].copy(), p0[:m].copy(), p1[:m].copy(), label[:m].copy(),
-                   kmer[:m].copy(), (code[:m].copy(), table))
+    return Records(None, pos[:m], strand[:m], pis[:m], p0[:m], p1[:m], label[:m], kmer[:m], (code[:m], table))
 
 
 def read_mods_file(path, byte_range=None):

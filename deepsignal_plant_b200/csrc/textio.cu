@@ -565,6 +565,71 @@ int dsp_format_features(const char* info_text, const int64_t* info_off, const ui
     return DSP_OK;
 }
 
+// positions of the first (up to) ten tabs of [b, e), eight bytes at a time: f[k] = start of field k; returns the
+// number of fields seen (capped at 11)
+inline int split_tabs(const char* b, const char* e, const char** f) {
+    int nf = 1;
+    f[0] = b;
+    const char* p = b;
+    const uint64_t TAB = 0x0909090909090909ull, LO = 0x0101010101010101ull, HI = 0x8080808080808080ull;
+    while (e - p >= 8 && nf <= 10) {
+        uint64_t w;
+        memcpy(&w, p, 8);
+        const uint64_t x = w ^ TAB;
+        uint64_t hit = (x - LO) & ~x & HI;                       // 0x80 in every byte that was a tab
+        while (hit && nf <= 10) {
+            const int byte = __builtin_ctzll(hit) >> 3;
+            f[nf++] = p + byte + 1;
+            hit &= hit - 1;
+        }
+        p += 8;
+    }
+    for (; p < e && nf <= 10; ++p)
+        if (*p == '\t') f[nf++] = p + 1;
+    return nf;
+}
+
+// float() of the spelling call_mods prints for its probabilities -- one integer digit, a point, one to six
+// fraction digits ("0.533558", "1.0") -- as exact integer / exact power of ten (one correctly rounded operation,
+// Clinger's fast path); anything else goes through parse_double
+inline bool parse_prob_fast(const char* b, const char* e, double* out) {
+    static const double P10[7] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6};
+    const int len = (int)(e - b);
+    if (len >= 3 && len <= 8 && b[1] == '.') {
+        unsigned mant = (unsigned)(b[0] - '0');
+        unsigned bad = mant > 9;
+        for (int k = 2; k < len; ++k) {
+            const unsigned c = (unsigned)(b[k] - '0');
+            bad |= c > 9;
+            mant = mant * 10 + c;
+        }
+        if (!bad) {
+            *out = (double)mant / P10[len - 2];
+            return true;
+        }
+    }
+    return parse_double(b, e, out);
+}
+
+// int() of a plain decimal field ([+-]digits, at most 18 of them); anything else goes through parse_int
+inline bool parse_int_fast(const char* b, const char* e, long long* out) {
+    const char* p = b;
+    bool neg = false;
+    if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+    const int nd = (int)(e - p);
+    if (nd >= 1 && nd <= 18) {
+        unsigned long long v = 0;
+        for (; p < e; ++p) {
+            const unsigned c = (unsigned)(*p - '0');
+            if (c > 9) return parse_int(b, e, out);
+            v = v * 10 + c;
+        }
+        *out = neg ? -(long long)v : (long long)v;
+        return true;
+    }
+    return parse_int(b, e, out);
+}
+
 // ---- call_mods lines -> columns (the input of call_freq) ----------------------------------------------------
 // ModRecord.__init__ (utils/txt_formater.py:8-21): words = line.strip().split("\t"); chromosome = words[0],
 // pos = int(words[1]), strand = words[2], pos_in_strand = int(words[3]), prob_0 = float(words[6]),
@@ -611,7 +676,12 @@ int dsp_parse_calls(const char* text, int64_t nbytes, int64_t max_records,
     DSP_REQUIRE(chrom_code && pos && strand && pos_in_strand && p0 && p1 && label && kmer && names && names_bytes && n_names,
                 DSP_ERR_INVALID, "dsp_parse_calls: null argument");
     const int P = n >= 4096 && nthreads > 1 ? nthreads : 1;
-    struct Local { std::unordered_map<std::string_view, int32_t> ids; std::vector<std::string_view> names; int64_t a = 0, b = 0; };
+    struct Local {
+        std::unordered_map<std::string_view, int32_t> ids; std::vector<std::string_view> names; int64_t a = 0, b = 0;
+        // names of up to 8 bytes (chr1 ... chrUn_xyz are longer and take the map): 256-slot table keyed by the bytes + length
+        uint64_t skey[256]; int32_t scode[256]; int sused = 0;
+        Local() { for (int i = 0; i < 256; ++i) { skey[i] = ~0ull; scode[i] = -1; } }
+    };
     std::vector<Local> locals((size_t)P);
     std::atomic<int64_t> bad_line{-1};
     std::atomic<int> bad_kind{0};                  // 1 malformed, 2 field too wide
@@ -619,41 +689,62 @@ int dsp_parse_calls(const char* text, int64_t nbytes, int64_t max_records,
         for (int64_t r = ra; r < rb; ++r) {
             Local& L = locals[(size_t)r];
             L.a = n * r / P; L.b = n * (r + 1) / P;
+            std::string_view last_name;
+            int32_t last_code = -1;
             for (int64_t i = L.a; i < L.b; ++i) {
                 int64_t lb = i ? newlines[(size_t)i - 1] + 1 : 0, le = i < n_nl ? newlines[(size_t)i] : eff_end;
                 while (lb < le && is_space(text[lb])) ++lb;                  // line.strip()
                 while (le > lb && is_space(text[le - 1])) --le;
                 const char* b = text + lb;
                 const char* e = text + le;
-                const char* f[11];
-                f[0] = b;
-                int nf = 1;
-                for (const char* q = b; nf <= 10;) {
-                    const char* t = (const char*)memchr(q, '\t', (size_t)(e - q));
-                    if (t == nullptr) break;
-                    f[nf++] = t + 1;
-                    q = t + 1;
-                }
+                const char* f[12];
+                const int nf = split_tabs(b, e, f);
                 int kind = 0;
                 if (nf < 10) kind = 1;                                       // also an empty line inside the file
                 else {
                     const char* fe[10];
                     for (int c = 0; c < 10; ++c) fe[c] = (c + 1 < nf) ? f[c + 1] - 1 : e;
                     long long v;
-                    if (!parse_int(f[1], fe[1], &v)) kind = 1; else pos[i] = v;
-                    if (!kind && !parse_int(f[3], fe[3], &v)) kind = 1; else if (!kind) pos_in_strand[i] = v;
-                    if (!kind && !parse_double(f[6], fe[6], &p0[i])) kind = 1;
-                    if (!kind && !parse_double(f[7], fe[7], &p1[i])) kind = 1;
-                    if (!kind && !parse_int(f[8], fe[8], &v)) kind = 1; else if (!kind) label[i] = (int32_t)v;
+                    if (!parse_int_fast(f[1], fe[1], &v)) kind = 1; else pos[i] = v;
+                    if (!kind && !parse_int_fast(f[3], fe[3], &v)) kind = 1; else if (!kind) pos_in_strand[i] = v;
+                    if (!kind && !parse_prob_fast(f[6], fe[6], &p0[i])) kind = 1;
+                    if (!kind && !parse_prob_fast(f[7], fe[7], &p1[i])) kind = 1;
+                    if (!kind && !parse_int_fast(f[8], fe[8], &v)) kind = 1; else if (!kind) label[i] = (int32_t)v;
                     const int64_t sl = fe[2] - f[2], kl = fe[9] - f[9];
                     if (!kind && (sl > STRAND_W || kl > KMER_W)) kind = 2;
                     if (!kind) {
-                        memset(strand + i * STRAND_W, 0, STRAND_W); memcpy(strand + i * STRAND_W, f[2], (size_t)sl);
-                        memset(kmer + i * KMER_W, 0, KMER_W); memcpy(kmer + i * KMER_W, f[9], (size_t)kl);
+                        uint32_t sw = 0;                                         // zero-padded cells, built in registers
+                        if (sl == 1) sw = (uint8_t)f[2][0]; else memcpy(&sw, f[2], (size_t)sl);
+                        memcpy(strand + i * STRAND_W, &sw, STRAND_W);
+                        uint64_t kw[3] = {0, 0, 0};
+                        if (kl <= 8 && f[9] + 8 <= text + nbytes) {             // the usual 5-mer: one masked 8-byte load
+                            uint64_t w;
+                            memcpy(&w, f[9], 8);
+                            kw[0] = kl == 8 ? w : (w & ((1ull << (8 * kl)) - 1ull));
+                        } else memcpy(kw, f[9], (size_t)kl);
+                        memcpy(kmer + i * KMER_W, kw, KMER_W);
                         const std::string_view name(f[0], (size_t)(fe[0] - f[0]));
-                        auto it = L.ids.find(name);
-                        if (it == L.ids.end()) { it = L.ids.emplace(name, (int32_t)L.names.size()).first; L.names.push_back(name); }
-                        chrom_code[i] = it->second;
+                        if (name != last_name) {                                 // calls come in runs of one chromosome
+                            int32_t code = -1;
+                            uint64_t key = 0;
+                            const bool small = name.size() <= 7 && L.sused < 192;
+                            uint32_t slot = 0;
+                            if (small) {
+                                memcpy(&key, name.data(), name.size());
+                                key |= (uint64_t)name.size() << 56;
+                                slot = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 56);
+                                while (L.skey[slot] != ~0ull && L.skey[slot] != key) slot = (slot + 1) & 255u;
+                                if (L.skey[slot] == key) code = L.scode[slot];
+                            }
+                            if (code < 0) {
+                                auto it = L.ids.find(name);
+                                if (it == L.ids.end()) { it = L.ids.emplace(name, (int32_t)L.names.size()).first; L.names.push_back(name); }
+                                code = it->second;
+                                if (small) { L.skey[slot] = key; L.scode[slot] = code; ++L.sused; }
+                            }
+                            last_name = name; last_code = code;
+                        }
+                        chrom_code[i] = last_code;
                     }
                 }
                 if (kind) {
