@@ -416,6 +416,43 @@ def _aggregate_device(keys, p0, p1, label, prob_cf, sort_by_key, device, max_rec
     return tuple(c[order] for c in cols)
 
 
+def _aggregate_compact(rec, prob_cf, sort_by_key, device):
+    """``Records`` with chromosome codes -> (key, first, s0, s1, met, unmet, cov, names in rank order) through
+    ``dsp_freq_aggregate_host``: host columns in, host rows out, site keys built on the device from the 4-byte codes and
+    the positions.  No torch in this path: the ``call_freq`` command line does not pay its import."""
+    codes, table = rec._codes
+    order = sorted(range(len(table)), key=lambda i: table[i])           # Python string order = the reference's sort order
+    rank = np.empty(max(len(table), 1), np.int64)
+    rank[order] = np.arange(len(table))
+    n = len(rec)
+    L = _native.lib()
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    code, pos, p0, p1, lab = c(codes, np.int32), c(rec.pos, np.int64), c(rec.p0, np.float64), c(rec.p1, np.float64), c(rec.label, np.int32)
+    prof = os.environ.get("DSP_B200_PROFILE")
+    t0 = time.perf_counter()
+    cap = min(n, 1 << 22)
+    while True:
+        o_key, o_first = np.empty(cap, np.uint64), np.empty(cap, np.int64)
+        o_p0, o_p1 = np.empty(cap, np.float64), np.empty(cap, np.float64)
+        o_met, o_unmet, o_cov = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32)
+        ns = C.c_int64(0)
+        p = lambda a: a.ctypes.data
+        rc = L.dsp_freq_aggregate_host(int(device), p(code), p(rank), len(rank), p(pos), p(p0), p(p1), p(lab), n, float(prob_cf),
+                                       int(bool(sort_by_key)), p(o_key), p(o_first), p(o_p0), p(o_p1), p(o_met), p(o_unmet), p(o_cov),
+                                       cap, C.byref(ns))
+        if rc == 4 and ns.value > cap:               # more sites than the first guess: size the rows exactly and repeat
+            cap = int(ns.value)
+            continue
+        if rc == 1 and b"positions must be" in (L.dsp_last_error() or b""):
+            raise ValueError("positions must be in [0, 2^%d)" % POS_BITS)
+        _native.check(rc, "dsp_freq_aggregate_host")
+        break
+    if prof:
+        print("call_freq host seconds: upload + keys + aggregate + download %.3f (incl. CUDA context creation)" % (time.perf_counter() - t0))
+    m = int(ns.value)
+    return (o_key[:m].view(np.int64), o_first[:m], o_p0[:m], o_p1[:m], o_met[:m], o_unmet[:m], o_cov[:m], [table[i] for i in order])
+
+
 def _aggregate_tensors(t_key, t_p0, t_p1, t_lab, prob_cf, sort_by_key, dev):
     """Device tensors in, device tensors out (rows = sites)."""
     import torch
@@ -449,9 +486,14 @@ def aggregate_records(rec, prob_cf, contig_name=None, sort_by_key=False, device=
         e = np.empty(0)
         return FreqTable(np.empty(0, object), e.astype(np.int64), np.empty(0, object), e.astype(np.int64), np.empty(0, object),
                          e, e, e.astype(np.int32), e.astype(np.int32), e.astype(np.int32), e.astype(np.int64), n_total, 0)
-    ids, names = rec.chrom_ranks()
-    keys = make_keys(ids, rec.pos)
-    k, first, s0, s1, met, unmet, cov = _aggregate_device(keys, rec.p0, rec.p1, rec.label, prob_cf, sort_by_key, device)
+    if rec._codes is not None and len(rec) <= MAX_RECORDS_PER_PASS:
+        # compact records (native parser): the site keys are built on the device from the 4-byte chromosome codes and
+        # the positions -- no 8-byte id / key columns, no extra passes over the records on the host
+        k, first, s0, s1, met, unmet, cov, names = _aggregate_compact(rec, prob_cf, sort_by_key, device)
+    else:
+        ids, names = rec.chrom_ranks()
+        keys = make_keys(ids, rec.pos)
+        k, first, s0, s1, met, unmet, cov = _aggregate_device(keys, rec.p0, rec.p1, rec.label, prob_cf, sort_by_key, device)
     k = k.view(np.uint64)
     names = np.asarray(names, dtype=object)
     chrom = names[(k >> np.uint64(POS_BITS)).astype(np.int64)]
@@ -465,9 +507,13 @@ def calculate_mods_frequency(mods_files, prob_cf, contig_name=None, device=0):
     argument order; returns a ``FreqTable`` (dict-like ``sitekey2stats``)."""
     if type(mods_files) is str:
         mods_files = [mods_files, ]
+    t0 = time.perf_counter()
     rec = Records.concat([read_mods_file(f) for f in mods_files])
+    t1 = time.perf_counter()
     count = len(rec)
     table = aggregate_records(rec, prob_cf, contig_name, False, device)
+    if os.environ.get("DSP_B200_PROFILE"):
+        print("call_freq host seconds: parse %.3f, keys + upload + aggregate + rows %.3f" % (t1 - t0, time.perf_counter() - t1))
     used = table.n_used
     if count > 0:
         if contig_name is None:
@@ -550,7 +596,10 @@ def _table_from_mapping(d):
 
 def write_sitekey2stats(sitekey2stats, result_file, is_sort, is_bed, is_gzip):
     """write methylfreq of sites into files (``call_mods_freq.py:77-122``)."""
+    t0 = time.perf_counter()
     text = render_table(sitekey2stats, is_sort, is_bed)
+    if os.environ.get("DSP_B200_PROFILE"):
+        print("call_freq host seconds: sort + render %.3f (%d bytes)" % (time.perf_counter() - t0, len(text)))
     if is_gzip:
         if not result_file.endswith(".gz"):
             result_file += ".gz"

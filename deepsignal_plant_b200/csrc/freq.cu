@@ -287,31 +287,13 @@ int sort_rows(Scratch& sc, cudaStream_t st, const SiteRow* rows, int64_t n, int 
 
 using namespace dsp;
 
-extern "C" int dsp_freq_aggregate(int device, const uint64_t* key, const double* p0, const double* p1,
-                                  const int32_t* label, int64_t n, double prob_cf, int sort_by_key,
-                                  uint64_t* out_key, int64_t* out_first, double* out_p0, double* out_p1,
-                                  int32_t* out_met, int32_t* out_unmet, int32_t* out_cov,
-                                  int64_t* n_sites_host, void* stream) {
-    DSP_REQUIRE(n_sites_host, DSP_ERR_INVALID, "dsp_freq_aggregate: n_sites_host is null");
-    *n_sites_host = 0;
-    DSP_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, DSP_ERR_INVALID,
-                "dsp_freq_aggregate: n=%lld out of range (shard the records: < 2^31 per call)", (long long)n);
-    if (n == 0) return DSP_OK;
-    DSP_REQUIRE(key && p0 && p1 && label && out_key && out_first && out_p0 && out_p1 && out_met && out_unmet && out_cov,
-                DSP_ERR_INVALID, "dsp_freq_aggregate: null pointer");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        set_error("dsp_freq_aggregate: no CUDA device available; this library has no CPU path");
-        return DSP_ERR_CUDA;
-    }
-    DSP_REQUIRE(device >= 0 && device < ndev, DSP_ERR_INVALID, "dsp_freq_aggregate: bad device %d", device);
-    int prev = -1;
-    cudaGetDevice(&prev);
-    if (prev != device) cudaSetDevice(device);
-    struct Restore { int p, d; ~Restore() { if (p != d && p >= 0) cudaSetDevice(p); } } restore{prev, device};
-    cudaStream_t st = (cudaStream_t)stream;
-    Scratch sc(device);
+namespace dsp {
+namespace {
+
+// the whole aggregation on device columns (current device = sc.device); outputs on the device, capacity n
+int aggregate_columns(Scratch& sc, cudaStream_t st, const uint64_t* key, const double* p0, const double* p1, const int32_t* label,
+                      int64_t n, double prob_cf, int sort_by_key, uint64_t* out_key, int64_t* out_first, double* out_p0,
+                      double* out_p1, int32_t* out_met, int32_t* out_unmet, int32_t* out_cov, int64_t* n_sites_host) {
     int rc;
     Rec* rec;
     if ((rc = sc.alloc(&rec, n))) return rc;
@@ -331,6 +313,108 @@ extern "C" int dsp_freq_aggregate(int device, const uint64_t* key, const double*
     DSP_CUDA(cudaGetLastError());
     DSP_CUDA(cudaStreamSynchronize(st));
     *n_sites_host = nseg;
+    return DSP_OK;
+}
+
+// key = (rank of the chromosome code << 40) | pos; flags positions outside [0, 2^40)
+__global__ void make_keys_kernel(const int32_t* __restrict__ code, const int64_t* __restrict__ rank, const int64_t* __restrict__ pos,
+                                 int64_t n, uint64_t* __restrict__ key, int* __restrict__ bad) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = pos[i];
+    if (p < 0 || p >= (1ll << 40)) *bad = 1;
+    key[i] = ((uint64_t)rank[code[i]] << 40) | (uint64_t)p;
+}
+
+int check_device(int device, const char* who) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("%s: no CUDA device available; this library has no CPU path", who);
+        return DSP_ERR_CUDA;
+    }
+    DSP_REQUIRE(device >= 0 && device < ndev, DSP_ERR_INVALID, "%s: bad device %d", who, device);
+    return DSP_OK;
+}
+
+}  // namespace
+}  // namespace dsp
+
+extern "C" int dsp_freq_aggregate(int device, const uint64_t* key, const double* p0, const double* p1,
+                                  const int32_t* label, int64_t n, double prob_cf, int sort_by_key,
+                                  uint64_t* out_key, int64_t* out_first, double* out_p0, double* out_p1,
+                                  int32_t* out_met, int32_t* out_unmet, int32_t* out_cov,
+                                  int64_t* n_sites_host, void* stream) {
+    DSP_REQUIRE(n_sites_host, DSP_ERR_INVALID, "dsp_freq_aggregate: n_sites_host is null");
+    *n_sites_host = 0;
+    DSP_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, DSP_ERR_INVALID,
+                "dsp_freq_aggregate: n=%lld out of range (shard the records: < 2^31 per call)", (long long)n);
+    if (n == 0) return DSP_OK;
+    DSP_REQUIRE(key && p0 && p1 && label && out_key && out_first && out_p0 && out_p1 && out_met && out_unmet && out_cov,
+                DSP_ERR_INVALID, "dsp_freq_aggregate: null pointer");
+    int rc = check_device(device, "dsp_freq_aggregate");
+    if (rc) return rc;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    struct Restore { int p, d; ~Restore() { if (p != d && p >= 0) cudaSetDevice(p); } } restore{prev, device};
+    Scratch sc(device);
+    return aggregate_columns(sc, (cudaStream_t)stream, key, p0, p1, label, n, prob_cf, sort_by_key, out_key, out_first, out_p0,
+                             out_p1, out_met, out_unmet, out_cov, n_sites_host);
+}
+
+extern "C" int dsp_freq_aggregate_host(int device, const int32_t* chrom_code, const int64_t* code_rank, int32_t n_codes,
+                                       const int64_t* pos, const double* p0, const double* p1, const int32_t* label,
+                                       int64_t n, double prob_cf, int sort_by_key,
+                                       uint64_t* out_key, int64_t* out_first, double* out_p0, double* out_p1,
+                                       int32_t* out_met, int32_t* out_unmet, int32_t* out_cov, int64_t out_cap,
+                                       int64_t* n_sites_host) {
+    DSP_REQUIRE(n_sites_host, DSP_ERR_INVALID, "dsp_freq_aggregate_host: n_sites_host is null");
+    *n_sites_host = 0;
+    DSP_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, DSP_ERR_INVALID,
+                "dsp_freq_aggregate_host: n=%lld out of range (shard the records: < 2^31 per call)", (long long)n);
+    if (n == 0) return DSP_OK;
+    DSP_REQUIRE(chrom_code && code_rank && n_codes > 0 && pos && p0 && p1 && label && out_key && out_first && out_p0 && out_p1 &&
+                out_met && out_unmet && out_cov, DSP_ERR_INVALID, "dsp_freq_aggregate_host: null pointer");
+    int rc = check_device(device, "dsp_freq_aggregate_host");
+    if (rc) return rc;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    struct Restore { int p, d; ~Restore() { if (p != d && p >= 0) cudaSetDevice(p); } } restore{prev, device};
+    cudaStream_t st = nullptr;
+    Scratch sc(device);
+    int32_t* d_code; int64_t *d_rank, *d_pos; double *d_p0, *d_p1; int32_t* d_lab; uint64_t* d_key; int* d_bad;
+    if ((rc = sc.alloc(&d_code, n)) || (rc = sc.alloc(&d_rank, n_codes)) || (rc = sc.alloc(&d_pos, n)) || (rc = sc.alloc(&d_p0, n)) ||
+        (rc = sc.alloc(&d_p1, n)) || (rc = sc.alloc(&d_lab, n)) || (rc = sc.alloc(&d_key, n)) || (rc = sc.alloc(&d_bad, 1))) return rc;
+    DSP_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    DSP_CUDA(cudaMemcpyAsync(d_code, chrom_code, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    DSP_CUDA(cudaMemcpyAsync(d_rank, code_rank, sizeof(int64_t) * n_codes, cudaMemcpyHostToDevice, st));
+    DSP_CUDA(cudaMemcpyAsync(d_pos, pos, sizeof(int64_t) * n, cudaMemcpyHostToDevice, st));
+    make_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_code, d_rank, d_pos, n, d_key, d_bad);
+    DSP_CUDA(cudaGetLastError());
+    DSP_CUDA(cudaMemcpyAsync(d_p0, p0, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    DSP_CUDA(cudaMemcpyAsync(d_p1, p1, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    DSP_CUDA(cudaMemcpyAsync(d_lab, label, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    int bad = 0;
+    DSP_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DSP_CUDA(cudaStreamSynchronize(st));
+    DSP_REQUIRE(!bad, DSP_ERR_INVALID, "positions must be in [0, 2^40)");
+    uint64_t* o_key; int64_t* o_first; double *o_p0, *o_p1; int32_t *o_met, *o_unmet, *o_cov;
+    if ((rc = sc.alloc(&o_key, n)) || (rc = sc.alloc(&o_first, n)) || (rc = sc.alloc(&o_p0, n)) || (rc = sc.alloc(&o_p1, n)) ||
+        (rc = sc.alloc(&o_met, n)) || (rc = sc.alloc(&o_unmet, n)) || (rc = sc.alloc(&o_cov, n))) return rc;
+    int64_t ns = 0;
+    if ((rc = aggregate_columns(sc, st, d_key, d_p0, d_p1, d_lab, n, prob_cf, sort_by_key, o_key, o_first, o_p0, o_p1, o_met, o_unmet,
+                                o_cov, &ns))) return rc;
+    *n_sites_host = ns;
+    DSP_REQUIRE(ns <= out_cap, DSP_ERR_NOMEM, "dsp_freq_aggregate_host: %lld sites, output capacity %lld", (long long)ns, (long long)out_cap);
+    DSP_CUDA(cudaMemcpy(out_key, o_key, sizeof(uint64_t) * ns, cudaMemcpyDeviceToHost));
+    DSP_CUDA(cudaMemcpy(out_first, o_first, sizeof(int64_t) * ns, cudaMemcpyDeviceToHost));
+    DSP_CUDA(cudaMemcpy(out_p0, o_p0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    DSP_CUDA(cudaMemcpy(out_p1, o_p1, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    DSP_CUDA(cudaMemcpy(out_met, o_met, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+    DSP_CUDA(cudaMemcpy(out_unmet, o_unmet, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+    DSP_CUDA(cudaMemcpy(out_cov, o_cov, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
     return DSP_OK;
 }
 

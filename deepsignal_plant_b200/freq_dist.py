@@ -330,8 +330,11 @@ def call_freq_distributed(mods_files, prob_cf, result_file, is_sort, is_bed, is_
     """``call_mods_frequency_to_file`` across the ranks of ``grp`` (default: the initialised process group).
     ``records``: this rank's calls as ``cf.Records`` already in memory (contiguous shards in rank order, e.g. what
     ``call_mods --freq_out`` has just produced) instead of files to parse."""
+    import time
     grp = grp or TorchGroup()
+    t0 = time.perf_counter()
     rec = records if records is not None else read_units(plan_units(mods_files, grp.world)[grp.rank])
+    t1 = time.perf_counter()
     own_backend = backend is None
     if own_backend:
         backend = DeviceBackend(grp.rank, grp.world, device, default_window_bytes(len(rec), grp), grp.all_gather_object)
@@ -340,8 +343,13 @@ def call_freq_distributed(mods_files, prob_cf, result_file, is_sort, is_bed, is_
     finally:
         if own_backend:
             backend.close()
+    t2 = time.perf_counter()
     text = cf.render_table(table, False, is_bed)
+    t3 = time.perf_counter()
     path = write_slices(text, result_file, is_gzip, grp)
+    if os.environ.get("DSP_B200_PROFILE"):
+        print("call_freq rank %d host seconds: parse %.3f, exchange + aggregate + meta + order %.3f, render %.3f, write %.3f"
+              % (grp.rank, t1 - t0, t2 - t1, t3 - t2, time.perf_counter() - t3))
     return table, n_considered, path
 
 

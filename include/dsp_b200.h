@@ -157,6 +157,19 @@ int dsp_freq_aggregate(int device, const uint64_t* key, const double* p0, const 
                        int32_t* out_met, int32_t* out_unmet, int32_t* out_cov,
                        int64_t* n_sites_host, void* stream);
 
+/* The same aggregation with HOST buffers, for a host that has no device-memory plumbing of its own (the call_freq
+ * command line: no torch import in the process).  Inputs are the columns dsp_parse_calls writes: chrom_code (n) indexes
+ * its name table; code_rank (n_codes, HOST) gives every code the rank of its name in the output's chromosome order
+ * (Python string order for the reference's --sort, call_mods_freq.py:88) -- site key = (code_rank[chrom_code] << 40) | pos,
+ * built on the device; pos must lie in [0, 2^40).  Outputs are HOST arrays of capacity out_cap (DSP_ERR_NOMEM with
+ * *n_sites_host set if more sites than that).  Uploads, aggregation and download run on the default stream. */
+int dsp_freq_aggregate_host(int device, const int32_t* chrom_code, const int64_t* code_rank, int32_t n_codes,
+                            const int64_t* pos, const double* p0, const double* p1, const int32_t* label,
+                            int64_t n, double prob_cf, int sort_by_key,
+                            uint64_t* out_key, int64_t* out_first, double* out_p0, double* out_p1,
+                            int32_t* out_met, int32_t* out_unmet, int32_t* out_cov, int64_t out_cap,
+                            int64_t* n_sites_host);
+
 /* ---- multi-GPU call_freq: one process per GPU, records exchanged over NVLink peer memory -----------------
  * The reference's only parallel form of the aggregation is per-contig worker processes over temp files
  * (call_mods_freq.py:154-215, 262-295).  Here every rank parses a contiguous shard of the records (file order,
