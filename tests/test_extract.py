@@ -526,3 +526,23 @@ def test_one_bad_read_is_skipped_not_fatal(tmp_path):
     want = ef.pack_reads([reads[i] for i in (0, 1, 3, 5)])
     for f in ("raw", "raw_off", "ev_off", "ev_start", "ev_len", "ev_base", "chrom_start"):
         assert np.array_equal(getattr(got, f), getattr(want, f)), f
+
+
+def test_mad_constant_equals_scipy_norm_ppf_statsmodels_itself_absent_here():
+    # statsmodels.robust.mad(a) = median(|a - median(a)| / c) with c = scipy.stats.norm.ppf(3/4) (statsmodels/robust/scale.py,
+    # `Gaussian = scipy.stats.norm`).  statsmodels is not in this image, so the formula stays "parity unpinned" against it
+    # (DESIGN.md section 1); the constant is pinned here against scipy, the library statsmodels takes it from, and against
+    # statsmodels itself wherever that can be imported.
+    from scipy.stats import norm
+    from oracle import extract_oracle as eo
+    assert eo.MAD_C == float(norm.ppf(0.75))
+    try:
+        from statsmodels import robust
+    except Exception:
+        return
+    if getattr(robust, "__dsp_stub__", False) or not hasattr(robust, "mad") or robust.mad is None:
+        return
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 1000, 1001):
+        a = rng.normal(0, 1, n) * 50
+        assert eo.mad(a) == float(robust.mad(a))
