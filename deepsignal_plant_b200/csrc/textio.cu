@@ -647,34 +647,48 @@ int dsp_parse_calls(const char* text, int64_t nbytes, int64_t max_records,
     constexpr int STRAND_W = 4, KMER_W = 24;
     DSP_REQUIRE(text && n_records && nbytes >= 0 && max_records >= 0, DSP_ERR_INVALID, "dsp_parse_calls: bad argument");
     *n_records = 0;
-    // lines = text.split('\n') with each line strip()-ed; blank lines die in the reference (IndexError) except a trailing one
-    std::vector<int64_t> newlines;
-    {
-        const int P = nthreads > 1 && nbytes >= (1 << 20) ? nthreads : 1;
-        std::vector<std::vector<int64_t>> part((size_t)P);
-        parallel_for(P, P, [&](int64_t a, int64_t b) {
-            for (int64_t r = a; r < b; ++r) {
-                const int64_t lo = nbytes * r / P, hi = nbytes * (r + 1) / P;
-                for (int64_t q = lo; q < hi;) {
-                    const char* nl = (const char*)memchr(text + q, '\n', (size_t)(hi - q));
-                    if (!nl) break;
-                    part[(size_t)r].push_back(nl - text);
-                    q = (nl - text) + 1;
-                }
-            }
-        }, 2);
-        for (auto& v : part) newlines.insert(newlines.end(), v.begin(), v.end());
-    }
+    // lines = text.split('\n') with each line strip()-ed; blank lines die in the reference (IndexError) except a trailing one.
     // trailing white space is not a line; everything before it is split at the newlines
     int64_t eff_end = nbytes;
     while (eff_end > 0 && is_space(text[eff_end - 1])) --eff_end;
-    const int64_t n_nl = std::lower_bound(newlines.begin(), newlines.end(), eff_end) - newlines.begin();
+    // newline positions below eff_end, found by all threads over byte ranges and kept per range (no merged copy: line i's
+    // newline is part[r][i - prefix[r]]); the counting call only counts
+    const int PN = nthreads > 1 && nbytes >= (1 << 20) ? nthreads : 1;
+    std::vector<std::vector<int64_t>> part((size_t)PN);
+    std::vector<int64_t> part_count((size_t)PN, 0);
+    const bool count_only = max_records == 0;
+    parallel_for(PN, PN, [&](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            const int64_t lo = eff_end * r / PN, hi = eff_end * (r + 1) / PN;
+            int64_t cnt = 0;
+            if (!count_only) part[(size_t)r].reserve((size_t)((hi - lo) / 48 + 16));
+            for (int64_t q = lo; q < hi;) {
+                const char* nl = (const char*)memchr(text + q, '\n', (size_t)(hi - q));
+                if (!nl) break;
+                if (!count_only) part[(size_t)r].push_back(nl - text);
+                ++cnt;
+                q = (nl - text) + 1;
+            }
+            part_count[(size_t)r] = cnt;
+        }
+    }, 2);
+    std::vector<int64_t> prefix((size_t)PN + 1, 0);
+    for (int r = 0; r < PN; ++r) prefix[(size_t)r + 1] = prefix[(size_t)r] + part_count[(size_t)r];
+    const int64_t n_nl = prefix[(size_t)PN];
     const int64_t n = eff_end > 0 ? n_nl + 1 : 0;
     *n_records = n;
-    if (max_records == 0) return DSP_OK;
+    if (count_only) return DSP_OK;
     DSP_REQUIRE(n <= max_records, DSP_ERR_NOMEM, "dsp_parse_calls: %lld records, buffers hold %lld", (long long)n, (long long)max_records);
     DSP_REQUIRE(chrom_code && pos && strand && pos_in_strand && p0 && p1 && label && kmer && names && names_bytes && n_names,
                 DSP_ERR_INVALID, "dsp_parse_calls: null argument");
+    // monotone cursor over the per-range newline lists
+    struct Cursor {
+        const std::vector<std::vector<int64_t>>& part; const std::vector<int64_t>& prefix; size_t r = 0;
+        int64_t at(int64_t i) {                                      // i ascending between calls
+            while (i >= prefix[r + 1]) ++r;
+            return part[r][(size_t)(i - prefix[r])];
+        }
+    };
     const int P = n >= 4096 && nthreads > 1 ? nthreads : 1;
     struct Local {
         std::unordered_map<std::string_view, int32_t> ids; std::vector<std::string_view> names; int64_t a = 0, b = 0;
@@ -691,8 +705,13 @@ int dsp_parse_calls(const char* text, int64_t nbytes, int64_t max_records,
             L.a = n * r / P; L.b = n * (r + 1) / P;
             std::string_view last_name;
             int32_t last_code = -1;
+            Cursor cur{part, prefix};
+            if (L.a < L.b && L.a > 0) { size_t r0 = 0; while (L.a - 1 >= prefix[r0 + 1]) ++r0; cur.r = r0; }
+            int64_t prev_nl = (L.a > 0 && L.a < L.b) ? cur.at(L.a - 1) : -1;
             for (int64_t i = L.a; i < L.b; ++i) {
-                int64_t lb = i ? newlines[(size_t)i - 1] + 1 : 0, le = i < n_nl ? newlines[(size_t)i] : eff_end;
+                const int64_t this_nl = i < n_nl ? cur.at(i) : eff_end;
+                int64_t lb = prev_nl + 1, le = this_nl;
+                prev_nl = this_nl;
                 while (lb < le && is_space(text[lb])) ++lb;                  // line.strip()
                 while (le > lb && is_space(text[le - 1])) --le;
                 const char* b = text + lb;
