@@ -20,7 +20,7 @@ SYMBOLS = (
     "dsp_parse_features", "dsp_format_calls", "dsp_freq_release_cache", "dsp_extract_features", "dsp_format_sampleinfo", "dsp_find_sites", "dsp_extract_features_f64",
     "dsp_format_features", "dsp_parse_calls", "dsp_format_freq",
     "dsp_comm_create", "dsp_comm_export", "dsp_comm_connect", "dsp_comm_destroy", "dsp_freq_aggregate_distributed",
-    "dsp_comm_route_rows", "dsp_comm_last_timing", "dsp_freq_aggregate_host",
+    "dsp_comm_route_rows", "dsp_comm_last_timing", "dsp_freq_aggregate_host", "dsp_device_warmup",
 )
 
 MODULES = {"both_bilstm": 0, "seq_bilstm": 1, "signal_bilstm": 2}
@@ -78,6 +78,7 @@ def lib():
                                      vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), vp]
     L.dsp_freq_aggregate_host.argtypes = [C.c_int, vp, vp, C.c_int32, vp, vp, vp, vp, i64, C.c_double, C.c_int,
                                           vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i64)]
+    L.dsp_device_warmup.argtypes = [C.c_int]
     L.dsp_selftest.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     i32 = C.c_int32
     L.dsp_parse_features.argtypes = [vp, i64, i32, i32, i32, i64, fp, fp, fp, fp, fp, vp, vp, i64, vp,

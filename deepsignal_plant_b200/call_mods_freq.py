@@ -502,12 +502,19 @@ def aggregate_records(rec, prob_cf, contig_name=None, sort_by_key=False, device=
     return FreqTable(chrom, pos, strand, pis, kmer, s0, s1, met, unmet, cov, first, n_total, int(cov.sum()))
 
 
+def _warm_device_in_background(device):
+    import threading
+    L = _native.lib()
+    threading.Thread(target=lambda: L.dsp_device_warmup(int(device)), daemon=True).start()
+
+
 def calculate_mods_frequency(mods_files, prob_cf, contig_name=None, device=0):
     """call mod_freq from call_mods files (``call_mods_freq.py:29-74``).  Files are read in
     argument order; returns a ``FreqTable`` (dict-like ``sitekey2stats``)."""
     if type(mods_files) is str:
         mods_files = [mods_files, ]
     t0 = time.perf_counter()
+    _warm_device_in_background(device)               # the CUDA context comes up while the files are parsed
     rec = Records.concat([read_mods_file(f) for f in mods_files])
     t1 = time.perf_counter()
     count = len(rec)

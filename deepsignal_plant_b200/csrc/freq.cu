@@ -418,6 +418,17 @@ extern "C" int dsp_freq_aggregate_host(int device, const int32_t* chrom_code, co
     return DSP_OK;
 }
 
+extern "C" int dsp_device_warmup(int device) {
+    int rc = check_device(device, "dsp_device_warmup");
+    if (rc) return rc;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    DSP_CUDA(cudaFree(nullptr));                      // creates the primary context
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return DSP_OK;
+}
+
 extern "C" int dsp_freq_release_cache(void) {
     std::lock_guard<std::mutex> lk(g_blocks_mu);
     int prev = -1;

@@ -170,6 +170,10 @@ int dsp_freq_aggregate_host(int device, const int32_t* chrom_code, const int64_t
                             int32_t* out_met, int32_t* out_unmet, int32_t* out_cov, int64_t out_cap,
                             int64_t* n_sites_host);
 
+/* Creates the CUDA context of `device` (a few hundred milliseconds in a fresh process).  The command lines call it from a
+ * side thread while they parse their input, so that the first real call does not wait for it. */
+int dsp_device_warmup(int device);
+
 /* ---- multi-GPU call_freq: one process per GPU, records exchanged over NVLink peer memory -----------------
  * The reference's only parallel form of the aggregation is per-contig worker processes over temp files
  * (call_mods_freq.py:154-215, 262-295).  Here every rank parses a contiguous shard of the records (file order,
