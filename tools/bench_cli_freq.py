@@ -34,8 +34,10 @@ def main():
         for _ in range(reps):
             f.write(block)
     sample = os.path.join(tmp, "sample.tsv")
-    with open(sample, "w") as f:
-        f.write(block[: block.index("\n", len(block) * min(a.ref_sample, a.block) // a.block - 1) + 1] if a.ref_sample < a.block else block)
+    if a.ref_sample > 0:                                        # the first ref_sample lines of the block (whole lines)
+        lines = block.split("\n")[:min(a.ref_sample, a.block)]
+        with open(sample, "w") as f:
+            f.write("\n".join(lines) + "\n")
     n = reps * a.block
     out = os.path.join(tmp, "freq.tsv")
     tail = ["-m", "deepsignal_plant_b200", "call_freq", "-i", path, "-o", out, "--sort"]
@@ -51,7 +53,7 @@ def main():
     res = {"command": "call_freq --sort, %d rank(s), fresh process" % a.ranks, "records": n, "file_GB": os.path.getsize(path) / 1e9,
            "sites": sites, "wall_s": dt, "records_per_s": n / dt, "host_breakdown": [l for l in r.stdout.splitlines() if "seconds" in l]}
     from oracle import ref_import
-    if ref_import.available():
+    if ref_import.available() and a.ref_sample > 0:
         code = ("import sys, time; sys.path.insert(0, %r)\nfrom oracle import ref_import\nm = ref_import.import_reference('call_mods_freq')\n"
                 "t0 = time.perf_counter(); t = m.calculate_mods_frequency([%r], 0.5); m.write_sitekey2stats(t, %r, True, False, False)\n"
                 "print('REF', time.perf_counter() - t0)\n" % (ROOT, sample, out + ".ref"))
