@@ -277,6 +277,15 @@ def call_mods_stream(model, batches, write, depth=2):
     return sites, (float(np.mean(acc)) if acc else 0.0), nb
 
 
+def host_threads(args, world=1):
+    """--host_threads: threads of the native parsers / formatters; 0 or absent = all cores, divided between the ranks
+    (--nproc keeps the reference's meaning and default -- a number of worker processes -- and is not used for this)."""
+    n = int(getattr(args, "host_threads", 0) or 0)
+    if n <= 0:
+        n = max(1, min(32, (os.cpu_count() or 1) // max(world, 1)))
+    return n
+
+
 def _shard_of_file(path, rank, world):
     """Contiguous byte shard of rank ``rank`` (lines that start inside it); ``None`` = whole file."""
     if world <= 1:
@@ -461,7 +470,7 @@ def call_mods(args):
         wq.put(data)
         if freq_out:
             from . import call_mods_freq as cf
-            r = cf.parse_calls_buffer(data, nthreads=max(1, args.nproc))
+            r = cf.parse_calls_buffer(data, nthreads=host_threads(args, world))
             if r is None:
                 r = cf.parse_lines(bytes(data).decode().splitlines())
             freq_parts.append(r)
@@ -498,7 +507,7 @@ def call_mods(args):
     idle = gz_single and rank > 0                              # nothing to read on this rank
     reader = None if idle else feature_io.FeatureFileReader(
         input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536), slots=6,
-        nthreads=max(1, args.nproc), byte_range=None if gz_single else _shard_of_file(input_path, rank, world))
+        nthreads=host_threads(args, world), byte_range=None if gz_single else _shard_of_file(input_path, rank, world))
     err = []
 
     def read():                                                # _read_features_file (:55-127)

@@ -53,7 +53,9 @@ def build_parser():
                    help="only 'no' (one output file) is supported")
     g.add_argument("--w_batch_num", action="store", type=int, required=False, default=200, help="accepted for compatibility")
     g.add_argument("--gzip", action="store_true", default=False, required=False)
-    ex.add_argument("--nproc", "-p", action="store", type=int, default=10, required=False, help="host threads for formatting")
+    ex.add_argument("--nproc", "-p", action="store", type=int, default=10, required=False,
+                    help="the reference's number of worker processes: kept with its default; the native formatters use --host_threads")
+    ex.add_argument("--host_threads", action="store", type=int, default=0, help="host threads for formatting; 0 = all cores")
     ex.add_argument("--f5_batch_size", action="store", type=int, default=30, required=False, help="reads per extraction chunk")
 
     g = cm.add_argument_group("INPUT")
@@ -104,7 +106,10 @@ def build_parser():
     g.add_argument("--freq_prob_cf", type=float, default=0.5, help="call_freq --prob_cf")
     g.add_argument("--freq_bed", action="store_true", default=False, help="call_freq --bed")
     g.add_argument("--freq_sort", action="store_true", default=False, help="call_freq --sort")
-    cm.add_argument("--nproc", "-p", action="store", type=int, default=10, help="host threads for parsing / formatting")
+    cm.add_argument("--nproc", "-p", action="store", type=int, default=10,
+                    help="the reference's number of worker processes: kept with its default; the native parser / formatter use --host_threads")
+    cm.add_argument("--host_threads", action="store", type=int, default=0,
+                    help="host threads for parsing / formatting; 0 (default) = all cores, shared evenly between the ranks of a torchrun job")
     cm.add_argument("--nproc_gpu", action="store", type=int, default=2,
                     help="accepted for compatibility; use torchrun for one process per GPU")
 

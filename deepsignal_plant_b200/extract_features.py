@@ -596,7 +596,7 @@ def extract_to_file(args):
                 dst.copy_(t[k], non_blocking=True)
                 host.append(dst)
             torch.cuda.current_stream(dev).synchronize()
-            text = format_features(batch, sites, *[h.numpy() for h in host], args.methy_label, nthreads=max(1, args.nproc),
+            text = format_features(batch, sites, *[h.numpy() for h in host], args.methy_label, nthreads=int(getattr(args, 'host_threads', 0) or 0) or min(32, os.cpu_count() or 1),
                                    as_array=True)
             wf.write(memoryview(text))
             total += len(sites)
