@@ -46,7 +46,7 @@ def main():
         n = reps * base_n
         torch.manual_seed(1234)
         torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
-        argv = ["call_mods", "-i", path, "-m", ckpt, "-o", out, "--nproc", str(a.nproc)]
+        argv = ["call_mods", "-i", path, "-m", ckpt, "-o", out, "--host_threads", str(a.nproc)]
         cli.main(argv)                                  # first run: page cache, CUDA context
         t0 = time.perf_counter()
         cli.main(argv)
@@ -68,7 +68,7 @@ def archive(a):
         torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
         argv = ["call_mods", "-i", path, "-m", ckpt, "-o", out, "--motifs", "CG", "--f5_batch_size", "130"]
         if a.extract:
-            argv = ["extract", "-i", path, "-o", out, "--motifs", "CG", "--f5_batch_size", "130", "--nproc", str(a.nproc)]
+            argv = ["extract", "-i", path, "-o", out, "--motifs", "CG", "--f5_batch_size", "130", "--host_threads", str(a.nproc)]
         cli.main(argv)
         t0 = time.perf_counter()
         cli.main(argv)
