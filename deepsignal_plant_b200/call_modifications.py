@@ -234,7 +234,11 @@ def load_model(args, device=0):
 def call_mods_stream(model, batches, write, depth=2):
     """Drive the model over an iterable of ``feature_io.FeatureBatch`` (page-locked tensors):
     batch i+1 is submitted before batch i is collected, so its host->device copies overlap
-    batch i's kernels; ``write(bytes)`` receives each batch's output lines in order.
+    batch i's kernels; a formatter thread turns finished batches into output lines (native code on the host
+    threads, outside the GIL) while this thread already waits for the next batch, and ``write(uint8 array)``
+    receives each batch's lines in order.  A batch is in use until its lines are written: readers that recycle
+    their slots need ``depth + 6`` of them (1 being filled, 2 queued in front of this function, ``depth`` in
+    flight, 1 queued for the formatter, 1 being formatted, 1 spare).
     Returns (sites, mean per-batch accuracy against the label column, batches) -- the
     bookkeeping ``_call_mods_q`` keeps (``:230,255-257``)."""
     from . import feature_io
@@ -244,36 +248,84 @@ def call_mods_stream(model, batches, write, depth=2):
     outs = []
     inflight = []
     sites, acc, nb = 0, [], 0
+    prof = {"wait for reader": 0.0, "submit": 0.0, "wait for device": 0.0, "wait for formatter": 0.0}
+    fprof = {"format": 0.0, "hand to writer": 0.0}
+    tick = time.perf_counter
+    pin = torch.cuda.is_available()                  # result staging only; the model itself refuses to run without a GPU
+    fq = queue.Queue(maxsize=1)
+    ferr = []
+
+    def formatter():                                 # the per-site text loop of _call_mods (:175-188), off the submit path
+        while True:
+            item = fq.get()
+            if item is None:
+                return
+            if ferr:
+                continue                             # keep draining so that the producer never blocks
+            try:
+                b, slot = item
+                probs, labels = slot[1][:b.n].numpy(), slot[2][:b.n].numpy()
+                t1 = tick()
+                text = feature_io.format_calls(b, probs, labels, as_array=True)     # no copy: the writer owns it from here
+                t2 = tick()
+                write(text)
+                fprof["format"] += t2 - t1
+                fprof["hand to writer"] += tick() - t2
+                acc.append(float(np.mean(b.labels.numpy() == labels)))
+                outs.append(slot)
+            except BaseException as e:               # surfaced in the calling thread
+                ferr.append(e)
+
+    ft = threading.Thread(target=formatter, daemon=True)
+    ft.start()
 
     def collect():
         nonlocal sites, nb
-        b, tk, (lg, pr, lb) = inflight.pop(0)
+        b, tk, slot = inflight.pop(0)
+        t0 = tick()
         model.wait_host(tk)
-        probs, labels = pr[:b.n].numpy(), lb[:b.n].numpy()
-        write(feature_io.format_calls(b, probs, labels))
-        acc.append(float(np.mean(b.labels.numpy() == labels)))
+        t1 = tick()
+        fq.put((b, slot))
+        prof["wait for device"] += t1 - t0
+        prof["wait for formatter"] += tick() - t1
         sites += b.n
         nb += 1
-        outs.append((lg, pr, lb))
 
-    for b in batches:
-        cap = b.kmer.shape[0]
-        slot = None
-        for i, o in enumerate(outs):
-            if o[0].shape[0] >= cap:
-                slot = outs.pop(i)
+    try:
+        it = iter(batches)
+        while not ferr:
+            t0 = tick()
+            b = next(it, None)
+            prof["wait for reader"] += tick() - t0
+            if b is None:
                 break
-        if slot is None:
-            slot = (torch.empty((cap, C_), dtype=torch.float32).pin_memory(),
-                    torch.empty((cap, C_), dtype=torch.float32).pin_memory(),
-                    torch.empty((cap,), dtype=torch.int32).pin_memory())
-        lg, pr, lb = slot
-        tk = model.submit_host(*b.arrays(), lg[:b.n], pr[:b.n], lb[:b.n])
-        inflight.append((b, tk, slot))
-        if len(inflight) >= depth:
+            cap = b.kmer.shape[0]
+            slot = None
+            for i, o in enumerate(list(outs)):
+                if o[0].shape[0] >= cap:
+                    outs.remove(o)
+                    slot = o
+                    break
+            if slot is None:
+                mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory() if pin else torch.empty(shape, dtype=dt)
+                slot = (mk((cap, C_), torch.float32), mk((cap, C_), torch.float32), mk((cap,), torch.int32))
+            lg, pr, lb = slot
+            t0 = tick()
+            tk = model.submit_host(*b.arrays(), lg[:b.n], pr[:b.n], lb[:b.n])
+            prof["submit"] += tick() - t0
+            inflight.append((b, tk, slot))
+            if len(inflight) >= depth:
+                collect()
+        while inflight:
             collect()
-    while inflight:
-        collect()
+    finally:
+        fq.put(None)
+        ft.join()
+    if ferr:
+        raise ferr[0]
+    if os.environ.get("DSP_B200_PROFILE"):
+        print("call_mods_stream host seconds: submitting thread: " + ", ".join("%s %.3f" % kv for kv in prof.items())
+              + "; formatter thread: " + ", ".join("%s %.3f" % kv for kv in fprof.items()))
     return sites, (float(np.mean(acc)) if acc else 0.0), nb
 
 
@@ -418,10 +470,42 @@ def call_mods(args):
         torch.cuda.set_device(device)
     args.model_path = model_path
     from_reads = input_path.endswith(".npz")                  # decoded reads instead of a feature file
-    gz_single = world > 1 and not from_reads and input_path.endswith(".gz")
+    from . import feature_bin
+    from_bin = not from_reads and feature_bin.is_feature_bin(input_path)      # binary feature hand-off (.dspf) instead of text
+    gz_single = world > 1 and not from_reads and not from_bin and input_path.endswith(".gz")
     if gz_single and rank == 0:
         print("call_mods: a gzip feature file cannot be cut into byte shards; rank 0 processes it alone "
               "(decompress it to use all %d GPUs)" % world)
+    # The reader starts before the model is built: its page-locked slots and the first batches are ready by the time the
+    # weights are packed (_read_features_file, :55-127, is a process of its own in the reference too)
+    rq = queue.Queue(maxsize=2)
+    err = []
+    rt = None
+    if not from_reads:
+        idle = gz_single and rank > 0                          # nothing to read on this rank
+        if from_bin:
+            # every rank reads a contiguous site range; sections go straight from the page cache into page-locked slots
+            reader = feature_bin.FeatureBinReader(input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536),
+                                                  slots=8, nthreads=host_threads(args, world))
+            if world > 1:
+                reader.site_range = (reader.total_sites * rank // world, reader.total_sites * (rank + 1) // world)
+        else:
+            reader = None if idle else feature_io.FeatureFileReader(
+                input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536), slots=8,
+                nthreads=host_threads(args, world), byte_range=None if gz_single else _shard_of_file(input_path, rank, world))
+
+        def read():
+            try:
+                if torch.cuda.is_available():
+                    torch.cuda.set_device(device)              # page-locked slots belong to this rank's GPU context
+                for b in (reader or ()):
+                    rq.put(b)
+            except BaseException as e:                         # surfaced in the main thread
+                err.append(e)
+            rq.put(None)
+
+        rt = threading.Thread(target=read, daemon=True)
+        rt.start()
     model = load_model(args, device)
     args.input_path = input_path
 
@@ -503,23 +587,6 @@ def call_mods(args):
         finish_freq()
         print("[main] call_mods costs %.2f seconds.." % (time.time() - start))
         return sites
-    rq = queue.Queue(maxsize=2)
-    idle = gz_single and rank > 0                              # nothing to read on this rank
-    reader = None if idle else feature_io.FeatureFileReader(
-        input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536), slots=6,
-        nthreads=host_threads(args, world), byte_range=None if gz_single else _shard_of_file(input_path, rank, world))
-    err = []
-
-    def read():                                                # _read_features_file (:55-127)
-        try:
-            for b in (reader or ()):
-                rq.put(b)
-        except BaseException as e:                             # surfaced in the main thread
-            err.append(e)
-        rq.put(None)
-
-    rt = threading.Thread(target=read, daemon=True)
-    rt.start()
 
     def batches():
         while True:

@@ -6,6 +6,8 @@ reference's flag names and defaults.
     python -m deepsignal_plant_b200 call_freq -i calls.tsv -o freq.tsv [--bed] [--sort]
 
     python -m deepsignal_plant_b200 extract   -i reads.npz -o features.tsv      # decoded reads -> the reference's feature file
+    python -m deepsignal_plant_b200 extract   -i reads.npz -o features.dspf     # ... -> binary hand-off (feature_bin.py)
+    python -m deepsignal_plant_b200 call_mods -i features.dspf -m model.ckpt -o calls.tsv      # same calls, no text parsing
 
 Multi-GPU: launch ``call_mods`` or ``call_freq`` under torchrun, one process per GPU.  ``call_mods`` cuts the feature
 file (or the reads archive) into contiguous shards and concatenates the output in file order, no collective on the
@@ -48,7 +50,9 @@ def build_parser():
     g.add_argument("--region", action="store", type=str, required=False, default=None)
     g.add_argument("--positions", action="store", type=str, required=False, default=None)
     g = ex.add_argument_group("OUTPUT")
-    g.add_argument("--write_path", "-o", action="store", type=str, required=True)
+    g.add_argument("--write_path", "-o", action="store", type=str, required=True,
+                   help="the feature file; a name ending in .dspf selects the binary hand-off format that call_mods reads "
+                        "without parsing text (feature_bin.py), anything else the reference's 12-column text")
     g.add_argument("--w_is_dir", action="store", type=str, required=False, default="no",
                    help="only 'no' (one output file) is supported")
     g.add_argument("--w_batch_num", action="store", type=int, required=False, default=200, help="accepted for compatibility")
@@ -60,7 +64,8 @@ def build_parser():
 
     g = cm.add_argument_group("INPUT")
     g.add_argument("--input_path", "-i", action="store", type=str, required=True,
-                   help="a signal_feature file from `deepsignal_plant extract` (plain or .gz), or a decoded-reads archive "
+                   help="a signal_feature file from `deepsignal_plant extract` (plain or .gz), a binary feature file (.dspf from "
+                        "`extract -o x.dspf` or feature_bin.pack_feature_file), or a decoded-reads archive "
                         "(.npz written by extract_features.save_reads) to extract and call in one pass")
     g.add_argument("--f5_batch_size", action="store", type=int, default=30, required=False,
                    help="reads per extraction chunk for a decoded-reads archive; feature files are cut by site count")

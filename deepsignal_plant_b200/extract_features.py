@@ -579,6 +579,25 @@ def extract_to_file(args):
     step = max(1, int(args.f5_batch_size))
     total = 0
     pinned = {}
+    from . import feature_bin
+    if args.write_path.endswith(feature_bin.SUFFIX):
+        # binary hand-off to call_mods: the float32 the text file's values become in FloatTensor, no text in between
+        if args.gzip:
+            raise ValueError("--gzip does not apply to a binary feature file (%s)" % feature_bin.SUFFIX)
+        nth = int(getattr(args, "host_threads", 0) or 0) or min(16, os.cpu_count() or 1)
+        with feature_bin.FeatureBinWriter(args.write_path, args.seq_len, args.signal_len) as w:
+            for lo in range(0, allreads.n_reads, step):
+                batch = allreads.slice(lo, min(lo + step, allreads.n_reads))
+                sites = find_sites_device(batch, motif_seqs, args.mod_loc, chrom2len, args.seq_len, positions, regioninfo, dev)
+                if len(sites) == 0:
+                    continue
+                t = extract_tensors(batch, sites, args.seq_len, args.signal_len, args.normalize_method, True, seed=total, device=dev)
+                info_text, info_off = sampleinfo_packed(batch, sites, nth)             # host work under the kernels
+                host = [t[k].cpu().numpy() for k in ("kmer", "base_means", "base_stds", "base_signal_lens", "signals")]
+                w.write(*host, args.methy_label, info_text, info_off)
+                total += len(sites)
+        print("[extract] {} sites from {} reads in {:.2f} seconds".format(total, allreads.n_reads, time.time() - start))
+        return total
     with (gzip.open(path, "wb") if args.gzip else open(path, "wb")) as wf:
         for lo in range(0, allreads.n_reads, step):
             batch = allreads.slice(lo, min(lo + step, allreads.n_reads))

@@ -262,10 +262,11 @@ class FeatureFileReader:
                 yield b
 
 
-def format_calls(batch, probs, labels, nthreads=None):
+def format_calls(batch, probs, labels, nthreads=None, as_array=False):
     """bytes of the call_mods lines of one batch (``call_modifications.py:175-188``), each
     terminated by a newline (what ``_write_predstr_to_file`` writes, ``:279-280``).
-    ``probs`` (n, 2) float32 and ``labels`` (n) int32: numpy arrays or CPU torch tensors."""
+    ``probs`` (n, 2) float32 and ``labels`` (n) int32: numpy arrays or CPU torch tensors.
+    ``as_array``: return the uint8 array the formatter wrote into instead of a bytes copy of it."""
     L = _native.lib()
     n = batch.n
     p = np.ascontiguousarray(np.asarray(probs, dtype=np.float32))
@@ -275,10 +276,10 @@ def format_calls(batch, probs, labels, nthreads=None):
     kmer = batch.kmer if isinstance(batch.kmer, np.ndarray) else batch.kmer.numpy()
     kmer = np.ascontiguousarray(kmer[:n], dtype=np.float32)
     cap = int(batch.info_off[n]) + n * (64 + batch.seq_len)
-    out = C.create_string_buffer(cap)
+    out = np.empty(max(cap, 1), np.uint8)                  # not zero-filled; the formatter's threads touch the pages
     used = C.c_int64(0)
     _native.check(L.dsp_format_calls(batch.info_text.ctypes.data, batch.info_off.ctypes.data, kmer.ctypes.data,
                                      batch.seq_len, p.ctypes.data, lab.ctypes.data, n,
-                                     out, cap, C.byref(used), int(nthreads or min(16, os.cpu_count() or 1))),
+                                     out.ctypes.data, cap, C.byref(used), int(nthreads or min(16, os.cpu_count() or 1))),
                   "dsp_format_calls")
-    return out.raw[:used.value]
+    return out[:used.value] if as_array else out[:used.value].tobytes()

@@ -3,7 +3,9 @@
 pinned batches -> CUDA forward -> native formatter -> output file.  Prints one JSON line.
 
     python tools/bench_cli.py [--sites 1000000]
-    python tools/bench_cli.py --archive [--reads 2000]     # decoded-reads archive -> extract + call in one pass"""
+    python tools/bench_cli.py --archive [--reads 2000]     # decoded-reads archive -> extract + call in one pass
+    python tools/bench_cli.py --binary --sites 100000000   # binary feature file (.dspf) -> calls file, FRESH process
+    python tools/bench_cli.py --binary --host-only         # the same pipeline with the device stubbed out (host ceiling, no GPU)"""
 import argparse
 import json
 import os
@@ -27,7 +29,13 @@ def main():
     ap.add_argument("--archive", action="store_true", help="input is a decoded-reads .npz (extract_features.save_reads)")
     ap.add_argument("--reads", type=int, default=2000)
     ap.add_argument("--extract", action="store_true", help="time `extract` (archive -> the reference's feature file) instead")
+    ap.add_argument("--binary", action="store_true", help="input is a binary feature file (feature_bin.py); timed in a fresh process")
+    ap.add_argument("--host-only", action="store_true", help="with --binary: stub the device out, in-process (no GPU needed)")
+    ap.add_argument("--dir", default=None, help="where the synthetic files go (default: a temporary directory)")
+    ap.add_argument("--keep-free-gb", type=float, default=8.0, help="with --binary: shrink --sites so that this much disk stays free")
     a = ap.parse_args()
+    if a.binary:
+        return binary(a)
     if a.archive or a.extract:
         return archive(a)
     base_n = 8192
@@ -55,6 +63,83 @@ def main():
         print(json.dumps({"metric": "call_mods command line, feature file -> calls file (sites/s, wall clock incl. model load)",
                           "sites": n, "lines_written": nout, "seconds": dt, "value": n / dt, "unit": "sites/s",
                           "input_bytes": os.path.getsize(path), "output_bytes": os.path.getsize(out), "host_threads": a.nproc}))
+
+
+class _NoDevice:
+    """Stands in for ModelBiLSTM in --host-only runs: takes the batches, returns at once (prob 0.5 / label 0)."""
+    num_classes = 2
+
+    def submit_host(self, kmer, means, stds, lens, signals, logits, probs, labels):
+        probs.numpy()[:] = 0.5
+        labels.numpy()[:] = 0
+        return 0
+
+    def wait_host(self, ticket):
+        return None
+
+
+def binary(a):
+    """`call_mods -i features.dspf`: a.sites synthetic sites (one 65 536-site block of distinct sites, repeated) ->
+    calls file.  The command runs in a fresh interpreter: start-up, imports, CUDA context and model load are inside the
+    wall clock.  The file has just been written, so it is read from the page cache."""
+    import shutil
+    import subprocess
+    from deepsignal_plant_b200 import feature_bin
+    block_n = 65536
+    feats = synthetic.make_features(block_n, 13, 16, seed=1)
+    info = synthetic.make_sampleinfo(block_n, seed=1)
+    off = np.zeros(block_n + 1, np.int64)
+    np.cumsum([len(x) for x in info], out=off[1:])
+    text = np.frombuffer("".join(info).encode(), np.uint8)
+    tmp = tempfile.mkdtemp(dir=a.dir)
+    try:
+        path, ckpt, out = os.path.join(tmp, "features.dspf"), os.path.join(tmp, "m.ckpt"), os.path.join(tmp, "calls.tsv")
+        per_site = 1040 + 4 + 8 + text.size / block_n + 90            # input + output bytes
+        room = shutil.disk_usage(tmp).free - a.keep_free_gb * 2 ** 30
+        sites = int(min(a.sites, max(block_n, room / per_site)))
+        reps = max(1, sites // block_n)
+        t0 = time.perf_counter()
+        with feature_bin.FeatureBinWriter(path, 13, 16) as w:
+            for _ in range(reps):
+                w.write(feats["kmer"], feats["base_means"], feats["base_stds"], feats["base_signal_lens"], feats["signals"], 0, text, off)
+        t_write = time.perf_counter() - t0
+        n = reps * block_n
+        torch.manual_seed(1234)
+        torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
+        argv = ["call_mods", "-i", path, "-m", ckpt, "-o", out, "--host_threads", str(a.nproc)]
+        env = dict(os.environ, DSP_B200_PROFILE="1", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        if a.host_only:
+            from deepsignal_plant_b200 import call_modifications as cm
+            cm.load_model = lambda args, device=0: _NoDevice()
+            if not torch.cuda.is_available():
+                torch.Tensor.pin_memory = lambda self, *args, **kw: self         # pageable slots: this run times host code only
+            os.environ["DSP_B200_PROFILE"] = "1"
+            t0 = time.perf_counter()
+            cli.main(argv)
+            dt = time.perf_counter() - t0
+            lines = []
+        else:
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, "-m", "deepsignal_plant_b200"] + argv, env=env, capture_output=True, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise SystemExit("call_mods failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+            lines = [l for l in r.stdout.splitlines() if "seconds" in l]
+        nout = 0
+        with open(out, "rb") as f:
+            while True:
+                blk = f.read(1 << 26)
+                if not blk:
+                    break
+                nout += blk.count(b"\n")
+        print(json.dumps({"metric": "call_mods command line, binary feature file (.dspf) -> calls file (sites/s, wall clock of a fresh "
+                                    "process incl. interpreter start, imports, CUDA context, model load)" if not a.host_only else
+                                    "call_mods host pipeline with the device stubbed out (in-process)",
+                          "sites": n, "sites_requested": a.sites, "lines_written": nout, "seconds": dt, "value": n / dt, "unit": "sites/s",
+                          "input_bytes": os.path.getsize(path), "output_bytes": os.path.getsize(out), "host_threads": a.nproc,
+                          "file_written_in_s": t_write, "host_breakdown": lines}))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def archive(a):
