@@ -231,7 +231,7 @@ def load_model(args, device=0):
     return model
 
 
-def call_mods_stream(model, batches, write, depth=2):
+def call_mods_stream(model, batches, write, depth=2, format_threads=None):
     """Drive the model over an iterable of ``feature_io.FeatureBatch`` (page-locked tensors):
     batch i+1 is submitted before batch i is collected, so its host->device copies overlap
     batch i's kernels; a formatter thread turns finished batches into output lines (native code on the host
@@ -254,6 +254,7 @@ def call_mods_stream(model, batches, write, depth=2):
     pin = torch.cuda.is_available()                  # result staging only; the model itself refuses to run without a GPU
     fq = queue.Queue(maxsize=1)
     ferr = []
+    t_begin = tick()
 
     def formatter():                                 # the per-site text loop of _call_mods (:175-188), off the submit path
         while True:
@@ -266,7 +267,7 @@ def call_mods_stream(model, batches, write, depth=2):
                 b, slot = item
                 probs, labels = slot[1][:b.n].numpy(), slot[2][:b.n].numpy()
                 t1 = tick()
-                text = feature_io.format_calls(b, probs, labels, as_array=True)     # no copy: the writer owns it from here
+                text = feature_io.format_calls(b, probs, labels, format_threads, as_array=True)     # no copy: the writer owns it
                 t2 = tick()
                 write(text)
                 fprof["format"] += t2 - t1
@@ -301,10 +302,9 @@ def call_mods_stream(model, batches, write, depth=2):
                 break
             cap = b.kmer.shape[0]
             slot = None
-            for i, o in enumerate(list(outs)):
-                if o[0].shape[0] >= cap:
-                    outs.remove(o)
-                    slot = o
+            for i in range(len(outs)):                   # the formatter thread only appends; this thread alone removes
+                if outs[i][0].shape[0] >= cap:
+                    slot = outs.pop(i)
                     break
             if slot is None:
                 mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory() if pin else torch.empty(shape, dtype=dt)
@@ -324,6 +324,7 @@ def call_mods_stream(model, batches, write, depth=2):
     if ferr:
         raise ferr[0]
     if os.environ.get("DSP_B200_PROFILE"):
+        print("call_mods_stream: %d sites in %.3f seconds = %.0f sites/s (first batch in to last batch out)" % (sites, tick() - t_begin, sites / max(tick() - t_begin, 1e-9)))
         print("call_mods_stream host seconds: submitting thread: " + ", ".join("%s %.3f" % kv for kv in prof.items())
               + "; formatter thread: " + ", ".join("%s %.3f" % kv for kv in fprof.items()))
     return sites, (float(np.mean(acc)) if acc else 0.0), nb
@@ -481,18 +482,19 @@ def call_mods(args):
     rq = queue.Queue(maxsize=2)
     err = []
     rt = None
+    depth = max(1, min(int(getattr(args, "stream_depth", 3) or 3), 6))           # batches in flight on the device
     if not from_reads:
         idle = gz_single and rank > 0                          # nothing to read on this rank
         if from_bin:
             # every rank reads a contiguous site range; sections go straight from the page cache into page-locked slots
             reader = feature_bin.FeatureBinReader(input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536),
-                                                  slots=8, nthreads=host_threads(args, world))
+                                                  slots=depth + 6, nthreads=int(getattr(args, "reader_threads", 0) or 0) or min(8, host_threads(args, world)))
             if world > 1:
                 reader.site_range = (reader.total_sites * rank // world, reader.total_sites * (rank + 1) // world)
         else:
             reader = None if idle else feature_io.FeatureFileReader(
-                input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536), slots=8,
-                nthreads=host_threads(args, world), byte_range=None if gz_single else _shard_of_file(input_path, rank, world))
+                input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536), slots=depth + 6,
+                nthreads=int(getattr(args, "reader_threads", 0) or 0) or host_threads(args, world), byte_range=None if gz_single else _shard_of_file(input_path, rank, world))
 
         def read():
             try:
@@ -595,7 +597,7 @@ def call_mods(args):
                 return
             yield b
 
-    sites, accuracy, nb = call_mods_stream(model, batches(), sink)
+    sites, accuracy, nb = call_mods_stream(model, batches(), sink, depth, int(getattr(args, "format_threads", 0) or 0) or min(8, host_threads(args, world)))
     rt.join()
     finish_writer()
     if err:

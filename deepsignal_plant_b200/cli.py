@@ -115,6 +115,12 @@ def build_parser():
                     help="the reference's number of worker processes: kept with its default; the native parser / formatter use --host_threads")
     cm.add_argument("--host_threads", action="store", type=int, default=0,
                     help="host threads for parsing / formatting; 0 (default) = all cores, shared evenly between the ranks of a torchrun job")
+    cm.add_argument("--reader_threads", action="store", type=int, default=0,
+                    help="host threads of the feature reader alone (0 = --host_threads for text, min(8, --host_threads) for .dspf)")
+    cm.add_argument("--format_threads", action="store", type=int, default=0,
+                    help="host threads of the output formatter alone (0 = min(8, --host_threads))")
+    cm.add_argument("--stream_depth", action="store", type=int, default=3,
+                    help="feature batches in flight on the device (1-6); the reader keeps this many + 6 page-locked slots")
     cm.add_argument("--nproc_gpu", action="store", type=int, default=2,
                     help="accepted for compatibility; use torchrun for one process per GPU")
 
@@ -138,10 +144,27 @@ def build_parser():
     return parser
 
 
+def _warm_device_while_importing():
+    """The CUDA context of this rank's GPU comes up on a side thread (dsp_device_warmup: ctypes only) while the main
+    thread imports torch and reads the checkpoint -- about a second of a fresh process's start-up, off the critical path.
+    Failures are left to the real call sites, which report them."""
+    import os
+    import threading
+
+    def warm():
+        try:
+            from . import _native
+            _native.lib().dsp_device_warmup(int(os.environ.get("LOCAL_RANK", "0")))
+        except Exception:                                   # noqa: BLE001 -- no GPU / no library: reported by call_mods itself
+            pass
+    threading.Thread(target=warm, daemon=True).start()
+
+
 def main(argv=None):
     parser = build_parser()
     args = parser.parse_args(argv)
     if args.module == "call_mods":
+        _warm_device_while_importing()
         from .call_modifications import call_mods
         call_mods(args)
     elif args.module == "extract":

@@ -171,11 +171,25 @@ class _HostOnlyModel:
         return None
 
 
-@pytest.mark.parametrize("batch_sites", [16, 100])
-def test_call_mods_stream_writes_batches_in_order_while_slots_recycle(tmp_path, batch_sites):
+def _repack(src, dst, block_sizes):
+    """Copy a .dspf file into blocks of the given sizes (cycled)."""
+    rd = feature_bin.FeatureBinReader(src, batch_sites=1 << 20, pinned=False, slots=1)
+    b = next(iter(rd))
+    arrs = [t.numpy() for t in b.arrays()] + [b.labels.numpy()]
+    with feature_bin.FeatureBinWriter(dst, rd.T, rd.S) as w:
+        a, k = 0, 0
+        while a < b.n:
+            z = min(a + block_sizes[k % len(block_sizes)], b.n)
+            w.write(*[x[a:z] for x in arrs], b.info_text, b.info_off[a:z + 1])
+            a, k = z, k + 1
+
+
+@pytest.mark.parametrize("batch_sites,block_sizes", [(16, (64,)), (100, (64,)), (128, (10, 64, 5, 100, 63))])
+def test_call_mods_stream_writes_batches_in_order_while_slots_recycle(tmp_path, batch_sites, block_sizes):
     from deepsignal_plant_b200 import call_modifications as cm
-    p = str(tmp_path / "f.dspf")
-    feature_bin.pack_feature_file(TEXT, p, batch_sites=64, nthreads=2)
+    p0, p = str(tmp_path / "f0.dspf"), str(tmp_path / "f.dspf")
+    feature_bin.pack_feature_file(TEXT, p0, nthreads=2)
+    _repack(p0, p, block_sizes)                                  # batches of unequal sizes: result slots of several sizes
     want = b"".join(feature_io.format_calls(b, *_HostOnlyModel.answer(b.base_means))
                     for b in feature_bin.FeatureBinReader(p, batch_sites=batch_sites, pinned=False, slots=2))
     got = []

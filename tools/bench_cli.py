@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--binary", action="store_true", help="input is a binary feature file (feature_bin.py); timed in a fresh process")
     ap.add_argument("--host-only", action="store_true", help="with --binary: stub the device out, in-process (no GPU needed)")
     ap.add_argument("--dir", default=None, help="where the synthetic files go (default: a temporary directory)")
+    ap.add_argument("--variants", default="", help="with --binary: extra timed runs, comma-separated reader_threads:format_threads:stream_depth")
+    ap.add_argument("--out-dir", default=None, help="with --binary: directory of the calls file (default: next to the input)")
     ap.add_argument("--keep-free-gb", type=float, default=8.0, help="with --binary: shrink --sites so that this much disk stays free")
     a = ap.parse_args()
     if a.binary:
@@ -94,14 +96,32 @@ def binary(a):
     tmp = tempfile.mkdtemp(dir=a.dir)
     try:
         path, ckpt, out = os.path.join(tmp, "features.dspf"), os.path.join(tmp, "m.ckpt"), os.path.join(tmp, "calls.tsv")
-        per_site = 1040 + 4 + 8 + text.size / block_n + 90            # input + output bytes
+        if a.out_dir:
+            out = os.path.join(tempfile.mkdtemp(dir=a.out_dir), "calls.tsv")
+        per_site = 1040 + 4 + 8 + text.size / block_n + (0 if a.out_dir else 90)            # input (+ output) bytes
         room = shutil.disk_usage(tmp).free - a.keep_free_gb * 2 ** 30
         sites = int(min(a.sites, max(block_n, room / per_site)))
         reps = max(1, sites // block_n)
+        variants = []
         t0 = time.perf_counter()
         with feature_bin.FeatureBinWriter(path, 13, 16) as w:
-            for _ in range(reps):
-                w.write(feats["kmer"], feats["base_means"], feats["base_stds"], feats["base_signal_lens"], feats["signals"], 0, text, off)
+            w.write(feats["kmer"], feats["base_means"], feats["base_stds"], feats["base_signal_lens"], feats["signals"], 0, text, off)
+        if reps > 1:                                       # the same block again and again, written by several threads
+            from concurrent.futures import ThreadPoolExecutor
+            with open(path, "rb") as f:
+                block = f.read()[feature_bin.HEADER_BYTES:]
+            fd = os.open(path, os.O_WRONLY)
+            try:
+                os.ftruncate(fd, feature_bin.HEADER_BYTES + reps * len(block))
+                def put(i):
+                    view, at = memoryview(block), feature_bin.HEADER_BYTES + i * len(block)
+                    while len(view):
+                        k = os.pwrite(fd, view, at)
+                        view, at = view[k:], at + k
+                with ThreadPoolExecutor(8) as ex:
+                    list(ex.map(put, range(1, reps)))
+            finally:
+                os.close(fd)
         t_write = time.perf_counter() - t0
         n = reps * block_n
         torch.manual_seed(1234)
@@ -117,14 +137,36 @@ def binary(a):
             t0 = time.perf_counter()
             cli.main(argv)
             dt = time.perf_counter() - t0
-            lines = []
+            lines, first_s, clocks = [], None, None
         else:
+            # an untimed first process on one block: the interpreter, torch and the CUDA libraries are paged in once per box
+            warm = os.path.join(tmp, "warm.dspf")
+            with feature_bin.FeatureBinWriter(warm, 13, 16) as w:
+                w.write(feats["kmer"], feats["base_means"], feats["base_stds"], feats["base_signal_lens"], feats["signals"], 0, text, off)
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, "-m", "deepsignal_plant_b200", "call_mods", "-i", warm, "-m", ckpt, "-o", out + ".warm"],
+                               env=env, capture_output=True, text=True)
+            first_s = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise SystemExit("call_mods failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+            import bench                                   # the repo's nvidia-smi sampler (clocks, power, throttle reasons)
+            sampler = bench.ClockSampler(0)
+            sampler.start()
             t0 = time.perf_counter()
             r = subprocess.run([sys.executable, "-m", "deepsignal_plant_b200"] + argv, env=env, capture_output=True, text=True)
             dt = time.perf_counter() - t0
+            clocks = sampler.summary()
+            clocks["power_w_series"] = [round(float(x[2])) for x in sampler.rows]
             if r.returncode != 0:
                 raise SystemExit("call_mods failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
             lines = [l for l in r.stdout.splitlines() if "seconds" in l]
+            for v in [x for x in a.variants.split(",") if x]:
+                rt_, ft_, dp_ = v.split(":")
+                t1 = time.perf_counter()
+                rv = subprocess.run([sys.executable, "-m", "deepsignal_plant_b200"] + argv + ["--reader_threads", rt_, "--format_threads", ft_,
+                                    "--stream_depth", dp_], env=env, capture_output=True, text=True)
+                variants.append({"reader_threads:format_threads:stream_depth": v, "seconds": time.perf_counter() - t1, "rc": rv.returncode,
+                                 "host_breakdown": [l for l in rv.stdout.splitlines() if "seconds" in l]})
         nout = 0
         with open(out, "rb") as f:
             while True:
@@ -137,9 +179,11 @@ def binary(a):
                                     "call_mods host pipeline with the device stubbed out (in-process)",
                           "sites": n, "sites_requested": a.sites, "lines_written": nout, "seconds": dt, "value": n / dt, "unit": "sites/s",
                           "input_bytes": os.path.getsize(path), "output_bytes": os.path.getsize(out), "host_threads": a.nproc,
-                          "file_written_in_s": t_write, "host_breakdown": lines}))
+                          "file_written_in_s": t_write, "one_block_process_s": first_s, "host_breakdown": lines, "clocks": clocks, "variants": variants}))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+        if a.out_dir:
+            shutil.rmtree(os.path.dirname(out), ignore_errors=True)
 
 
 def archive(a):
