@@ -508,11 +508,125 @@ def _warm_device_in_background(device):
     threading.Thread(target=lambda: L.dsp_device_warmup(int(device)), daemon=True).start()
 
 
-def calculate_mods_frequency(mods_files, prob_cf, contig_name=None, device=0):
-    """call mod_freq from call_mods files (``call_mods_freq.py:29-74``).  Files are read in
-    argument order; returns a ``FreqTable`` (dict-like ``sitekey2stats``)."""
+# ---- bounded host memory: key-hash shards, the files re-read once per shard ---------------------------------------
+# The reference streams its input line by line through a dict (``call_mods_freq.py:45-66``); what it keeps is one
+# SiteStats per site.  Here the parsed columns of every record of a pass sit in host memory (HOST_RECORD_BYTES each)
+# until the GPU has them, so an input that does not fit is aggregated shard by shard: shard s of S holds the records
+# whose site key hashes to s.  A site's records never span two shards and keep their file order inside one, so every
+# float64 sum is the one-pass sum; rows carry the global index of their first callable record, which restores the
+# dict's insertion order at the end.  The price is parsing: the files are read S times (128 M records/s on 16 threads).
+
+HOST_RECORD_BYTES = 80
+STREAM_CHUNK_BYTES = 1 << 30
+
+
+def default_host_record_budget():
+    """Records whose parsed columns fit in half of the host memory that is available now (at most one aggregation pass)."""
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError, AttributeError):
+        avail = 16 << 30
+    return int(min(MAX_RECORDS_PER_PASS, max(1 << 20, avail // 2 // HOST_RECORD_BYTES)))
+
+
+def estimate_records(mods_files):
+    """Upper-ish estimate of the number of call_mods lines without reading the files: bytes / (mean line length of the
+    first plain file's first MB); a .gz file counts 5 x its size."""
+    total, line = 0, None
+    for f in mods_files:
+        size = os.path.getsize(f)
+        if f.endswith(".gz"):
+            size *= 5
+        elif line is None and size:
+            with open(f, "rb") as fh:
+                head = fh.read(1 << 20)
+            if head.count(b"\n"):
+                line = len(head) / head.count(b"\n")
+        total += size
+    return int(total / max(line or 50.0, 20.0) * 1.05) + 1
+
+
+def _file_chunks(mods_files, chunk_bytes):
+    """(path, byte_range) pieces in file order; a line belongs to the piece its first byte lies in; .gz files go whole."""
+    for f in mods_files:
+        size = os.path.getsize(f)
+        if size == 0:
+            continue
+        if f.endswith(".gz") or size <= chunk_bytes:
+            yield f, None
+        else:
+            for lo in range(0, size, chunk_bytes):
+                yield f, (lo, min(lo + chunk_bytes, size))
+
+
+def calculate_mods_frequency_streaming(mods_files, prob_cf, contigs=None, device=0, max_host_records=None, shards=None,
+                                       chunk_bytes=None):
+    """``calculate_mods_frequency`` with host memory bounded by ``max_host_records`` records (+ one chunk of the input):
+    -> ``FreqTable`` with the same rows, order and bits as the one-pass result.  ``contigs``: None or the set of
+    chromosome names to keep (``call_mods_freq.py:52``).  ``shards`` overrides the shard count derived from the
+    estimated input size."""
     if type(mods_files) is str:
         mods_files = [mods_files, ]
+    budget = int(max_host_records or default_host_record_budget())
+    if shards is None:
+        shards = max(1, -(-int(estimate_records(mods_files) * 1.25) // budget))       # hashing balances sites, not records
+    shards = int(shards)
+    chunk_bytes = int(chunk_bytes or STREAM_CHUNK_BYTES)
+    wanted = None if contigs is None else set(contigs)
+    gid = {}                                           # chromosome name -> id, first-seen order: the same in every pass
+    tables, n_total = [], 0
+    for s in range(shards):
+        parts, gidx, base = [], [], 0
+        for path, rng in _file_chunks(mods_files, chunk_bytes):
+            rec = read_mods_file(path, byte_range=rng)
+            n = len(rec)
+            if n == 0:
+                continue
+            codes, table = rec.chrom_codes()
+            ids = np.array([gid.setdefault(nm, len(gid)) for nm in table], np.int64)[codes]
+            keep = owner_of_key(make_keys(ids, rec.pos), shards) == s if shards > 1 else np.ones(n, bool)
+            if wanted is not None:
+                keep &= rec.chrom_in(wanted)
+            idx = np.flatnonzero(keep)
+            if idx.size:
+                parts.append(rec.select(idx))
+                gidx.append(idx + base)
+            base += n
+            del rec, codes, ids, keep
+        n_total = base
+        if not parts:
+            continue
+        sub = Records.concat(parts)
+        g = np.concatenate(gidx)
+        del parts, gidx
+        t = aggregate_records(sub, prob_cf, None, False, device)
+        t.first_index = g[t.first_index]               # global record index of the site's first callable record
+        tables.append(t)
+        del sub, g
+    table = FreqTable.concat(tables)
+    table = table.reorder(np.argsort(table.first_index, kind="stable"))
+    table.n_records = n_total
+    return table
+
+
+def calculate_mods_frequency(mods_files, prob_cf, contig_name=None, device=0, max_host_records=None):
+    """call mod_freq from call_mods files (``call_mods_freq.py:29-74``).  Files are read in
+    argument order; returns a ``FreqTable`` (dict-like ``sitekey2stats``).  An input whose parsed records would not
+    fit in ``max_host_records`` (default: half of the available host memory) goes through
+    ``calculate_mods_frequency_streaming``."""
+    if type(mods_files) is str:
+        mods_files = [mods_files, ]
+    budget = int(max_host_records or default_host_record_budget())
+    if estimate_records(mods_files) > budget:
+        _warm_device_in_background(device)
+        table = calculate_mods_frequency_streaming(mods_files, prob_cf, None if contig_name is None else {contig_name}, device, budget)
+        count, used = table.n_records, table.n_used
+        if count > 0:
+            if contig_name is None:
+                print("{:.2f}% ({} of {}) calls used..".format(used / float(count) * 100, used, count))
+            else:
+                print("{:.2f}% ({} of {}) calls used for {}..".format(used / float(count) * 100, used, count, contig_name))
+        return table
     t0 = time.perf_counter()
     _warm_device_in_background(device)               # the CUDA context comes up while the files are parsed
     rec = Records.concat([read_mods_file(f) for f in mods_files])
@@ -709,7 +823,7 @@ def call_mods_frequency_to_file(args):
         return
     if contigs is None:
         print("read the input files..")
-        sites_stats = calculate_mods_frequency(mods_files, args.prob_cf)
+        sites_stats = calculate_mods_frequency(mods_files, args.prob_cf, max_host_records=int(getattr(args, "max_host_records", 0) or 0) or None)
         print("write the result..")
         write_sitekey2stats(sites_stats, args.result_file, args.sort, args.bed, args.gzip)
     else:
@@ -719,6 +833,14 @@ def call_mods_frequency_to_file(args):
         # GPU pass in the reference's concatenation order.
         print("start processing {} contigs..".format(len(contigs)))
         wanted = set(contigs)
+        budget = int(getattr(args, "max_host_records", 0) or 0) or default_host_record_budget()
+        if estimate_records(mods_files) > budget:
+            # too large to hold even once: the listed contigs in key-hash shards, rows put in the per-contig order afterwards
+            table = calculate_mods_frequency_streaming(mods_files, args.prob_cf, wanted, 0, budget)
+            print("{} of {} calls used for {} contigs..".format(table.n_used, table.n_records, len(contigs)))
+            write_sitekey2stats(order_by_contig(table, contigs, args.sort), args.result_file, False, args.bed, args.gzip)
+            print("[main]call_freq costs %.1f seconds.." % (time.time() - start))
+            return
         parts, n_all = [], 0
         for f in mods_files:
             r = read_mods_file(f)

@@ -141,6 +141,9 @@ def build_parser():
                         "per-contig mode (call_mods_freq.py:203-215)")
     g.add_argument("--nproc", action="store", type=int, required=False, default=1,
                    help="accepted for compatibility (the reference's per-contig worker processes; here: torchrun ranks)")
+    g.add_argument("--max_host_records", action="store", type=int, required=False, default=0,
+                   help="records whose parsed columns may sit in host memory at once (80 bytes each; 0 = half of the available "
+                        "memory); a larger input is aggregated in key-hash shards, the files re-read once per shard, same table")
     return parser
 
 

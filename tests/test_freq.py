@@ -284,3 +284,98 @@ def test_gpu_freq_key_hash_passes_equal_one_pass(sort_by_key):
     assert len(one[0]) == len(many[0]) > 2000
     for a, b in zip(one, many):
         assert a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+# ---- bounded host memory: key-hash shards, the files re-read once per shard ------------------------------------------
+def _standin_aggregate_records(rec, prob_cf, contig_name=None, sort_by_key=False, device=0):
+    """TEST stand-in for the device aggregation (cf.aggregate_records) with the oracle's semantics -- float64 left to
+    right per key in record order, rows in first-callable-appearance order -- so that the streaming host logic runs on a
+    CPU box.  Lives in tests/: the package has no CPU path."""
+    assert contig_name is None and not sort_by_key
+    chrom, pos, p0, p1, lab = rec.chrom.tolist(), rec.pos.tolist(), rec.p0.tolist(), rec.p1.tolist(), rec.label.tolist()
+    table = {}
+    for i in range(len(rec)):
+        if abs(p0[i] - p1[i]) < prob_cf:
+            continue
+        r = table.get((chrom[i], pos[i]))
+        if r is None:
+            r = table[(chrom[i], pos[i])] = [i, 0.0, 0.0, 0, 0]
+        r[1] += p0[i]; r[2] += p1[i]
+        r[3 if lab[i] == 1 else 4] += 1
+    first = np.array([r[0] for r in table.values()], np.int64)
+    strand, pis, kmer = rec.meta_at(first)
+    col = lambda j, dt: np.array([r[j] for r in table.values()], dt)
+    return cf.FreqTable(np.array([k[0] for k in table], object), np.array([k[1] for k in table], np.int64), strand, pis, kmer,
+                        col(1, np.float64), col(2, np.float64), col(3, np.int32), col(4, np.int32),
+                        (col(3, np.int32) + col(4, np.int32)), first, len(rec), int(sum(r[3] + r[4] for r in table.values())))
+
+
+def _two_files(tmp_path, lines):
+    third = len(lines) // 3
+    a, b, c = tmp_path / "a.tsv", tmp_path / "b.tsv.gz", tmp_path / "c.tsv"
+    a.write_text("\n".join(lines[:third]) + "\n")
+    with gzip.open(b, "wt") as f:
+        f.write("\n".join(lines[third:2 * third]) + "\n")
+    c.write_text("\n".join(lines[2 * third:]) + "\n")
+    return [str(a), str(b), str(c)]
+
+
+@pytest.mark.parametrize("name", FREQ_CASES)
+@pytest.mark.parametrize("shards,chunk", [(1, 1 << 30), (3, 700_000), (8, 40_000)])
+def test_streaming_shards_give_the_reference_bytes_with_a_standin_device(name, shards, chunk, tmp_path, monkeypatch):
+    monkeypatch.setattr(cf, "aggregate_records", _standin_aggregate_records)
+    e = cases.MANIFEST["freq"][name]
+    lines = inputs(e["input"])
+    files = _two_files(tmp_path, lines)
+    t = cf.calculate_mods_frequency_streaming(files, e["prob_cf"], shards=shards, chunk_bytes=chunk)
+    assert t.n_records == len(lines)
+    assert cf.render_table(t, e["sort"], e["bed"]) == cases.read_gz(name + ".txt.gz")
+
+
+def test_streaming_is_chosen_by_the_record_budget_and_filters_contigs(tmp_path, monkeypatch, capsys):
+    monkeypatch.setattr(cf, "aggregate_records", _standin_aggregate_records)
+    monkeypatch.setattr(cf, "_warm_device_in_background", lambda device: None)
+    lines = inputs("synth")
+    files = _two_files(tmp_path, lines)
+    est = cf.estimate_records(files)
+    assert 0.8 * len(lines) < est < 2.5 * len(lines)          # the .gz member counts 5 x its size
+    t = cf.calculate_mods_frequency(files, 0.5, max_host_records=20000)           # ~100 000 records: several shards
+    assert "calls used.." in capsys.readouterr().out
+    assert cf.render_table(t) == freq_oracle.render(freq_oracle.aggregate(lines, 0.5))
+    one = cf.calculate_mods_frequency(files, 0.5, contig_name="chr3", max_host_records=20000)
+    assert cf.render_table(one) == freq_oracle.render(freq_oracle.aggregate(lines, 0.5, "chr3")) and one.n_records == len(lines)
+    assert len(cf.calculate_mods_frequency_streaming(files, 0.5, contigs={"nothing"}, shards=2)) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["freq_synth_cf0p5_unsorted_tsv", "freq_edge_cf0p0_sorted_bed"])
+def test_gpu_streaming_call_freq_equals_reference_bytes(name, tmp_path):
+    # the same through the real device aggregation and the command line: --max_host_records far below the input size
+    from deepsignal_plant_b200 import cli
+    e = cases.MANIFEST["freq"][name]
+    lines = inputs(e["input"])
+    files = _two_files(tmp_path, lines)
+    t = cf.calculate_mods_frequency_streaming(files, e["prob_cf"], shards=5, chunk_bytes=300_000)
+    assert cf.render_table(t, e["sort"], e["bed"]) == cases.read_gz(name + ".txt.gz")
+    out = tmp_path / "out.txt"
+    argv = ["call_freq", "-o", str(out), "--prob_cf", str(e["prob_cf"]), "--max_host_records", str(max(4, len(lines) // 7))]
+    for f in files:
+        argv += ["-i", f]
+    assert cli.main(argv + (["--sort"] if e["sort"] else []) + (["--bed"] if e["bed"] else [])) == 0
+    assert out.read_text() == cases.read_gz(name + ".txt.gz")
+
+
+@pytest.mark.gpu
+def test_gpu_streaming_contigs_mode_equals_the_in_memory_mode(tmp_path):
+    from deepsignal_plant_b200 import cli
+    lines = inputs("synth")
+    files = _two_files(tmp_path, lines)
+    outs = []
+    for extra in ([], ["--max_host_records", "9000"]):
+        out = tmp_path / ("o%d.txt" % len(outs))
+        argv = ["call_freq", "-o", str(out), "--prob_cf", "0.2", "--contigs", "chr3,chr11,chr1", "--sort"] + extra
+        for f in files:
+            argv += ["-i", f]
+        assert cli.main(argv) == 0
+        outs.append(out.read_text())
+    assert outs[0] == outs[1] and outs[0].count("\n") > 100
