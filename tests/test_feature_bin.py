@@ -208,3 +208,28 @@ def test_call_mods_stream_surfaces_a_failing_writer(tmp_path):
         raise OSError("disk full")
     with pytest.raises(OSError, match="disk full"):
         cm.call_mods_stream(_HostOnlyModel(), feature_bin.FeatureBinReader(p, batch_sites=32, pinned=False, slots=8), broken)
+
+
+@pytest.mark.gpu
+def test_two_ranks_take_contiguous_site_ranges_of_a_binary_file(tmp_path):
+    # torchrun, 2 ranks (sharing the GPU here): every rank reads its site range of the .dspf file, rank 0 concatenates the
+    # parts in rank order -> the sites of the file, in file order, exactly once
+    import subprocess
+    import sys
+    import torch
+    from deepsignal_plant_b200.models import ModelBiLSTM
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    binary = str(tmp_path / "f.dspf")
+    feature_bin.pack_feature_file(TEXT, binary, batch_sites=100)
+    ckpt = str(tmp_path / "m.ckpt")
+    torch.manual_seed(1234)
+    torch.save(ModelBiLSTM(13, 16, 3, 1, 2, 0, 256, 16, 4, True, True).state_dict(), ckpt)
+    out = str(tmp_path / "calls.tsv")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29741", "-m", "deepsignal_plant_b200", "call_mods", "-i", binary, "-m", ckpt, "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    _, info = collect(feature_bin.FeatureBinReader(binary, pinned=False))
+    lines = open(out).read().splitlines()
+    assert len(lines) == FEAT["n"] and ["\t".join(l.split("\t")[:6]) for l in lines] == info
+    assert all(abs(float(l.split("\t")[6]) + float(l.split("\t")[7]) - 1.0) < 2e-6 for l in lines)
