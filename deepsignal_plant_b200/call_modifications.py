@@ -609,21 +609,44 @@ def call_mods(args):
     return sites
 
 
+def _copy_into(src_path, dst_path, offset):
+    """Copy the whole of ``src_path`` into ``dst_path`` at byte ``offset`` (in the kernel where the filesystem allows)."""
+    size = os.path.getsize(src_path)
+    with open(src_path, "rb") as src, open(dst_path, "r+b") as dst:
+        done = 0
+        if hasattr(os, "copy_file_range"):
+            try:
+                while done < size:
+                    k = os.copy_file_range(src.fileno(), dst.fileno(), min(size - done, 1 << 30), done, offset + done)
+                    if k <= 0:
+                        break
+                    done += k
+            except OSError:                                     # across filesystems / not supported: plain copy below
+                pass
+        src.seek(done)
+        dst.seek(offset + done)
+        while done < size:
+            blk = src.read(min(1 << 24, size - done))
+            if not blk:
+                raise IOError("%s shrank while it was merged" % src_path)
+            dst.write(blk)
+            done += len(blk)
+
+
 def _merge_parts(result_file, rank, world):
-    """Rank 0 concatenates the per-rank parts in rank order (contiguous shards -> input order)."""
+    """The per-rank parts become one file in rank order (contiguous shards -> input order): the ranks exchange their
+    part sizes, rank 0 sizes the result, and every rank copies ITS part to its offset -- the merge is as parallel as
+    the run was, instead of one process re-writing everybody's output (58 GB of calls for 10^9 sites)."""
     if world <= 1:
         return
     import torch.distributed as dist
-    dist.barrier()
+    part = "%s.part%05d" % (result_file, rank)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, os.path.getsize(part))
     if rank == 0:
         with open(result_file, "wb") as out:
-            for r in range(world):
-                part = "%s.part%05d" % (result_file, r)
-                with open(part, "rb") as f:
-                    while True:
-                        blk = f.read(1 << 24)
-                        if not blk:
-                            break
-                        out.write(blk)
-                os.remove(part)
+            out.truncate(sum(sizes))
+    dist.barrier()
+    _copy_into(part, result_file, sum(sizes[:rank]))
+    os.remove(part)
     dist.barrier()

@@ -1,5 +1,7 @@
 """CPU: host-side mirror of the reference interface (constructor, state_dict contract,
 text formatting, synthetic data) -- no kernel calls."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -131,3 +133,18 @@ def test_command_line_accepts_the_reference_flags():
             c.batch_size, c.motifs, c.mod_loc) == ("both_bilstm", 13, 16, 3, 1, 2, 256, 16, 4, 512, "CG", 0)
     f = parser.parse_args(["call_freq", "-i", "a", "-i", "b", "-o", "o"])
     assert f.input_path == ["a", "b"] and f.prob_cf == 0.5 and not f.bed and not f.sort
+
+
+def test_rank_parts_merge_in_rank_order(tmp_path):
+    # call_mods under torchrun: every rank copies its own part to its offset of the one result file (gloo, 3 ranks)
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "calls.tsv")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "3", "--master-addr", "127.0.0.1",
+           "--master-port", str(29400 + os.getpid() % 500), os.path.join(root, "tests", "merge_parts_worker.py"), out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    want = b"".join((b"rank %d line\n" % k) * (0 if k == 1 else 1000 * (k + 1) + 7) for k in range(3))
+    assert open(out, "rb").read() == want
+    assert sorted(os.listdir(tmp_path)) == ["calls.tsv"]               # the parts are gone
