@@ -208,8 +208,10 @@ def command_line_run(sites, timeout_s=150, extra=()):
     binary feature file of `sites` sites, timed in a FRESH process by tools/bench_cli.py --binary: interpreter start,
     imports, CUDA context, checkpoint load, the stream, the calls file.  Never raises: a failure is reported in the object."""
     import re
+    import tempfile
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_cli.py"), "--binary", "--sites", str(int(sites))] + list(extra),
+        where = ["--dir", "/dev/shm", "--out-dir", tempfile.gettempdir()] if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else []
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_cli.py"), "--binary", "--sites", str(int(sites))] + where + list(extra),
                            capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
         rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if r.returncode != 0 or not rows:
@@ -222,7 +224,7 @@ def command_line_run(sites, timeout_s=150, extra=()):
                 stream = {"sites_per_s": int(m.group(1)) / max(float(m.group(2)), 1e-9), "seconds": float(m.group(2))}
         return {"metric": "call_mods command line, binary feature file -> calls file, wall clock of a fresh process (sites/s)",
                 "value": d["value"], "unit": UNIT, "sites": d["sites"], "seconds": d["seconds"], "lines_written": d["lines_written"],
-                "stream": stream, "input_bytes": d["input_bytes"], "output_bytes": d["output_bytes"], "host_threads": d["host_threads"],
+                "stream": stream, "startup_s": (d["seconds"] - stream["seconds"]) if stream else None, "input_bytes": d["input_bytes"], "output_bytes": d["output_bytes"], "host_threads": d["host_threads"],
                 "host_breakdown": d.get("host_breakdown"), "power_w_mean_under_load": (d.get("clocks") or {}).get("power_w_mean_under_load"),
                 "note": "start-up (interpreter, import torch, CUDA context, model load: ~3 s) is inside `seconds`; `stream` = first batch in "
                         "to last batch out; the 100 M-site run of the same command is profiles/r02_cli_binary_100M.json"}
@@ -243,7 +245,7 @@ def main():
     ap.add_argument("--no-freq", dest="no_freq", action="store_true", help="skip the call_freq measurement (the `freq` object)")
     ap.add_argument("--freq-records", dest="freq_records", type=int, default=50_000_000, help="call_freq records per GPU")
     ap.add_argument("--no-cli", dest="no_cli", action="store_true", help="skip the command-line measurement (the `cli` object)")
-    ap.add_argument("--cli-sites", dest="cli_sites", type=int, default=16_000_000, help="sites of the command-line measurement")
+    ap.add_argument("--cli-sites", dest="cli_sites", type=int, default=32_000_000, help="sites of the command-line measurement")
     ap.add_argument("--meas-skip-y", action="store_true",
                     help="measurement only (INVALID as a result): after warm-up, skip the inter-layer activation stores")
     # BASELINE.json configs[3]: the other model variants (not the headline line)
