@@ -53,3 +53,17 @@ def test_traffic_capture_is_tied_to_the_kernel_source():
         assert t == d["dram_bytes_per_site"] * 65536
     else:
         assert t is None and "re-capture" in detail["reason"]
+
+
+def test_command_line_object_reports_instead_of_raising():
+    # bench.py's `cli` object runs tools/bench_cli.py --binary in a subprocess: with the device stubbed out it yields the
+    # numbers of the host pipeline; without a GPU the real command fails and the object says so -- the bench line never
+    # depends on it
+    sys.path.insert(0, ROOT)
+    import bench
+    d = bench.command_line_run(70000, extra=["--host-only"])
+    assert "unavailable" not in d and d["sites"] == 65536 == d["lines_written"] and d["value"] > 0 and d["unit"] == "sites/s"
+    import torch
+    if not torch.cuda.is_available():
+        d = bench.command_line_run(70000)
+        assert set(d) == {"unavailable"} and "CUDA" in d["unavailable"]
