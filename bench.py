@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--no-freq", dest="no_freq", action="store_true", help="skip the call_freq measurement (the `freq` object)")
     ap.add_argument("--freq-records", dest="freq_records", type=int, default=50_000_000, help="call_freq records per GPU")
     ap.add_argument("--no-cli", dest="no_cli", action="store_true", help="skip the command-line measurement (the `cli` object)")
-    ap.add_argument("--cli-sites", dest="cli_sites", type=int, default=32_000_000, help="sites of the command-line measurement")
+    ap.add_argument("--cli-sites", dest="cli_sites", type=int, default=64_000_000, help="sites of the command-line measurement")
     ap.add_argument("--meas-skip-y", action="store_true",
                     help="measurement only (INVALID as a result): after warm-up, skip the inter-layer activation stores")
     # BASELINE.json configs[3]: the other model variants (not the headline line)
