@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--host-only", action="store_true", help="with --binary: stub the device out, in-process (no GPU needed)")
     ap.add_argument("--dir", default=None, help="where the synthetic files go (default: a temporary directory)")
     ap.add_argument("--variants", default="", help="with --binary: extra timed runs, comma-separated reader_threads:format_threads:stream_depth")
+    ap.add_argument("--block-sites", type=int, default=65536, help="with --binary: distinct synthetic sites per block (tests use fewer)")
     ap.add_argument("--out-dir", default=None, help="with --binary: directory of the calls file (default: next to the input)")
     ap.add_argument("--keep-free-gb", type=float, default=8.0, help="with --binary: shrink --sites so that this much disk stays free")
     a = ap.parse_args()
@@ -87,7 +88,7 @@ def binary(a):
     import shutil
     import subprocess
     from deepsignal_plant_b200 import feature_bin
-    block_n = 65536
+    block_n = max(1, int(a.block_sites))
     feats = synthetic.make_features(block_n, 13, 16, seed=1)
     info = synthetic.make_sampleinfo(block_n, seed=1)
     off = np.zeros(block_n + 1, np.int64)
