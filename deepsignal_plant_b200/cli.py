@@ -8,6 +8,7 @@ reference's flag names and defaults.
     python -m deepsignal_plant_b200 extract   -i reads.npz -o features.tsv      # decoded reads -> the reference's feature file
     python -m deepsignal_plant_b200 extract   -i reads.npz -o features.dspf     # ... -> binary hand-off (feature_bin.py)
     python -m deepsignal_plant_b200 call_mods -i features.dspf -m model.ckpt -o calls.tsv      # same calls, no text parsing
+    python -m deepsignal_plant_b200 pack_features -i features.tsv -o features.dspf             # an existing text file -> binary
 
 Multi-GPU: launch ``call_mods`` or ``call_freq`` under torchrun, one process per GPU.  ``call_mods`` cuts the feature
 file (or the reads archive) into contiguous shards and concatenates the output in file order, no collective on the
@@ -61,6 +62,12 @@ def build_parser():
                     help="the reference's number of worker processes: kept with its default; the native formatters use --host_threads")
     ex.add_argument("--host_threads", action="store", type=int, default=0, help="host threads for formatting; 0 = all cores")
     ex.add_argument("--f5_batch_size", action="store", type=int, default=30, required=False, help="reads per extraction chunk")
+
+    pk = sub.add_parser("pack_features", description="convert a text feature file of `extract` (plain or .gz) into the binary "
+                                                     "hand-off format that call_mods reads without parsing text (.dspf, feature_bin.py)")
+    pk.add_argument("--input_path", "-i", action="store", type=str, required=True, help="the 12-column text feature file")
+    pk.add_argument("--write_path", "-o", action="store", type=str, required=True, help="the binary feature file to write")
+    pk.add_argument("--host_threads", action="store", type=int, default=0, help="parser threads; 0 = all cores")
 
     g = cm.add_argument_group("INPUT")
     g.add_argument("--input_path", "-i", action="store", type=str, required=True,
@@ -173,6 +180,10 @@ def main(argv=None):
     elif args.module == "extract":
         from .extract_features import extract_to_file
         extract_to_file(args)
+    elif args.module == "pack_features":
+        from .feature_bin import pack_feature_file
+        n = pack_feature_file(args.input_path, args.write_path, nthreads=args.host_threads or None)
+        print("[pack_features] {} sites -> {}".format(n, args.write_path))
     elif args.module == "call_freq":
         from .call_mods_freq import call_mods_frequency_to_file
         call_mods_frequency_to_file(args)

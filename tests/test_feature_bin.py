@@ -48,6 +48,15 @@ def test_binary_file_equals_the_parsed_text_file(tmp_path, block_sites, batch_si
         assert got[k].tobytes() == g[k].tobytes(), k
 
 
+def test_pack_features_command_line(tmp_path, capsys):
+    from deepsignal_plant_b200 import cli
+    a, b = str(tmp_path / "a.dspf"), str(tmp_path / "b.dspf")
+    assert cli.main(["pack_features", "-i", TEXT, "-o", a, "--host_threads", "2"]) == 0
+    assert "%d sites" % FEAT["n"] in capsys.readouterr().out
+    feature_bin.pack_feature_file(TEXT, b, nthreads=2)
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
 def test_site_range_shards_cover_the_file_once(tmp_path):
     p = str(tmp_path / "f.dspf")
     n = feature_bin.pack_feature_file(TEXT, p, batch_sites=100, nthreads=2)
