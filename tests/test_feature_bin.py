@@ -48,6 +48,16 @@ def test_binary_file_equals_the_parsed_text_file(tmp_path, block_sites, batch_si
         assert got[k].tobytes() == g[k].tobytes(), k
 
 
+def test_file_format_is_pinned(tmp_path):
+    # the bytes of the packed golden feature file: a change of the layout (or of a parsed value) shows up here, so files
+    # that users have written keep being readable
+    p = str(tmp_path / "f.dspf")
+    feature_bin.pack_feature_file(TEXT, p, nthreads=2)
+    data = open(p, "rb").read()
+    assert len(data) == 262592 and data[:8] == b"DSPFEAT1" and data[64:72] == b"DSPFBLK1"
+    assert hashlib.sha256(data).hexdigest() == "4e64f983ced19dbae89375954ef314c60526c175a6cdfa429c0e63ddc1903297"
+
+
 def test_pack_features_command_line(tmp_path, capsys):
     from deepsignal_plant_b200 import cli
     a, b = str(tmp_path / "a.dspf"), str(tmp_path / "b.dspf")
