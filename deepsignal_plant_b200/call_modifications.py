@@ -496,11 +496,15 @@ def call_mods(args):
                 input_path, args.seq_len, args.signal_len, batch_sites=getattr(args, "max_batch", 65536), slots=depth + 6,
                 nthreads=int(getattr(args, "reader_threads", 0) or 0) or host_threads(args, world), byte_range=None if gz_single else _shard_of_file(input_path, rank, world))
 
+        stop_reading = threading.Event()
+
         def read():
             try:
                 if torch.cuda.is_available():
                     torch.cuda.set_device(device)              # page-locked slots belong to this rank's GPU context
                 for b in (reader or ()):
+                    if stop_reading.is_set():
+                        break
                     rq.put(b)
             except BaseException as e:                         # surfaced in the main thread
                 err.append(e)
@@ -508,7 +512,20 @@ def call_mods(args):
 
         rt = threading.Thread(target=read, daemon=True)
         rt.start()
-    model = load_model(args, device)
+
+        def abandon_reader():                                  # the model could not be built: let the reader thread end
+            stop_reading.set()
+            while rt.is_alive():
+                try:
+                    rq.get(timeout=0.1)
+                except queue.Empty:
+                    pass
+    try:
+        model = load_model(args, device)
+    except BaseException:
+        if rt is not None:
+            abandon_reader()
+        raise
     args.input_path = input_path
 
     result_file = args.result_file

@@ -522,10 +522,20 @@ STREAM_CHUNK_BYTES = 1 << 30
 
 def default_host_record_budget():
     """Records whose parsed columns fit in half of the host memory that is available now (at most one aggregation pass)."""
-    try:
-        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
-    except (ValueError, OSError, AttributeError):
-        avail = 16 << 30
+    avail = None
+    try:                                               # MemAvailable counts the page cache the kernel can drop (the input
+        with open("/proc/meminfo") as f:               # files that were just read sit there); free pages alone do not
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    avail = int(line.split()[1]) * 1024
+                    break
+    except (OSError, ValueError, IndexError):
+        pass
+    if avail is None:
+        try:
+            avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+        except (ValueError, OSError, AttributeError):
+            avail = 16 << 30
     return int(min(MAX_RECORDS_PER_PASS, max(1 << 20, avail // 2 // HOST_RECORD_BYTES)))
 
 
